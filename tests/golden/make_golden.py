@@ -1,0 +1,246 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED
+reference binary (oracle/_ref/lmp_serial, built by oracle/build_ref.sh from
+/root/reference) on small parity decks.  Run in the build container only:
+
+    bash oracle/build_ref.sh && python tests/golden/make_golden.py
+
+The decks follow SURVEY.md Appendix B (B1 USHER stream, B2/B5 normal force,
+B4 tangential force, B3 ballistic bookkeeping) plus a T=0 DPD force deck and a
+two-atom RanMars deck.  All buffer regions are built from the EXACT box bounds
+(SURVEY Q13), written as %.17g literals computed here (LAMMPS' own variable
+evaluation of 0.15*xhi differs from IEEE by 1 ulp) and atom sorting is disabled (`atom_modify sort 0 0`) so dump row
+order == LAMMPS local index order.
+"""
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+LMP = os.path.join(ROOT, "oracle", "_ref", "lmp_serial")
+DATA = "/root/reference/examples/OBMD_DPD/dpd_8map_obmd.data"
+
+NOISE = re.compile(r"^(FixNVE|linear_momentum|nlocal:|v\[i\]|f\[i\]|x\[i\]|atom->tag|dtf|sumforces|"
+                   r"pre_exchange|g_perp_global|avec :::|modify :::|Atom::map_init)")
+
+HEAD = """
+units           lj
+boundary        f p p
+atom_style      atomic
+atom_modify     sort 0 0
+comm_modify     vel yes
+newton          on
+read_data       {data}
+region          leftB block {xlo:.17g} {xlB:.17g} {ylo:.17g} {yhi:.17g} {zlo:.17g} {zhi:.17g}
+region          rightB block {xrB:.17g} {xhi:.17g} {ylo:.17g} {yhi:.17g} {zlo:.17g} {zhi:.17g}
+region          leftshear block {ls}
+region          rightshear block {rs}
+pair_style      dpd {T} 1.0 2616
+pair_coeff      * * {a0} {gamma} 1.0
+neighbor        0.4 bin
+neigh_modify    delay 0 every 1
+timestep        {dt}
+"""
+
+# Box of the shipped data file and the buffer length, as Python doubles.  Every
+# bound is written into the decks with %.17g so that LAMMPS parses exactly the
+# doubles the tests hand to the oracle / the CUDA path (tests/oracle_api.py
+# default_regions does the same arithmetic).
+BOX = ((0.0, 33.59462486002239), (0.0, 11.198208286674133), (0.0, 11.198208286674133))
+BUF = 0.15 * BOX[0][1]
+
+FIX = ("fix 2 all obmd 1 1 6111 {pxx} {pxy} {pxz} {dpxx} {freq} {alpha} {tau} {nbuf} "
+       "region1 leftB region2 rightB region3 leftshear region4 rightshear "
+       "region5 leftB region6 rightB buffersize {B:.17g} gfac 0.25 stepparallel 0 stepperp 1 "
+       "maxattempt {maxattempt} usher 1 31.03 1.0 0.02 10000 1.5 1.0 40 charged 0\n")
+
+
+def run_deck(name, text, workdir):
+    path = os.path.join(workdir, "in." + name)
+    with open(path, "w") as fh:
+        fh.write(text)
+    out = os.path.join(workdir, "out." + name)
+    with open(out, "w") as fh:
+        subprocess.check_call([LMP, "-in", path, "-log", "none"], cwd=workdir, stdout=fh,
+                              stderr=subprocess.STDOUT)
+    with open(out) as fh:
+        return [ln.rstrip("\n") for ln in fh if not NOISE.match(ln)]
+
+
+def read_dump(path):
+    """-> list of (step, ndarray rows) for a `dump custom` text file."""
+    frames = []
+    with open(path) as fh:
+        lines = fh.read().split("\n")
+    i = 0
+    while i < len(lines):
+        if lines[i].startswith("ITEM: TIMESTEP"):
+            step = int(lines[i + 1]); n = int(lines[i + 3])
+            assert lines[i + 8].startswith("ITEM: ATOMS")
+            rows = np.array([ln.split() for ln in lines[i + 9:i + 9 + n]], dtype=np.float64)
+            frames.append((step, rows))
+            i += 9 + n
+        else:
+            i += 1
+    return frames
+
+
+def head(**kw):
+    (xlo, xhi), (ylo, yhi), (zlo, zhi) = BOX
+    S = kw.pop("shear", 0.0)
+    d = dict(data=DATA, T=1.0, a0=209.6, gamma=4.5, dt=0.001464, xlo=xlo, xhi=xhi, ylo=ylo,
+             yhi=yhi, zlo=zlo, zhi=zhi, xlB=xlo + BUF, xrB=xhi - BUF)
+    if S > 0.0:
+        d["ls"] = "%.17g %.17g %.17g %.17g %.17g %.17g" % (xlo, xlo + S, ylo, yhi, zlo, zhi)
+        d["rs"] = "%.17g %.17g %.17g %.17g %.17g %.17g" % (xhi - S, xhi, ylo, yhi, zlo, zhi)
+    else:
+        d["ls"] = d["rs"] = "0.0 0.0 0.0 0.0 0.0 0.0"
+    d.update(kw)
+    return HEAD.format(**d)
+
+
+def fix(**kw):
+    d = dict(pxx=188.0, pxy=0, pxz=0, dpxx=0, freq=0, alpha=0.7, tau=0.005, nbuf=1327, maxattempt=1,
+             B=BUF)
+    d.update(kw)
+    return FIX.format(**d)
+
+
+def parse_usher(lines):
+    """USHER verdict lines -> (accepted, E as printed, iterations or -1)."""
+    out = []
+    for ln in lines:
+        m = re.match(r"USHER accepts at E = (\S+) in attempt No\. \d+ with (\d+) iterations", ln)
+        if m:
+            out.append((1, float(m.group(1)), int(m.group(2)))); continue
+        m = re.match(r"USHER denies at E = (\S+) at attempt", ln)
+        if m:
+            out.append((0, float(m.group(1)), -1))
+    return np.array(out, dtype=np.float64).reshape(-1, 3)
+
+
+def main():
+    if not os.path.exists(LMP):
+        sys.exit("oracle/_ref/lmp_serial missing: run `bash oracle/build_ref.sh` first")
+    wd = tempfile.mkdtemp(prefix="obmd_golden_")
+    print("working in", wd)
+
+    # ---- shipped configuration (input fixture: ids + coordinates, read_data order) ----
+    deck = head() + "dump d all custom 1 dump.in id type x y z\ndump_modify d format float %.17g\nrun 0\n"
+    run_deck("input", deck, wd)
+    (_, rows), = read_dump(os.path.join(wd, "dump.in"))
+    tag0 = rows[:, 0].astype(np.int32); x0 = rows[:, 2:5].copy()
+    box = np.array(BOX)
+    np.savez_compressed(os.path.join(HERE, "dpd_8map_obmd.npz"), tag=tag0, x=x0, box=box)
+    print("input:", len(tag0), "atoms")
+
+    # ---- B1: USHER / RanPark / tag stream on static atoms ----
+    deck = (head() + fix(alpha=1.0, nbuf=2000) +
+            "dump d all custom 12 dump.b1 id x y z\ndump_modify d format float %.17g\n"
+            "thermo 1\nthermo_style custom step atoms\nrun 12\n")
+    lines = run_deck("b1", deck, wd)
+    frames = read_dump(os.path.join(wd, "dump.b1"))
+    step, rows = frames[-1]
+    assert step == 12
+    ver = parse_usher(lines)
+    n0 = len(tag0)
+    np.savez_compressed(os.path.join(HERE, "b1_usher_static.npz"),
+                        verdicts=ver, final_tag=rows[:, 0].astype(np.int32),
+                        inserted_x=rows[n0:, 1:4].copy(), nsteps=12)
+    print("b1: trials", len(ver), "accepted", int(ver[:, 0].sum()), "final atoms", len(rows))
+
+    # ---- B2/B5: normal force distribution, static atoms, pair force zeroed ----
+    deck = (head(a0=0.0, gamma=0.0) + fix(dpxx=10.0, freq=5.0) +
+            "dump d all custom 1 dump.b2 id fx fy fz\ndump_modify d format float %.17g\nrun 3\n")
+    run_deck("b2", deck, wd)
+    frames = read_dump(os.path.join(wd, "dump.b2"))
+    np.savez_compressed(os.path.join(HERE, "b2_normal_force.npz"),
+                        **{"f%d" % s: r[:, 1:4].copy() for s, r in frames})
+    print("b2: frames", [s for s, _ in frames])
+
+    # ---- B4: tangential force, shear regions 2.5 wide ----
+    deck = (head(a0=0.0, gamma=0.0, shear=2.5) + fix(pxy=2.0, pxz=-1.0) +
+            "dump d all custom 1 dump.b4 id fx fy fz\ndump_modify d format float %.17g\nrun 1\n")
+    run_deck("b4", deck, wd)
+    frames = read_dump(os.path.join(wd, "dump.b4"))
+    np.savez_compressed(os.path.join(HERE, "b4_shear_force.npz"), f1=frames[-1][1][:, 1:4].copy())
+    print("b4: ok")
+
+    # ---- B3: ballistic deletion / insertion bookkeeping, 20 steps ----
+    deck = (head(a0=0.0, gamma=0.0, dt=0.01) +
+            "velocity all create 25.0 4928459 loop geom\nfix 1 all nve\n" +
+            fix(alpha=1.0, tau=0.05, nbuf=2000) +
+            "dump d all custom 20 dump.b3 id x y z vx vy vz fx fy fz\n"
+            "dump_modify d format float %.17g\nrun 20\n")
+    lines = run_deck("b3", deck, wd)
+    frames = read_dump(os.path.join(wd, "dump.b3"))
+    (s0, r0), (s1, r1) = frames
+    assert (s0, s1) == (0, 20)
+    ndel = sum(1 for ln in lines if ln.startswith("Deleting"))
+    ver = parse_usher(lines)
+    np.savez_compressed(os.path.join(HERE, "b3_ballistic.npz"),
+                        v0=r0[:, 4:7].copy(), tag20=r1[:, 0].astype(np.int32),
+                        x20=r1[:, 1:4].copy(), v20=r1[:, 4:7].copy(), f20=r1[:, 7:10].copy(),
+                        ndel=ndel, nins=int(ver[:, 0].sum()))
+    print("b3: deletions", ndel, "insertions", int(ver[:, 0].sum()), "atoms", len(r1))
+
+    # ---- deterministic DPD forces: T = 0 (sigma = 0), thermal velocities ----
+    deck = (head(T=0.0) + "velocity all create 1.0 4928459 loop geom\n"
+            "dump d all custom 1 dump.p0 id vx vy vz fx fy fz\ndump_modify d format float %.17g\n"
+            "thermo_style custom step pe press pxx pyy pzz pxy pxz pyz\n"
+            "thermo_modify format float %.15g norm no\nrun 0\n")
+    lines = run_deck("p0", deck, wd)
+    (_, rows), = read_dump(os.path.join(wd, "dump.p0"))
+    th = None
+    for k, ln in enumerate(lines):
+        if ln.split()[:2] == ["Step", "PotEng"]:
+            th = np.array(lines[k + 1].split(), dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "p0_pair_T0.npz"), v=rows[:, 1:4].copy(),
+                        f=rows[:, 4:7].copy(), thermo=th)
+    print("p0: thermo", th)
+
+    # ---- RanMars: two static atoms, one Gaussian per step ----
+    two = os.path.join(wd, "two.data")
+    with open(two, "w") as fh:
+        fh.write("two atoms\n\n2 atoms\n1 atom types\n\n0.0 10.0 xlo xhi\n0.0 10.0 ylo yhi\n"
+                 "0.0 10.0 zlo zhi\n\nMasses\n\n1 1.0\n\nAtoms\n\n1 1 5.0 5.0 5.0\n2 1 5.5 5.0 5.0\n")
+    deck = ("units lj\nboundary f p p\natom_style atomic\natom_modify sort 0 0\ncomm_modify vel yes\n"
+            "read_data two.data\npair_style dpd 1.0 1.0 2616\npair_coeff * * 209.6 4.5 1.0\n"
+            "timestep 0.001464\ndump d all custom 1 dump.rm id fx\n"
+            "dump_modify d format float %.17g\nrun 16\n")
+    run_deck("rm", deck, wd)
+    frames = read_dump(os.path.join(wd, "dump.rm"))
+    fx = np.array([r[0, 1] for _, r in frames])
+    np.savez_compressed(os.path.join(HERE, "ranmars_two_atoms.npz"), fx=fx)
+    print("ranmars: fx[0..2]", fx[:3])
+
+    # ---- R1 steady-exchange thermo trace (statistical parity reference) ----
+    deck = (head() + "fix 1 all nve\n" + fix(alpha=1.0, nbuf=1895) +
+            "thermo 10\nthermo_style custom step atoms temp press\n"
+            "thermo_modify format float %.15g lost ignore\nrun 400\n")
+    lines = run_deck("r1", deck, wd)
+    th = []
+    on = False
+    for ln in lines:
+        w = ln.split()
+        if w[:2] == ["Step", "Atoms"]:
+            on = True; continue
+        if on:
+            if len(w) == 4 and w[0].isdigit():
+                th.append([float(t) for t in w])
+            elif w and w[0] == "Loop":
+                on = False
+    ver = parse_usher(lines)
+    ndel = sum(1 for ln in lines if ln.startswith("Deleting"))
+    np.savez_compressed(os.path.join(HERE, "r1_thermo.npz"), thermo=np.array(th), ndel=ndel,
+                        ntrials=len(ver), nacc=int(ver[:, 0].sum()))
+    print("r1: steps", len(th), "ndel", ndel, "trials", len(ver), "accepted", int(ver[:, 0].sum()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,161 @@
+"""Pin the CPU oracle (oracle/obmd_oracle.c) against golden vectors produced by the
+UNMODIFIED reference binary (tests/golden/make_golden.py).  CPU only."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+
+import oracle_api as O
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name))
+
+
+@pytest.fixture(scope="module")
+def shipped():
+    d = load("dpd_8map_obmd.npz")
+    return d["tag"], d["x"], d["box"]
+
+
+def sig6(v):
+    return float("%.6g" % v)
+
+
+def test_ranpark_known_answers():
+    L = O.lib()
+    s = C.c_int(6111)
+    seq = [L.orc_ranpark_uniform(C.byref(s)) for _ in range(40)]
+    # independent restatement of random_park.cpp:43-50 in exact integer arithmetic
+    t = 6111
+    for k in range(40):
+        t = (16807 * t) % 2147483647
+        assert seq[k] == t * (1.0 / 2147483647)
+    assert L.orc_ranpark_skip(6111, 40) == t
+    assert L.orc_ranpark_skip(6111, 0) == 6111
+    assert L.orc_ranpark_skip(12345, 1000003) == (pow(16807, 1000003, 2147483647) * 12345) % 2147483647
+
+
+def test_ranmars_against_reference_two_atom_deck():
+    """fx on atom 1 of a static dimer = one RanMars Gaussian per step (pair_dpd.cpp:122)."""
+    L = O.lib()
+    fx_ref = load("ranmars_two_atoms.npz")["fx"]
+    st = (C.c_char * 2048)()
+    L.orc_ranmars_init(st, 2616)
+    a0, gamma, rc, dt = 209.6, 4.5, 1.0, 0.001464
+    sigma = math.sqrt(2.0 * 1.0 * 1.0 * gamma)
+    dtinvsqrt = 1.0 / math.sqrt(dt)
+    delx = 5.0 - 5.5
+    r = math.sqrt(delx * delx)
+    rinv = 1.0 / r
+    wd = 1.0 - r / rc
+    for n in range(len(fx_ref)):
+        xi = L.orc_ranmars_gaussian(st)
+        fpair = a0 * wd
+        fpair -= gamma * wd * wd * 0.0 * rinv
+        fpair *= 1.0
+        fpair += 1.0 * sigma * wd * xi * dtinvsqrt
+        fpair *= rinv
+        assert delx * fpair == fx_ref[n], n
+
+
+def test_b1_usher_stream_bit_exact(shipped):
+    """RanPark trial stream, USHER verdicts, accepted positions and tags."""
+    tag, x, box = shipped
+    L = O.lib()
+    g = load("b1_usher_static.npz")
+    for use_cells in (0, 1):
+        p = O.make_fix(box[:, 0], box[:, 1], alpha=1.0, nbuf=2000.0, use_cells=use_cells)
+        a = O.OracleAtoms(x, tag=tag)
+        trials = (O.Trial * 4096)()
+        ver = []
+        for _ in range(int(g["nsteps"])):
+            L.orc_fix_pre_exchange(C.byref(p), C.byref(a.c), trials, 4096)
+            for k in range(p.last_ntrials):
+                t = trials[k]
+                ver.append((t.accepted, sig6(t.energy), t.iter if t.accepted else -1))
+        ref = g["verdicts"]
+        assert len(ver) == len(ref)
+        got = np.array(ver, dtype=np.float64)
+        assert np.array_equal(got[:, 0], ref[:, 0])
+        assert np.array_equal(got[:, 2], ref[:, 2])
+        assert np.allclose(got[:, 1], ref[:, 1], rtol=2e-6, atol=0)
+        assert np.array_equal(a.view("tag"), g["final_tag"])
+        assert np.array_equal(a.view("x")[len(tag):], g["inserted_x"])  # bit-exact
+
+
+def _post_force_once(p, a):
+    L = O.lib()
+    L.orc_fix_pre_exchange(C.byref(p), C.byref(a.c), None, 0)
+    a.f[:] = 0.0
+    L.orc_fix_post_force(C.byref(p), C.byref(a.c))
+
+
+def test_b2_normal_force_bit_exact(shipped):
+    tag, x, box = shipped
+    g = load("b2_normal_force.npz")
+    p = O.make_fix(box[:, 0], box[:, 1], a0=0.0, gamma=0.0, dpxx=10.0, freq=5.0)
+    a = O.OracleAtoms(x, tag=tag)
+    assert not g["f0"].any()          # setup() forces are exactly zero (Q3)
+    for s in (1, 2, 3):
+        _post_force_once(p, a)
+        assert a.n == len(tag)
+        assert np.array_equal(a.view("f"), g["f%d" % s]), s
+    ly = box[1, 1] - box[1, 0]; lz = box[2, 1] - box[2, 0]
+    left = x[:, 0] < 0.15 * box[0, 1]
+    want = (188.0 + 10.0 * math.sin(2 * math.pi * 5.0 * 3 * 0.001464)) * ly * lz
+    assert abs(a.view("f")[left, 0].sum() - want) < 1e-8 * want
+
+
+def test_b4_shear_force_bit_exact(shipped):
+    tag, x, box = shipped
+    g = load("b4_shear_force.npz")
+    p = O.make_fix(box[:, 0], box[:, 1], a0=0.0, gamma=0.0, pxy=2.0, pxz=-1.0, shear_size=2.5)
+    a = O.OracleAtoms(x, tag=tag)
+    _post_force_once(p, a)
+    assert np.array_equal(a.view("f"), g["f1"])
+
+
+def test_b3_ballistic_bookkeeping_bit_exact(shipped):
+    """20 steps of delete / insert / weights / NVE / PBC: order, x, v, f."""
+    tag, x, box = shipped
+    g = load("b3_ballistic.npz")
+    L = O.lib()
+    p = O.make_fix(box[:, 0], box[:, 1], a0=0.0, gamma=0.0, dt=0.01, alpha=1.0, tau=0.05,
+                   nbuf=2000.0)
+    a = O.OracleAtoms(x, v=g["v0"], tag=tag)
+    trials = (O.Trial * 4096)()
+    ndel = nins = 0
+    for s in range(1, 21):
+        L.orc_step(C.byref(p), C.byref(a.c), 0, s, trials, 4096)
+        ndel += p.last_ndel; nins += p.last_naccept
+    assert (ndel, nins) == (int(g["ndel"]), int(g["nins"]))
+    assert np.array_equal(a.view("tag"), g["tag20"])
+    assert np.array_equal(a.view("x"), g["x20"])
+    assert np.array_equal(a.view("v"), g["v20"])
+    assert np.array_equal(a.view("f"), g["f20"])
+
+
+def test_p0_pair_forces_T0(shipped):
+    """Deterministic DPD (sigma = 0) forces, energy and pressure tensor vs the reference."""
+    tag, x, box = shipped
+    g = load("p0_pair_T0.npz")
+    L = O.lib()
+    p = O.make_fix(box[:, 0], box[:, 1], temperature=0.0)
+    a = O.OracleAtoms(x, v=g["v"], tag=tag)
+    eng = C.c_double(); vir = (C.c_double * 6)()
+    L.orc_pair_compute(C.byref(p), C.byref(a.c), 0, 0, C.byref(eng), vir)
+    f = a.view("f"); fr = g["f"]
+    scale = np.maximum(np.abs(fr), np.abs(fr).mean())
+    assert np.max(np.abs(f - fr) / scale) < 1e-9     # tolerance stated by north_star
+    th = g["thermo"]   # step pe press pxx pyy pzz pxy pxz pyz
+    assert abs(eng.value - th[1]) < 1e-9 * abs(th[1])
+    vol = np.prod(box[:, 1] - box[:, 0])
+    v = g["v"]
+    ke = [np.sum(v[:, i] * v[:, j]) for i, j in ((0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2))]
+    pt = [(ke[k] + vir[k]) / vol for k in range(6)]
+    assert np.allclose(pt, th[3:9], rtol=1e-9, atol=1e-9)
