@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- OBMD-DPD atom-steps/s on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py --gpus 1 --steps K --warmup W            # our arm (CUDA, C ABI)
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path
+
+A "step" is one MD timestep of the whole hot path (FixNVE halves, cell build, fix obmd
+pre_exchange incl. batched USHER, PairDPD, fix obmd post_force) over every atom.  Workload at
+N=1: BASELINE config 2, "OBMD-DPD fluid at equilibrium, 1M particles" = the shipped
+configuration tiled 4x5x4 (1 010 960 atoms), steady-exchange regime R1 (alpha 1.0,
+nbuf = int(0.15 N)), see SURVEY 8(d).  value = sum over steps of the atom count / device time
+(CUDA events on the library's stream, max over ranks).  e2e = the same metric through the C ABI
+with HOST buffers: every step uploads x,v from pinned memory, runs the hooks, reads forces (and
+the atom arrays when insertions/deletions changed them) back -- the flow of the LAMMPS plugin.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "OBMD-DPD atom-steps/sec"
+UNIT = "atom-steps/s"
+PAIR_BYTES_PER_ATOM = 80.0   # x,v,tag,type in + f out
+USHER = (1, 31.03, 1.0, 0.02, 1e4, 1.5, 1.0, 40)
+
+
+def shipped():
+    d = np.load(os.path.join(ROOT, "tests", "golden", "dpd_8map_obmd.npz"))
+    return d["x"].copy(), d["box"].copy()
+
+
+def tiled(reps):
+    x, box = shipped()
+    L = box[:, 1] - box[:, 0]
+    parts = [x + np.array([i, j, k]) * L for i in range(reps[0]) for j in range(reps[1])
+             for k in range(reps[2])]
+    X = np.concatenate(parts)
+    B = np.array([[0.0, L[0] * reps[0]], [0.0, L[1] * reps[1]], [0.0, L[2] * reps[2]]])
+    return X, B
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows),
+                "reasons": reasons}
+
+
+def build_sim(x, box, device, regime="R1", temperature=1.0):
+    import common_cases as cc
+    n = len(x)
+    if regime == "R1":
+        kw = dict(alpha=1.0, nbuf=float(int(0.15 * n)))
+    else:
+        kw = dict(alpha=0.7, nbuf=float(int(0.7 * 0.15 * n)))
+    sim = cc.device_sim(box, device=device, temperature=temperature, **kw)
+    tag = np.arange(1, n + 1, dtype=np.int32)
+    sim.upload(x, np.zeros_like(x), np.ones(n, np.int32), tag, capacity=int(1.15 * n))
+    sim.setup(0)
+    return sim, kw
+
+
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    reps = tuple(args.reps)
+    x, box = tiled(reps)
+    n0 = len(x)
+    sim, kw = build_sim(x, box, local, args.regime)
+    stream = torch.cuda.ExternalStream(sim.L.obmd_stream(sim.h), device=local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step = 1
+    sim.run(step, args.equil); step += args.equil          # untimed equilibration from v = 0
+    for _ in range(args.warmup):
+        sim.run(step, 1); step += 1
+    sim.timing(True); sim.timing_reset()
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    l0 = sim.launches
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    atom_steps = 0
+    e0.record(stream)
+    for _ in range(args.steps):
+        sim.run(step, 1); step += 1
+        atom_steps += sim.nlocal
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = sim.launches - l0
+    sampler.stop_flag = True; sampler.join()
+    fam = {}
+    for name in ("nve", "bin", "sort", "pre_exchange", "usher", "pbc", "pair", "post_force"):
+        t, nl = sim.timing_get(name)
+        fam[name] = {"ms_per_step": t / args.steps, "launches_per_step": nl / args.steps}
+    sim.timing(False)
+    st = sim.fix_state()
+
+    # ---- e2e through the C ABI with host buffers (plugin flow) ----
+    e2e = None
+    if args.e2e_steps > 0:
+        e2e = e2e_run(sim, args.e2e_steps, step, barrier)
+        step += args.e2e_steps
+
+    t = torch.tensor([ms, float(atom_steps), e2e["seconds"] if e2e else 0.0,
+                      float(e2e["atom_steps"]) if e2e else 0.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms = tmax[0].item(); atom_steps = tsum[1].item()
+        if e2e:
+            e2e["seconds"] = tmax[2].item(); e2e["atom_steps"] = tsum[3].item()
+    if rank == 0:
+        hbm, how = peaks()
+        pair_ms = fam["pair"]["ms_per_step"]
+        natoms_avg = atom_steps / args.steps / world
+        achieved = PAIR_BYTES_PER_ATOM * natoms_avg / (pair_ms * 1e-3) / 1e9 if pair_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "pair_dram_bytes.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": atom_steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "OBMD-DPD fluid, shipped configuration tiled %dx%dx%d = %d atoms per GPU, "
+                                   "regime %s (alpha %.1f, nbuf %d), T=1, dt=0.001464, rc=1, usher 31.03"
+                                   % (reps + (n0, args.regime, kw["alpha"], int(kw["nbuf"]))),
+                       "atoms_per_gpu": n0, "parallelism": "replicas only" if world > 1 else "single GPU",
+                       "l2": "per-step working set (%.0f MB) exceeds the 126 MB L2" % (n0 * 168 / 1e6),
+                       "equil_steps": args.equil,
+                       "inserted": int(st.ninserted), "deleted": int(st.ndeleted)},
+            "gpu_launches": int(launches),
+            "kernel_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in fam.items()},
+            "roofline": {"kernel": "k_pair_dpd", "bound": "hbm", "achieved": achieved, "peak": hbm,
+                         "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic, "peak_source": how,
+                         "algorithmic_bytes_per_atom": PAIR_BYTES_PER_ATOM,
+                         "note": "fp64-pipe bound, not HBM bound: see DESIGN.md section 6"},
+            "clocks": sampler.summary(),
+        }
+        if e2e:
+            line["e2e"] = {"value": e2e["atom_steps"] / e2e["seconds"], "unit": UNIT,
+                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                           "steps": args.e2e_steps}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_budget)
+        print(json.dumps(line), flush=True)
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def e2e_run(sim, nsteps, step, barrier):
+    """Plugin flow: host owns x,v,f (pinned); per step upload x,v, run the device hooks, read f
+    (and the full atom arrays when the fix inserted/deleted) back; the host does the NVE halves as
+    LAMMPS' FixNVE would."""
+    import torch
+    out = sim.download()
+    n = sim.nlocal
+    cap = int(n * 1.1) + 4096
+    pin = lambda *shape, dt=torch.float64: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+    X, V, F = pin(cap, 3), pin(cap, 3), pin(cap, 3)
+    X[:n], V[:n], F[:n] = out["x"], out["v"], out["f"]
+    dt = 0.001464
+    dtf = 0.5 * dt
+    h2d = d2h = 0
+    atom_steps = 0
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(nsteps):
+        V[:n] += dtf * F[:n]            # FixNVE::initial_integrate on the host (mass 1)
+        X[:n] += dt * V[:n]
+        sim.upload_xv(X[:n], V[:n]); h2d += 48 * n
+        sim.build_cells()
+        rep, _ = sim.pre_exchange()
+        sim.pbc()
+        sim.pair_compute(step + s)
+        sim.post_force()
+        m = sim.nlocal
+        if rep.ndel or rep.naccept:     # atom arrays changed: the shim refreshes the host copy
+            o = sim.download(("x", "v", "f"))
+            X[:m], V[:m], F[:m] = o["x"], o["v"], o["f"]; d2h += 72 * m
+        else:
+            o = sim.download(("x", "f"))
+            X[:m], F[:m] = o["x"], o["f"]; d2h += 48 * m
+        n = m
+        V[:n] += dtf * F[:n]            # FixNVE::final_integrate
+        atom_steps += n
+    barrier()
+    sec = time.perf_counter() - t0
+    return {"seconds": sec, "atom_steps": atom_steps, "h2d": h2d // nsteps, "d2h": d2h // nsteps}
+
+
+# ------------------------------------------------------------------ reference arm / CPU baseline
+
+DECK = """units lj
+boundary f p p
+atom_style atomic
+comm_modify vel yes
+newton on
+read_data {data}
+region leftB block 0.0 {xlB:.17g} 0.0 {yhi:.17g} 0.0 {zhi:.17g}
+region rightB block {xrB:.17g} {xhi:.17g} 0.0 {yhi:.17g} 0.0 {zhi:.17g}
+region leftshear block 0.0 0.0 0.0 0.0 0.0 0.0
+region rightshear block 0.0 0.0 0.0 0.0 0.0 0.0
+pair_style dpd 1.0 1.0 2616
+pair_coeff * * 209.6 4.5 1.0
+neighbor 0.4 bin
+neigh_modify delay 0 every 1
+timestep 0.001464
+fix 1 all nve
+fix 2 all obmd 1 1 6111 188.0 0 0 0 0 {alpha} 0.005 {nbuf} region1 leftB region2 rightB region3 leftshear region4 rightshear region5 leftB region6 rightB buffersize {B:.17g} gfac 0.25 stepparallel 0 stepperp 1 maxattempt 1 usher 1 31.03 1.0 0.02 10000 1.5 1.0 40 charged 0
+thermo_style custom step atoms
+thermo {nsteps}
+run {nsteps}
+"""
+
+
+def ref_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "lmp_serial")
+    return p if os.path.exists(p) else None
+
+
+def run_reference(reps, nsteps, regime="R1"):
+    """Run the unmodified reference (oracle/_ref/lmp_serial, 1 core, MPI stubs) on the tiled deck;
+    returns (atom_steps, loop_seconds)."""
+    x, box = tiled(reps)
+    n = len(x)
+    wd = tempfile.mkdtemp(prefix="obmd_ref_")
+    data = os.path.join(wd, "tiled.data")
+    with open(data, "w") as fh:
+        fh.write("tiled OBMD_DPD\n\n%d atoms\n1 atom types\n\n0.0 %.17g xlo xhi\n0.0 %.17g ylo yhi\n"
+                 "0.0 %.17g zlo zhi\n\nMasses\n\n1 1\n\nAtoms\n\n" % (n, box[0, 1], box[1, 1], box[2, 1]))
+        ids = np.arange(1, n + 1)
+        np.savetxt(fh, np.column_stack([ids, np.ones(n), x]), fmt="%d %d %.6f %.6f %.6f")
+    B = 0.15 * box[0, 1]
+    alpha, nbuf = (1.0, int(0.15 * n)) if regime == "R1" else (0.7, int(0.7 * 0.15 * n))
+    deck = DECK.format(data=data, xlB=B, xrB=box[0, 1] - B, xhi=box[0, 1], yhi=box[1, 1], zhi=box[2, 1],
+                       alpha=alpha, nbuf=nbuf, B=B, nsteps=nsteps)
+    inp = os.path.join(wd, "in.ref")
+    open(inp, "w").write(deck)
+    out = os.path.join(wd, "out.ref")
+    with open(out, "w") as fh:     # the reference prints ~40 debug lines per step
+        subprocess.check_call([ref_binary(), "-in", inp, "-log", "none"], cwd=wd, stdout=fh,
+                              stderr=subprocess.STDOUT)
+    loop = None
+    atoms = []
+    for ln in open(out, errors="replace"):
+        w = ln.split()
+        if ln.startswith("Loop time of"):
+            loop = float(w[3])
+        elif len(w) == 2 and w[0].isdigit() and w[1].isdigit():
+            atoms.append(int(w[1]))
+    for f in (data, inp, out):
+        os.remove(f)
+    navg = 0.5 * (atoms[0] + atoms[-1]) if atoms else n
+    return navg * nsteps, loop
+
+
+def ref_cost_per_step(n, area_tiles):
+    """Rough serial cost model of the reference: ~2.1 us/atom-step for
+    neigh+pair+fix scans, plus brute-force USHER: ~130 trials per shipped cross-section per step,
+    ~5 iterations each, ~3.5 ns per atom per iteration."""
+    return 2.1e-6 * n + 130 * area_tiles * 5 * 3.5e-9 * n
+
+
+def pick_sample(total_steps, budget_s):
+    for reps in ((4, 5, 4), (4, 2, 2), (4, 1, 2), (4, 1, 1), (2, 1, 1), (1, 1, 1)):
+        n = 12637 * reps[0] * reps[1] * reps[2]
+        if (ref_cost_per_step(n, reps[1] * reps[2]) + 0.0) * total_steps + 4e-6 * n <= budget_s:
+            return reps
+    return (1, 1, 1)
+
+
+def cpu_baseline(budget_s=25.0, steps=4, reps=None):
+    if ref_binary() is None:
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                "sample": "oracle/_ref/lmp_serial missing (run oracle/build_ref.sh)"}
+    reps = reps or pick_sample(steps, budget_s)
+    a, loop = run_reference(reps, steps)
+    n = 12637 * reps[0] * reps[1] * reps[2]
+    return {"value": a / loop, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": "%d steps of the R1 deck tiled %dx%dx%d (%d atoms), unmodified reference "
+                      "(LAMMPS 7Feb2024 + src/OBMD, g++ -O3, MPI stubs, 1 core), LAMMPS loop time %.2f s"
+                      % (steps, reps[0], reps[1], reps[2], n, loop)}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total = args.steps + args.warmup
+    reps = pick_sample(total, args.ref_budget)
+    n = 12637 * reps[0] * reps[1] * reps[2]
+    if ref_binary() is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/lmp_serial not built"}))
+        return
+    # warm-up and timed steps are separate runs of the binary: LAMMPS' loop time excludes setup
+    if args.warmup > 0:
+        run_reference(reps, args.warmup)
+    a, loop = run_reference(reps, args.steps)
+    val = a / loop
+    x, box = tiled(tuple(args.reps))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * loop / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "OBMD-DPD fluid, shipped configuration tiled %dx%dx%d = %d atoms, regime R1; "
+                                   "reference timed on a bounded sample: tiling %dx%dx%d = %d atoms"
+                                   % (tuple(args.reps) + (len(x),) + reps + (n,))},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference",
+                             "sample": "%d timed steps, tiling %dx%dx%d (%d atoms), lmp_serial 1 core"
+                                       % (args.steps, reps[0], reps[1], reps[2], n)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reps", type=int, nargs=3, default=[4, 5, 4], help="tiling of the shipped box")
+    ap.add_argument("--regime", default="R1", choices=["R0", "R1"])
+    ap.add_argument("--equil", type=int, default=300, help="untimed equilibration steps from v = 0")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--ref-budget", type=float, default=150.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

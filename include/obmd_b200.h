@@ -1,0 +1,191 @@
+/* obmd_b200.h -- C ABI of libobmd_b200.so: the B200 (sm_100a) implementation of the
+ * OBMD-DPD hot path of chocolatesoup/OBMD-LAMMPS-extension.
+ *
+ * This is the drop-in boundary.  A LAMMPS style shim (host/lammps_plugin.cpp) or any
+ * other host binds exactly these entry points; every one cites the reference
+ * interface it replaces (paths relative to /root/reference/code/src).  Plain pointers
+ * and sizes only: no C++ or torch types cross this line.  All functions return 0 on
+ * success and a negative obmd_status on failure; obmd_last_error() gives the message
+ * the shim hands to LAMMPS' error->all() (reference error behaviour:
+ * fix_obmd_merged.cpp:72,91,171-191,2160-2163; pair_dpd.cpp:197-205).
+ * There is no CPU fallback: without a CUDA device obmd_create() fails.
+ *
+ * Host arrays use LAMMPS' layout (atom.h): x,v,f = double[n][3] (AoS), type/tag/image =
+ * int[n] (LAMMPS_SMALLBIG: tagint = imageint = int32), index = LAMMPS local index.
+ * Device arrays are cell-sorted SoA planes; every atom carries its LAMMPS local
+ * index so that deletion/insertion bookkeeping and USHER summation order are
+ * reproduced exactly.
+ */
+#ifndef OBMD_B200_H
+#define OBMD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OBMD_MAXTYPES 8
+#define OBMD_ABI_VERSION 1
+
+typedef struct obmd_ctx obmd_ctx;
+
+enum obmd_status {
+  OBMD_OK = 0,
+  OBMD_ERR_CUDA = -1,      /* CUDA runtime error (message has the call site) */
+  OBMD_ERR_ARG = -2,       /* illegal argument, mirrors "Illegal fix obmd command" */
+  OBMD_ERR_STATE = -3,     /* call order violated (e.g. compute before upload) */
+  OBMD_ERR_CAPACITY = -4,  /* a fixed-capacity device buffer overflowed */
+  OBMD_ERR_NONFINITE = -5, /* non-numeric coordinates (domain.cpp:540-545) */
+  OBMD_ERR_USHER = -6      /* |f| < 1e-6 with E > etarget: the reference spins forever (Q10) */
+};
+
+/* region block (region_block.cpp:289-293: closed interval on all three axes) */
+typedef struct { double lo[3], hi[3]; } obmd_block;
+
+/* `fix ID group obmd ntype nfreq seed pxx pxy pxz dpxx freq alpha tau nbuf keyword ...`
+ * after parsing (fix_obmd_merged.cpp:88-164 positional, :1881-2164 keywords; defaults
+ * as in :1883-1939).  ATOM mode, usher, charged 0. */
+typedef struct {
+  int ntype, nfreq, seed;
+  double pxx, pxy, pxz, dpxx, freq, alpha, tau, nbuf;
+  obmd_block region[6];   /* region1..6: left/right buffer, left/right shear, left/right insertion */
+  double buffer_size, g_fac;
+  int step_parallel, step_perp; /* must be 0 / 1 (Q4) */
+  int maxattempt;
+  int usherflag;
+  double etarget, ds0, dtheta0, uovlp, dsovlp, eps;
+  int nattempt;
+} obmd_fix_args;
+
+/* Restartable fix state (the reference sets restart_global but saves nothing). */
+typedef struct {
+  int rng_seed;            /* RanPark state (random_park.cpp:43-50) */
+  double simulation_time;  /* fix_obmd_merged.cpp:610 */
+  double momentumForce_left[3], momentumForce_right[3];
+  double shearForce_left[3], shearForce_right[3];
+  long long ninserted, ndeleted;
+} obmd_fix_state;
+
+/* Per-call report of pre_exchange (what the reference prints to stdout, Q8). */
+typedef struct {
+  int ndel;                 /* atoms deleted (try_deleting, :639-865) */
+  int cnt_left, cnt_right;  /* Group::count(igroup, region1/2) (:582-583) */
+  int ninsert_left, ninsert_right; /* :586-589 */
+  int ntrials, naccept;     /* USHER trials run / atoms created */
+  int usher_rounds;         /* speculative-commit rounds used */
+  int maxtag;               /* find_maxid before insertion (:1860-1875) */
+  int nlocal;               /* atoms after the call */
+  double vnewl[3], vnewr[3];
+} obmd_pre_exchange_report;
+
+/* One USHER trial (diagnostics / parity tests). */
+typedef struct {
+  double start[3], end[3];
+  double energy;
+  int iter, accepted, side, tag;
+} obmd_trial;
+
+/* ---- lifetime --------------------------------------------------------------- */
+int obmd_abi_version(void);
+/* device: CUDA ordinal.  Fails with OBMD_ERR_CUDA when no sm_100 device is usable. */
+int obmd_create(obmd_ctx **out, int device);
+void obmd_destroy(obmd_ctx *ctx);
+const char *obmd_last_error(const obmd_ctx *ctx); /* ctx may be NULL: last create error */
+
+/* ---- domain / atom types (domain.h boxlo/boxhi, atom->mass) ------------------- */
+/* boundary f p p, orthogonal.  Needs >= 3 cells of size max(cut) in y and z. */
+int obmd_set_box(obmd_ctx *ctx, const double boxlo[3], const double boxhi[3]);
+int obmd_set_masses(obmd_ctx *ctx, int ntypes, const double *mass /* [ntypes+1], 1-based */);
+int obmd_set_timestep(obmd_ctx *ctx, double dt); /* update->dt */
+/* x-slab owned by this rank [sublo, subhi) for multi-GPU runs (domain->sublo/subhi[0]);
+ * default = whole box. */
+int obmd_set_subdomain(obmd_ctx *ctx, double sublo_x, double subhi_x);
+
+/* ---- pair_style dpd (DPD-BASIC/pair_dpd.cpp) --------------------------------- */
+/* PairDPD::settings (:195-216): pair_style dpd T cut_global seed */
+int obmd_pair_settings(obmd_ctx *ctx, double temperature, double cut_global, int seed);
+/* PairDPD::coeff (:222-251): pair_coeff itype jtype a0 gamma [cut]; cut <= 0 -> cut_global */
+int obmd_pair_coeff(obmd_ctx *ctx, int itype, int jtype, double a0, double gamma, double cut);
+/* PairDPD::init_style + init_one (:257-291): sigma = sqrt(2 kB T gamma), symmetrise, build the
+ * cell grid.  boltz = force->boltz (1 in lj units). */
+int obmd_pair_init(obmd_ctx *ctx, double boltz);
+/* PairDPD::single (:401-418), host-side scalar for callers that probe the potential. */
+double obmd_pair_single(const obmd_ctx *ctx, int itype, int jtype, double rsq, double *fforce);
+
+/* ---- fix obmd (OBMD/fix_obmd_merged.cpp) ------------------------------------- */
+/* constructor + init (:66-287, :321-536): validates args, seeds RanPark(seed) and warms it
+ * 30 draws, zeroes simulation_time and the flux forces (Q3). */
+int obmd_fix_create(obmd_ctx *ctx, const obmd_fix_args *args);
+int obmd_fix_set_flux(obmd_ctx *ctx, double pxx, double pxy, double pxz, double dpxx, double freq,
+                      double alpha, double tau, double nbuf); /* v_ variables, :563-572 */
+int obmd_fix_get_state(const obmd_ctx *ctx, obmd_fix_state *out);
+int obmd_fix_set_state(obmd_ctx *ctx, const obmd_fix_state *in);
+
+/* ---- atoms: host <-> device --------------------------------------------------- */
+/* Upload n owned atoms in LAMMPS local order (atom->x, v, type, tag, image; f may be NULL).
+ * natoms_capacity: device capacity to reserve (>= n; insertions grow nlocal). */
+int obmd_upload(obmd_ctx *ctx, int n, const double *x, const double *v, const double *f,
+                const int *type, const int *tag, const int *image, int capacity);
+/* Refresh only positions/velocities of the n atoms already resident (same local order). */
+int obmd_upload_xv(obmd_ctx *ctx, int n, const double *x, const double *v);
+/* Download in LAMMPS local order; any pointer may be NULL.  Returns nlocal in *n. */
+int obmd_download(obmd_ctx *ctx, int *n, double *x, double *v, double *f, int *type, int *tag,
+                  int *image);
+int obmd_nlocal(const obmd_ctx *ctx);
+
+/* ---- per-step hooks, in the order Verlet::run calls them (verlet.cpp:229-363) -- */
+/* FixNVE::initial_integrate (fix_nve.cpp:80-145) */
+int obmd_nve_initial(obmd_ctx *ctx);
+/* NBinStandard::bin_atoms + NPairBin::build role (nbin_standard.cpp:221-261,
+ * npair_bin.cpp:52-253): cell index, counting sort of the SoA planes.  Atoms outside the
+ * box in x are parked behind the live range for pre_exchange to delete. */
+int obmd_build_cells(obmd_ctx *ctx);
+/* FixObmdMerged::pre_exchange (:550-633): delete, count, USHER insert, flux forces.
+ * Requires obmd_build_cells() on the current positions.  report/trials may be NULL. */
+int obmd_pre_exchange(obmd_ctx *ctx, obmd_pre_exchange_report *report, obmd_trial *trials,
+                      int maxtrials);
+/* Domain::pbc (domain.cpp:529-640) for boundary f p p: wrap y,z and update image flags. */
+int obmd_pbc(obmd_ctx *ctx);
+/* Verlet::force_clear + PairDPD::compute (:66-163) (+ virial_fdotr_compute, pair.cpp:1735).
+ * ntimestep keys the counter RNG.  eflag/vflag != 0 also reduce eng_vdwl / virial[6]. */
+int obmd_pair_compute(obmd_ctx *ctx, long long ntimestep, int eflag, int vflag);
+int obmd_pair_tallies(obmd_ctx *ctx, double *eng_vdwl, double virial[6]);
+/* FixObmdMerged::post_force (:1229-1240): reg_force x2 + reg_force_perp x2 */
+int obmd_post_force(obmd_ctx *ctx);
+/* FixNVE::final_integrate (fix_nve.cpp:185-244) */
+int obmd_nve_final(obmd_ctx *ctx);
+/* nsteps full timesteps, device resident, in exactly the order above.  first_step = the
+ * timestep number of the first step (update->ntimestep + 1). */
+int obmd_run(obmd_ctx *ctx, long long first_step, int nsteps);
+
+/* ---- observables (compute temp / ke, used by the statistical parity checks) ---- */
+/* out[0] = sum m v^2 (2*KE), out[1..3] = total momentum, out[4] = nlocal */
+int obmd_reduce_kinetic(obmd_ctx *ctx, double out[5]);
+/* 1-D profiles along x in nbins bins over the box: count[nbins], vx sums [nbins] */
+int obmd_profile_x(obmd_ctx *ctx, int nbins, double *count, double *mvx);
+
+/* ---- multi-GPU slab decomposition (replaces CommBrick::exchange/borders, ----------
+ *      comm_brick.cpp:652-978): pack/unpack device buffers the host moves with NCCL. -- */
+/* Atoms that left [sublo,subhi) in x: count and pack (11 doubles/atom as AtomVec::pack_exchange:
+ * x v tag type image) into caller-owned DEVICE buffers for the left/right neighbour. */
+int obmd_migrate_pack(obmd_ctx *ctx, double *dev_left, double *dev_right, int cap_atoms,
+                      int *nleft, int *nright);
+int obmd_migrate_unpack(obmd_ctx *ctx, const double *dev_buf, int natoms);
+/* Ghost slabs of width cut next to each x face: 8 doubles/ghost (x v tag type). */
+int obmd_halo_pack(obmd_ctx *ctx, double *dev_left, double *dev_right, int cap_atoms, int *nleft,
+                   int *nright);
+int obmd_halo_unpack(obmd_ctx *ctx, const double *dev_from_left, int nl, const double *dev_from_right,
+                     int nr);
+
+/* ---- timing / introspection ----------------------------------------------------- */
+/* Accumulated CUDA-event milliseconds and launch counts per kernel family since the last
+ * reset.  names: "bin", "sort", "pair", "post_force", "nve", "pre_exchange", "usher", "pbc". */
+int obmd_timing_enable(obmd_ctx *ctx, int on);
+int obmd_timing_get(obmd_ctx *ctx, const char *name, double *ms, long long *launches);
+int obmd_timing_reset(obmd_ctx *ctx);
+long long obmd_launch_count(const obmd_ctx *ctx); /* kernels launched since create */
+void *obmd_stream(const obmd_ctx *ctx);            /* cudaStream_t the kernels run on */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,647 @@
+// C-ABI entry points of libobmd_b200.so (include/obmd_b200.h): context, parameters,
+// host<->device marshalling in LAMMPS layout, the per-step hook sequence.
+#include <cmath>
+#include <cstddef>
+#include <cstdlib>
+
+#include "ctx.h"
+
+char g_create_err[1024] = "no error";
+
+int obmd_fail(obmd_ctx *c, int code, const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(c ? c->err : g_create_err, 1024, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+extern "C" int obmd_abi_version(void) { return OBMD_ABI_VERSION; }
+
+extern "C" const char *obmd_last_error(const obmd_ctx *c) { return c ? c->err : g_create_err; }
+
+extern "C" int obmd_create(obmd_ctx **out, int device)
+{
+  obmd_ctx *c = nullptr;
+  if (!out) return obmd_fail(c, OBMD_ERR_ARG, "obmd_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return obmd_fail(c, OBMD_ERR_CUDA, "obmd_create: no CUDA device (%s); there is no CPU fallback",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev)
+    return obmd_fail(c, OBMD_ERR_ARG, "obmd_create: device %d out of range [0,%d)", device, ndev);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return obmd_fail(c, OBMD_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return obmd_fail(c, OBMD_ERR_CUDA,
+                     "obmd_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                     device, prop.major, prop.minor);
+  if ((e = cudaSetDevice(device)) != cudaSuccess)
+    return obmd_fail(c, OBMD_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  c = new obmd_ctx();
+  c->device = device;
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
+      (e = cudaMalloc(&c->sc_d, sizeof(StepScalars))) != cudaSuccess ||
+      (e = cudaMallocHost(&c->sc_h, sizeof(StepScalars))) != cudaSuccess) {
+    obmd_fail(nullptr, OBMD_ERR_CUDA, "obmd_create: %s", cudaGetErrorString(e));
+    delete c;
+    return OBMD_ERR_CUDA;
+  }
+  cudaMemset(c->sc_d, 0, sizeof(StepScalars));
+  memset(c->sc_h, 0, sizeof(StepScalars));
+  memset(&c->pt, 0, sizeof(c->pt));
+  memset(&c->grid, 0, sizeof(c->grid));
+  memset(&c->fa, 0, sizeof(c->fa));
+  memset(&c->fs, 0, sizeof(c->fs));
+  memset(&c->fd, 0, sizeof(c->fd));
+  memset(&c->rep, 0, sizeof(c->rep));
+  memset(c->setflag, 0, sizeof(c->setflag));
+  memset(&c->cur, 0, sizeof(Planes));
+  memset(&c->alt, 0, sizeof(Planes));
+  for (int t = 0; t <= MAXT; t++) c->mass[t] = 0.0;
+  snprintf(c->err, sizeof(c->err), "no error");
+  *out = c;
+  return OBMD_OK;
+}
+
+static void free_planes(Planes &p)
+{
+  cudaFree(p.x); cudaFree(p.y); cudaFree(p.z); cudaFree(p.vx); cudaFree(p.vy); cudaFree(p.vz);
+  cudaFree(p.tag); cudaFree(p.lidx); cudaFree(p.type); cudaFree(p.image);
+  memset(&p, 0, sizeof(p));
+}
+
+extern "C" void obmd_destroy(obmd_ctx *c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_planes(c->cur);
+  free_planes(c->alt);
+  cudaFree(c->fx); cudaFree(c->fy); cudaFree(c->fz);
+  cudaFree(c->cid); cudaFree(c->rank); cudaFree(c->perm);
+  cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->scan_tmp);
+  cudaFree(c->extra_head); cudaFree(c->extra_next); cudaFree(c->extra_cell);
+  cudaFree(c->stage_d); cudaFree(c->stage_i);
+  cudaFree(c->sc_d); cudaFreeHost(c->sc_h);
+  cudaFree(c->del_key); cudaFree(c->del_val); cudaFree(c->tail_key); cudaFree(c->tail_val); cudaFree(c->del_src);
+  cudaFree(c->tr_d); cudaFree(c->tr_prev_d); cudaFree(c->tr_path); cudaFree(c->tr_npts);
+  cudaFree(c->tr_list); cudaFree(c->tr_changed); cudaFree(c->acc_list);
+  if (c->tr_h) cudaFreeHost(c->tr_h);
+  cudaFree(c->partials);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  for (auto &p : c->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+// ---- domain ------------------------------------------------------------------------
+
+extern "C" int obmd_set_box(obmd_ctx *c, const double boxlo[3], const double boxhi[3])
+{
+  NEED(c && boxlo && boxhi, OBMD_ERR_ARG, "obmd_set_box: NULL argument");
+  for (int d = 0; d < 3; d++)
+    NEED(boxhi[d] > boxlo[d], OBMD_ERR_ARG, "obmd_set_box: box has no extent in dimension %d", d);
+  for (int d = 0; d < 3; d++) {
+    c->boxlo[d] = boxlo[d];
+    c->boxhi[d] = boxhi[d];
+  }
+  c->sublo = boxlo[0];
+  c->subhi = boxhi[0];
+  c->have_box = true;
+  c->pair_ready = false;
+  return OBMD_OK;
+}
+
+extern "C" int obmd_set_subdomain(obmd_ctx *c, double sublo_x, double subhi_x)
+{
+  NEED(c && c->have_box, OBMD_ERR_STATE, "obmd_set_subdomain: set the box first");
+  NEED(subhi_x > sublo_x, OBMD_ERR_ARG, "obmd_set_subdomain: empty slab");
+  c->sublo = sublo_x;
+  c->subhi = subhi_x;
+  return OBMD_OK;
+}
+
+extern "C" int obmd_set_masses(obmd_ctx *c, int ntypes, const double *mass)
+{
+  NEED(c && mass, OBMD_ERR_ARG, "obmd_set_masses: NULL argument");
+  NEED(ntypes >= 1 && ntypes <= MAXT, OBMD_ERR_ARG, "obmd_set_masses: ntypes must be in [1,%d]", MAXT);
+  for (int t = 1; t <= ntypes; t++)
+    NEED(mass[t] > 0.0, OBMD_ERR_ARG, "Invalid mass value for type %d", t);
+  c->ntypes = ntypes;
+  for (int t = 1; t <= ntypes; t++) c->mass[t] = mass[t];
+  c->pair_ready = false;
+  return OBMD_OK;
+}
+
+extern "C" int obmd_set_timestep(obmd_ctx *c, double dt)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  NEED(dt > 0.0, OBMD_ERR_ARG, "obmd_set_timestep: dt must be > 0");
+  c->dt = dt;
+  return OBMD_OK;
+}
+
+// ---- pair_style dpd -------------------------------------------------------------------
+
+extern "C" int obmd_pair_settings(obmd_ctx *c, double temperature, double cut_global, int seed)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  NEED(seed > 0, OBMD_ERR_ARG, "Illegal pair_style command");  // pair_dpd.cpp:205
+  NEED(cut_global > 0.0, OBMD_ERR_ARG, "Illegal pair_style command");
+  c->temperature = temperature;
+  c->cut_global = cut_global;
+  c->pair_seed = seed;
+  for (int i = 1; i <= MAXT; i++)  // :211-216 reset cutoffs that have been explicitly set
+    for (int j = i; j <= MAXT; j++)
+      if (c->setflag[i][j]) c->pt.cut[i][j] = cut_global;
+  c->have_pair = true;
+  c->pair_ready = false;
+  return OBMD_OK;
+}
+
+extern "C" int obmd_pair_coeff(obmd_ctx *c, int itype, int jtype, double a0, double gamma, double cut)
+{
+  NEED(c && c->have_pair, OBMD_ERR_STATE, "obmd_pair_coeff: call obmd_pair_settings first");
+  NEED(c->ntypes > 0, OBMD_ERR_STATE, "obmd_pair_coeff: call obmd_set_masses first");
+  NEED(itype >= 1 && jtype >= 1 && itype <= c->ntypes && jtype <= c->ntypes, OBMD_ERR_ARG,
+       "Incorrect args for pair coefficients");
+  int i = itype < jtype ? itype : jtype, j = itype < jtype ? jtype : itype;
+  c->pt.a0[i][j] = a0;
+  c->pt.gamma[i][j] = gamma;
+  c->pt.cut[i][j] = cut > 0.0 ? cut : c->cut_global;
+  c->setflag[i][j] = true;
+  c->pair_ready = false;
+  return OBMD_OK;
+}
+
+__global__ void k_fill_int(int *p, int n, int v)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+extern "C" int obmd_pair_init(obmd_ctx *c, double boltz)
+{
+  NEED(c && c->have_pair && c->have_box && c->ntypes > 0, OBMD_ERR_STATE,
+       "obmd_pair_init: box, masses and pair settings must be set first");
+  PairTab &pt = c->pt;
+  pt.ntypes = c->ntypes;
+  pt.cutmax = 0.0;
+  c->boltz = boltz;
+  for (int i = 1; i <= c->ntypes; i++)
+    for (int j = i; j <= c->ntypes; j++) {
+      NEED(c->setflag[i][j], OBMD_ERR_STATE, "All pair coeffs are not set");  // pair_dpd.cpp:281
+      pt.sigma[i][j] = sqrt(2.0 * boltz * c->temperature * pt.gamma[i][j]);
+      pt.cut[j][i] = pt.cut[i][j];
+      pt.a0[j][i] = pt.a0[i][j];
+      pt.gamma[j][i] = pt.gamma[i][j];
+      pt.sigma[j][i] = pt.sigma[i][j];
+      pt.cutsq[i][j] = pt.cutsq[j][i] = pt.cut[i][j] * pt.cut[i][j];
+      if (pt.cut[i][j] > pt.cutmax) pt.cutmax = pt.cut[i][j];
+    }
+  for (int t = 0; t <= MAXT; t++) pt.mass[t] = c->mass[t];
+  pt.seed = (unsigned) c->pair_seed;
+  pt.dtinvsqrt = c->dt > 0.0 ? 1.0 / sqrt(c->dt) : 0.0;
+  // cell grid: cell size >= cutmax
+  Grid &g = c->grid;
+  int nn[3];
+  for (int d = 0; d < 3; d++) {
+    double L = c->boxhi[d] - c->boxlo[d];
+    nn[d] = (int) floor(L / pt.cutmax);
+    if (nn[d] < 1) nn[d] = 1;
+    g.lo[d] = c->boxlo[d];
+    g.hi[d] = c->boxhi[d];
+    g.prd[d] = L;
+    g.half[d] = 0.5 * L;
+    g.inv[d] = nn[d] / L;
+  }
+  NEED(nn[1] >= 3 && nn[2] >= 3, OBMD_ERR_ARG,
+       "obmd_pair_init: periodic box needs >= 3 cells of size cut (%g) in y and z", pt.cutmax);
+  NEED((double) nn[0] * nn[1] * nn[2] < 2.0e9, OBMD_ERR_CAPACITY, "obmd_pair_init: too many cells");
+  g.nx = nn[0];
+  g.ny = nn[1];
+  g.nz = nn[2];
+  g.ncell = nn[0] * nn[1] * nn[2];
+  if (g.ncell + 2 > c->cell_cap) {
+    cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->scan_tmp); cudaFree(c->extra_head);
+    c->cell_cap = g.ncell + 2;
+    CK(cudaMalloc(&c->cell_count, sizeof(int) * c->cell_cap));
+    CK(cudaMalloc(&c->cell_start, sizeof(int) * c->cell_cap));
+    CK(cudaMalloc(&c->scan_tmp, sizeof(int) * (c->cell_cap / 4096 + 2)));
+    CK(cudaMalloc(&c->extra_head, sizeof(int) * c->cell_cap));
+  }
+  LAUNCH(k_fill_int, cdiv(c->cell_cap, 256), 256, 0, c->extra_head, c->cell_cap, -1);
+  CK(cudaStreamSynchronize(c->stream));
+  c->nextra = 0;
+  c->pair_ready = true;
+  c->cells_valid = false;
+  return OBMD_OK;
+}
+
+extern "C" double obmd_pair_single(const obmd_ctx *c, int itype, int jtype, double rsq, double *fforce)
+{
+  // pair_dpd.cpp:401-418 with factor_dpd = 1
+  double r = sqrt(rsq);
+  if (!c || r < 1.0e-10) {
+    if (fforce) *fforce = 0.0;
+    return 0.0;
+  }
+  double rinv = 1.0 / r;
+  double wd = 1.0 - r / c->pt.cut[itype][jtype];
+  if (fforce) *fforce = c->pt.a0[itype][jtype] * wd * 1.0 * rinv;
+  return 0.5 * c->pt.a0[itype][jtype] * c->pt.cut[itype][jtype] * wd * wd;
+}
+
+// ---- fix obmd ----------------------------------------------------------------------------
+
+static double ranpark_uniform_host(int &seed)  // random_park.cpp:43-50
+{
+  int k = seed / 127773;
+  seed = 16807 * (seed - k * 127773) - 2836 * k;
+  if (seed < 0) seed += 2147483647;
+  return (1.0 / 2147483647) * seed;
+}
+
+extern "C" int obmd_fix_create(obmd_ctx *c, const obmd_fix_args *a)
+{
+  NEED(c && a, OBMD_ERR_ARG, "obmd_fix_create: NULL argument");
+  NEED(c->have_box && c->ntypes > 0, OBMD_ERR_STATE, "obmd_fix_create: set box and masses first");
+  NEED(a->seed > 0, OBMD_ERR_ARG, "Illegal fix obmd command");                         // :91
+  NEED(a->ntype > 0 && a->ntype <= c->ntypes, OBMD_ERR_ARG,
+       "Invalid atom type in fix obmd command");                                        // :171-172
+  NEED(a->buffer_size > 0.0, OBMD_ERR_ARG,
+       "Illegal fix obmd command. Parameter buffersize should be larger than 0.0");     // :1988-1990
+  NEED(a->g_fac >= 0.0 && a->g_fac <= 1.0, OBMD_ERR_ARG,
+       "Illegal fix obmd command. Parameter gfac should be between 0.0 and 1.0");       // :1995-1996
+  NEED(a->step_parallel == 0, OBMD_ERR_ARG,
+       "For now, only the smooth transition distribution function is implemented.");    // :2013-2015
+  NEED(a->step_perp == 1, OBMD_ERR_ARG,
+       "For now, only the heaviside step distribution function is implemented.");       // :2019-2020
+  NEED(a->usherflag == 1, OBMD_ERR_ARG, "You must pick either usher or near");          // :2163
+  NEED(a->nattempt >= 1 && a->nattempt <= 4096, OBMD_ERR_ARG, "Illegal fix obmd command");
+  NEED(a->maxattempt >= 1, OBMD_ERR_ARG, "Illegal fix obmd command");
+  NEED(a->tau != 0.0, OBMD_ERR_ARG, "Illegal fix obmd command");
+  const obmd_block &r1 = a->region[0];  // :181-191 insertion region inside the box
+  NEED(!(r1.lo[0] < c->boxlo[0] || r1.hi[0] > c->boxhi[0] || r1.lo[1] < c->boxlo[1] ||
+         r1.hi[1] > c->boxhi[1] || r1.lo[2] < c->boxlo[2] || r1.hi[2] > c->boxhi[2]),
+       OBMD_ERR_ARG, "Insertion region extends outside simulation box");
+  c->fa = *a;
+  memset(&c->fs, 0, sizeof(c->fs));
+  c->fs.rng_seed = a->seed;  // :275-276 RanPark(seed), 30 warm-up draws
+  for (int ii = 0; ii < 30; ii++) ranpark_uniform_host(c->fs.rng_seed);
+  FixDev &fd = c->fd;
+  for (int r = 0; r < 6; r++) fd.region[r] = a->region[r];
+  for (int d = 0; d < 3; d++) {
+    fd.boxlo[d] = c->boxlo[d];
+    fd.boxhi[d] = c->boxhi[d];
+  }
+  fd.buffer_size = a->buffer_size;
+  fd.g_fac = a->g_fac;
+  fd.ntype = a->ntype;
+  fd.etarget = a->etarget;
+  fd.ds0 = a->ds0;
+  fd.uovlp = a->uovlp;
+  fd.dsovlp = a->dsovlp;
+  fd.eps = a->eps;
+  fd.nattempt = a->nattempt;
+  c->have_fix = true;
+  return OBMD_OK;
+}
+
+extern "C" int obmd_fix_set_flux(obmd_ctx *c, double pxx, double pxy, double pxz, double dpxx, double freq,
+                                 double alpha, double tau, double nbuf)
+{
+  NEED(c && c->have_fix, OBMD_ERR_STATE, "obmd_fix_set_flux: call obmd_fix_create first");
+  NEED(tau != 0.0, OBMD_ERR_ARG, "Illegal fix obmd command");
+  c->fa.pxx = pxx; c->fa.pxy = pxy; c->fa.pxz = pxz; c->fa.dpxx = dpxx; c->fa.freq = freq;
+  c->fa.alpha = alpha; c->fa.tau = tau; c->fa.nbuf = nbuf;
+  return OBMD_OK;
+}
+
+extern "C" int obmd_fix_get_state(const obmd_ctx *c, obmd_fix_state *out)
+{
+  if (!c || !out || !c->have_fix) return OBMD_ERR_STATE;
+  *out = c->fs;
+  return OBMD_OK;
+}
+
+extern "C" int obmd_fix_set_state(obmd_ctx *c, const obmd_fix_state *in)
+{
+  NEED(c && in && c->have_fix, OBMD_ERR_STATE, "obmd_fix_set_state: call obmd_fix_create first");
+  NEED(in->rng_seed > 0, OBMD_ERR_ARG, "Invalid seed for Park random # generator");
+  c->fs = *in;
+  return OBMD_OK;
+}
+
+// ---- atoms: host <-> device -----------------------------------------------------------
+
+template <typename T>
+static cudaError_t regrow(T *&p, size_t oldn, size_t newn, cudaStream_t s)
+{
+  T *q = nullptr;
+  cudaError_t e = cudaMalloc(&q, sizeof(T) * newn);
+  if (e != cudaSuccess) return e;
+  if (p && oldn) e = cudaMemcpyAsync(q, p, sizeof(T) * oldn, cudaMemcpyDeviceToDevice, s);
+  cudaStreamSynchronize(s);
+  cudaFree(p);
+  p = q;
+  return e;
+}
+
+int obmd_ensure_capacity(obmd_ctx *c, int cap)
+{
+  if (cap <= c->cap) return OBMD_OK;
+  size_t o = (size_t) c->cap, nn = (size_t) cap + (size_t) cap / 8 + 4096;
+  NEED(nn < 2000000000ull, OBMD_ERR_CAPACITY, "too many atoms for 32-bit indexing");
+  Planes *pl[2] = {&c->cur, &c->alt};
+  for (int k = 0; k < 2; k++) {
+    Planes &p = *pl[k];
+    CK(regrow(p.x, o, nn, c->stream)); CK(regrow(p.y, o, nn, c->stream)); CK(regrow(p.z, o, nn, c->stream));
+    CK(regrow(p.vx, o, nn, c->stream)); CK(regrow(p.vy, o, nn, c->stream)); CK(regrow(p.vz, o, nn, c->stream));
+    CK(regrow(p.tag, o, nn, c->stream)); CK(regrow(p.lidx, o, nn, c->stream));
+    CK(regrow(p.type, o, nn, c->stream)); CK(regrow(p.image, o, nn, c->stream));
+  }
+  CK(regrow(c->fx, o, nn, c->stream)); CK(regrow(c->fy, o, nn, c->stream)); CK(regrow(c->fz, o, nn, c->stream));
+  CK(regrow(c->cid, o, nn, c->stream)); CK(regrow(c->rank, o, nn, c->stream));
+  CK(regrow(c->perm, o, nn, c->stream));
+  CK(regrow(c->extra_next, o, nn, c->stream)); CK(regrow(c->extra_cell, o, nn, c->stream));
+  CK(regrow(c->stage_d, 9 * o, 9 * nn, c->stream));
+  CK(regrow(c->stage_i, 3 * o, 3 * nn, c->stream));
+  c->cap = (int) nn;
+  return OBMD_OK;
+}
+
+__global__ void k_unpack_upload(Planes p, double *fx, double *fy, double *fz, const double *sx,
+                                const double *sv, const double *sf, const int *st, const int *sg,
+                                const int *si, int n)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  p.x[i] = sx[3 * i]; p.y[i] = sx[3 * i + 1]; p.z[i] = sx[3 * i + 2];
+  p.vx[i] = sv[3 * i]; p.vy[i] = sv[3 * i + 1]; p.vz[i] = sv[3 * i + 2];
+  if (sf) { fx[i] = sf[3 * i]; fy[i] = sf[3 * i + 1]; fz[i] = sf[3 * i + 2]; }
+  else { fx[i] = 0.0; fy[i] = 0.0; fz[i] = 0.0; }
+  p.type[i] = st[i];
+  p.tag[i] = sg[i];
+  p.image[i] = si ? si[i] : IMG0;
+  p.lidx[i] = i;
+}
+
+extern "C" int obmd_upload(obmd_ctx *c, int n, const double *x, const double *v, const double *f,
+                           const int *type, const int *tag, const int *image, int capacity)
+{
+  NEED(c && x && v && type && tag, OBMD_ERR_ARG, "obmd_upload: NULL argument");
+  NEED(n > 0, OBMD_ERR_ARG, "obmd_upload: n must be > 0");
+  int rc = obmd_ensure_capacity(c, capacity > n ? capacity : n + n / 8 + 1024);
+  if (rc) return rc;
+  if (c->pair_ready) fix_clear_extras(c);
+  double *sx = c->stage_d, *sv = c->stage_d + 3 * (size_t) c->cap, *sf = c->stage_d + 6 * (size_t) c->cap;
+  int *st = c->stage_i, *sg = c->stage_i + c->cap, *si = c->stage_i + 2 * (size_t) c->cap;
+  CK(cudaMemcpyAsync(sx, x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(sv, v, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+  if (f) CK(cudaMemcpyAsync(sf, f, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(st, type, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(sg, tag, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  if (image) CK(cudaMemcpyAsync(si, image, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(k_unpack_upload, cdiv(n, 256), 256, 0, c->cur, c->fx, c->fy, c->fz, sx, sv, f ? sf : nullptr, st,
+         sg, image ? si : nullptr, n);
+  CK(cudaStreamSynchronize(c->stream));
+  c->n = n;
+  c->nsorted = c->nparked = c->nextra = 0;
+  c->cells_valid = false;
+  c->forces_valid = (f != nullptr);
+  return OBMD_OK;
+}
+
+__global__ void k_unpack_xv(Planes p, const double *sx, const double *sv, int n)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int i = p.lidx[s];
+  p.x[s] = sx[3 * i]; p.y[s] = sx[3 * i + 1]; p.z[s] = sx[3 * i + 2];
+  p.vx[s] = sv[3 * i]; p.vy[s] = sv[3 * i + 1]; p.vz[s] = sv[3 * i + 2];
+}
+
+extern "C" int obmd_upload_xv(obmd_ctx *c, int n, const double *x, const double *v)
+{
+  NEED(c && x && v, OBMD_ERR_ARG, "obmd_upload_xv: NULL argument");
+  NEED(n == c->n, OBMD_ERR_STATE, "obmd_upload_xv: n (%d) differs from the resident atom count (%d)", n,
+       c->n);
+  double *sx = c->stage_d, *sv = c->stage_d + 3 * (size_t) c->cap;
+  CK(cudaMemcpyAsync(sx, x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(sv, v, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(k_unpack_xv, cdiv(n, 256), 256, 0, c->cur, sx, sv, n);
+  CK(cudaStreamSynchronize(c->stream));
+  c->cells_valid = false;
+  return OBMD_OK;
+}
+
+__global__ void k_pack_download(Planes p, const double *fx, const double *fy, const double *fz, double *sx,
+                                double *sv, double *sf, int *st, int *sg, int *si, int n)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int i = p.lidx[s];
+  sx[3 * i] = p.x[s]; sx[3 * i + 1] = p.y[s]; sx[3 * i + 2] = p.z[s];
+  sv[3 * i] = p.vx[s]; sv[3 * i + 1] = p.vy[s]; sv[3 * i + 2] = p.vz[s];
+  sf[3 * i] = fx[s]; sf[3 * i + 1] = fy[s]; sf[3 * i + 2] = fz[s];
+  st[i] = p.type[s];
+  sg[i] = p.tag[s];
+  si[i] = p.image[s];
+}
+
+extern "C" int obmd_download(obmd_ctx *c, int *n_out, double *x, double *v, double *f, int *type, int *tag,
+                             int *image)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  NEED(c->nparked == 0, OBMD_ERR_STATE,
+       "obmd_download: atoms outside the box are parked; call obmd_pre_exchange first");
+  const int n = c->n;
+  if (n_out) *n_out = n;
+  if (n == 0) return OBMD_OK;
+  double *sx = c->stage_d, *sv = c->stage_d + 3 * (size_t) c->cap, *sf = c->stage_d + 6 * (size_t) c->cap;
+  int *st = c->stage_i, *sg = c->stage_i + c->cap, *si = c->stage_i + 2 * (size_t) c->cap;
+  LAUNCH(k_pack_download, cdiv(n, 256), 256, 0, c->cur, c->fx, c->fy, c->fz, sx, sv, sf, st, sg, si, n);
+  if (x) CK(cudaMemcpyAsync(x, sx, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+  if (v) CK(cudaMemcpyAsync(v, sv, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+  if (f) CK(cudaMemcpyAsync(f, sf, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+  if (type) CK(cudaMemcpyAsync(type, st, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  if (tag) CK(cudaMemcpyAsync(tag, sg, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  if (image) CK(cudaMemcpyAsync(image, si, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return OBMD_OK;
+}
+
+extern "C" int obmd_nlocal(const obmd_ctx *c) { return c ? c->n : 0; }
+
+// ---- hooks -------------------------------------------------------------------------------
+
+extern "C" int obmd_nve_initial(obmd_ctx *c)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  return fix_nve_initial(c);
+}
+
+extern "C" int obmd_nve_final(obmd_ctx *c)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  return fix_nve_final(c);
+}
+
+extern "C" int obmd_build_cells(obmd_ctx *c)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  fix_clear_extras(c);
+  return cells_build(c);
+}
+
+extern "C" int obmd_pre_exchange(obmd_ctx *c, obmd_pre_exchange_report *report, obmd_trial *trials,
+                                 int maxtrials)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  int rc = fix_pre_exchange(c, trials, maxtrials);
+  if (report) *report = c->rep;
+  return rc;
+}
+
+extern "C" int obmd_pbc(obmd_ctx *c)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  return fix_pbc(c);
+}
+
+extern "C" int obmd_pair_compute(obmd_ctx *c, long long ntimestep, int eflag, int vflag)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  NEED(c->nparked == 0, OBMD_ERR_STATE,
+       "obmd_pair_compute: %d atoms are outside the box in x; obmd_pre_exchange must delete them first",
+       c->nparked);
+  return pair_compute(c, ntimestep, eflag, vflag);
+}
+
+extern "C" int obmd_pair_tallies(obmd_ctx *c, double *eng_vdwl, double virial[6])
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  int rc = read_scalars(c);
+  if (rc) return rc;
+  if (eng_vdwl) *eng_vdwl = c->sc_h->eng;
+  if (virial)
+    for (int k = 0; k < 6; k++) virial[k] = c->sc_h->virial[k];
+  return OBMD_OK;
+}
+
+extern "C" int obmd_post_force(obmd_ctx *c)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  return fix_post_force(c);
+}
+
+extern "C" int obmd_run(obmd_ctx *c, long long first_step, int nsteps)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  NEED(c->have_fix && c->pair_ready, OBMD_ERR_STATE, "obmd_run: pair style and fix must be initialised");
+  int rc;
+  for (int s = 0; s < nsteps; s++) {  // verlet.cpp:229-363
+    if ((rc = fix_nve_initial(c))) return rc;
+    fix_clear_extras(c);
+    if ((rc = cells_build(c))) return rc;
+    if ((rc = fix_pre_exchange(c, nullptr, 0))) return rc;
+    if ((rc = fix_pbc(c))) return rc;
+    if ((rc = pair_compute(c, first_step + s, 0, 0))) return rc;
+    if ((rc = fix_post_force(c))) return rc;
+    if ((rc = fix_nve_final(c))) return rc;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return OBMD_OK;
+}
+
+extern "C" int obmd_reduce_kinetic(obmd_ctx *c, double out[5])
+{
+  NEED(c && out, OBMD_ERR_ARG, "NULL argument");
+  return fix_reduce_kinetic(c, out);
+}
+
+extern "C" int obmd_profile_x(obmd_ctx *c, int nbins, double *count, double *mvx)
+{
+  NEED(c && count && mvx, OBMD_ERR_ARG, "NULL argument");
+  return fix_profile_x(c, nbins, count, mvx);
+}
+
+// ---- timing ------------------------------------------------------------------------------
+
+static cudaEvent_t pool_get(obmd_ctx *c)
+{
+  if (!c->ev_pool.empty()) {
+    cudaEvent_t e = c->ev_pool.back();
+    c->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+void timer_begin(obmd_ctx *c, cudaEvent_t *e0)
+{
+  *e0 = pool_get(c);
+  cudaEventRecord(*e0, c->stream);
+}
+
+void timer_end(obmd_ctx *c, const char *name, cudaEvent_t e0, long long launches)
+{
+  cudaEvent_t e1 = pool_get(c);
+  cudaEventRecord(e1, c->stream);
+  c->pending.push_back(PendingTimer{name, e0, e1, launches});
+}
+
+static void timers_resolve(obmd_ctx *c)
+{
+  if (c->pending.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  for (const PendingTimer &p : c->pending) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.e0, p.e1);
+    TimerSlot &s = c->timers[p.name];
+    s.ms += ms;
+    s.launches += p.launches;
+    c->ev_pool.push_back(p.e0);
+    c->ev_pool.push_back(p.e1);
+  }
+  c->pending.clear();
+}
+
+extern "C" int obmd_timing_enable(obmd_ctx *c, int on)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  timers_resolve(c);
+  c->timing = on != 0;
+  return OBMD_OK;
+}
+
+extern "C" int obmd_timing_get(obmd_ctx *c, const char *name, double *ms, long long *launches)
+{
+  NEED(c && name, OBMD_ERR_ARG, "NULL argument");
+  timers_resolve(c);
+  auto it = c->timers.find(name);
+  if (ms) *ms = it == c->timers.end() ? 0.0 : it->second.ms;
+  if (launches) *launches = it == c->timers.end() ? 0 : it->second.launches;
+  return OBMD_OK;
+}
+
+extern "C" int obmd_timing_reset(obmd_ctx *c)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  timers_resolve(c);
+  c->timers.clear();
+  return OBMD_OK;
+}
+
+extern "C" long long obmd_launch_count(const obmd_ctx *c) { return c ? c->launches : 0; }
+extern "C" void *obmd_stream(const obmd_ctx *c) { return c ? (void *) c->stream : nullptr; }

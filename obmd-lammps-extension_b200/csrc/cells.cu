@@ -1,0 +1,191 @@
+// Binned cell list build: replaces NBinStandard::bin_atoms (nbin_standard.cpp:221-261),
+// NBin::coord2bin (nbin.cpp:139-170) and -- because the pair kernel walks cells directly --
+// the role of NPairBin::build (npair_bin.cpp:52-253) and Atom::sort (atom.cpp:2288-2378).
+//
+// Counting sort of the SoA planes by cell: k_bin (cell id + arrival rank + histogram) ->
+// exclusive scan -> k_perm (slot -> old slot) -> k_cell_order (sort each cell's few entries by
+// old slot so the layout, and with it every fp64 summation order downstream, is independent of
+// atomic arrival order) -> k_gather (move the 10 planes).  Atoms outside the box in x get the
+// key ncell and land behind the live range, where pre_exchange deletes them.
+//
+// All kernels are HBM-bound streaming kernels: coalesced SoA accesses, grids sized to cover n.
+#include "ctx.h"
+
+__global__ void k_bin(Planes p, int n, Grid g, int *__restrict__ cid, int *__restrict__ rank,
+                      int *__restrict__ cell_count, StepScalars *sc)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x = p.x[i], y = p.y[i], z = p.z[i];
+  if (!(isfinite(x) && isfinite(y) && isfinite(z))) {
+    sc->nonfinite = 1;  // domain.cpp:540-545
+    x = g.lo[0] - 1.0;  // park it
+    y = g.lo[1];
+    z = g.lo[2];
+  }
+  int c;
+  if (x < g.lo[0] || x > g.hi[0])  // fix_obmd_merged.cpp:669: strictly outside [boxlo, boxhi]
+    c = g.ncell;
+  else
+    c = (cell_cx(g, x) * g.ny + cell_cy(g, y)) * g.nz + cell_cz(g, z);
+  cid[i] = c;
+  rank[i] = atomicAdd(&cell_count[c], 1);
+}
+
+// ---- exclusive scan of cell_count[0..m) into cell_start[0..m], three small kernels -----
+#define SCAN_T 512
+#define SCAN_E 8  // elements per thread -> 4096 per block
+
+__global__ void k_scan_block(const int *__restrict__ in, int *__restrict__ out, int *__restrict__ sums,
+                             int m)
+{
+  __shared__ int warp_tot[SCAN_T / 32];
+  int base = blockIdx.x * SCAN_T * SCAN_E + threadIdx.x * SCAN_E;
+  int v[SCAN_E], s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_E; k++) {
+    v[k] = (base + k < m) ? in[base + k] : 0;
+    s += v[k];
+  }
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int t = (lane < SCAN_T / 32) ? warp_tot[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, t, d);
+      if (lane >= d) t += u;
+    }
+    if (lane < SCAN_T / 32) warp_tot[lane] = t;  // inclusive over warps
+  }
+  __syncthreads();
+  int excl = inc - s + (w ? warp_tot[w - 1] : 0);
+#pragma unroll
+  for (int k = 0; k < SCAN_E; k++) {
+    if (base + k < m) out[base + k] = excl;
+    excl += v[k];
+  }
+  if (threadIdx.x == SCAN_T - 1) sums[blockIdx.x] = warp_tot[SCAN_T / 32 - 1];
+}
+
+__global__ void k_scan_sums(int *sums, int nb)
+{
+  // one block; sequential over chunks of blockDim with a running carry
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < nb; b0 += blockDim.x) {
+    int i = b0 + threadIdx.x;
+    int v = (i < nb) ? sums[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int d = 1; d < blockDim.x; d <<= 1) {
+      int t = (threadIdx.x >= d) ? sh[threadIdx.x - d] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nb) sums[i] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry += sh[threadIdx.x];
+    __syncthreads();
+  }
+}
+
+__global__ void k_scan_add(int *__restrict__ out, const int *__restrict__ sums, int m, int total_slot,
+                           int n)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) out[i] += sums[i / (SCAN_T * SCAN_E)];
+  if (i == 0) out[total_slot] = n;
+}
+
+__global__ void k_perm(const int *__restrict__ cid, const int *__restrict__ rank,
+                       const int *__restrict__ cell_start, int *__restrict__ perm, int n)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) perm[cell_start[cid[i]] + rank[i]] = i;
+}
+
+// One thread per cell: its entries are few (rho * rc^3 ~ 3), insertion sort in place.
+__global__ void k_cell_order(const int *__restrict__ cell_start, int *__restrict__ perm, int ncell)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  int b = cell_start[c], e = cell_start[c + 1];
+  for (int a = b + 1; a < e; a++) {
+    int v = perm[a], k = a - 1;
+    while (k >= b && perm[k] > v) {
+      perm[k + 1] = perm[k];
+      k--;
+    }
+    perm[k + 1] = v;
+  }
+}
+
+__global__ void k_gather(Planes src, Planes dst, const int *__restrict__ perm, int n)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int j = perm[i];
+  dst.x[i] = src.x[j];
+  dst.y[i] = src.y[j];
+  dst.z[i] = src.z[j];
+  dst.vx[i] = src.vx[j];
+  dst.vy[i] = src.vy[j];
+  dst.vz[i] = src.vz[j];
+  dst.tag[i] = src.tag[j];
+  dst.lidx[i] = src.lidx[j];
+  dst.type[i] = src.type[j];
+  dst.image[i] = src.image[j];
+}
+
+int cells_build(obmd_ctx *c)
+{
+  NEED(c->pair_ready, OBMD_ERR_STATE, "obmd_build_cells: call obmd_pair_init first");
+  NEED(c->n > 0, OBMD_ERR_STATE, "obmd_build_cells: no atoms uploaded");
+  const Grid &g = c->grid;
+  const int n = c->n, m = g.ncell + 1;
+  {
+    ScopedTimer t(c, "bin");
+    CK(cudaMemsetAsync(c->cell_count, 0, sizeof(int) * (m + 1), c->stream));
+    CK(cudaMemsetAsync(&c->sc_d->nonfinite, 0, sizeof(int), c->stream));
+    LAUNCH(k_bin, cdiv(n, 256), 256, 0, c->cur, n, g, c->cid, c->rank, c->cell_count, c->sc_d);
+    int nb = cdiv(m, SCAN_T * SCAN_E);
+    LAUNCH(k_scan_block, nb, SCAN_T, 0, c->cell_count, c->cell_start, c->scan_tmp, m);
+    LAUNCH(k_scan_sums, 1, 1024, 0, c->scan_tmp, nb);
+    LAUNCH(k_scan_add, cdiv(m, 256), 256, 0, c->cell_start, c->scan_tmp, m, m, n);
+  }
+  {
+    ScopedTimer t(c, "sort");
+    LAUNCH(k_perm, cdiv(n, 256), 256, 0, c->cid, c->rank, c->cell_start, c->perm, n);
+    LAUNCH(k_cell_order, cdiv(g.ncell, 128), 128, 0, c->cell_start, c->perm, g.ncell);
+    LAUNCH(k_gather, cdiv(n, 256), 256, 0, c->cur, c->alt, c->perm, n);
+    Planes t2 = c->cur;
+    c->cur = c->alt;
+    c->alt = t2;
+  }
+  // nsorted = cell_start[ncell]; it is needed on the host to size later launches.
+  int nlive = 0;
+  CK(cudaMemcpyAsync(&c->sc_h->ntail, &c->cell_start[g.ncell], sizeof(int), cudaMemcpyDeviceToHost,
+                     c->stream));
+  CK(cudaMemcpyAsync(&c->sc_h->nonfinite, &c->sc_d->nonfinite, sizeof(int), cudaMemcpyDeviceToHost,
+                     c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  nlive = c->sc_h->ntail;
+  NEED(!c->sc_h->nonfinite, OBMD_ERR_NONFINITE, "Non-numeric atom coords - simulation unstable");
+  c->nsorted = nlive;
+  c->nparked = n - nlive;
+  c->nextra = 0;
+  c->cells_valid = true;
+  c->forces_valid = false;
+  return OBMD_OK;
+}

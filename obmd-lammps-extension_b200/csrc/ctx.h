@@ -1,0 +1,239 @@
+// Internal context of libobmd_b200.so (not part of the ABI; see include/obmd_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "obmd_b200.h"
+
+#define MAXT OBMD_MAXTYPES
+#define IMG0 ((512 << 20) | (512 << 10) | 512)  // lmptype.h IMGMAX in all three fields
+#define IMGMASK 1023
+#define IMGBITS 10
+#define IMG2BITS 20
+
+#define NSM 148  // B200 SM count: grids are sized in multiples of this where they are persistent
+
+// ---- device-side parameter blocks (passed by value to kernels) -----------------
+
+// SoA planes of one atom buffer.  Index = storage slot (cell-sorted after build_cells).
+struct Planes {
+  double *x, *y, *z, *vx, *vy, *vz;
+  int *tag, *lidx, *type, *image;
+};
+
+// Cell grid: cell size >= max cutoff; linear index (cx*ny + cy)*nz + cz, x slowest, z fastest,
+// so each open-boundary buffer is one contiguous slot range and a z-row of a stencil is contiguous.
+struct Grid {
+  int nx, ny, nz, ncell;
+  double lo[3], hi[3], prd[3], inv[3], half[3];
+};
+
+struct PairTab {
+  int ntypes;
+  double a0[MAXT + 1][MAXT + 1], gamma[MAXT + 1][MAXT + 1], sigma[MAXT + 1][MAXT + 1];
+  double cut[MAXT + 1][MAXT + 1], cutsq[MAXT + 1][MAXT + 1];
+  double cutmax;
+  double dtinvsqrt;
+  unsigned seed;
+  double mass[MAXT + 1];
+};
+
+struct FixDev {  // what the fix kernels need
+  obmd_block region[6];
+  double boxlo[3], boxhi[3];
+  double buffer_size, g_fac;
+  int ntype;
+  double etarget, ds0, uovlp, dsovlp, eps;
+  int nattempt;
+};
+
+// Device-resident per-step scalars (one struct, read back with a single small copy).
+struct StepScalars {
+  int cnt_left, cnt_right;  // Group::count
+  int maxtag;
+  int ntail;                // survivors with lidx >= nprime found by the scan
+  int nonfinite;            // non-numeric coordinate seen while binning
+  int usher_error;          // see OBMD_ERR_USHER / capacity
+  int nchanged;             // USHER commit: trials whose state changed this round
+  int ndirty;
+  int naccept;
+  int rng_seed;             // RanPark state after the deletion draws
+  double vnewl[3], vnewr[3];
+  double gsum[4];           // G_left, G_right, Gperp_left, Gperp_right
+  double kin[5];
+  double eng, virial[6];
+};
+
+struct PendingTimer;
+struct TimerSlot {
+  double ms = 0.0;
+  long long launches = 0;
+};
+
+struct obmd_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  char err[1024] = {0};
+  long long launches = 0;
+  bool timing = false;
+  std::map<std::string, TimerSlot> timers;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<struct PendingTimer> pending;
+
+  // domain
+  bool have_box = false;
+  double boxlo[3], boxhi[3];
+  double sublo, subhi;
+  int ntypes = 0;
+  double mass[MAXT + 1];
+  double dt = 0.0;
+  // pair
+  bool have_pair = false, pair_ready = false;
+  double temperature = 0.0, cut_global = 0.0, boltz = 1.0;
+  int pair_seed = 0;
+  bool setflag[MAXT + 1][MAXT + 1];
+  PairTab pt;
+  Grid grid;
+  // fix
+  bool have_fix = false;
+  obmd_fix_args fa;
+  obmd_fix_state fs;
+  FixDev fd;
+
+  // atoms
+  int cap = 0;      // capacity of every per-atom plane
+  int n = 0;        // atoms stored (live + parked + extras)
+  int nsorted = 0;  // [0,nsorted) cell-sorted live atoms
+  int nparked = 0;  // [nsorted, nsorted+nparked) atoms outside the box in x (before pre_exchange)
+  int nextra = 0;   // atoms appended by USHER after the sort: [nsorted, nsorted+nextra)
+  bool cells_valid = false;
+  bool forces_valid = false;
+  Planes cur, alt;
+  double *fx = nullptr, *fy = nullptr, *fz = nullptr;
+  int *cid = nullptr, *rank = nullptr, *perm = nullptr;
+  int *cell_count = nullptr, *cell_start = nullptr, *scan_tmp = nullptr;
+  int cell_cap = 0;
+  int *extra_head = nullptr, *extra_next = nullptr, *extra_cell = nullptr;
+  // staging for host <-> device in LAMMPS layout
+  double *stage_d = nullptr;  // 9*cap doubles
+  int *stage_i = nullptr;     // 3*cap ints
+  // scalars
+  StepScalars *sc_d = nullptr;
+  StepScalars *sc_h = nullptr;  // pinned
+  // deletion scratch
+  int del_cap = 0;
+  int *del_key = nullptr, *del_val = nullptr, *tail_key = nullptr, *tail_val = nullptr;
+  int *del_src = nullptr;
+  // USHER scratch
+  int tr_cap = 0, tr_natt = 0;
+  obmd_trial *tr_d = nullptr;       // trial records (state of the latest round)
+  obmd_trial *tr_prev_d = nullptr;  // state of the previous round
+  obmd_trial *tr_h = nullptr;       // pinned copy
+  double *tr_path = nullptr;        // [tr_cap][(natt+1)*3]
+  int *tr_npts = nullptr;
+  int *tr_list = nullptr;           // trials to evaluate this round
+  int *tr_changed = nullptr;        // changed flags
+  int *acc_list = nullptr;          // compacted accepted trial ids of the previous round
+  double *partials = nullptr;       // block partial sums for deterministic reductions
+  int partial_cap = 0;
+  // last pre_exchange report
+  obmd_pre_exchange_report rep;
+};
+
+// ---- error helpers -----------------------------------------------------------------
+int obmd_fail(obmd_ctx *c, int code, const char *fmt, ...);
+extern char g_create_err[1024];
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return obmd_fail(c, OBMD_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, \
+                       cudaGetErrorString(e_));                                               \
+  } while (0)
+
+#define NEED(cond, code, ...) \
+  do {                        \
+    if (!(cond)) return obmd_fail(c, code, __VA_ARGS__); \
+  } while (0)
+
+// Kernel launch with bookkeeping; `c` must be in scope.
+#define LAUNCH(kern, grid, block, smem, ...)                    \
+  do {                                                          \
+    kern<<<(grid), (block), (smem), c->stream>>>(__VA_ARGS__);  \
+    c->launches++;                                              \
+  } while (0)
+
+// Sync-free kernel-family timer: records a CUDA event pair on the launching stream and defers
+// cudaEventElapsedTime to obmd_timing_get(), so timing can stay on inside a timed region.
+struct PendingTimer {
+  const char *name;
+  cudaEvent_t e0, e1;
+  long long launches;
+};
+void timer_begin(obmd_ctx *c, cudaEvent_t *e0);
+void timer_end(obmd_ctx *c, const char *name, cudaEvent_t e0, long long launches);
+
+struct ScopedTimer {
+  obmd_ctx *c;
+  const char *name;
+  long long l0;
+  cudaEvent_t e0 = nullptr;
+  ScopedTimer(obmd_ctx *c_, const char *n) : c(c_), name(n), l0(c_->launches)
+  {
+    if (c->timing) timer_begin(c, &e0);
+  }
+  ~ScopedTimer()
+  {
+    if (c->timing && e0) timer_end(c, name, e0, c->launches - l0);
+  }
+};
+
+static inline int cdiv(long long a, int b) { return (int) ((a + b - 1) / b); }
+
+// ---- internal entry points of the translation units ---------------------------------
+int obmd_ensure_capacity(obmd_ctx *c, int cap);
+int cells_build(obmd_ctx *c);                                   // cells.cu
+int pair_compute(obmd_ctx *c, long long step, int eflag, int vflag);  // pair.cu
+int fix_nve_initial(obmd_ctx *c);                               // fix.cu
+int fix_nve_final(obmd_ctx *c);
+int fix_pbc(obmd_ctx *c);
+int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials);
+int fix_post_force(obmd_ctx *c);
+int fix_reduce_kinetic(obmd_ctx *c, double out[5]);
+int fix_profile_x(obmd_ctx *c, int nbins, double *count, double *mvx);
+int fix_clear_extras(obmd_ctx *c);
+int read_scalars(obmd_ctx *c);  // copies *sc_d to *sc_h and synchronises the stream
+
+// ---- small device helpers shared by the TUs --------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ int cell_cx(const Grid &g, double x)
+{
+  int k = (int) floor((x - g.lo[0]) * g.inv[0]);
+  return min(max(k, 0), g.nx - 1);
+}
+__device__ __forceinline__ int cell_wrap(int k, int n)
+{
+  k %= n;
+  return k < 0 ? k + n : k;
+}
+__device__ __forceinline__ int cell_cy(const Grid &g, double y)
+{
+  return cell_wrap((int) floor((y - g.lo[1]) * g.inv[1]), g.ny);
+}
+__device__ __forceinline__ int cell_cz(const Grid &g, double z)
+{
+  return cell_wrap((int) floor((z - g.lo[2]) * g.inv[2]), g.nz);
+}
+__device__ __forceinline__ bool block_inside(const obmd_block &b, double x, double y, double z)
+{
+  return x >= b.lo[0] && x <= b.hi[0] && y >= b.lo[1] && y <= b.hi[1] && z >= b.lo[2] && z <= b.hi[2];
+}
+#endif

@@ -1,0 +1,310 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/obmd_b200.h), against
+ (a) golden vectors produced by the unmodified reference binary (tests/golden/), and
+ (b) the CPU oracle on the same seeded inputs.
+Bars (BASELINE.json north_star): insertion/deletion counts, accepted USHER positions and atom-ID
+bookkeeping bit-exact; deterministic per-atom forces within 1e-9 relative."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import common_cases as cc
+import oracle_api as O
+
+pytestmark = pytest.mark.gpu
+
+FTOL = 1e-9   # relative force tolerance stated by north_star
+
+
+@pytest.fixture(scope="module")
+def shipped():
+    return cc.shipped()
+
+
+def test_smoke_entry():
+    cc.smoke_check()
+
+
+def test_pair_T0_forces_energy_virial_vs_reference(shipped):
+    """pair_style dpd 0.0 (sigma = 0): forces, eng_vdwl, pressure tensor vs the reference run."""
+    tag, x, box = shipped
+    g = cc.load("p0_pair_T0.npz")
+    sim = cc.device_sim(box, temperature=0.0, fix=False)
+    sim.upload(x, g["v"], np.ones(len(x), np.int32), tag)
+    sim.build_cells()
+    sim.pbc()
+    sim.pair_compute(0, eflag=1, vflag=1)
+    out = sim.download(("f", "tag"))
+    assert np.array_equal(out["tag"], tag)
+    assert cc.mixed_rel_err(out["f"], g["f"]) < FTOL
+    eng, vir = sim.pair_tallies()
+    th = g["thermo"]
+    assert abs(eng - th[1]) < 1e-9 * abs(th[1])
+    vol = np.prod(box[:, 1] - box[:, 0])
+    v = g["v"]
+    ke = [np.sum(v[:, i] * v[:, j]) for i, j in ((0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2))]
+    pt = [(ke[k] + vir[k]) / vol for k in range(6)]
+    assert np.allclose(pt, th[3:9], rtol=1e-9, atol=1e-9)
+    # Newton's third law: full-list evaluation conserves momentum to rounding
+    assert np.abs(out["f"].sum(0)).max() < 1e-7
+    sim.close()
+
+
+def test_pair_random_term_vs_oracle(shipped):
+    """T = 1: same counter-based Gaussian on both sides (fp32 intrinsics on the device)."""
+    tag, x, box = shipped
+    v = np.random.default_rng(3).normal(0, 1, x.shape)
+    sim = cc.device_sim(box, fix=False)
+    sim.upload(x, v, np.ones(len(x), np.int32), tag)
+    sim.build_cells(); sim.pbc(); sim.pair_compute(17)
+    f = sim.download(("f",))["f"]
+    p, a = cc.oracle_sim(box, x, v=v, tag=tag)
+    O.lib().orc_pair_compute(C.byref(p), C.byref(a.c), 1, 17, None, None)
+    fr = a.view("f")
+    assert cc.mixed_rel_err(f, fr) < 2e-5     # fp32 Box-Muller: __logf/__cosf vs libm
+    assert np.abs(f.sum(0)).max() < 1e-7      # random forces are pairwise antisymmetric
+    # a different timestep gives a different random force, the same step reproduces exactly
+    sim.pair_compute(18); f2 = sim.download(("f",))["f"]
+    sim.pair_compute(17); f3 = sim.download(("f",))["f"]
+    assert np.abs(f2 - f).max() > 1.0 and np.array_equal(f3, f)
+    sim.close()
+
+
+def test_b1_usher_stream_bit_exact(shipped):
+    """RanPark trial stream, USHER verdicts, accepted positions, tags: 12 calls on static atoms."""
+    tag, x, box = shipped
+    g = cc.load("b1_usher_static.npz")
+    kw = dict(alpha=1.0, nbuf=2000.0)
+    sim = cc.device_sim(box, **kw)
+    sim.upload(x, np.zeros_like(x), np.ones(len(x), np.int32), tag)
+    p, a = cc.oracle_sim(box, x, tag=tag, **kw)
+    L = O.lib()
+    trials = (O.Trial * 4096)()
+    ver = []
+    for s in range(int(g["nsteps"])):
+        sim.build_cells()
+        rep, tr = sim.pre_exchange(maxtrials=4096)
+        L.orc_fix_pre_exchange(C.byref(p), C.byref(a.c), trials, 4096)
+        assert (rep.cnt_left, rep.cnt_right, rep.ninsert_left, rep.ninsert_right) == \
+            (p.last_cnt_left, p.last_cnt_right, p.last_ninsert_left, p.last_ninsert_right)
+        assert rep.ntrials == p.last_ntrials and rep.naccept == p.last_naccept
+        for k in range(rep.ntrials):
+            t, o = tr[k], trials[k]
+            assert tuple(t.start) == tuple(o.start), (s, k)
+            assert tuple(t.end) == tuple(o.end), (s, k)
+            assert t.energy == o.energy and t.iter == o.iter, (s, k)
+            assert (t.accepted, t.side, t.tag) == (o.accepted, o.side, o.tag), (s, k)
+            ver.append((t.accepted, float("%.6g" % t.energy), t.iter if t.accepted else -1))
+        assert sim.fix_state().rng_seed == p.rng_seed
+    ref = g["verdicts"]
+    got = np.array(ver, dtype=np.float64)
+    assert len(got) == len(ref)
+    assert np.array_equal(got[:, 0], ref[:, 0]) and np.array_equal(got[:, 2], ref[:, 2])
+    out = sim.download(("x", "tag"))
+    assert np.array_equal(out["tag"], g["final_tag"])
+    assert np.array_equal(out["x"][len(tag):], g["inserted_x"])
+    assert np.array_equal(out["x"][:len(tag)], x)
+    sim.close()
+
+
+@pytest.mark.parametrize("case", ["b2", "b4"])
+def test_buffer_force_distribution_vs_reference(shipped, case):
+    tag, x, box = shipped
+    if case == "b2":
+        g = cc.load("b2_normal_force.npz"); kw = dict(a0=0.0, gamma=0.0, dpxx=10.0, freq=5.0)
+        frames = [g["f1"], g["f2"], g["f3"]]
+    else:
+        g = cc.load("b4_shear_force.npz"); kw = dict(a0=0.0, gamma=0.0, pxy=2.0, pxz=-1.0, shear_size=2.5)
+        frames = [g["f1"]]
+    sim = cc.device_sim(box, **kw)
+    sim.upload(x, np.zeros_like(x), np.ones(len(x), np.int32), tag)
+    for fr in frames:
+        sim.build_cells()
+        rep, _ = sim.pre_exchange()
+        assert rep.ndel == 0 and rep.ntrials == 0
+        sim.pbc(); sim.pair_compute(0); sim.post_force()
+        f = sim.download(("f",))["f"]
+        assert cc.mixed_rel_err(f, fr) < FTOL
+        assert np.array_equal(f == 0.0, fr == 0.0)     # exactly the same atoms are touched
+    sim.close()
+
+
+def test_b3_ballistic_bookkeeping(shipped):
+    """20 ballistic steps: 234 deletions, 485 insertions; tag-by-local-index order identical to the
+    reference; x, v, f to rounding (the weight sum G is a tree reduction here, a serial sum there)."""
+    tag, x, box = shipped
+    g = cc.load("b3_ballistic.npz")
+    kw = dict(a0=0.0, gamma=0.0, dt=0.01, alpha=1.0, tau=0.05, nbuf=2000.0)
+    sim = cc.device_sim(box, **kw)
+    sim.upload(x, g["v0"], np.ones(len(x), np.int32), tag)
+    sim.setup(0)
+    ndel = nins = 0
+    for s in range(1, 21):
+        rep, _ = sim.step(s)
+        ndel += rep.ndel; nins += rep.naccept
+    assert (ndel, nins) == (int(g["ndel"]), int(g["nins"]))
+    out = sim.download()
+    assert np.array_equal(out["tag"], g["tag20"])
+    assert np.allclose(out["x"], g["x20"], rtol=0, atol=1e-11)
+    assert np.allclose(out["v"], g["v20"], rtol=0, atol=1e-10)
+    assert cc.mixed_rel_err(out["f"], g["f20"]) < FTOL
+    st = sim.fix_state()
+    assert st.ndeleted == ndel and st.ninserted == nins
+    sim.close()
+
+
+def test_run_equals_hook_sequence(shipped):
+    """obmd_run() == nve_initial/build/pre_exchange/pbc/pair/post_force/nve_final, bit for bit."""
+    tag, x, box = shipped
+    v = np.random.default_rng(5).normal(0, 1, x.shape)
+    kw = dict(alpha=1.0, nbuf=1895.0)
+    outs = []
+    for mode in (0, 1):
+        sim = cc.device_sim(box, **kw)
+        sim.upload(x, v, np.ones(len(x), np.int32), tag)
+        sim.setup(0)
+        if mode == 0:
+            for s in range(1, 11):
+                sim.step(s)
+        else:
+            sim.run(1, 10)
+        outs.append(sim.download())
+        sim.close()
+    for k in ("tag", "x", "v", "f"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def test_deletion_compaction_order_vs_oracle():
+    """Many simultaneous deletions on both faces: AtomVec::copy(last, hole) order, RanPark draw
+    count, deleted momentum -- all bit-exact vs the oracle (fix_obmd_merged.cpp:639-865)."""
+    tag, x, box = cc.shipped()
+    rng = np.random.default_rng(11)
+    x = x.copy()
+    out_l = rng.choice(len(x), 300, replace=False)
+    x[out_l[:150], 0] = -rng.uniform(1e-6, 0.5, 150)
+    x[out_l[150:], 0] = box[0, 1] + rng.uniform(1e-6, 0.5, 150)
+    x[-1, 0] = -0.25          # the last atom is itself a hole
+    x[-3, 0] = box[0, 1] + 0.1
+    v = rng.normal(0, 1, x.shape)
+    kw = dict(alpha=0.1, nbuf=100.0)   # no insertion
+    sim = cc.device_sim(box, **kw)
+    sim.upload(x, v, np.ones(len(x), np.int32), tag)
+    sim.build_cells()
+    rep, _ = sim.pre_exchange()
+    p, a = cc.oracle_sim(box, x, v=v, tag=tag, **kw)
+    O.lib().orc_fix_pre_exchange(C.byref(p), C.byref(a.c), None, 0)
+    assert rep.ndel == p.last_ndel and rep.nlocal == a.n
+    assert tuple(rep.vnewl) == tuple(p.vnewl) and tuple(rep.vnewr) == tuple(p.vnewr)
+    out = sim.download(("x", "v", "tag"))
+    assert np.array_equal(out["tag"], a.view("tag"))
+    assert np.array_equal(out["x"], a.view("x")) and np.array_equal(out["v"], a.view("v"))
+    s = sim.fix_state()
+    assert s.rng_seed == p.rng_seed
+    assert tuple(s.momentumForce_left) == tuple(p.momentumForce_left)
+    assert tuple(s.momentumForce_right) == tuple(p.momentumForce_right)
+    sim.close()
+
+
+def test_usher_conflicting_insertions_vs_oracle(shipped):
+    """Empty buffers force hundreds of trials per call, many of them interacting with atoms
+    accepted earlier in the same call: the speculative-commit rounds must reproduce the serial
+    result exactly."""
+    tag, x, box = shipped
+    B = 0.15 * box[0, 1]
+    keep = (x[:, 0] > B) & (x[:, 0] < box[0, 1] - B)     # remove every buffer atom
+    xs, ts = x[keep], tag[keep]
+    kw = dict(alpha=1.0, nbuf=1895.0, tau=0.01, usher=(1, 31.03, 1.0, 0.02, 1e4, 1.5, 1.0, 40))
+    sim = cc.device_sim(box, **kw)
+    sim.upload(xs, np.zeros_like(xs), np.ones(len(xs), np.int32), ts, capacity=len(x) * 2)
+    p, a = cc.oracle_sim(box, xs, tag=ts, **kw)
+    L = O.lib()
+    trials = (O.Trial * 8192)()
+    rounds = 0
+    for s in range(4):
+        sim.build_cells()
+        rep, tr = sim.pre_exchange(maxtrials=8192)
+        L.orc_fix_pre_exchange(C.byref(p), C.byref(a.c), trials, 8192)
+        assert rep.ntrials == p.last_ntrials and rep.naccept == p.last_naccept, s
+        assert rep.ntrials > 100
+        for k in range(rep.ntrials):
+            assert tuple(tr[k].end) == tuple(trials[k].end), (s, k)
+            assert (tr[k].accepted, tr[k].tag, tr[k].iter) == (trials[k].accepted, trials[k].tag, trials[k].iter)
+            assert tr[k].energy == trials[k].energy
+        rounds = max(rounds, rep.usher_rounds)
+    assert rounds >= 2      # the conflict path was actually exercised
+    out = sim.download(("x", "tag"))
+    assert np.array_equal(out["tag"], a.view("tag")) and np.array_equal(out["x"], a.view("x"))
+    sim.close()
+
+
+def test_r1_steady_exchange_statistics(shipped):
+    """Stochastic observables of the shipped deck in the steady-exchange regime (alpha 1.0,
+    nbuf 1895, T = 1) against a 400-step run of the reference: kinetic temperature, atom count and
+    insertion/deletion rates agree within statistical error (different RNG streams by design)."""
+    tag, x, box = shipped
+    g = cc.load("r1_thermo.npz")
+    th = g["thermo"]                       # step atoms temp press, every 10 steps
+    kw = dict(alpha=1.0, nbuf=1895.0)
+    sim = cc.device_sim(box, **kw)
+    sim.upload(x, np.zeros_like(x), np.ones(len(x), np.int32), tag, capacity=2 * len(x))
+    sim.setup(0)
+    temps, natoms = [], []
+    for blk in range(40):
+        sim.run(1 + 10 * blk, 10)
+        k = sim.kinetic()
+        n = int(k[4])
+        # LAMMPS' thermo temp keeps the dof of the initial atom count (compute temp is not
+        # dynamic/dof by default), so compare sum(m v^2) / (3 N0 - 3) with the reference column
+        temps.append(k[0] / (3.0 * len(tag) - 3.0))
+        natoms.append(n)
+    st = sim.fix_state()
+    temps = np.array(temps); natoms = np.array(natoms)
+    ref_T = th[1:, 2]; ref_N = th[1:, 1]
+    # the fluid heats from v = 0 towards T ~ 1: compare the trajectory of block means
+    for lo, hi in ((0, 10), (10, 20), (20, 40)):
+        assert abs(temps[lo:hi].mean() - ref_T[lo:hi].mean()) < 0.02, (lo, temps[lo:hi].mean(), ref_T[lo:hi].mean())
+    assert np.abs(natoms - ref_N).max() < 120         # +-sqrt(N_events)-level wander
+    assert abs(st.ndeleted - int(g["ndel"])) < 0.1 * int(g["ndel"])
+    assert abs(st.ninserted - int(g["nacc"])) < 0.1 * int(g["nacc"])
+    sim.close()
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (1 010 960 atoms, 4x5x4 tiling): size-independent properties."""
+    tag, x, box = cc.tiled((4, 5, 4))
+    n = len(x)
+    assert n == 1010960
+    v = np.random.default_rng(2).normal(0, 1, x.shape)
+    nbuf = float(int(0.15 * n))
+    kw = dict(alpha=1.0, nbuf=nbuf)
+    sim = cc.device_sim(box, **kw)
+    sim.upload(x, v, np.ones(n, np.int32), tag, capacity=int(1.2 * n))
+    sim.setup(0)
+    f0 = sim.download(("f",))["f"]
+    assert np.abs(f0.sum(0)).max() < 1e-9 * np.abs(f0).sum()       # momentum conservation
+    rep, _ = sim.step(1)
+    out = sim.download()
+    m = len(out["tag"])
+    assert m == n - rep.ndel + rep.naccept == rep.nlocal
+    assert len(np.unique(out["tag"])) == m                          # tags stay unique
+    assert rep.ntrials > 1000 and rep.naccept > 0
+    # prescribed flux: the force added to each buffer sums to F (fix_obmd_merged.cpp:608-630)
+    st = sim.fix_state()
+    B = 0.15 * box[0, 1]
+    sim.build_cells(); sim.pbc(); sim.pair_compute(5)
+    fa = sim.download(("f",))["f"]
+    sim.post_force()
+    o2 = sim.download(("f", "x"))
+    df = o2["f"] - fa
+    left = o2["x"][:, 0] <= B
+    right = o2["x"][:, 0] >= box[0, 1] - B
+    FL = np.array(st.momentumForce_left); FR = np.array(st.momentumForce_right)
+    assert np.allclose(df[left].sum(0), FL, rtol=1e-10, atol=1e-6)
+    assert np.allclose(df[right].sum(0), FR, rtol=1e-10, atol=1e-6)
+    assert not df[~(left | right)].any()
+    # determinism: the same inputs give the same bits
+    sim2 = cc.device_sim(box, **kw)
+    sim2.upload(x, v, np.ones(n, np.int32), tag, capacity=int(1.2 * n))
+    sim2.setup(0)
+    assert np.array_equal(sim2.download(("f",))["f"], f0)
+    sim.close(); sim2.close()
