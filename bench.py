@@ -185,7 +185,8 @@ def ours(args):
                        "atoms_per_gpu": n0, "parallelism": "replicas only" if world > 1 else "single GPU",
                        "l2": "per-step working set (%.0f MB) exceeds the 126 MB L2" % (n0 * 168 / 1e6),
                        "equil_steps": args.equil,
-                       "inserted": int(st.ninserted), "deleted": int(st.ndeleted)},
+                       "inserted": int(st.ninserted), "deleted": int(st.ndeleted),
+                       "usher_trials": int(st.ntrials), "usher_rounds": int(st.nrounds)},
             "gpu_launches": int(launches),
             "kernel_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in fam.items()},
             "roofline": {"kernel": "k_pair_dpd", "bound": "hbm", "achieved": achieved, "peak": hbm,

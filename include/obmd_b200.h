@@ -63,6 +63,7 @@ typedef struct {
   double momentumForce_left[3], momentumForce_right[3];
   double shearForce_left[3], shearForce_right[3];
   long long ninserted, ndeleted;
+  long long ntrials, nrounds; /* USHER trials run / speculative-commit rounds, cumulative */
 } obmd_fix_state;
 
 /* Per-call report of pre_exchange (what the reference prints to stdout, Q8). */

@@ -38,7 +38,8 @@ class FixState(C.Structure):
     _fields_ = [("rng_seed", C.c_int), ("simulation_time", C.c_double),
                 ("momentumForce_left", C.c_double * 3), ("momentumForce_right", C.c_double * 3),
                 ("shearForce_left", C.c_double * 3), ("shearForce_right", C.c_double * 3),
-                ("ninserted", C.c_longlong), ("ndeleted", C.c_longlong)]
+                ("ninserted", C.c_longlong), ("ndeleted", C.c_longlong),
+                ("ntrials", C.c_longlong), ("nrounds", C.c_longlong)]
 
 
 class PreExchangeReport(C.Structure):

@@ -44,7 +44,12 @@ extern "C" int obmd_create(obmd_ctx **out, int device)
     return obmd_fail(c, OBMD_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
   c = new obmd_ctx();
   c->device = device;
-  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if ((e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
+      (e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&c->ev_sorted, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&c->ev_int, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
       (e = cudaMalloc(&c->sc_d, sizeof(StepScalars))) != cudaSuccess ||
       (e = cudaMallocHost(&c->sc_h, sizeof(StepScalars))) != cudaSuccess) {
@@ -81,6 +86,7 @@ extern "C" void obmd_destroy(obmd_ctx *c)
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->stream2);
   free_planes(c->cur);
   free_planes(c->alt);
   cudaFree(c->fx); cudaFree(c->fy); cudaFree(c->fz);
@@ -89,15 +95,17 @@ extern "C" void obmd_destroy(obmd_ctx *c)
   cudaFree(c->extra_head); cudaFree(c->extra_next); cudaFree(c->extra_cell);
   cudaFree(c->stage_d); cudaFree(c->stage_i);
   cudaFree(c->sc_d); cudaFreeHost(c->sc_h);
-  cudaFree(c->del_key); cudaFree(c->del_val); cudaFree(c->tail_key); cudaFree(c->tail_val); cudaFree(c->del_src);
+  cudaFree(c->del_key); cudaFree(c->del_val); cudaFree(c->tail_key); cudaFree(c->tail_val); cudaFree(c->del_src); cudaFree(c->del_mv);
   cudaFree(c->tr_d); cudaFree(c->tr_prev_d); cudaFree(c->tr_path); cudaFree(c->tr_npts);
-  cudaFree(c->tr_list); cudaFree(c->tr_changed); cudaFree(c->acc_list);
+  cudaFree(c->tr_list); cudaFree(c->tr_changed); cudaFree(c->acc_list); cudaFree(c->tr_bbox);
   if (c->tr_h) cudaFreeHost(c->tr_h);
   cudaFree(c->partials);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   for (auto &p : c->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
+  cudaEventDestroy(c->ev_sorted); cudaEventDestroy(c->ev_int);
   cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->stream2);
   delete c;
 }
 
@@ -358,6 +366,7 @@ static cudaError_t regrow(T *&p, size_t oldn, size_t newn, cudaStream_t s)
 int obmd_ensure_capacity(obmd_ctx *c, int cap)
 {
   if (cap <= c->cap) return OBMD_OK;
+  cudaStreamSynchronize(c->stream2);  // side-stream kernels may still hold the old pointers
   size_t o = (size_t) c->cap, nn = (size_t) cap + (size_t) cap / 8 + 4096;
   NEED(nn < 2000000000ull, OBMD_ERR_CAPACITY, "too many atoms for 32-bit indexing");
   Planes *pl[2] = {&c->cur, &c->alt};
@@ -548,13 +557,31 @@ extern "C" int obmd_run(obmd_ctx *c, long long first_step, int nsteps)
   NEED(c, OBMD_ERR_ARG, "NULL context");
   NEED(c->have_fix && c->pair_ready, OBMD_ERR_STATE, "obmd_run: pair style and fix must be initialised");
   int rc;
+  ColRange ipbc, ipair, opbc, opair;
+  const bool ov = c->overlap && fix_zones(c, ipbc, ipair, opbc, opair);
   for (int s = 0; s < nsteps; s++) {  // verlet.cpp:229-363
     if ((rc = fix_nve_initial(c))) return rc;
     fix_clear_extras(c);
+    if ((rc = obmd_ensure_capacity(c, c->n + c->n / 32 + 4096))) return rc;
     if ((rc = cells_build(c))) return rc;
-    if ((rc = fix_pre_exchange(c, nullptr, 0))) return rc;
-    if ((rc = fix_pbc(c))) return rc;
-    if ((rc = pair_compute(c, first_step + s, 0, 0))) return rc;
+    if (ov) {
+      // The interior (columns pre_exchange never reads) is wrapped and its pair forces are
+      // computed on the side stream while the main stream runs the latency-bound USHER rounds.
+      CK(cudaEventRecord(c->ev_sorted, c->stream));
+      CK(cudaStreamWaitEvent(c->stream2, c->ev_sorted, 0));
+      if ((rc = fix_pbc_cols(c, ipbc, c->stream2))) return rc;
+      if ((rc = pair_compute_cols(c, first_step + s, ipair, c->stream2))) return rc;
+      CK(cudaEventRecord(c->ev_int, c->stream2));
+      if ((rc = fix_pre_exchange(c, nullptr, 0))) return rc;
+      if ((rc = fix_pbc_cols(c, opbc, c->stream))) return rc;
+      CK(cudaStreamWaitEvent(c->stream, c->ev_int, 0));
+      if ((rc = pair_compute_cols(c, first_step + s, opair, c->stream))) return rc;
+      c->forces_valid = true;
+    } else {
+      if ((rc = fix_pre_exchange(c, nullptr, 0))) return rc;
+      if ((rc = fix_pbc(c))) return rc;
+      if ((rc = pair_compute(c, first_step + s, 0, 0))) return rc;
+    }
     if ((rc = fix_post_force(c))) return rc;
     if ((rc = fix_nve_final(c))) return rc;
   }
@@ -588,16 +615,16 @@ static cudaEvent_t pool_get(obmd_ctx *c)
   return e;
 }
 
-void timer_begin(obmd_ctx *c, cudaEvent_t *e0)
+void timer_begin(obmd_ctx *c, cudaEvent_t *e0, cudaStream_t st)
 {
   *e0 = pool_get(c);
-  cudaEventRecord(*e0, c->stream);
+  cudaEventRecord(*e0, st);
 }
 
-void timer_end(obmd_ctx *c, const char *name, cudaEvent_t e0, long long launches)
+void timer_end(obmd_ctx *c, const char *name, cudaEvent_t e0, long long launches, cudaStream_t st)
 {
   cudaEvent_t e1 = pool_get(c);
-  cudaEventRecord(e1, c->stream);
+  cudaEventRecord(e1, st);
   c->pending.push_back(PendingTimer{name, e0, e1, launches});
 }
 
@@ -605,6 +632,7 @@ static void timers_resolve(obmd_ctx *c)
 {
   if (c->pending.empty()) return;
   cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->stream2);
   for (const PendingTimer &p : c->pending) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, p.e0, p.e1);

@@ -78,7 +78,10 @@ struct TimerSlot {
 
 struct obmd_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;   // main stream (high priority): everything the fix orders
+  cudaStream_t stream2 = nullptr;  // side stream: interior pbc + PairDPD overlapped with USHER
+  cudaEvent_t ev_sorted = nullptr, ev_int = nullptr;
+  bool overlap = true;
   char err[1024] = {0};
   long long launches = 0;
   bool timing = false;
@@ -131,6 +134,7 @@ struct obmd_ctx {
   int del_cap = 0;
   int *del_key = nullptr, *del_val = nullptr, *tail_key = nullptr, *tail_val = nullptr;
   int *del_src = nullptr;
+  double *del_mv = nullptr;
   // USHER scratch
   int tr_cap = 0, tr_natt = 0;
   obmd_trial *tr_d = nullptr;       // trial records (state of the latest round)
@@ -138,6 +142,7 @@ struct obmd_ctx {
   obmd_trial *tr_h = nullptr;       // pinned copy
   double *tr_path = nullptr;        // [tr_cap][(natt+1)*3]
   int *tr_npts = nullptr;
+  double *tr_bbox = nullptr;        // [tr_cap][6] bounding box of the evaluated points
   int *tr_list = nullptr;           // trials to evaluate this round
   int *tr_changed = nullptr;        // changed flags
   int *acc_list = nullptr;          // compacted accepted trial ids of the previous round
@@ -170,6 +175,19 @@ extern char g_create_err[1024];
     kern<<<(grid), (block), (smem), c->stream>>>(__VA_ARGS__);  \
     c->launches++;                                              \
   } while (0)
+#define LAUNCH_ON(st, kern, grid, block, smem, ...)             \
+  do {                                                          \
+    kern<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);       \
+    c->launches++;                                              \
+  } while (0)
+
+// A set of cell columns (cx intervals; x is the slowest cell index, so each interval is one
+// contiguous slot range) plus, optionally, the atoms inserted after the sort.
+struct ColRange {
+  int n;            // number of intervals (0..2)
+  int a[2], b[2];   // inclusive column intervals
+  int extras;       // also visit [nsorted, nsorted + nextra)
+};
 
 // Sync-free kernel-family timer: records a CUDA event pair on the launching stream and defers
 // cudaEventElapsedTime to obmd_timing_get(), so timing can stay on inside a timed region.
@@ -178,21 +196,23 @@ struct PendingTimer {
   cudaEvent_t e0, e1;
   long long launches;
 };
-void timer_begin(obmd_ctx *c, cudaEvent_t *e0);
-void timer_end(obmd_ctx *c, const char *name, cudaEvent_t e0, long long launches);
+void timer_begin(obmd_ctx *c, cudaEvent_t *e0, cudaStream_t st);
+void timer_end(obmd_ctx *c, const char *name, cudaEvent_t e0, long long launches, cudaStream_t st);
 
 struct ScopedTimer {
   obmd_ctx *c;
   const char *name;
   long long l0;
+  cudaStream_t st;
   cudaEvent_t e0 = nullptr;
-  ScopedTimer(obmd_ctx *c_, const char *n) : c(c_), name(n), l0(c_->launches)
+  ScopedTimer(obmd_ctx *c_, const char *n, cudaStream_t s = nullptr)
+      : c(c_), name(n), l0(c_->launches), st(s ? s : c_->stream)
   {
-    if (c->timing) timer_begin(c, &e0);
+    if (c->timing) timer_begin(c, &e0, st);
   }
   ~ScopedTimer()
   {
-    if (c->timing && e0) timer_end(c, name, e0, c->launches - l0);
+    if (c->timing && e0) timer_end(c, name, e0, c->launches - l0, st);
   }
 };
 
@@ -202,6 +222,12 @@ static inline int cdiv(long long a, int b) { return (int) ((a + b - 1) / b); }
 int obmd_ensure_capacity(obmd_ctx *c, int cap);
 int cells_build(obmd_ctx *c);                                   // cells.cu
 int pair_compute(obmd_ctx *c, long long step, int eflag, int vflag);  // pair.cu
+int pair_compute_cols(obmd_ctx *c, long long step, const ColRange &cr, cudaStream_t st);
+int fix_pbc_cols(obmd_ctx *c, const ColRange &cr, cudaStream_t st);
+ColRange all_columns(const obmd_ctx *c);
+ColRange fix_region_columns(const obmd_ctx *c, int r0, int r1, int margin);
+bool fix_zones(const obmd_ctx *c, ColRange &int_pbc, ColRange &int_pair, ColRange &out_pbc,
+               ColRange &out_pair);
 int fix_nve_initial(obmd_ctx *c);                               // fix.cu
 int fix_nve_final(obmd_ctx *c);
 int fix_pbc(obmd_ctx *c);

@@ -13,6 +13,8 @@
 #define EPSILON_FIX 1.0e-6   // fix_obmd_merged.cpp:62
 #define EPSILON_DPD 1.0e-10  // pair_dpd.cpp:36
 #define MY_PI 3.14159265358979323846
+#define FB_BLOCKS (NSM * 2)  // fixed grid of the grid-stride region kernels (2 CTAs per SM)
+#define FB_THREADS 256
 
 // =====================================================================================
 // integrator and periodic wrap
@@ -69,10 +71,22 @@ __device__ __forceinline__ void wrap_dim(double &x, int &image, double lo, doubl
   }
 }
 
-__global__ void k_pbc(Planes p, int n, Grid g)
+__global__ void k_pbc(Planes p, ColRange cr, int nsorted, int nextra, Grid g,
+                      const int *__restrict__ cell_start)
 {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nyz = g.ny * g.nz;
+  int i = -1;
+  for (int k = 0; k < cr.n; k++) {
+    int b = cell_start[cr.a[k] * nyz], e = cell_start[(cr.b[k] + 1) * nyz];
+    if (gidx < e - b) {
+      i = b + gidx;
+      break;
+    }
+    gidx -= e - b;
+  }
+  if (i < 0 && cr.extras && gidx >= 0 && gidx < nextra) i = nsorted + gidx;
+  if (i < 0) return;
   double y = p.y[i], z = p.z[i];
   if (y < g.lo[1] || y >= g.hi[1] || z < g.lo[2] || z >= g.hi[2]) {
     int im = p.image[i];
@@ -102,12 +116,16 @@ int fix_nve_final(obmd_ctx *c)
   return OBMD_OK;
 }
 
-int fix_pbc(obmd_ctx *c)
+int fix_pbc_cols(obmd_ctx *c, const ColRange &cr, cudaStream_t st)
 {
-  ScopedTimer t(c, "pbc");
-  LAUNCH(k_pbc, cdiv(c->n, 256), 256, 0, c->cur, c->n, c->grid);
+  NEED(c->cells_valid, OBMD_ERR_STATE, "obmd_pbc: cell list is stale (call obmd_build_cells)");
+  ScopedTimer t(c, "pbc", st);
+  const int n = c->nsorted + c->nextra;
+  if (n > 0) LAUNCH_ON(st, k_pbc, cdiv(n, 256), 256, 0, c->cur, cr, c->nsorted, c->nextra, c->grid, c->cell_start);
   return OBMD_OK;
 }
+
+int fix_pbc(obmd_ctx *c) { return fix_pbc_cols(c, all_columns(c), c->stream); }
 
 // =====================================================================================
 // pre_exchange, part 1: scan + deletion bookkeeping
@@ -116,15 +134,15 @@ int fix_pbc(obmd_ctx *c)
 // One pass over the live atoms: Group::count for both buffers (group.cpp:793-811, closed block on
 // the not-yet-wrapped coordinates, Q9), find_maxid (:1860-1875), and the list of survivors whose
 // local index is >= nprime (they will be moved into the holes the deletions leave).
-__global__ void k_scan_atoms(Planes p, int nlive, FixDev fd, StepScalars *sc, int *__restrict__ tail_key,
-                             int *__restrict__ tail_val, int tail_cap)
+// The id pass touches only the two int planes (8 B/atom); positions are read only in the cell
+// columns that overlap the two buffer regions, so the interior can be wrapped and its forces
+// computed on the side stream while this runs (obmd_run).
+__global__ void k_scan_ids(Planes p, int nlive, StepScalars *sc, int *__restrict__ tail_key,
+                           int *__restrict__ tail_val, int tail_cap)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int cl = 0, cr = 0, mt = 0;
+  int mt = 0;
   if (i < nlive) {
-    double x = p.x[i], y = p.y[i], z = p.z[i];
-    cl = block_inside(fd.region[0], x, y, z);
-    cr = block_inside(fd.region[1], x, y, z);
     mt = p.tag[i];
     int li = p.lidx[i];
     if (li >= nlive) {
@@ -135,15 +153,30 @@ __global__ void k_scan_atoms(Planes p, int nlive, FixDev fd, StepScalars *sc, in
       }
     }
   }
+  for (int d = 16; d > 0; d >>= 1) mt = max(mt, __shfl_down_sync(0xffffffffu, mt, d));
+  if ((threadIdx.x & 31) == 0 && mt) atomicMax(&sc->maxtag, mt);
+}
+
+__global__ void k_count_regions(Planes p, ColRange cr, Grid g, FixDev fd,
+                                const int *__restrict__ cell_start, StepScalars *sc)
+{
+  const int nyz = g.ny * g.nz;
+  int cl = 0, cright = 0;
+  for (int k = 0; k < cr.n; k++) {
+    int b = cell_start[cr.a[k] * nyz], e = cell_start[(cr.b[k] + 1) * nyz];
+    for (int i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) {
+      double x = p.x[i], y = p.y[i], z = p.z[i];
+      cl += block_inside(fd.region[0], x, y, z);
+      cright += block_inside(fd.region[1], x, y, z);
+    }
+  }
   for (int d = 16; d > 0; d >>= 1) {
     cl += __shfl_down_sync(0xffffffffu, cl, d);
-    cr += __shfl_down_sync(0xffffffffu, cr, d);
-    mt = max(mt, __shfl_down_sync(0xffffffffu, mt, d));
+    cright += __shfl_down_sync(0xffffffffu, cright, d);
   }
   if ((threadIdx.x & 31) == 0) {
     if (cl) atomicAdd(&sc->cnt_left, cl);
-    if (cr) atomicAdd(&sc->cnt_right, cr);
-    if (mt) atomicMax(&sc->maxtag, mt);
+    if (cright) atomicAdd(&sc->cnt_right, cright);
   }
 }
 
@@ -180,69 +213,72 @@ __device__ void bitonic_desc(int *key, int *val, int npad)
 //    the entry created at position p settles at p iff p < nprime.  Only the ndel positions
 //    >= nprime need the walk: src[k] = storage slot of the survivor that ends up in the k-th
 //    effective hole (holes counted downwards, skipping the run of holes at the very top).
-__global__ void k_delete_fixup(Planes p, int nlive, int ndel, int npad_del, int npad_tail, FixDev fd,
-                               PairTab pt, StepScalars *sc, int *del_key, int *del_val, int *tail_key,
-                               int *tail_val, int *del_src)
+#define DEL_SMEM 2048  // deletions handled entirely in shared memory (more fall back to global)
+
+__global__ void __launch_bounds__(1024)
+    k_delete_fixup(Planes p, int nlive, int ndel, int npad_del, int npad_tail, FixDev fd, PairTab pt,
+                   StepScalars *sc, int *del_key, int *del_val, int *tail_key, int *tail_val,
+                   int *del_src, double *del_mv)
 {
+  __shared__ int s_dkey[DEL_SMEM], s_tkey[DEL_SMEM], s_tval[DEL_SMEM], s_src[DEL_SMEM];
+  const bool small = (npad_del <= DEL_SMEM && npad_tail <= DEL_SMEM);
+  const int ntail = sc->ntail;
+  // working arrays: shared memory when they fit (the usual few hundred deletions per step)
+  int *dkey = small ? s_dkey : del_key, *dval = small ? s_src : del_val;
+  int *tkey = small ? s_tkey : tail_key, *tval = small ? s_tval : tail_val;
   for (int k = threadIdx.x; k < npad_del; k += blockDim.x) {
-    if (k < ndel) {
-      del_key[k] = p.lidx[nlive + k];
-      del_val[k] = nlive + k;
-    } else {
-      del_key[k] = -1;
-      del_val[k] = -1;
-    }
+    dkey[k] = (k < ndel) ? p.lidx[nlive + k] : -1;
+    dval[k] = (k < ndel) ? nlive + k : -1;
   }
-  int ntail = sc->ntail;
-  for (int k = ntail + threadIdx.x; k < npad_tail; k += blockDim.x) {
-    tail_key[k] = -1;
-    tail_val[k] = -1;
+  for (int k = threadIdx.x; k < npad_tail; k += blockDim.x) {
+    tkey[k] = (k < ntail) ? tail_key[k] : -1;
+    tval[k] = (k < ntail) ? tail_val[k] : -1;
   }
   __syncthreads();
-  bitonic_desc(del_key, del_val, npad_del);
-  bitonic_desc(tail_key, tail_val, npad_tail);
-  if (threadIdx.x == 0) {
+  bitonic_desc(dkey, dval, npad_del);
+  bitonic_desc(tkey, tval, npad_tail);
+  // momentum contributions m*v of the deleted atoms, in descending local index order
+  const double mid = 0.5 * (fd.boxhi[0] + fd.boxlo[0]);
+  for (int k = threadIdx.x; k < ndel; k += blockDim.x) {
+    int s = dval[k];
+    double m = pt.mass[p.type[s]];
+    del_mv[4 * k + 0] = m * p.vx[s];
+    del_mv[4 * k + 1] = m * p.vy[s];
+    del_mv[4 * k + 2] = m * p.vz[s];
+    del_mv[4 * k + 3] = (p.x[s] < mid) ? 0.0 : 1.0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {  // six serial sums (left/right x three components), reference order (:827-837)
+    const int comp = threadIdx.x % 3;
+    const double side = (threadIdx.x < 3) ? 0.0 : 1.0;
+    double acc = 0.0;
+    for (int k = 0; k < ndel; k++)
+      if (del_mv[4 * k + 3] == side) acc += del_mv[4 * k + comp];
+    if (threadIdx.x < 3) sc->vnewl[comp] = acc;
+    else sc->vnewr[comp] = acc;
+  }
+  if (threadIdx.x == 32) {  // hole walk, on a different warp than the sums
     const int n = nlive + ndel;  // nlocal before the deletion; nprime = nlive
-    double mid = 0.5 * (fd.boxhi[0] + fd.boxlo[0]);
-    double vl0 = 0, vl1 = 0, vl2 = 0, vr0 = 0, vr1 = 0, vr2 = 0;
-    for (int k = 0; k < ndel; k++) {
-      int s = del_val[k];
-      double m = pt.mass[p.type[s]];
-      if (p.x[s] < mid) {
-        vl0 += m * p.vx[s];
-        vl1 += m * p.vy[s];
-        vl2 += m * p.vz[s];
-      } else {
-        vr0 += m * p.vx[s];
-        vr1 += m * p.vy[s];
-        vr2 += m * p.vz[s];
-      }
-    }
+    int *src = small ? s_src : del_src;  // dval is dead once del_mv is written (small: same array)
     int z = 0;
-    while (z < ndel && del_key[z] == n - 1 - z) z++;
+    while (z < ndel && dkey[z] == n - 1 - z) z++;
     const int heff = ndel - z;
     int is = 0, id = z, bad = 0;
     for (int k = 0; k < heff; k++) {
       int pos = n - 1 - z - k;
-      if (is < ntail && tail_key[is] == pos) del_src[k] = tail_val[is++];
-      else if (id < ndel && del_key[id] == pos) {
-        del_src[k] = del_src[id - z];
+      if (is < ntail && tkey[is] == pos) src[k] = tval[is++];
+      else if (id < ndel && dkey[id] == pos) {
+        src[k] = src[id - z];
         id++;
       } else
         bad = 1;
     }
     if (is != ntail) bad = 1;
     for (int k = 0; k < heff && !bad; k++) {
-      int h = del_key[z + k];
-      if (h < nlive) p.lidx[del_src[k]] = h;
+      int h = dkey[z + k];
+      if (h < nlive) p.lidx[src[k]] = h;
     }
     if (bad) sc->usher_error = OBMD_ERR_STATE;  // bookkeeping invariant violated
-    sc->vnewl[0] = vl0;
-    sc->vnewl[1] = vl1;
-    sc->vnewl[2] = vl2;
-    sc->vnewr[0] = vr0;
-    sc->vnewr[1] = vr1;
-    sc->vnewr[2] = vr2;
   }
 }
 
@@ -270,7 +306,8 @@ static int ranpark_skip(int seed, long long n)  // random_park.cpp:43-50 applied
 // =====================================================================================
 
 #define USH_WARPS 4
-#define USH_CAP 192  // contributions per energy evaluation held per warp
+#define USH_CAP 96    // contributions per energy evaluation held per warp (mean 13 at rho = 3)
+#define USH_CAND 448  // atoms in the 27 stencil cells of a point (mean 81 at rho = 3)
 
 struct UsherCfg {
   int ntrL, ntr;      // trials for the left region come first (maxattempt == 1)
@@ -300,19 +337,23 @@ __device__ __forceinline__ double ranpark_uniform(int &seed)
 }
 
 struct WarpHits {
-  int key[USH_CAP];
-  double e[USH_CAP], fx[USH_CAP], fy[USH_CAP], fz[USH_CAP];
+  int key[USH_CAP];   // LAMMPS local index of the contributing atom
+  int tj[USH_CAP];    // its type
+  double e[USH_CAP], fx[USH_CAP], fy[USH_CAP], fz[USH_CAP];  // pass A: rsq, del; pass B: phi, f
   int skey[USH_CAP];  // rank-sorted order: slot -> source
+  int cand[USH_CAND]; // storage slots of the atoms in the 27 stencil cells
 };
 
-// contribution of one neighbour at (xj,yj,zj) of type tj to the trial point: literal energy()
-// body (:1791-1806) + PairDPD::single
-__device__ __forceinline__ bool usher_contrib(const double c[3], double xj, double yj, double zj, int it,
-                                              int tj, const Grid &g, const PairTab &pt, double &e,
-                                              double &fx, double &fy, double &fz)
+// Pass A of energy() (:1791-1800): separation with the reference's minimum_image loop
+// (domain.cpp:980-1008, y and z periodic) and the cutoff test.
+__device__ __forceinline__ bool usher_screen(const double c[3], double xj, double yj, double zj, int it,
+                                             int tj, const Grid &g, const PairTab &pt, double &rsq,
+                                             double &delx, double &dely, double &delz)
 {
-  double delx = c[0] - xj, dely = c[1] - yj, delz = c[2] - zj;
-  while (fabs(dely) > g.half[1]) {  // domain.cpp:980-1008, y and z periodic
+  delx = c[0] - xj;
+  dely = c[1] - yj;
+  delz = c[2] - zj;
+  while (fabs(dely) > g.half[1]) {
     if (dely < 0.0) dely += g.prd[1];
     else dely -= g.prd[1];
   }
@@ -320,8 +361,14 @@ __device__ __forceinline__ bool usher_contrib(const double c[3], double xj, doub
     if (delz < 0.0) delz += g.prd[2];
     else delz -= g.prd[2];
   }
-  double rsq = delx * delx + dely * dely + delz * delz;
-  if (!(rsq < pt.cutsq[it][tj])) return false;
+  rsq = delx * delx + dely * dely + delz * delz;
+  return rsq < pt.cutsq[it][tj];
+}
+
+// Pass B: PairDPD::single (pair_dpd.cpp:401-418, factor_dpd = 1) and fpair*del (:1801-1805)
+__device__ __forceinline__ void usher_single(int it, int tj, const PairTab &pt, double rsq, double &e,
+                                             double &fx, double &fy, double &fz)
+{
   double r = sqrt(rsq);
   double fforce, phi;
   if (r < EPSILON_DPD) {
@@ -335,10 +382,9 @@ __device__ __forceinline__ bool usher_contrib(const double c[3], double xj, doub
     phi = 1.0 * phi;
   }
   e = phi;
-  fx = fforce * delx;
-  fy = fforce * dely;
-  fz = fforce * delz;
-  return true;
+  fx = fforce * fx;
+  fy = fforce * fy;
+  fz = fforce * fz;
 }
 
 // One warp evaluates E and f at point c: gathers contributions from the 27 cells and from the
@@ -353,51 +399,71 @@ __device__ void usher_energy(const double c[3], int t, const Planes &p, const Gr
   const unsigned lt = (1u << lane) - 1u;
   const int it = fd.ntype;
   int nh = 0;
+  // Lanes 0..26 each own one stencil cell: one round trip fetches all 27 cell ranges, a warp scan
+  // turns them into a flat candidate list, and the candidates are then visited 32 at a time with
+  // independent loads (two dependent global round trips per energy evaluation instead of 54).
   int cx = cell_cx(g, c[0]), cy = cell_cy(g, c[1]), cz = cell_cz(g, c[2]);
-  for (int ox = -1; ox <= 1; ox++) {
+  int jb = 0, cnt = 0;
+  if (lane < 27) {
+    int ox = lane / 9 - 1, oy = (lane / 3) % 3 - 1, oz = lane % 3 - 1;
     int bx = cx + ox;
-    if (bx < 0 || bx >= g.nx) continue;
-    for (int oy = -1; oy <= 1; oy++) {
-      int by = cell_wrap(cy + oy, g.ny);
-      for (int oz = -1; oz <= 1; oz++) {
-        int bz = cell_wrap(cz + oz, g.nz);
-        int cc = (bx * g.ny + by) * g.nz + bz;
-        int jb = cell_start[cc], je = cell_start[cc + 1];
-        for (int j0 = jb; j0 < je; j0 += 32) {
-          int j = j0 + lane;
-          bool hit = false;
-          double e = 0, fx = 0, fy = 0, fz = 0;
-          int key = 0;
-          if (j < je) {
-            hit = usher_contrib(c, p.x[j], p.y[j], p.z[j], it, p.type[j], g, pt, e, fx, fy, fz);
-            key = p.lidx[j];
-          }
-          unsigned m = __ballot_sync(0xffffffffu, hit);
-          if (hit) {
-            int s = nh + __popc(m & lt);
-            if (s < USH_CAP) {
-              H.key[s] = key;
-              H.e[s] = e;
-              H.fx[s] = fx;
-              H.fy[s] = fy;
-              H.fz[s] = fz;
-            }
-          }
-          nh += __popc(m);
-        }
-      }
+    if (bx >= 0 && bx < g.nx) {
+      int cc = (bx * g.ny + cell_wrap(cy + oy, g.ny)) * g.nz + cell_wrap(cz + oz, g.nz);
+      jb = cell_start[cc];
+      cnt = cell_start[cc + 1] - jb;
     }
   }
-  // atoms created by earlier trials of this call (they sit at local indices nbase + rank)
+  int off = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, off, d);
+    if (lane >= d) off += v;
+  }
+  const int ncand = __shfl_sync(0xffffffffu, off, 31);
+  off -= cnt;  // exclusive
+  if (ncand > USH_CAND) {
+    if (lane == 0) sc->usher_error = OBMD_ERR_CAPACITY;
+  } else {
+    for (int k = 0; k < cnt; k++) H.cand[off + k] = jb + k;
+  }
+  __syncwarp();
+  const int nc = ncand > USH_CAND ? 0 : ncand;
+  // pass A over the stencil atoms: cheap screen, hits compacted into the warp's list
+  for (int q0 = 0; q0 < nc; q0 += 32) {
+    int q = q0 + lane;
+    bool hit = false;
+    double rsq = 0, dx = 0, dy = 0, dz = 0;
+    int key = 0, tj = 0;
+    if (q < nc) {
+      int j = H.cand[q];
+      tj = p.type[j];
+      key = p.lidx[j];
+      hit = usher_screen(c, p.x[j], p.y[j], p.z[j], it, tj, g, pt, rsq, dx, dy, dz);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      int s2 = nh + __popc(m & lt);
+      if (s2 < USH_CAP) {
+        H.key[s2] = key;
+        H.tj[s2] = tj;
+        H.e[s2] = rsq;
+        H.fx[s2] = dx;
+        H.fy[s2] = dy;
+        H.fz[s2] = dz;
+      }
+    }
+    nh += __popc(m);
+  }
+  // ... and over the atoms created by earlier trials of this call (local indices nbase + rank)
   for (int k0 = 0; k0 < u.nacc_prev; k0 += 32) {
     int k = k0 + lane;
     bool hit = false;
-    double e = 0, fx = 0, fy = 0, fz = 0;
+    double rsq = 0, dx = 0, dy = 0, dz = 0;
     if (k < u.nacc_prev) {
       int tp = acc_list[k];
       if (tp < t) {
         const obmd_trial &q = prev[tp];
-        hit = usher_contrib(c, q.end[0], q.end[1], q.end[2], it, fd.ntype, g, pt, e, fx, fy, fz);
+        hit = usher_screen(c, q.end[0], q.end[1], q.end[2], it, fd.ntype, g, pt, rsq, dx, dy, dz);
       }
     }
     unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -405,10 +471,11 @@ __device__ void usher_energy(const double c[3], int t, const Planes &p, const Gr
       int s = nh + __popc(m & lt);
       if (s < USH_CAP) {
         H.key[s] = u.nbase + k;
-        H.e[s] = e;
-        H.fx[s] = fx;
-        H.fy[s] = fy;
-        H.fz[s] = fz;
+        H.tj[s] = fd.ntype;
+        H.e[s] = rsq;
+        H.fx[s] = dx;
+        H.fy[s] = dy;
+        H.fz[s] = dz;
       }
     }
     nh += __popc(m);
@@ -418,8 +485,14 @@ __device__ void usher_energy(const double c[3], int t, const Planes &p, const Gr
     nh = USH_CAP;
   }
   __syncwarp();
-  // rank sort by key (keys are distinct local indices)
+  // pass B (dense: usually a single sweep) + rank sort by key (keys are distinct local indices)
   for (int s = lane; s < nh; s += 32) {
+    double e, fx = H.fx[s], fy = H.fy[s], fz = H.fz[s];
+    usher_single(it, H.tj[s], pt, H.e[s], e, fx, fy, fz);
+    H.e[s] = e;
+    H.fx[s] = fx;
+    H.fy[s] = fy;
+    H.fz[s] = fz;
     int k = H.key[s], r = 0;
     for (int q = 0; q < nh; q++) r += (H.key[q] < k);
     H.skey[r] = s;
@@ -444,11 +517,12 @@ __device__ void usher_energy(const double c[3], int t, const Planes &p, const Gr
 
 // One warp per trial in `list`.  Writes the trial record and the points at which the energy was
 // evaluated (needed by the dirty test of the next round).
-__global__ void __launch_bounds__(USH_WARPS * 32)
+__global__ void __launch_bounds__(USH_WARPS * 32, 8)
     k_usher_eval(const int *__restrict__ list, int nlist, Planes p, Grid g, PairTab pt, FixDev fd,
                  const int *__restrict__ cell_start, UsherCfg u, const int *__restrict__ acc_list,
                  const obmd_trial *__restrict__ prev, obmd_trial *__restrict__ cur,
-                 double *__restrict__ path, int *__restrict__ npts, StepScalars *sc)
+                 double *__restrict__ path, int *__restrict__ npts, double *__restrict__ bbox,
+                 const int *__restrict__ kfirst, StepScalars *sc)
 {
   __shared__ WarpHits hits[USH_WARPS];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -469,6 +543,15 @@ __global__ void __launch_bounds__(USH_WARPS * 32)
 
   double *mypath = path + (size_t) t * (u.natt + 1) * 3;
   int i = 0, np = 0;
+  if (list) {
+    // Re-run of a trial whose neighbourhood changed: everything before the first affected
+    // evaluation point is unchanged, so resume there (the state at the top of iteration k is
+    // exactly (path[k], i = k)).
+    i = np = kfirst[t];
+    c[0] = mypath[3 * i];
+    c[1] = mypath[3 * i + 1];
+    c[2] = mypath[3 * i + 2];
+  }
   double E = 0.0, f[3];
   while (i < u.natt) {
     usher_energy(c, t, p, g, pt, fd, cell_start, u, acc_list, prev, hits[w], sc, E, f);
@@ -515,12 +598,23 @@ __global__ void __launch_bounds__(USH_WARPS * 32)
     r.tag = 0;
     cur[t] = r;
     npts[t] = np;
+    // bounding box of the evaluated points (dirty test of the next round)
+    double lo[3] = {mypath[0], mypath[1], mypath[2]}, hi[3] = {mypath[0], mypath[1], mypath[2]};
+    for (int k = 1; k < np; k++)
+      for (int d = 0; d < 3; d++) {
+        lo[d] = fmin(lo[d], mypath[3 * k + d]);
+        hi[d] = fmax(hi[d], mypath[3 * k + d]);
+      }
+    for (int d = 0; d < 3; d++) {
+      bbox[(size_t) t * 6 + d] = lo[d];
+      bbox[(size_t) t * 6 + 3 + d] = hi[d];
+    }
   }
 }
 
-// changed[t] = the trial's state (accepted, end) differs between the two latest rounds
+// chg_list = trials whose state (accepted, end) differs between the two latest rounds
 __global__ void k_usher_diff(const obmd_trial *__restrict__ prev, const obmd_trial *__restrict__ cur,
-                             int ntr, int first_round, int *__restrict__ changed, StepScalars *sc)
+                             int ntr, int first_round, int *__restrict__ chg_list, StepScalars *sc)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntr) return;
@@ -531,41 +625,78 @@ __global__ void k_usher_diff(const obmd_trial *__restrict__ prev, const obmd_tri
     ch = (a.accepted != b.accepted) ||
         (b.accepted && (a.end[0] != b.end[0] || a.end[1] != b.end[1] || a.end[2] != b.end[2]));
   }
-  changed[t] = ch;
-  if (ch) atomicAdd(&sc->nchanged, 1);
+  if (ch) chg_list[atomicAdd(&sc->nchanged, 1)] = t;
 }
 
+// all points involved lie inside the box, so one periodic shift suffices
 __device__ __forceinline__ bool near_pt(const double *a, const double *b, const Grid &g, double rsqmax)
 {
   double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
-  dy -= g.prd[1] * rint(dy / g.prd[1]);
-  dz -= g.prd[2] * rint(dz / g.prd[2]);
+  if (dy > g.half[1]) dy -= g.prd[1];
+  else if (dy < -g.half[1]) dy += g.prd[1];
+  if (dz > g.half[2]) dz -= g.prd[2];
+  else if (dz < -g.half[2]) dz += g.prd[2];
   return dx * dx + dy * dy + dz * dz <= rsqmax;
+}
+
+// is coordinate v (or a periodic image) within rc of the interval [lo, hi]?
+__device__ __forceinline__ bool axis_near(double v, double lo, double hi, double rc, double L, bool periodic)
+{
+  lo -= rc;
+  hi += rc;
+  if (v >= lo && v <= hi) return true;
+  if (!periodic) return false;
+  return (v + L >= lo && v + L <= hi) || (v - L >= lo && v - L <= hi);
+}
+
+__device__ __forceinline__ bool near_bbox(const double *a, const double *bb, const Grid &g, double rc)
+{
+  return axis_near(a[0], bb[0], bb[3], rc, 0.0, false) && axis_near(a[1], bb[1], bb[4], rc, g.prd[1], true) &&
+      axis_near(a[2], bb[2], bb[5], rc, g.prd[2], true);
 }
 
 // A trial must be re-run when an earlier trial whose state changed has its old or new atom
 // within the cutoff of any point the trial evaluated (a superset test with a small margin).
+// kfirst[t] = index of the first such point: the re-run resumes there.
 __global__ void k_usher_dirty(const obmd_trial *__restrict__ prev, const obmd_trial *__restrict__ cur,
-                              int ntr, int first_round, const int *__restrict__ changed,
-                              const double *__restrict__ path, const int *__restrict__ npts, int natt,
-                              Grid g, double rsqmax, int *__restrict__ list, StepScalars *sc)
+                              int ntr, int first_round, const int *__restrict__ chg_list,
+                              const double *__restrict__ path, const int *__restrict__ npts,
+                              const double *__restrict__ bbox, int natt, Grid g, double rc, double rsqmax,
+                              int *__restrict__ list, int *__restrict__ kfirst, StepScalars *sc)
 {
   int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (t >= ntr) return;
   const double *mp = path + (size_t) t * (natt + 1) * 3;
-  int np = npts[t];
-  bool dirty = false;
-  for (int q = lane; q < t && !dirty; q += 32) {
-    if (!changed[q]) continue;
-    bool oldacc = !first_round && prev[q].accepted, newacc = cur[q].accepted;
-    for (int k = 0; k < np && !dirty; k++) {
-      if (oldacc && near_pt(prev[q].end, mp + 3 * k, g, rsqmax)) dirty = true;
-      if (newacc && near_pt(cur[q].end, mp + 3 * k, g, rsqmax)) dirty = true;
+  const double *bb = bbox + (size_t) t * 6;
+  const int np = npts[t], nchg = sc->nchanged;
+  int kf = np;  // first affected point seen by this lane
+  for (int qi = lane; qi < nchg; qi += 32) {
+    int q = chg_list[qi];
+    if (q >= t) continue;
+    bool oldacc = !first_round && prev[q].accepted && near_bbox(prev[q].end, bb, g, rc);
+    bool newacc = cur[q].accepted && near_bbox(cur[q].end, bb, g, rc);
+    if (!oldacc && !newacc) continue;
+    for (int k = 0; k < kf; k++) {
+      if ((oldacc && near_pt(prev[q].end, mp + 3 * k, g, rsqmax)) ||
+          (newacc && near_pt(cur[q].end, mp + 3 * k, g, rsqmax))) {
+        kf = k;
+        break;
+      }
     }
   }
-  dirty = __any_sync(0xffffffffu, dirty);
-  if (dirty && lane == 0) list[atomicAdd(&sc->ndirty, 1)] = t;
+  for (int d = 16; d > 0; d >>= 1) kf = min(kf, __shfl_xor_sync(0xffffffffu, kf, d));
+  if (kf < np && lane == 0) {
+    kfirst[t] = kf;
+    list[atomicAdd(&sc->ndirty, 1)] = t;
+  }
+}
+
+// prev <- cur for every trial (grid copy)
+__global__ void k_usher_copy(obmd_trial *__restrict__ prev, const obmd_trial *__restrict__ cur, int ntr)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < ntr) prev[t] = cur[t];
 }
 
 // prev <- cur and the ordered list of accepted trial ids (one block, ordered compaction)
@@ -579,10 +710,7 @@ __global__ void k_usher_acc(obmd_trial *__restrict__ prev, const obmd_trial *__r
   for (int t0 = 0; t0 < ntr; t0 += blockDim.x) {
     int t = t0 + threadIdx.x;
     int a = 0;
-    if (t < ntr) {
-      prev[t] = cur[t];
-      a = cur[t].accepted;
-    }
+    if (t < ntr) a = cur[t].accepted;
     unsigned m = __ballot_sync(0xffffffffu, a);
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane == 0) wsum[w] = __popc(m);
@@ -626,16 +754,31 @@ __global__ void k_usher_commit(Planes p, int nsorted, int maxtag, int nbase, Gri
   }
 }
 
-// single thread: push in descending k so each cell's list runs in ascending k (deterministic)
+// Per-cell lists of the inserted atoms in ascending k (deterministic): atom k links to the next
+// k' > k in the same cell; the first atom of a cell becomes its head.  One block, cells staged in
+// shared memory, O(nacc) work per thread.
 __global__ void k_extra_link(const int *__restrict__ extra_cell, int nacc, int *__restrict__ extra_head,
                              int *__restrict__ extra_next)
 {
-  if (blockIdx.x == 0 && threadIdx.x == 0)
-    for (int k = nacc - 1; k >= 0; k--) {
-      int cc = extra_cell[k];
-      extra_next[k] = extra_head[cc];
-      extra_head[cc] = k;
-    }
+  extern __shared__ int cellsh[];
+  for (int k = threadIdx.x; k < nacc; k += blockDim.x) cellsh[k] = extra_cell[k];
+  __syncthreads();
+  for (int k = threadIdx.x; k < nacc; k += blockDim.x) {
+    int cc = cellsh[k], nxt = -1;
+    for (int q = k + 1; q < nacc; q++)
+      if (cellsh[q] == cc) {
+        nxt = q;
+        break;
+      }
+    extra_next[k] = nxt;
+    bool first = true;
+    for (int q = 0; q < k; q++)
+      if (cellsh[q] == cc) {
+        first = false;
+        break;
+      }
+    if (first) extra_head[cc] = k;
+  }
 }
 
 __global__ void k_extra_clear(const int *__restrict__ extra_cell, int nacc, int *__restrict__ extra_head)
@@ -657,14 +800,15 @@ static int ensure_trials(obmd_ctx *c, int ntr, int natt)
   int cap = ntr > c->tr_cap ? ntr + ntr / 2 + 256 : c->tr_cap;
   int na = natt > c->tr_natt ? natt : c->tr_natt;
   cudaFree(c->tr_d); cudaFree(c->tr_prev_d); cudaFree(c->tr_path); cudaFree(c->tr_npts);
-  cudaFree(c->tr_list); cudaFree(c->tr_changed); cudaFree(c->acc_list);
+  cudaFree(c->tr_list); cudaFree(c->tr_changed); cudaFree(c->acc_list); cudaFree(c->tr_bbox);
   if (c->tr_h) cudaFreeHost(c->tr_h);
+  CK(cudaMalloc(&c->tr_bbox, sizeof(double) * 6 * cap));
   CK(cudaMalloc(&c->tr_d, sizeof(obmd_trial) * cap));
   CK(cudaMalloc(&c->tr_prev_d, sizeof(obmd_trial) * cap));
   CK(cudaMalloc(&c->tr_path, sizeof(double) * 3 * (size_t) cap * (na + 1)));
   CK(cudaMalloc(&c->tr_npts, sizeof(int) * cap));
   CK(cudaMalloc(&c->tr_list, sizeof(int) * cap));
-  CK(cudaMalloc(&c->tr_changed, sizeof(int) * cap));
+  CK(cudaMalloc(&c->tr_changed, sizeof(int) * 2 * cap));  // changed flags | kfirst
   CK(cudaMalloc(&c->acc_list, sizeof(int) * cap));
   CK(cudaMallocHost(&c->tr_h, sizeof(obmd_trial) * cap));
   c->tr_cap = cap;
@@ -677,6 +821,93 @@ int read_scalars(obmd_ctx *c)
   CK(cudaMemcpyAsync(c->sc_h, c->sc_d, sizeof(StepScalars), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return OBMD_OK;
+}
+
+// cell columns overlapped by region block r (one column of slack each side for rounding)
+static void region_cols(const obmd_ctx *c, int r, int margin, int &a, int &e)
+{
+  const Grid &g = c->grid;
+  const obmd_block &b = c->fd.region[r];
+  a = (int) floor((b.lo[0] - g.lo[0]) * g.inv[0]) - 1 - margin;
+  e = (int) floor((b.hi[0] - g.lo[0]) * g.inv[0]) + 1 + margin;
+  a = a < 0 ? 0 : a;
+  e = e > g.nx - 1 ? g.nx - 1 : e;
+}
+
+static int merge_intervals(int *lo, int *hi, int n)
+{
+  for (int i = 1; i < n; i++)
+    for (int k = i; k > 0 && lo[k] < lo[k - 1]; k--) {
+      int t = lo[k]; lo[k] = lo[k - 1]; lo[k - 1] = t;
+      t = hi[k]; hi[k] = hi[k - 1]; hi[k - 1] = t;
+    }
+  int m = 0;
+  for (int i = 0; i < n; i++) {
+    if (hi[i] < lo[i]) continue;
+    if (m > 0 && lo[i] <= hi[m - 1] + 1) {
+      if (hi[i] > hi[m - 1]) hi[m - 1] = hi[i];
+    } else {
+      lo[m] = lo[i];
+      hi[m] = hi[i];
+      m++;
+    }
+  }
+  return m;
+}
+
+// columns of regions r0 and r1 as a ColRange (at most two disjoint intervals)
+ColRange fix_region_columns(const obmd_ctx *c, int r0, int r1, int margin)
+{
+  int lo[2], hi[2];
+  region_cols(c, r0, margin, lo[0], hi[0]);
+  region_cols(c, r1, margin, lo[1], hi[1]);
+  int m = merge_intervals(lo, hi, 2);
+  ColRange cr;
+  memset(&cr, 0, sizeof(cr));
+  cr.n = m;
+  for (int k = 0; k < m; k++) {
+    cr.a[k] = lo[k];
+    cr.b[k] = hi[k];
+  }
+  return cr;
+}
+
+// Split the cell columns into the part pre_exchange reads (buffer regions for the counts,
+// insertion regions +-1 column for USHER) and the largest untouched run [ga, gb].  The interior
+// can be wrapped (columns ga..gb) and its pair forces computed (columns ga+1..gb-1) on the side
+// stream while pre_exchange runs; the rest follows on the main stream.
+bool fix_zones(const obmd_ctx *c, ColRange &int_pbc, ColRange &int_pair, ColRange &out_pbc,
+               ColRange &out_pair)
+{
+  int lo[4], hi[4];
+  region_cols(c, 0, 0, lo[0], hi[0]);
+  region_cols(c, 1, 0, lo[1], hi[1]);
+  region_cols(c, 4, 1, lo[2], hi[2]);
+  region_cols(c, 5, 1, lo[3], hi[3]);
+  int m = merge_intervals(lo, hi, 4);
+  const int nx = c->grid.nx;
+  int ga = 0, gb = -1;
+  for (int k = 0; k <= m; k++) {
+    int a = (k == 0) ? 0 : hi[k - 1] + 1;
+    int b = (k == m) ? nx - 1 : lo[k] - 1;
+    if (b - a > gb - ga) {
+      ga = a;
+      gb = b;
+    }
+  }
+  if (gb - ga + 1 < 6) return false;
+  memset(&int_pbc, 0, sizeof(ColRange));
+  memset(&int_pair, 0, sizeof(ColRange));
+  memset(&out_pbc, 0, sizeof(ColRange));
+  memset(&out_pair, 0, sizeof(ColRange));
+  int_pbc.n = 1; int_pbc.a[0] = ga; int_pbc.b[0] = gb;
+  int_pair.n = 1; int_pair.a[0] = ga + 1; int_pair.b[0] = gb - 1;
+  out_pbc.extras = out_pair.extras = 1;
+  if (ga > 0) { out_pbc.a[out_pbc.n] = 0; out_pbc.b[out_pbc.n] = ga - 1; out_pbc.n++; }
+  if (gb < nx - 1) { out_pbc.a[out_pbc.n] = gb + 1; out_pbc.b[out_pbc.n] = nx - 1; out_pbc.n++; }
+  out_pair.a[0] = 0; out_pair.b[0] = ga; out_pair.n = 1;
+  out_pair.a[1] = gb; out_pair.b[1] = nx - 1; out_pair.n = 2;
+  return true;
 }
 
 int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
@@ -695,20 +926,24 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
     CK(cudaMemsetAsync(c->sc_d->vnewl, 0, 6 * sizeof(double), c->stream));
     if (ndel > c->del_cap) {
       cudaFree(c->del_key); cudaFree(c->del_val); cudaFree(c->tail_key); cudaFree(c->tail_val);
-      cudaFree(c->del_src);
+      cudaFree(c->del_src); cudaFree(c->del_mv);
       c->del_cap = next_pow2(ndel + 1024);
       CK(cudaMalloc(&c->del_src, sizeof(int) * c->del_cap));
+      CK(cudaMalloc(&c->del_mv, sizeof(double) * 4 * c->del_cap));
       CK(cudaMalloc(&c->del_key, sizeof(int) * c->del_cap));
       CK(cudaMalloc(&c->del_val, sizeof(int) * c->del_cap));
       CK(cudaMalloc(&c->tail_key, sizeof(int) * c->del_cap));
       CK(cudaMalloc(&c->tail_val, sizeof(int) * c->del_cap));
     }
-    LAUNCH(k_scan_atoms, cdiv(nlive > 0 ? nlive : 1, 256), 256, 0, c->cur, nlive, c->fd, c->sc_d,
-           c->tail_key, c->tail_val, c->del_cap);
+    LAUNCH(k_scan_ids, cdiv(nlive > 0 ? nlive : 1, 256), 256, 0, c->cur, nlive, c->sc_d, c->tail_key,
+           c->tail_val, c->del_cap);
+    ColRange bufcols = fix_region_columns(c, 0, 1, 0);
+    LAUNCH(k_count_regions, FB_BLOCKS, FB_THREADS, 0, c->cur, bufcols, c->grid, c->fd, c->cell_start,
+           c->sc_d);
     if (ndel > 0) {
       int npad = next_pow2(ndel);
       LAUNCH(k_delete_fixup, 1, 1024, 0, c->cur, nlive, ndel, npad, npad, c->fd, c->pt, c->sc_d,
-             c->del_key, c->del_val, c->tail_key, c->tail_val, c->del_src);
+             c->del_key, c->del_val, c->tail_key, c->tail_val, c->del_src, c->del_mv);
     }
     if ((rc = read_scalars(c))) return rc;
   }
@@ -759,12 +994,14 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
     for (;; round++) {
       NEED(round <= ntr + 1, OBMD_ERR_STATE, "fix obmd: USHER commit did not converge");
       LAUNCH(k_usher_eval, cdiv(nlist, USH_WARPS), USH_WARPS * 32, 0, list, nlist, c->cur, c->grid, c->pt,
-             c->fd, c->cell_start, u, c->acc_list, c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts, c->sc_d);
+             c->fd, c->cell_start, u, c->acc_list, c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts, c->tr_bbox, c->tr_changed + c->tr_cap, c->sc_d);
       CK(cudaMemsetAsync(&c->sc_d->nchanged, 0, 2 * sizeof(int), c->stream));  // nchanged, ndirty
       LAUNCH(k_usher_diff, cdiv(ntr, 256), 256, 0, c->tr_prev_d, c->tr_d, ntr, round == 0 ? 1 : 0,
              c->tr_changed, c->sc_d);
       LAUNCH(k_usher_dirty, cdiv(ntr, 4), 128, 0, c->tr_prev_d, c->tr_d, ntr, round == 0 ? 1 : 0,
-             c->tr_changed, c->tr_path, c->tr_npts, u.natt, c->grid, rsqmax, c->tr_list, c->sc_d);
+             c->tr_changed, c->tr_path, c->tr_npts, c->tr_bbox, u.natt, c->grid, c->pt.cutmax * (1.0 + 1e-9),
+             rsqmax, c->tr_list, c->tr_changed + c->tr_cap, c->sc_d);
+      LAUNCH(k_usher_copy, cdiv(ntr, 256), 256, 0, c->tr_prev_d, c->tr_d, ntr);
       LAUNCH(k_usher_acc, 1, 1024, 0, c->tr_prev_d, c->tr_d, ntr, c->acc_list, c->sc_d);
       if ((rc = read_scalars(c))) return rc;
       NEED(c->sc_h->usher_error != OBMD_ERR_USHER, OBMD_ERR_USHER,
@@ -778,12 +1015,14 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
       u.nacc_prev = nacc;
     }
     rep.usher_rounds = round + 1;
+    c->fs.ntrials += ntr;
+    c->fs.nrounds += round + 1;
     // every trial consumes exactly three draws (ATOM mode, uniform distribution, block region)
     c->fs.rng_seed = ranpark_skip(c->fs.rng_seed, 3LL * ntr);
     if (nacc > 0) {
       LAUNCH(k_usher_commit, cdiv(nacc, 128), 128, 0, c->cur, nlive, s.maxtag, nlive, c->grid, c->fd,
              c->tr_d, c->acc_list, nacc, c->extra_head, c->extra_next, c->extra_cell, c->fx, c->fy, c->fz);
-      LAUNCH(k_extra_link, 1, 32, 0, c->extra_cell, nacc, c->extra_head, c->extra_next);
+      LAUNCH(k_extra_link, 1, 256, sizeof(int) * nacc, c->extra_cell, nacc, c->extra_head, c->extra_next);
     }
     if (trials && maxtrials > 0) {
       int ncopy = ntr < maxtrials ? ntr : maxtrials;
@@ -873,8 +1112,6 @@ __device__ __forceinline__ double g_par_global_term(const FixDev &fd, double mas
   return g;
 }
 
-#define FB_BLOCKS (NSM * 2)
-#define FB_THREADS 256
 
 // Pass 1 (g_par_global_charged :1244, g_perp_global_charged :1344): weight sums of the four
 // regions.  Fixed grid, grid-stride over the contiguous slot ranges, warp-shuffle + block tree,

@@ -9,11 +9,23 @@
 // symmetric counter-based N(0,1) variate keyed on (min tag, max tag, seed, timestep), identical
 // for the (i,j) and (j,i) evaluations so Newton's third law holds exactly (DESIGN.md "RNG").
 //
+// Kernel shape (v2).  Only ~15 % of the 81 stencil candidates of an atom lie inside the cutoff, so
+// a straight "test then evaluate" loop runs the expensive branch at ~1/3 lane occupancy (ncu, r01:
+// 11.4 active threads per instruction).  Each thread therefore works in two phases:
+//   1. distance screen: walk the 9 stencil rows (the 3 z-cells of a row are one contiguous slot
+//      range because z is the fastest cell index), and push the slots that pass rsq < cutsq into a
+//      per-thread list in shared memory (k-major layout -> conflict free);
+//   2. evaluate the listed pairs densely (sqrt, div, drag, counter RNG), in list order, so the
+//      summation order is fixed by the cell layout alone.
+// The minimum-image correction is applied only by atoms that sit in a boundary cell in y or z.
+//
 // Roofline: algorithmic traffic is 80 B/atom (x,v,tag,type in, f out); neighbour reads are
-// served by L1/L2.  The kernel is fp64-pipe bound, not HBM bound.
+// served by L1/L2.  The kernel is fp64-pipe/issue bound, not HBM bound.
 #include "ctx.h"
 
 #define EPSILON_DPD 1.0e-10  // pair_dpd.cpp:36
+#define PAIR_T 128           // threads per block
+#define PAIR_HCAP 40         // listed hits per thread (mean 12.6 at rho = 3); overflow is evaluated inline
 
 __device__ __forceinline__ double dpd_gaussian(int tagi, int tagj, unsigned step, unsigned seed)
 {
@@ -37,102 +49,158 @@ struct PairAcc {
   double fx, fy, fz, e, v0, v1, v2, v3, v4, v5;
 };
 
-template <bool SINGLE_TYPE, bool TALLY>
-__device__ __forceinline__ void pair_ij(const Planes &p, const PairTab &pt, int j, double xi, double yi,
-                                        double zi, double vxi, double vyi, double vzi, int tagi, int ti,
-                                        const Grid &g, unsigned step, bool random_on, PairAcc &a)
+struct AtomI {
+  double x, y, z, vx, vy, vz;
+  int tag, type;
+  bool bnd;  // sits in a boundary cell in y or z: needs the minimum-image shift
+};
+
+__device__ __forceinline__ void min_image(const Grid &g, double &dely, double &delz)
 {
-  double delx = xi - p.x[j];
-  double dely = yi - p.y[j];
-  double delz = zi - p.z[j];
-  // minimum image in y,z (boundary f p p); positions are wrapped, one shift suffices
   if (dely > g.half[1]) dely -= g.prd[1];
   else if (dely < -g.half[1]) dely += g.prd[1];
   if (delz > g.half[2]) delz -= g.prd[2];
   else if (delz < -g.half[2]) delz += g.prd[2];
+}
+
+// pair_dpd.cpp:117-146 for a pair already known to be inside the cutoff
+template <bool SINGLE_TYPE, bool TALLY>
+__device__ __forceinline__ void pair_eval(const Planes &p, const PairTab &pt, const Grid &g, int j,
+                                          const AtomI &a, unsigned step, bool random_on, PairAcc &acc)
+{
+  double delx = a.x - p.x[j], dely = a.y - p.y[j], delz = a.z - p.z[j];
+  if (a.bnd) min_image(g, dely, delz);
   double rsq = delx * delx + dely * dely + delz * delz;
   int tj = SINGLE_TYPE ? 1 : p.type[j];
-  if (rsq < pt.cutsq[ti][tj]) {
-    double r = sqrt(rsq);
-    if (r < EPSILON_DPD) return;
-    double rinv = 1.0 / r;
-    double delvx = vxi - p.vx[j], delvy = vyi - p.vy[j], delvz = vzi - p.vz[j];
-    double dot = delx * delvx + dely * delvy + delz * delvz;
-    double wd = 1.0 - r / pt.cut[ti][tj];
-    double fpair = pt.a0[ti][tj] * wd;
-    fpair -= pt.gamma[ti][tj] * wd * wd * dot * rinv;
-    if (random_on) {
-      double randnum = dpd_gaussian(tagi, p.tag[j], step, pt.seed);
-      fpair += pt.sigma[ti][tj] * wd * randnum * pt.dtinvsqrt;
-    }
-    fpair *= rinv;
-    a.fx += delx * fpair;
-    a.fy += dely * fpair;
-    a.fz += delz * fpair;
-    if (TALLY) {
-      a.e += 0.5 * (0.5 * pt.a0[ti][tj] * pt.cut[ti][tj] * wd * wd);
-      double h = 0.5 * fpair;
-      a.v0 += h * delx * delx;
-      a.v1 += h * dely * dely;
-      a.v2 += h * delz * delz;
-      a.v3 += h * delx * dely;
-      a.v4 += h * delx * delz;
-      a.v5 += h * dely * delz;
-    }
+  double r = sqrt(rsq);
+  if (r < EPSILON_DPD) return;
+  double rinv = 1.0 / r;
+  double delvx = a.vx - p.vx[j], delvy = a.vy - p.vy[j], delvz = a.vz - p.vz[j];
+  double dot = delx * delvx + dely * delvy + delz * delvz;
+  double wd = 1.0 - r / pt.cut[a.type][tj];
+  double fpair = pt.a0[a.type][tj] * wd;
+  fpair -= pt.gamma[a.type][tj] * wd * wd * dot * rinv;
+  if (random_on) {
+    double randnum = dpd_gaussian(a.tag, p.tag[j], step, pt.seed);
+    fpair += pt.sigma[a.type][tj] * wd * randnum * pt.dtinvsqrt;
+  }
+  fpair *= rinv;
+  acc.fx += delx * fpair;
+  acc.fy += dely * fpair;
+  acc.fz += delz * fpair;
+  if (TALLY) {
+    acc.e += 0.5 * (0.5 * pt.a0[a.type][tj] * pt.cut[a.type][tj] * wd * wd);
+    double h = 0.5 * fpair;
+    acc.v0 += h * delx * delx;
+    acc.v1 += h * dely * dely;
+    acc.v2 += h * delz * delz;
+    acc.v3 += h * delx * dely;
+    acc.v4 += h * delx * delz;
+    acc.v5 += h * dely * delz;
   }
 }
 
+template <bool SINGLE_TYPE>
+__device__ __forceinline__ bool pair_screen(const Planes &p, const PairTab &pt, const Grid &g, int j,
+                                            const AtomI &a)
+{
+  double delx = a.x - p.x[j], dely = a.y - p.y[j], delz = a.z - p.z[j];
+  if (a.bnd) min_image(g, dely, delz);
+  double rsq = delx * delx + dely * dely + delz * delz;
+  int tj = SINGLE_TYPE ? 1 : p.type[j];
+  return rsq < pt.cutsq[a.type][tj];
+}
+
+// slot of the g-th atom of a column set (intervals in order, then the inserted atoms); -1 if none
+__device__ __forceinline__ int colrange_slot(const ColRange &cr, int gidx, const Grid &g,
+                                             const int *__restrict__ cell_start, int nsorted, int nextra)
+{
+  const int nyz = g.ny * g.nz;
+  for (int k = 0; k < cr.n; k++) {
+    int b = cell_start[cr.a[k] * nyz], e = cell_start[(cr.b[k] + 1) * nyz];
+    if (gidx < e - b) return b + gidx;
+    gidx -= e - b;
+  }
+  if (cr.extras && gidx < nextra) return nsorted + gidx;
+  return -1;
+}
+
 template <bool SINGLE_TYPE, bool TALLY>
-__global__ void __launch_bounds__(128)
-    k_pair_dpd(Planes p, int n, int nsorted, int nextra, Grid g, PairTab pt,
+__global__ void __launch_bounds__(PAIR_T)
+    k_pair_dpd(Planes p, ColRange cr, int nsorted, int nextra, Grid g, PairTab pt,
                const int *__restrict__ cell_start, const int *__restrict__ extra_head,
                const int *__restrict__ extra_next, double *__restrict__ fx, double *__restrict__ fy,
                double *__restrict__ fz, unsigned step, int random_on, double *__restrict__ partials)
 {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  PairAcc a = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (i < n) {
-    double xi = p.x[i], yi = p.y[i], zi = p.z[i];
-    double vxi = p.vx[i], vyi = p.vy[i], vzi = p.vz[i];
-    int tagi = p.tag[i];
-    int ti = SINGLE_TYPE ? 1 : p.type[i];
-    int cx = cell_cx(g, xi), cy = cell_cy(g, yi), cz = cell_cz(g, zi);
+  __shared__ int hits[PAIR_HCAP * PAIR_T];
+  const int i = colrange_slot(cr, blockIdx.x * PAIR_T + threadIdx.x, g, cell_start, nsorted, nextra);
+  int *myhits = hits + threadIdx.x;
+  PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (i >= 0) {
+    AtomI a;
+    a.x = p.x[i]; a.y = p.y[i]; a.z = p.z[i];
+    a.vx = p.vx[i]; a.vy = p.vy[i]; a.vz = p.vz[i];
+    a.tag = p.tag[i];
+    a.type = SINGLE_TYPE ? 1 : p.type[i];
+    const int cx = cell_cx(g, a.x), cy = cell_cy(g, a.y), cz = cell_cz(g, a.z);
+    a.bnd = (cy == 0 || cy == g.ny - 1 || cz == 0 || cz == g.nz - 1);
+    // z extent of the stencil row: one contiguous segment, plus a wrapped single cell at the faces
+    const int za = max(cz - 1, 0), zb = min(cz + 1, g.nz - 1);
+    const int zw = (cz == 0) ? g.nz - 1 : ((cz == g.nz - 1) ? 0 : -1);
+    int nh = 0;
     for (int ox = -1; ox <= 1; ox++) {
-      int bx = cx + ox;
+      const int bx = cx + ox;
       if (bx < 0 || bx >= g.nx) continue;
       for (int oy = -1; oy <= 1; oy++) {
         int by = cy + oy;
         by = by < 0 ? by + g.ny : (by >= g.ny ? by - g.ny : by);
-        int row = (bx * g.ny + by) * g.nz;
-        for (int oz = -1; oz <= 1; oz++) {
-          int bz = cz + oz;
-          bz = bz < 0 ? bz + g.nz : (bz >= g.nz ? bz - g.nz : bz);
-          int cc = row + bz;
-          int jb = cell_start[cc], je = cell_start[cc + 1];
+        const int row = (bx * g.ny + by) * g.nz;
+        for (int seg = 0; seg < 2; seg++) {
+          int jb, je;
+          if (seg == 0) {
+            jb = cell_start[row + za];
+            je = cell_start[row + zb + 1];
+          } else {
+            if (zw < 0) break;
+            jb = cell_start[row + zw];
+            je = cell_start[row + zw + 1];
+          }
           for (int j = jb; j < je; j++) {
             if (j == i) continue;
-            pair_ij<SINGLE_TYPE, TALLY>(p, pt, j, xi, yi, zi, vxi, vyi, vzi, tagi, ti, g, step,
-                                        random_on != 0, a);
+            if (pair_screen<SINGLE_TYPE>(p, pt, g, j, a)) {
+              if (nh < PAIR_HCAP) {
+                myhits[nh * PAIR_T] = j;
+                nh++;
+              } else {
+                pair_eval<SINGLE_TYPE, TALLY>(p, pt, g, j, a, step, random_on != 0, acc);
+              }
+            }
           }
-          if (nextra > 0) {
-            for (int e = extra_head[cc]; e >= 0; e = extra_next[e]) {
+        }
+        if (nextra > 0) {  // atoms inserted after the sort hang off per-cell lists
+          for (int oz = -1; oz <= 1; oz++) {
+            int bz = cz + oz;
+            bz = bz < 0 ? bz + g.nz : (bz >= g.nz ? bz - g.nz : bz);
+            for (int e = extra_head[row + bz]; e >= 0; e = extra_next[e]) {
               int j = nsorted + e;
               if (j == i) continue;
-              pair_ij<SINGLE_TYPE, TALLY>(p, pt, j, xi, yi, zi, vxi, vyi, vzi, tagi, ti, g, step,
-                                          random_on != 0, a);
+              if (pair_screen<SINGLE_TYPE>(p, pt, g, j, a))
+                pair_eval<SINGLE_TYPE, TALLY>(p, pt, g, j, a, step, random_on != 0, acc);
             }
           }
         }
       }
     }
-    fx[i] = a.fx;
-    fy[i] = a.fy;
-    fz[i] = a.fz;
+    for (int k = 0; k < nh; k++)
+      pair_eval<SINGLE_TYPE, TALLY>(p, pt, g, myhits[k * PAIR_T], a, step, random_on != 0, acc);
+    fx[i] = acc.fx;
+    fy[i] = acc.fy;
+    fz[i] = acc.fz;
   }
   if (TALLY) {
     // deterministic block reduction of (e, v[6]) -> partials[block][7]
-    __shared__ double sh[7][4];
-    double v[7] = {a.e, a.v0, a.v1, a.v2, a.v3, a.v4, a.v5};
+    __shared__ double sh[7][PAIR_T / 32];
+    double v[7] = {acc.e, acc.v0, acc.v1, acc.v2, acc.v3, acc.v4, acc.v5};
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 7; k++) {
@@ -144,7 +212,7 @@ __global__ void __launch_bounds__(128)
     __syncthreads();
     if (threadIdx.x < 7) {
       double s = 0.0;
-      for (int ww = 0; ww < (int) (blockDim.x >> 5); ww++) s += sh[threadIdx.x][ww];
+      for (int ww = 0; ww < PAIR_T / 32; ww++) s += sh[threadIdx.x][ww];
       partials[blockIdx.x * 7 + threadIdx.x] = s;
     }
   }
@@ -171,13 +239,32 @@ __global__ void k_pair_tally_final(const double *__restrict__ partials, int nblo
   }
 }
 
-int pair_compute(obmd_ctx *c, long long step, int eflag, int vflag)
+ColRange all_columns(const obmd_ctx *c)
 {
-  NEED(c->cells_valid, OBMD_ERR_STATE, "obmd_pair_compute: cell list is stale (call obmd_build_cells)");
-  ScopedTimer t(c, "pair");
-  const int n = c->nsorted + c->nextra;
-  const int nb = cdiv(n, 128);
-  const bool tally = eflag || vflag;
+  ColRange cr;
+  cr.n = 1;
+  cr.a[0] = 0;
+  cr.b[0] = c->grid.nx - 1;
+  cr.a[1] = cr.b[1] = 0;
+  cr.extras = 1;
+  return cr;
+}
+
+// upper bound of the atoms in a column set, for sizing the grid without a device read-back
+static int colrange_bound(const obmd_ctx *c, const ColRange &cr)
+{
+  long long cols = 0;
+  for (int k = 0; k < cr.n; k++) cols += cr.b[k] - cr.a[k] + 1;
+  if (cols >= c->grid.nx) return c->nsorted + (cr.extras ? c->nextra : 0);
+  // no per-column counts on the host: launch for every sorted atom, surplus threads exit at once
+  return c->nsorted + (cr.extras ? c->nextra : 0);
+}
+
+static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &cr, cudaStream_t st)
+{
+  const int nmax = colrange_bound(c, cr);
+  if (nmax <= 0) return OBMD_OK;
+  const int nb = cdiv(nmax, PAIR_T);
   const bool single = (c->ntypes == 1);
   const int random_on = c->temperature > 0.0 ? 1 : 0;
   c->pt.dtinvsqrt = 1.0 / sqrt(c->dt);
@@ -186,15 +273,32 @@ int pair_compute(obmd_ctx *c, long long step, int eflag, int vflag)
     c->partial_cap = nb * 7 + 1024;
     CK(cudaMalloc(&c->partials, sizeof(double) * c->partial_cap));
   }
-#define PAIR_ARGS                                                                              \
-  c->cur, n, c->nsorted, c->nextra, c->grid, c->pt, c->cell_start, c->extra_head, c->extra_next, \
+#define PAIR_ARGS                                                                             \
+  c->cur, cr, c->nsorted, c->nextra, c->grid, c->pt, c->cell_start, c->extra_head, c->extra_next, \
       c->fx, c->fy, c->fz, (unsigned) step, random_on, c->partials
-  if (single && !tally) LAUNCH((k_pair_dpd<true, false>), nb, 128, 0, PAIR_ARGS);
-  else if (single && tally) LAUNCH((k_pair_dpd<true, true>), nb, 128, 0, PAIR_ARGS);
-  else if (!single && !tally) LAUNCH((k_pair_dpd<false, false>), nb, 128, 0, PAIR_ARGS);
-  else LAUNCH((k_pair_dpd<false, true>), nb, 128, 0, PAIR_ARGS);
-  if (tally) LAUNCH(k_pair_tally_final, 1, 256, 0, c->partials, nb, c->sc_d);
+  if (single && !tally) LAUNCH_ON(st, (k_pair_dpd<true, false>), nb, PAIR_T, 0, PAIR_ARGS);
+  else if (single && tally) LAUNCH_ON(st, (k_pair_dpd<true, true>), nb, PAIR_T, 0, PAIR_ARGS);
+  else if (!single && !tally) LAUNCH_ON(st, (k_pair_dpd<false, false>), nb, PAIR_T, 0, PAIR_ARGS);
+  else LAUNCH_ON(st, (k_pair_dpd<false, true>), nb, PAIR_T, 0, PAIR_ARGS);
+  if (tally) LAUNCH_ON(st, k_pair_tally_final, 1, 256, 0, c->partials, nb, c->sc_d);
   CK(cudaGetLastError());
+  return OBMD_OK;
+}
+
+// forces of the atoms in a column set only (used by obmd_run to overlap the interior with USHER)
+int pair_compute_cols(obmd_ctx *c, long long step, const ColRange &cr, cudaStream_t st)
+{
+  NEED(c->cells_valid, OBMD_ERR_STATE, "pair_compute_cols: cell list is stale");
+  ScopedTimer t(c, "pair", st);
+  return pair_launch(c, step, false, cr, st);
+}
+
+int pair_compute(obmd_ctx *c, long long step, int eflag, int vflag)
+{
+  NEED(c->cells_valid, OBMD_ERR_STATE, "obmd_pair_compute: cell list is stale (call obmd_build_cells)");
+  ScopedTimer t(c, "pair");
+  int rc = pair_launch(c, step, eflag || vflag, all_columns(c), c->stream);
+  if (rc) return rc;
   c->forces_valid = true;
   return OBMD_OK;
 }
