@@ -152,6 +152,8 @@ int obmd_pair_compute(obmd_ctx *ctx, long long ntimestep, int eflag, int vflag);
 int obmd_pair_tallies(obmd_ctx *ctx, double *eng_vdwl, double virial[6]);
 /* FixObmdMerged::post_force (:1229-1240): reg_force x2 + reg_force_perp x2 */
 int obmd_post_force(obmd_ctx *ctx);
+/* Verlet::force_clear on the device copy (lets a host shim read back only what post_force added). */
+int obmd_zero_forces(obmd_ctx *ctx);
 /* FixNVE::final_integrate (fix_nve.cpp:185-244) */
 int obmd_nve_final(obmd_ctx *ctx);
 /* nsteps full timesteps, device resident, in exactly the order above.  first_step = the

@@ -92,6 +92,7 @@ SIGNATURES = {
     "obmd_pair_compute": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int]),
     "obmd_pair_tallies": (C.c_int, [C.c_void_p, _dp, _dp]),
     "obmd_post_force": (C.c_int, [C.c_void_p]),
+    "obmd_zero_forces": (C.c_int, [C.c_void_p]),
     "obmd_nve_final": (C.c_int, [C.c_void_p]),
     "obmd_run": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int]),
     "obmd_reduce_kinetic": (C.c_int, [C.c_void_p, _dp]),

@@ -552,6 +552,17 @@ extern "C" int obmd_post_force(obmd_ctx *c)
   return fix_post_force(c);
 }
 
+extern "C" int obmd_zero_forces(obmd_ctx *c)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  if (c->n > 0) {
+    CK(cudaMemsetAsync(c->fx, 0, sizeof(double) * c->n, c->stream));
+    CK(cudaMemsetAsync(c->fy, 0, sizeof(double) * c->n, c->stream));
+    CK(cudaMemsetAsync(c->fz, 0, sizeof(double) * c->n, c->stream));
+  }
+  return OBMD_OK;
+}
+
 extern "C" int obmd_run(obmd_ctx *c, long long first_step, int nsteps)
 {
   NEED(c, OBMD_ERR_ARG, "NULL context");

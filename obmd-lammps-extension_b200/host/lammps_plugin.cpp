@@ -1,0 +1,487 @@
+// LAMMPS style shim: registers `fix obmd` and `pair_style dpd` from a plugin and forwards them to
+// libobmd_b200.so through the C ABI (include/obmd_b200.h).  Input-script syntax, hook points and
+// coefficients are the reference's (OBMD/fix_obmd_merged.{h,cpp}, DPD-BASIC/pair_dpd.{h,cpp}); this
+// file only marshals arguments and LAMMPS-owned host pointers.  It is "stage A" of the residency
+// ladder (DESIGN.md / INTEGRATION.md): LAMMPS keeps FixNVE, Domain::pbc and Comm on the host, so
+// every step uploads x,v (48 B/atom) and downloads f (24 B/atom).
+//
+// Build (needs the LAMMPS headers, i.e. only where the reference tree is mounted):
+//   make -C obmd-lammps-extension_b200/host plugin LAMMPS_SRC=/root/reference/code/src
+// Use:  first line of the deck:  plugin load /path/to/libobmd_b200_lammps.so
+// The classes are deliberately NOT named FixObmdMerged / PairDPD: the host binary exports its own
+// symbols (ENABLE_EXPORTS) and would interpose them (SURVEY 8b "Gotcha").
+#include "atom.h"
+#include "atom_vec.h"
+#include "comm.h"
+#include "domain.h"
+#include "error.h"
+#include "fix.h"
+#include "force.h"
+#include "group.h"
+#include "lammpsplugin.h"
+#include "memory.h"
+#include "pair.h"
+#include "region.h"
+#include "update.h"
+#include "version.h"
+
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "obmd_b200.h"
+
+using namespace LAMMPS_NS;
+using namespace FixConst;
+
+namespace {
+
+// One device context per LAMMPS instance, shared by the pair style and the fix.
+struct Shared {
+  obmd_ctx *ctx = nullptr;
+  int users = 0;
+  bool box_set = false, pair_ready = false;
+  int resident = 0;       // atoms resident on the device (LAMMPS local order)
+  bigint xv_step = -1;    // timestep whose x,v are on the device
+};
+std::map<LAMMPS *, Shared> g_shared;
+
+Shared &acquire(LAMMPS *lmp)
+{
+  Shared &s = g_shared[lmp];
+  if (!s.ctx) {
+    int dev = 0;
+    if (const char *e = getenv("OBMD_B200_DEVICE")) dev = atoi(e);
+    if (obmd_create(&s.ctx, dev) != OBMD_OK)
+      lmp->error->all(FLERR, "obmd_b200: {}", obmd_last_error(nullptr));
+  }
+  s.users++;
+  return s;
+}
+
+void release(LAMMPS *lmp)
+{
+  auto it = g_shared.find(lmp);
+  if (it == g_shared.end()) return;
+  if (--it->second.users <= 0) {
+    obmd_destroy(it->second.ctx);
+    g_shared.erase(it);
+  }
+}
+
+#define OBMD_CK(lmp, s, call)                                                        \
+  do {                                                                               \
+    if ((call) != OBMD_OK) (lmp)->error->all(FLERR, "{}", obmd_last_error((s).ctx)); \
+  } while (0)
+
+void push_domain(LAMMPS *lmp, Shared &s)
+{
+  Domain *d = lmp->domain;
+  if (d->triclinic) lmp->error->all(FLERR, "obmd_b200 requires an orthogonal box");
+  if (d->xperiodic || !d->yperiodic || !d->zperiodic)
+    lmp->error->all(FLERR, "obmd_b200 requires boundary f p p");
+  if (lmp->comm->nprocs > 1)
+    lmp->error->all(FLERR, "obmd_b200 plugin (stage A) runs on one MPI rank; use obmd_run for slabs");
+  OBMD_CK(lmp, s, obmd_set_box(s.ctx, d->boxlo, d->boxhi));
+  OBMD_CK(lmp, s, obmd_set_masses(s.ctx, lmp->atom->ntypes, lmp->atom->mass));
+  OBMD_CK(lmp, s, obmd_set_timestep(s.ctx, lmp->update->dt));
+  s.box_set = true;
+}
+
+void upload_all(LAMMPS *lmp, Shared &s)
+{
+  Atom *a = lmp->atom;
+  OBMD_CK(lmp, s, obmd_upload(s.ctx, a->nlocal, &a->x[0][0], &a->v[0][0], nullptr, a->type, a->tag,
+                              a->image, a->nmax));
+  s.resident = a->nlocal;
+  s.xv_step = lmp->update->ntimestep;
+}
+
+// ------------------------------------------------------------------------------------------
+// pair_style dpd T rc seed ; pair_coeff i j a0 gamma [rc]      (DPD-BASIC/pair_dpd.cpp)
+// ------------------------------------------------------------------------------------------
+class PairDPDB200 : public Pair {
+ public:
+  PairDPDB200(LAMMPS *lmp) : Pair(lmp), sh(acquire(lmp))
+  {
+    writedata = 1;
+    no_virial_fdotr_compute = 1;  // the device returns the virial itself
+  }
+  ~PairDPDB200() override
+  {
+    if (allocated) {
+      memory->destroy(setflag);
+      memory->destroy(cutsq);
+      memory->destroy(cut);
+      memory->destroy(a0);
+      memory->destroy(gamma);
+    }
+    release(lmp);
+  }
+
+  void settings(int narg, char **arg) override  // pair_dpd.cpp:195-216
+  {
+    if (narg != 3) error->all(FLERR, "Illegal pair_style command");
+    temperature = utils::numeric(FLERR, arg[0], false, lmp);
+    cut_global = utils::numeric(FLERR, arg[1], false, lmp);
+    seed = utils::inumeric(FLERR, arg[2], false, lmp);
+    if (seed <= 0) error->all(FLERR, "Illegal pair_style command");
+    if (allocated)
+      for (int i = 1; i <= atom->ntypes; i++)
+        for (int j = i; j <= atom->ntypes; j++)
+          if (setflag[i][j]) cut[i][j] = cut_global;
+  }
+
+  void coeff(int narg, char **arg) override  // pair_dpd.cpp:222-251
+  {
+    if (narg < 4 || narg > 5) error->all(FLERR, "Incorrect args for pair coefficients");
+    if (!allocated) allocate();
+    int ilo, ihi, jlo, jhi;
+    utils::bounds(FLERR, arg[0], 1, atom->ntypes, ilo, ihi, error);
+    utils::bounds(FLERR, arg[1], 1, atom->ntypes, jlo, jhi, error);
+    double a0_one = utils::numeric(FLERR, arg[2], false, lmp);
+    double gamma_one = utils::numeric(FLERR, arg[3], false, lmp);
+    double cut_one = cut_global;
+    if (narg == 5) cut_one = utils::numeric(FLERR, arg[4], false, lmp);
+    int count = 0;
+    for (int i = ilo; i <= ihi; i++)
+      for (int j = MAX(jlo, i); j <= jhi; j++) {
+        a0[i][j] = a0_one;
+        gamma[i][j] = gamma_one;
+        cut[i][j] = cut_one;
+        setflag[i][j] = 1;
+        count++;
+      }
+    if (count == 0) error->all(FLERR, "Incorrect args for pair coefficients");
+  }
+
+  void init_style() override  // pair_dpd.cpp:257-273, but no neighbour request: cells live on the GPU
+  {
+    if (force->newton_pair == 0 && comm->me == 0)
+      error->warning(FLERR, "Pair dpd needs newton pair on for momentum conservation");
+    push_domain(lmp, sh);
+    OBMD_CK(lmp, sh, obmd_pair_settings(sh.ctx, temperature, cut_global, seed));
+    for (int i = 1; i <= atom->ntypes; i++)
+      for (int j = i; j <= atom->ntypes; j++) {
+        if (setflag[i][j] == 0) error->all(FLERR, "All pair coeffs are not set");
+        OBMD_CK(lmp, sh, obmd_pair_coeff(sh.ctx, i, j, a0[i][j], gamma[i][j], cut[i][j]));
+      }
+    OBMD_CK(lmp, sh, obmd_pair_init(sh.ctx, force->boltz));
+    sh.pair_ready = true;
+  }
+
+  double init_one(int i, int j) override  // pair_dpd.cpp:279-291
+  {
+    if (setflag[i][j] == 0) error->all(FLERR, "All pair coeffs are not set");
+    cut[j][i] = cut[i][j];
+    a0[j][i] = a0[i][j];
+    gamma[j][i] = gamma[i][j];
+    return cut[i][j];
+  }
+
+  void compute(int eflag, int vflag) override  // pair_dpd.cpp:66-163
+  {
+    ev_init(eflag, vflag);
+    Atom *a = atom;
+    OBMD_CK(lmp, sh, obmd_set_timestep(sh.ctx, update->dt));
+    if (sh.resident != a->nlocal) upload_all(lmp, sh);
+    else OBMD_CK(lmp, sh, obmd_upload_xv(sh.ctx, a->nlocal, &a->x[0][0], &a->v[0][0]));
+    OBMD_CK(lmp, sh, obmd_build_cells(sh.ctx));
+    OBMD_CK(lmp, sh, obmd_pair_compute(sh.ctx, update->ntimestep, eflag_either, vflag_either));
+    int n = 0;
+    if ((int) fbuf.size() < 3 * a->nmax) fbuf.resize(3 * (size_t) a->nmax);
+    OBMD_CK(lmp, sh, obmd_download(sh.ctx, &n, nullptr, nullptr, fbuf.data(), nullptr, nullptr, nullptr));
+    double **f = a->f;
+    for (int i = 0; i < n; i++) {
+      f[i][0] += fbuf[3 * i];
+      f[i][1] += fbuf[3 * i + 1];
+      f[i][2] += fbuf[3 * i + 2];
+    }
+    if (eflag_either || vflag_either) {
+      double e, v[6];
+      OBMD_CK(lmp, sh, obmd_pair_tallies(sh.ctx, &e, v));
+      if (eflag_global) eng_vdwl += e;
+      if (vflag_global)
+        for (int k = 0; k < 6; k++) virial[k] += v[k];
+    }
+  }
+
+  double single(int, int, int itype, int jtype, double rsq, double, double factor_dpd,
+                double &fforce) override  // pair_dpd.cpp:401-418
+  {
+    double ff = 0.0;
+    double phi = obmd_pair_single(sh.ctx, itype, jtype, rsq, &ff);
+    fforce = ff * factor_dpd;
+    return factor_dpd * phi;
+  }
+
+ private:
+  void allocate()
+  {
+    allocated = 1;
+    int n = atom->ntypes;
+    memory->create(setflag, n + 1, n + 1, "pair:setflag");
+    for (int i = 1; i <= n; i++)
+      for (int j = i; j <= n; j++) setflag[i][j] = 0;
+    memory->create(cutsq, n + 1, n + 1, "pair:cutsq");
+    memory->create(cut, n + 1, n + 1, "pair:cut");
+    memory->create(a0, n + 1, n + 1, "pair:a0");
+    memory->create(gamma, n + 1, n + 1, "pair:gamma");
+  }
+  Shared &sh;
+  double cut_global = 0.0, temperature = 0.0;
+  int seed = 0;
+  double **cut = nullptr, **a0 = nullptr, **gamma = nullptr;
+  std::vector<double> fbuf;
+};
+
+// ------------------------------------------------------------------------------------------
+// fix ID group obmd ntype nfreq seed pxx pxy pxz dpxx freq alpha tau nbuf keyword value ...
+// (OBMD/fix_obmd_merged.cpp:66-287 constructor, :1881-2164 options)
+// ------------------------------------------------------------------------------------------
+class FixObmdB200 : public Fix {
+ public:
+  FixObmdB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg), sh(acquire(lmp))
+  {
+    if (narg < 14) error->all(FLERR, "Illegal fix obmd command (check # of arguments)");
+    if (igroup != 0) error->all(FLERR, "obmd_b200: fix obmd supports group all only");
+    restart_global = 1;
+    time_depend = 1;
+    memset(&fa, 0, sizeof(fa));
+    fa.ntype = utils::inumeric(FLERR, arg[3], false, lmp);
+    fa.nfreq = utils::inumeric(FLERR, arg[4], false, lmp);
+    fa.seed = utils::inumeric(FLERR, arg[5], false, lmp);
+    if (fa.seed <= 0) error->all(FLERR, "Illegal fix obmd command");
+    double *dst[8] = {&fa.pxx, &fa.pxy, &fa.pxz, &fa.dpxx, &fa.freq, &fa.alpha, &fa.tau, &fa.nbuf};
+    for (int k = 0; k < 8; k++) {
+      if (strstr(arg[6 + k], "v_") == arg[6 + k]) varname[k] = &arg[6 + k][2];
+      else *dst[k] = utils::numeric(FLERR, arg[6 + k], false, lmp);
+    }
+    options(narg - 14, &arg[14]);
+    if (fa.ntype <= 0 || fa.ntype > atom->ntypes)
+      error->all(FLERR, "Invalid atom type in fix obmd command");
+    if (atom->tag_enable == 0) error->all(FLERR, "Cannot use fix obmd unless atoms have IDs");
+    force_reneighbor = 1;  // :279-281
+    next_reneighbor = update->ntimestep + 1;
+  }
+  ~FixObmdB200() override { release(lmp); }
+
+  int setmask() override  // :311-317
+  {
+    int mask = 0;
+    mask |= PRE_EXCHANGE;
+    mask |= POST_FORCE;
+    return mask;
+  }
+
+  void init() override  // :321-536 (region lookup; variables are resolved each step)
+  {
+    for (int r = 0; r < 6; r++) {
+      Region *reg = domain->get_region_by_id(idregion[r]);
+      if (!reg) error->all(FLERR, "Region ID for fix obmd does not exist");
+      if (reg->bboxflag == 0) error->all(FLERR, "Fix obmd region does not support a bounding box");
+      fa.region[r].lo[0] = reg->extent_xlo; fa.region[r].hi[0] = reg->extent_xhi;
+      fa.region[r].lo[1] = reg->extent_ylo; fa.region[r].hi[1] = reg->extent_yhi;
+      fa.region[r].lo[2] = reg->extent_zlo; fa.region[r].hi[2] = reg->extent_zhi;
+    }
+    if (!sh.box_set) push_domain(lmp, sh);
+    if (!created) {
+      OBMD_CK(lmp, sh, obmd_fix_create(sh.ctx, &fa));
+      created = true;
+    }
+  }
+
+  void setup(int vflag) override  // :542-545
+  {
+    if (utils::strmatch(update->integrate_style, "^verlet")) post_force(vflag);
+  }
+
+  void pre_exchange() override  // :550-633
+  {
+    refresh_variables();
+    Atom *a = atom;
+    OBMD_CK(lmp, sh, obmd_set_timestep(sh.ctx, update->dt));
+    upload_all(lmp, sh);
+    OBMD_CK(lmp, sh, obmd_build_cells(sh.ctx));
+    obmd_pre_exchange_report rep;
+    OBMD_CK(lmp, sh, obmd_pre_exchange(sh.ctx, &rep, nullptr, 0));
+    if (rep.ndel || rep.naccept) {
+      // the fix changed the atom arrays: refresh LAMMPS' copy in local order (same bookkeeping as
+      // AtomVec::copy / create_atom, :827-841, :1121-1150)
+      while (rep.nlocal > a->nmax) a->avec->grow(0);
+      // group masks are not mirrored on the device: survivors moved into holes come from the tail,
+      // so remember (tag -> mask) of the tail and of every old slot's tag
+      const int nold = a->nlocal;
+      std::vector<tagint> oldtag(a->tag, a->tag + nold);
+      std::unordered_map<tagint, int> tailmask;
+      for (int i = nold - rep.ndel < 0 ? 0 : nold - rep.ndel; i < nold; i++) tailmask[a->tag[i]] = a->mask[i];
+      int n = 0;
+      OBMD_CK(lmp, sh, obmd_download(sh.ctx, &n, &a->x[0][0], &a->v[0][0], nullptr, a->type, a->tag,
+                                     a->image));
+      const int nkeep = nold - rep.ndel;
+      for (int i = 0; i < nkeep && i < n; i++)
+        if (a->tag[i] != oldtag[i]) {
+          auto it = tailmask.find(a->tag[i]);
+          if (it != tailmask.end()) a->mask[i] = it->second;
+        }
+      for (int i = nkeep; i < n; i++) a->mask[i] = 1 | groupbit;
+      a->natoms += (bigint) rep.naccept - (bigint) rep.ndel;
+      a->nlocal = n;
+      a->nghost = 0;
+      if (a->map_style != Atom::MAP_NONE) {
+        a->map_init();
+        a->map_set();
+      }
+      sh.resident = n;
+    }
+    next_reneighbor += fa.nfreq;  // :632
+  }
+
+  void post_force(int) override  // :1229-1240
+  {
+    if (update->ntimestep % nevery) return;
+    Atom *a = atom;
+    if (sh.resident != a->nlocal || !sh.pair_ready) return;  // setup() before the first pair compute
+    OBMD_CK(lmp, sh, obmd_zero_forces(sh.ctx));
+    OBMD_CK(lmp, sh, obmd_post_force(sh.ctx));
+    int n = 0;
+    if ((int) fbuf.size() < 3 * a->nmax) fbuf.resize(3 * (size_t) a->nmax);
+    OBMD_CK(lmp, sh, obmd_download(sh.ctx, &n, nullptr, nullptr, fbuf.data(), nullptr, nullptr, nullptr));
+    double **f = a->f;
+    for (int i = 0; i < n; i++) {
+      f[i][0] += fbuf[3 * i];
+      f[i][1] += fbuf[3 * i + 1];
+      f[i][2] += fbuf[3 * i + 2];
+    }
+  }
+
+ private:
+  void refresh_variables()  // :563-572; v_pxx/v_pxy/v_pxz work here (the reference segfaults, Q2)
+  {
+    bool any = false;
+    double *dst[8] = {&fa.pxx, &fa.pxy, &fa.pxz, &fa.dpxx, &fa.freq, &fa.alpha, &fa.tau, &fa.nbuf};
+    for (int k = 0; k < 8; k++) {
+      if (varname[k].empty()) continue;
+      int iv = input_variable_find(varname[k].c_str());
+      if (iv < 0) error->all(FLERR, "Variable name for fix obmd does not exist");
+      *dst[k] = input_variable_equal(iv);
+      any = true;
+    }
+    if (any)
+      OBMD_CK(lmp, sh, obmd_fix_set_flux(sh.ctx, fa.pxx, fa.pxy, fa.pxz, fa.dpxx, fa.freq, fa.alpha,
+                                         fa.tau, fa.nbuf));
+  }
+  int input_variable_find(const char *name);
+  double input_variable_equal(int iv);
+
+  void options(int narg, char **arg)  // :1881-2164, ATOM mode keywords
+  {
+    fa.g_fac = 0.25;
+    fa.buffer_size = 0.30 * (domain->boxhi[0] - domain->boxlo[0]);
+    fa.etarget = 3.6; fa.ds0 = 0.1; fa.dtheta0 = 0.35; fa.uovlp = 10000.0; fa.dsovlp = 3.0;
+    fa.eps = 0.15; fa.nattempt = 40; fa.maxattempt = 1;
+    fa.step_parallel = 0; fa.step_perp = 1; fa.usherflag = 0;
+    int nearflag = 0, iarg = 0;
+    while (iarg < narg) {
+      if (strncmp(arg[iarg], "region", 6) == 0 && strlen(arg[iarg]) == 7 && arg[iarg][6] >= '1' &&
+          arg[iarg][6] <= '6') {
+        if (!domain->get_region_by_id(arg[iarg + 1]))
+          error->all(FLERR, "Region ID {} for fix obmd does not exist", arg[iarg + 1]);
+        idregion[arg[iarg][6] - '1'] = arg[iarg + 1];
+        iarg += 2;
+      } else if (strcmp(arg[iarg], "buffersize") == 0) {
+        fa.buffer_size = utils::numeric(FLERR, arg[iarg + 1], false, lmp);
+        if (fa.buffer_size <= 0.0)
+          error->all(FLERR, "Illegal fix obmd command. Parameter buffersize should be larger than 0.0");
+        iarg += 2;
+      } else if (strcmp(arg[iarg], "gfac") == 0) {
+        fa.g_fac = utils::numeric(FLERR, arg[iarg + 1], false, lmp);
+        if (fa.g_fac < 0.0 || fa.g_fac > 1.0)
+          error->all(FLERR, "Illegal fix obmd command. Parameter gfac should be between 0.0 and 1.0");
+        iarg += 2;
+      } else if (strcmp(arg[iarg], "stepparallel") == 0) {
+        fa.step_parallel = utils::inumeric(FLERR, arg[iarg + 1], false, lmp);
+        if (fa.step_parallel != 0)
+          error->all(FLERR, "For now, only the smooth transition distribution function is implemented.");
+        iarg += 2;
+      } else if (strcmp(arg[iarg], "stepperp") == 0) {
+        fa.step_perp = utils::inumeric(FLERR, arg[iarg + 1], false, lmp);
+        if (fa.step_perp != 1)
+          error->all(FLERR, "For now, only the heaviside step distribution function is implemented.");
+        iarg += 2;
+      } else if (strcmp(arg[iarg], "maxattempt") == 0) {
+        fa.maxattempt = utils::inumeric(FLERR, arg[iarg + 1], false, lmp);
+        iarg += 2;
+      } else if (strcmp(arg[iarg], "usher") == 0) {
+        if (iarg + 9 > narg) error->all(FLERR, "Illegal fix obmd command");
+        fa.usherflag = utils::inumeric(FLERR, arg[iarg + 1], false, lmp);
+        if (fa.usherflag == 1 && nearflag == 1) error->all(FLERR, "You can not have both usher and near");
+        fa.etarget = utils::numeric(FLERR, arg[iarg + 2], false, lmp);
+        fa.ds0 = utils::numeric(FLERR, arg[iarg + 3], false, lmp);
+        fa.dtheta0 = utils::numeric(FLERR, arg[iarg + 4], false, lmp);
+        fa.uovlp = utils::numeric(FLERR, arg[iarg + 5], false, lmp);
+        fa.dsovlp = utils::numeric(FLERR, arg[iarg + 6], false, lmp);
+        fa.eps = utils::numeric(FLERR, arg[iarg + 7], false, lmp);
+        fa.nattempt = utils::inumeric(FLERR, arg[iarg + 8], false, lmp);
+        iarg += 9;
+      } else if (strcmp(arg[iarg], "charged") == 0) {
+        if (utils::inumeric(FLERR, arg[iarg + 1], false, lmp) == 1)
+          error->all(FLERR, "You can not use charged without MOLECULE mode");
+        iarg += 2;
+      } else if (strcmp(arg[iarg], "near") == 0) {
+        nearflag = 1;
+        error->all(FLERR, "obmd_b200: only usher insertion is implemented on the device path");
+      } else
+        error->all(FLERR, "Illegal fix obmd command");
+    }
+    if (fa.usherflag == 0 && nearflag == 0) error->all(FLERR, "You must pick either usher or near");
+    for (int r = 0; r < 6; r++)
+      if (idregion[r].empty())
+        error->all(FLERR, r < 2 ? "Must specify a region in fix obmd"
+                                : "Region ID for fix obmd does not exist");
+  }
+
+  Shared &sh;
+  obmd_fix_args fa;
+  bool created = false;
+  std::string idregion[6];
+  std::string varname[8];
+  std::vector<double> fbuf;
+};
+
+}    // namespace
+
+#include "input.h"
+#include "variable.h"
+int FixObmdB200::input_variable_find(const char *name) { return input->variable->find(name); }
+double FixObmdB200::input_variable_equal(int iv)
+{
+  if (!input->variable->equalstyle(iv)) error->all(FLERR, "Variable for fix obmd is invalid style");
+  return input->variable->compute_equal(iv);
+}
+
+static Pair *pair_creator(LAMMPS *lmp) { return new PairDPDB200(lmp); }
+static Fix *fix_creator(LAMMPS *lmp, int argc, char **argv) { return new FixObmdB200(lmp, argc, argv); }
+
+extern "C" void lammpsplugin_init(void *lmp, void *handle, void *regfunc)
+{
+  lammpsplugin_t plugin;
+  lammpsplugin_regfunc register_plugin = (lammpsplugin_regfunc) regfunc;
+  plugin.version = LAMMPS_VERSION;
+  plugin.author = "obmd_b200";
+  plugin.handle = handle;
+
+  plugin.style = "pair";
+  plugin.name = "dpd";  // same name as the built-in: overrides it (PLUGIN/plugin.cpp:169-174)
+  plugin.info = "pair_style dpd on B200 (libobmd_b200)";
+  plugin.creator.v1 = (lammpsplugin_factory1 *) &pair_creator;
+  (*register_plugin)(&plugin, lmp);
+
+  plugin.style = "fix";
+  plugin.name = "obmd";  // overrides the built-in fix obmd (PLUGIN/plugin.cpp:228-233)
+  plugin.info = "fix obmd on B200 (libobmd_b200)";
+  plugin.creator.v2 = (lammpsplugin_factory2 *) &fix_creator;
+  (*register_plugin)(&plugin, lmp);
+}

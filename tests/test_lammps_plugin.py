@@ -1,0 +1,137 @@
+"""Drop-in test: the UNMODIFIED reference LAMMPS binary (oracle/_ref/lmp_serial) loads
+obmd-lammps-extension_b200/libobmd_b200_lammps.so with `plugin load`, which overrides the built-in
+`fix obmd` and `pair_style dpd`; the same decks that produced the golden fixtures are then run
+through the CUDA path and compared with those fixtures.  GPU box only."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import common_cases as cc
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LMP = os.path.join(ROOT, "oracle", "_ref", "lmp_serial")
+PLUGIN = os.path.join(ROOT, "obmd-lammps-extension_b200", "libobmd_b200_lammps.so")
+
+HEAD = """plugin load {plugin}
+units           lj
+boundary        f p p
+atom_style      atomic
+atom_modify     sort 0 0
+comm_modify     vel yes
+newton          on
+read_data       {data}
+region          leftB block {xlo:.17g} {xlB:.17g} {ylo:.17g} {yhi:.17g} {zlo:.17g} {zhi:.17g}
+region          rightB block {xrB:.17g} {xhi:.17g} {ylo:.17g} {yhi:.17g} {zlo:.17g} {zhi:.17g}
+region          leftshear block 0.0 0.0 0.0 0.0 0.0 0.0
+region          rightshear block 0.0 0.0 0.0 0.0 0.0 0.0
+pair_style      dpd {T} 1.0 2616
+pair_coeff      * * {a0} {gamma} 1.0
+neighbor        0.4 bin
+neigh_modify    delay 0 every 1
+timestep        {dt}
+"""
+FIX = ("fix 2 all obmd 1 1 6111 188.0 0 0 0 0 {alpha} {tau} {nbuf} region1 leftB region2 rightB "
+       "region3 leftshear region4 rightshear region5 leftB region6 rightB buffersize {B:.17g} gfac 0.25 "
+       "stepparallel 0 stepperp 1 maxattempt 1 usher 1 31.03 1.0 0.02 10000 1.5 1.0 40 charged 0\n")
+
+
+def need():
+    if not (os.path.exists(LMP) and os.path.exists(PLUGIN)):
+        pytest.skip("reference binary or plugin not built (oracle/build_ref.sh, host/Makefile)")
+
+
+def write_data(path, tag, x, box):
+    with open(path, "w") as fh:
+        fh.write("shipped OBMD_DPD configuration\n\n%d atoms\n1 atom types\n\n" % len(x))
+        for d, n in enumerate("xyz"):
+            fh.write("%.17g %.17g %slo %shi\n" % (box[d, 0], box[d, 1], n, n))
+        fh.write("\nMasses\n\n1 1\n\nAtoms\n\n")
+        for t, r in zip(tag, x):
+            fh.write("%d 1 %.17g %.17g %.17g\n" % (t, r[0], r[1], r[2]))
+
+
+def read_dump(path):
+    frames = []
+    lines = open(path).read().split("\n")
+    i = 0
+    while i < len(lines):
+        if lines[i].startswith("ITEM: TIMESTEP"):
+            step = int(lines[i + 1]); n = int(lines[i + 3])
+            rows = np.array([ln.split() for ln in lines[i + 9:i + 9 + n]], dtype=np.float64)
+            frames.append((step, rows)); i += 9 + n
+        else:
+            i += 1
+    return frames
+
+
+def run(tmp_path, body, **kw):
+    tag, x, box = cc.shipped()
+    data = str(tmp_path / "shipped.data")
+    write_data(data, tag, x, box)
+    B = 0.15 * box[0, 1]
+    d = dict(plugin=PLUGIN, data=data, T=1.0, a0=209.6, gamma=4.5, dt=0.001464, xlo=box[0, 0], xhi=box[0, 1],
+             ylo=box[1, 0], yhi=box[1, 1], zlo=box[2, 0], zhi=box[2, 1], xlB=box[0, 0] + B, xrB=box[0, 1] - B)
+    d.update(kw)
+    deck = HEAD.format(**d) + body
+    inp = str(tmp_path / "in.deck")
+    open(inp, "w").write(deck)
+    out = subprocess.run([LMP, "-in", inp, "-log", "none"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "Overriding built-in fix style obmd from plugin" in out.stdout + out.stderr or \
+        "Overriding built-in pair style dpd from plugin" in out.stdout + out.stderr
+    return out.stdout, tag, x, box, B
+
+
+def test_plugin_pair_forces_T0(tmp_path):
+    need()
+    body = ("velocity all create 1.0 4928459 loop geom\n"
+            "dump d all custom 1 dump.p0 id vx vy vz fx fy fz\ndump_modify d format float %.17g\n"
+            "thermo_style custom step pe press pxx pyy pzz pxy pxz pyz\n"
+            "thermo_modify format float %.15g norm no\nrun 0\n")
+    out, tag, x, box, B = run(tmp_path, body, T=0.0)
+    g = cc.load("p0_pair_T0.npz")
+    (_, rows), = read_dump(str(tmp_path / "dump.p0"))
+    assert np.array_equal(rows[:, 1:4], g["v"])            # same LAMMPS, same velocity command
+    assert cc.mixed_rel_err(rows[:, 4:7], g["f"]) < 1e-9
+    th = None
+    lines = out.split("\n")
+    for k, ln in enumerate(lines):
+        if ln.split()[:2] == ["Step", "PotEng"]:
+            th = np.array(lines[k + 1].split(), dtype=np.float64)
+    assert th is not None and np.allclose(th[1:], g["thermo"][1:], rtol=1e-9, atol=1e-9)
+
+
+def test_plugin_usher_static_bit_exact(tmp_path):
+    need()
+    tag, x, box = cc.shipped()
+    B = 0.15 * box[0, 1]
+    body = (FIX.format(alpha=1.0, tau=0.005, nbuf=2000, B=B) +
+            "dump d all custom 12 dump.b1 id x y z\ndump_modify d format float %.17g\nrun 12\n")
+    run(tmp_path, body)
+    g = cc.load("b1_usher_static.npz")
+    step, rows = read_dump(str(tmp_path / "dump.b1"))[-1]
+    assert step == 12
+    assert np.array_equal(rows[:, 0].astype(np.int32), g["final_tag"])
+    assert np.array_equal(rows[len(tag):, 1:4], g["inserted_x"])
+
+
+def test_plugin_ballistic_bookkeeping(tmp_path):
+    need()
+    tag, x, box = cc.shipped()
+    B = 0.15 * box[0, 1]
+    body = ("velocity all create 25.0 4928459 loop geom\nfix 1 all nve\n" +
+            FIX.format(alpha=1.0, tau=0.05, nbuf=2000, B=B) +
+            "dump d all custom 20 dump.b3 id x y z vx vy vz fx fy fz\n"
+            "dump_modify d format float %.17g\nrun 20\n")
+    run(tmp_path, body, a0=0.0, gamma=0.0, dt=0.01)
+    g = cc.load("b3_ballistic.npz")
+    (s0, r0), (s1, r1) = read_dump(str(tmp_path / "dump.b3"))
+    assert (s0, s1) == (0, 20)
+    assert np.array_equal(r1[:, 0].astype(np.int32), g["tag20"])
+    assert np.allclose(r1[:, 1:4], g["x20"], rtol=0, atol=1e-11)
+    assert np.allclose(r1[:, 4:7], g["v20"], rtol=0, atol=1e-10)
+    assert cc.mixed_rel_err(r1[:, 7:10], g["f20"]) < 1e-9
