@@ -97,9 +97,6 @@ const char *obmd_last_error(const obmd_ctx *ctx); /* ctx may be NULL: last creat
 int obmd_set_box(obmd_ctx *ctx, const double boxlo[3], const double boxhi[3]);
 int obmd_set_masses(obmd_ctx *ctx, int ntypes, const double *mass /* [ntypes+1], 1-based */);
 int obmd_set_timestep(obmd_ctx *ctx, double dt); /* update->dt */
-/* x-slab owned by this rank [sublo, subhi) for multi-GPU runs (domain->sublo/subhi[0]);
- * default = whole box. */
-int obmd_set_subdomain(obmd_ctx *ctx, double sublo_x, double subhi_x);
 
 /* ---- pair_style dpd (DPD-BASIC/pair_dpd.cpp) --------------------------------- */
 /* PairDPD::settings (:195-216): pair_style dpd T cut_global seed */
@@ -156,6 +153,9 @@ int obmd_post_force(obmd_ctx *ctx);
 int obmd_zero_forces(obmd_ctx *ctx);
 /* FixNVE::final_integrate (fix_nve.cpp:185-244) */
 int obmd_nve_final(obmd_ctx *ctx);
+/* Verlet::setup (verlet.cpp:92-163): [exchange, borders,] neighbour build, pair forces,
+ * fix setup -> post_force.  ntimestep keys the counter RNG. */
+int obmd_setup(obmd_ctx *ctx, long long ntimestep);
 /* nsteps full timesteps, device resident, in exactly the order above.  first_step = the
  * timestep number of the first step (update->ntimestep + 1). */
 int obmd_run(obmd_ctx *ctx, long long first_step, int nsteps);
@@ -166,18 +166,18 @@ int obmd_reduce_kinetic(obmd_ctx *ctx, double out[5]);
 /* 1-D profiles along x in nbins bins over the box: count[nbins], vx sums [nbins] */
 int obmd_profile_x(obmd_ctx *ctx, int nbins, double *count, double *mvx);
 
-/* ---- multi-GPU slab decomposition (replaces CommBrick::exchange/borders, ----------
- *      comm_brick.cpp:652-978): pack/unpack device buffers the host moves with NCCL. -- */
-/* Atoms that left [sublo,subhi) in x: count and pack (11 doubles/atom as AtomVec::pack_exchange:
- * x v tag type image) into caller-owned DEVICE buffers for the left/right neighbour. */
-int obmd_migrate_pack(obmd_ctx *ctx, double *dev_left, double *dev_right, int cap_atoms,
-                      int *nleft, int *nright);
-int obmd_migrate_unpack(obmd_ctx *ctx, const double *dev_buf, int natoms);
-/* Ghost slabs of width cut next to each x face: 8 doubles/ghost (x v tag type). */
-int obmd_halo_pack(obmd_ctx *ctx, double *dev_left, double *dev_right, int cap_atoms, int *nleft,
-                   int *nright);
-int obmd_halo_unpack(obmd_ctx *ctx, const double *dev_from_left, int nl, const double *dev_from_right,
-                     int nr);
+/* ---- multi-GPU: x-slab decomposition over NCCL (replaces CommBrick::exchange/borders, ------
+ *      comm_brick.cpp:652-978, and the fix's MPI_Allreduce/Scan calls) ------------ */
+/* One process per GPU.  Rank 0 creates the id (ncclGetUniqueId), the host broadcasts the 128 bytes
+ * (MPI in LAMMPS, torch.distributed in bench.py), every rank calls obmd_comm_init before
+ * obmd_upload.  Rank r then owns a contiguous range of cell columns along x and uploads only the
+ * atoms inside it; obmd_run / obmd_setup do the migration, the halo and the packed allreduces.
+ * The insertion regions (region5/6) must lie inside the first / last rank's slab. */
+int obmd_comm_unique_id(char *out128);
+int obmd_comm_init(obmd_ctx *ctx, int rank, int nranks, const char *id128);
+int obmd_comm_finalize(obmd_ctx *ctx);
+/* x-range [lo, hi) of the columns this rank owns (what the host uses to split the atoms). */
+int obmd_comm_slab(const obmd_ctx *ctx, double *lo, double *hi);
 
 /* ---- timing / introspection ----------------------------------------------------- */
 /* Accumulated CUDA-event milliseconds and launch counts per kernel family since the last

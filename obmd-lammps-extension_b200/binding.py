@@ -72,7 +72,6 @@ SIGNATURES = {
     "obmd_set_box": (C.c_int, [C.c_void_p, _dp, _dp]),
     "obmd_set_masses": (C.c_int, [C.c_void_p, C.c_int, _dp]),
     "obmd_set_timestep": (C.c_int, [C.c_void_p, C.c_double]),
-    "obmd_set_subdomain": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "obmd_pair_settings": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int]),
     "obmd_pair_coeff": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
     "obmd_pair_init": (C.c_int, [C.c_void_p, C.c_double]),
@@ -94,13 +93,14 @@ SIGNATURES = {
     "obmd_post_force": (C.c_int, [C.c_void_p]),
     "obmd_zero_forces": (C.c_int, [C.c_void_p]),
     "obmd_nve_final": (C.c_int, [C.c_void_p]),
+    "obmd_setup": (C.c_int, [C.c_void_p, C.c_longlong]),
     "obmd_run": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int]),
     "obmd_reduce_kinetic": (C.c_int, [C.c_void_p, _dp]),
     "obmd_profile_x": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
-    "obmd_migrate_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _ip, _ip]),
-    "obmd_migrate_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
-    "obmd_halo_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _ip, _ip]),
-    "obmd_halo_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "obmd_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "obmd_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "obmd_comm_finalize": (C.c_int, [C.c_void_p]),
+    "obmd_comm_slab": (C.c_int, [C.c_void_p, _dp, _dp]),
     "obmd_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "obmd_timing_get": (C.c_int, [C.c_void_p, C.c_char_p, _dp, C.POINTER(C.c_longlong)]),
     "obmd_timing_reset": (C.c_int, [C.c_void_p]),
@@ -382,12 +382,29 @@ class ObmdB200:
         return rep, tr
 
     def setup(self, ntimestep=0):
-        """Verlet::setup (verlet.cpp:92-163): pbc, neighbour build, pair forces, fix setup ->
-        post_force with the (zero-initialised, Q3) flux forces."""
-        self.build_cells()
-        self.pbc()
-        self.pair_compute(ntimestep)
-        self.post_force()
+        """Verlet::setup (verlet.cpp:92-163): [exchange, borders,] neighbour build, pair forces,
+        fix setup -> post_force with the (zero-initialised, Q3) flux forces."""
+        self._ck(self.L.obmd_setup(self.h, ntimestep))
+
+    # ---- slab decomposition ----------------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        buf = C.create_string_buffer(128)
+        rc = lib().obmd_comm_unique_id(buf)
+        if rc != 0:
+            raise ObmdError(rc, lib().obmd_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, rank, nranks, uid):
+        self._ck(self.L.obmd_comm_init(self.h, rank, nranks, uid))
+
+    def comm_finalize(self):
+        self._ck(self.L.obmd_comm_finalize(self.h))
+
+    def comm_slab(self):
+        lo = C.c_double(); hi = C.c_double()
+        self._ck(self.L.obmd_comm_slab(self.h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
 
     def run(self, first_step, nsteps):
         self._ck(self.L.obmd_run(self.h, first_step, nsteps))

@@ -52,7 +52,9 @@ extern "C" int obmd_create(obmd_ctx **out, int device)
       (e = cudaEventCreateWithFlags(&c->ev_int, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
       (e = cudaMalloc(&c->sc_d, sizeof(StepScalars))) != cudaSuccess ||
-      (e = cudaMallocHost(&c->sc_h, sizeof(StepScalars))) != cudaSuccess) {
+      (e = cudaMallocHost(&c->sc_h, sizeof(StepScalars))) != cudaSuccess ||
+      (e = cudaMalloc(&c->red_d, 64 * sizeof(double))) != cudaSuccess ||
+      (e = cudaMallocHost(&c->red_h, 64 * sizeof(double))) != cudaSuccess) {
     obmd_fail(nullptr, OBMD_ERR_CUDA, "obmd_create: %s", cudaGetErrorString(e));
     delete c;
     return OBMD_ERR_CUDA;
@@ -95,6 +97,8 @@ extern "C" void obmd_destroy(obmd_ctx *c)
   cudaFree(c->extra_head); cudaFree(c->extra_next); cudaFree(c->extra_cell);
   cudaFree(c->stage_d); cudaFree(c->stage_i);
   cudaFree(c->sc_d); cudaFreeHost(c->sc_h);
+  cudaFree(c->red_d); cudaFreeHost(c->red_h);
+  cudaFree(c->sendL); cudaFree(c->sendR); cudaFree(c->recvL); cudaFree(c->recvR);
   cudaFree(c->del_key); cudaFree(c->del_val); cudaFree(c->tail_key); cudaFree(c->tail_val); cudaFree(c->del_src); cudaFree(c->del_mv);
   cudaFree(c->tr_d); cudaFree(c->tr_prev_d); cudaFree(c->tr_path); cudaFree(c->tr_npts);
   cudaFree(c->tr_list); cudaFree(c->tr_changed); cudaFree(c->acc_list); cudaFree(c->tr_bbox);
@@ -124,15 +128,6 @@ extern "C" int obmd_set_box(obmd_ctx *c, const double boxlo[3], const double box
   c->subhi = boxhi[0];
   c->have_box = true;
   c->pair_ready = false;
-  return OBMD_OK;
-}
-
-extern "C" int obmd_set_subdomain(obmd_ctx *c, double sublo_x, double subhi_x)
-{
-  NEED(c && c->have_box, OBMD_ERR_STATE, "obmd_set_subdomain: set the box first");
-  NEED(subhi_x > sublo_x, OBMD_ERR_ARG, "obmd_set_subdomain: empty slab");
-  c->sublo = sublo_x;
-  c->subhi = subhi_x;
   return OBMD_OK;
 }
 
@@ -189,6 +184,8 @@ extern "C" int obmd_pair_coeff(obmd_ctx *c, int itype, int jtype, double a0, dou
   return OBMD_OK;
 }
 
+int setup_grid(obmd_ctx *c);
+
 __global__ void k_fill_int(int *p, int n, int v)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,7 +214,15 @@ extern "C" int obmd_pair_init(obmd_ctx *c, double boltz)
   for (int t = 0; t <= MAXT; t++) pt.mass[t] = c->mass[t];
   pt.seed = (unsigned) c->pair_seed;
   pt.dtinvsqrt = c->dt > 0.0 ? 1.0 / sqrt(c->dt) : 0.0;
-  // cell grid: cell size >= cutmax
+  c->pair_ready = true;
+  return setup_grid(c);
+}
+
+// Cell grid (cell size >= cutmax) and this rank's window of it: owned columns [gx0, gx1) plus one
+// ghost column towards each x-neighbour.
+int setup_grid(obmd_ctx *c)
+{
+  const PairTab &pt = c->pt;
   Grid &g = c->grid;
   int nn[3];
   for (int d = 0; d < 3; d++) {
@@ -232,14 +237,25 @@ extern "C" int obmd_pair_init(obmd_ctx *c, double boltz)
   }
   NEED(nn[1] >= 3 && nn[2] >= 3, OBMD_ERR_ARG,
        "obmd_pair_init: periodic box needs >= 3 cells of size cut (%g) in y and z", pt.cutmax);
-  NEED((double) nn[0] * nn[1] * nn[2] < 2.0e9, OBMD_ERR_CAPACITY, "obmd_pair_init: too many cells");
-  g.nx = nn[0];
+  NEED(nn[0] >= 2 * c->nranks, OBMD_ERR_ARG, "slab run: fewer than 2 cell columns per rank (%d columns, %d ranks)",
+       nn[0], c->nranks);
+  const int P = c->nranks, r = c->myrank;
+  const int per = nn[0] / P, rem = nn[0] % P;
+  c->gx0 = r * per + (r < rem ? r : rem);
+  c->gx1 = c->gx0 + per + (r < rem ? 1 : 0);
+  g.gnx = nn[0];
+  g.cxoff = c->gx0 > 0 ? c->gx0 - 1 : 0;
+  const int hi = c->gx1 < nn[0] ? c->gx1 + 1 : nn[0];
+  g.nx = hi - g.cxoff;
+  g.own_a = c->gx0 - g.cxoff;
+  g.own_b = c->gx1 - 1 - g.cxoff;
   g.ny = nn[1];
   g.nz = nn[2];
-  g.ncell = nn[0] * nn[1] * nn[2];
-  if (g.ncell + 2 > c->cell_cap) {
+  NEED((double) g.nx * nn[1] * nn[2] < 2.0e9, OBMD_ERR_CAPACITY, "obmd_pair_init: too many cells");
+  g.ncell = g.nx * nn[1] * nn[2];
+  if (g.ncell + 6 > c->cell_cap) {
     cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->scan_tmp); cudaFree(c->extra_head);
-    c->cell_cap = g.ncell + 2;
+    c->cell_cap = g.ncell + 6;
     CK(cudaMalloc(&c->cell_count, sizeof(int) * c->cell_cap));
     CK(cudaMalloc(&c->cell_start, sizeof(int) * c->cell_cap));
     CK(cudaMalloc(&c->scan_tmp, sizeof(int) * (c->cell_cap / 4096 + 2)));
@@ -247,8 +263,7 @@ extern "C" int obmd_pair_init(obmd_ctx *c, double boltz)
   }
   LAUNCH(k_fill_int, cdiv(c->cell_cap, 256), 256, 0, c->extra_head, c->cell_cap, -1);
   CK(cudaStreamSynchronize(c->stream));
-  c->nextra = 0;
-  c->pair_ready = true;
+  c->nextra = c->narr = c->nghost = c->nins = 0;
   c->cells_valid = false;
   return OBMD_OK;
 }
@@ -423,7 +438,8 @@ extern "C" int obmd_upload(obmd_ctx *c, int n, const double *x, const double *v,
          sg, image ? si : nullptr, n);
   CK(cudaStreamSynchronize(c->stream));
   c->n = n;
-  c->nsorted = c->nparked = c->nextra = 0;
+  c->nsorted = c->nparked = c->nextra = c->narr = c->nghost = c->nins = 0;
+  c->pre_begun = false;
   c->cells_valid = false;
   c->forces_valid = (f != nullptr);
   return OBMD_OK;
@@ -472,6 +488,10 @@ extern "C" int obmd_download(obmd_ctx *c, int *n_out, double *x, double *v, doub
   NEED(c, OBMD_ERR_ARG, "NULL context");
   NEED(c->nparked == 0, OBMD_ERR_STATE,
        "obmd_download: atoms outside the box are parked; call obmd_pre_exchange first");
+  if (c->nghost > 0) {
+    int rc = fix_compact_extras(c);
+    if (rc) return rc;
+  }
   const int n = c->n;
   if (n_out) *n_out = n;
   if (n == 0) return OBMD_OK;
@@ -563,18 +583,58 @@ extern "C" int obmd_zero_forces(obmd_ctx *c)
   return OBMD_OK;
 }
 
+extern "C" int obmd_setup(obmd_ctx *c, long long ntimestep)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  NEED(c->pair_ready, OBMD_ERR_STATE, "obmd_setup: pair style must be initialised");
+  int rc;
+  fix_clear_extras(c);
+  if ((rc = obmd_ensure_capacity(c, c->n + c->n / 32 + 4096))) return rc;
+  if ((rc = cells_build(c))) return rc;
+  NEED(c->nparked == 0, OBMD_ERR_STATE, "obmd_setup: %d atoms lie outside the box in x", c->nparked);
+  if (c->nranks > 1 && (rc = comm_exchange(c))) return rc;
+  if ((rc = fix_pbc(c))) return rc;
+  if ((rc = pair_compute(c, ntimestep, 0, 0))) return rc;
+  if (c->have_fix && (rc = fix_post_force(c))) return rc;
+  if ((rc = fix_compact_extras(c))) return rc;
+  CK(cudaStreamSynchronize(c->stream));
+  return OBMD_OK;
+}
+
+extern "C" int obmd_comm_slab(const obmd_ctx *c, double *lo, double *hi)
+{
+  if (!c || !lo || !hi || !c->pair_ready) return OBMD_ERR_STATE;
+  const Grid &g = c->grid;
+  *lo = g.lo[0] + c->gx0 / g.inv[0];
+  *hi = (c->gx1 >= g.gnx) ? g.hi[0] : g.lo[0] + c->gx1 / g.inv[0];
+  return OBMD_OK;
+}
+
 extern "C" int obmd_run(obmd_ctx *c, long long first_step, int nsteps)
 {
   NEED(c, OBMD_ERR_ARG, "NULL context");
   NEED(c->have_fix && c->pair_ready, OBMD_ERR_STATE, "obmd_run: pair style and fix must be initialised");
   int rc;
   ColRange ipbc, ipair, opbc, opair;
-  const bool ov = c->overlap && fix_zones(c, ipbc, ipair, opbc, opair);
+  const bool ov = c->overlap && c->nranks == 1 && fix_zones(c, ipbc, ipair, opbc, opair);
   for (int s = 0; s < nsteps; s++) {  // verlet.cpp:229-363
     if ((rc = fix_nve_initial(c))) return rc;
     fix_clear_extras(c);
     if ((rc = obmd_ensure_capacity(c, c->n + c->n / 32 + 4096))) return rc;
     if ((rc = cells_build(c))) return rc;
+    if (c->nranks > 1) {
+      // slab run: deletion sums first (the arrivals reuse the parked slots), then migration + halo
+      // (Comm::exchange / borders), then the rest of pre_exchange with the ghosts in place
+      if ((rc = fix_pre_begin(c))) return rc;
+      if ((rc = comm_exchange(c))) return rc;
+      if ((rc = fix_pre_exchange(c, nullptr, 0))) return rc;
+      if ((rc = fix_pbc(c))) return rc;
+      if ((rc = pair_compute(c, first_step + s, 0, 0))) return rc;
+      if ((rc = fix_post_force(c))) return rc;
+      if ((rc = fix_compact_extras(c))) return rc;
+      if ((rc = fix_nve_final(c))) return rc;
+      continue;
+    }
     if (ov) {
       // The interior (columns pre_exchange never reads) is wrapped and its pair forces are
       // computed on the side stream while the main stream runs the latency-bound USHER rounds.

@@ -26,8 +26,12 @@ __global__ void k_bin(Planes p, int n, Grid g, int *__restrict__ cid, int *__res
   int c;
   if (x < g.lo[0] || x > g.hi[0])  // fix_obmd_merged.cpp:669: strictly outside [boxlo, boxhi]
     c = g.ncell;
-  else
-    c = (cell_cx(g, x) * g.ny + cell_cy(g, y)) * g.nz + cell_cz(g, z);
+  else {
+    int lc = cell_cx(g, x);
+    if (lc < g.own_a) c = g.ncell + 1;       // left the slab: migrates to the left neighbour
+    else if (lc > g.own_b) c = g.ncell + 2;  // ... to the right neighbour
+    else c = (lc * g.ny + cell_cy(g, y)) * g.nz + cell_cz(g, z);
+  }
   cid[i] = c;
   rank[i] = atomicAdd(&cell_count[c], 1);
 }
@@ -131,7 +135,7 @@ __global__ void k_cell_order(const int *__restrict__ cell_start, int *__restrict
   }
 }
 
-__global__ void k_gather(Planes src, Planes dst, const int *__restrict__ perm, int n)
+__global__ void k_gather(Planes src, Planes dst, const int *__restrict__ perm, int n, int renumber)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -143,7 +147,7 @@ __global__ void k_gather(Planes src, Planes dst, const int *__restrict__ perm, i
   dst.vy[i] = src.vy[j];
   dst.vz[i] = src.vz[j];
   dst.tag[i] = src.tag[j];
-  dst.lidx[i] = src.lidx[j];
+  dst.lidx[i] = renumber ? i : src.lidx[j];  // slab mode: local order = storage order
   dst.type[i] = src.type[j];
   dst.image[i] = src.image[j];
 }
@@ -153,7 +157,7 @@ int cells_build(obmd_ctx *c)
   NEED(c->pair_ready, OBMD_ERR_STATE, "obmd_build_cells: call obmd_pair_init first");
   NEED(c->n > 0, OBMD_ERR_STATE, "obmd_build_cells: no atoms uploaded");
   const Grid &g = c->grid;
-  const int n = c->n, m = g.ncell + 1;
+  const int n = c->n, m = g.ncell + 3;  // + parked, migrate-left, migrate-right
   {
     ScopedTimer t(c, "bin");
     CK(cudaMemsetAsync(c->cell_count, 0, sizeof(int) * (m + 1), c->stream));
@@ -168,23 +172,36 @@ int cells_build(obmd_ctx *c)
     ScopedTimer t(c, "sort");
     LAUNCH(k_perm, cdiv(n, 256), 256, 0, c->cid, c->rank, c->cell_start, c->perm, n);
     LAUNCH(k_cell_order, cdiv(g.ncell, 128), 128, 0, c->cell_start, c->perm, g.ncell);
-    LAUNCH(k_gather, cdiv(n, 256), 256, 0, c->cur, c->alt, c->perm, n);
+    LAUNCH(k_gather, cdiv(n, 256), 256, 0, c->cur, c->alt, c->perm, n, c->nranks > 1 ? 1 : 0);
     Planes t2 = c->cur;
     c->cur = c->alt;
     c->alt = t2;
   }
-  // nsorted = cell_start[ncell]; it is needed on the host to size later launches.
-  int nlive = 0;
-  CK(cudaMemcpyAsync(&c->sc_h->ntail, &c->cell_start[g.ncell], sizeof(int), cudaMemcpyDeviceToHost,
-                     c->stream));
+  // segment starts (sorted | parked | migrate-left | migrate-right) are needed on the host
+  int *seg = reinterpret_cast<int *>(c->red_h);
+  CK(cudaMemcpyAsync(seg, &c->cell_start[g.ncell], sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (c->nranks > 1) {  // slot ranges of the two boundary columns: what the halo exchange sends
+    const int nyz = g.ny * g.nz;
+    CK(cudaMemcpyAsync(seg + 4, &c->cell_start[g.own_a * nyz], sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(seg + 5, &c->cell_start[(g.own_a + 1) * nyz], sizeof(int), cudaMemcpyDeviceToHost,
+                       c->stream));
+    CK(cudaMemcpyAsync(seg + 6, &c->cell_start[g.own_b * nyz], sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(seg + 7, &c->cell_start[(g.own_b + 1) * nyz], sizeof(int), cudaMemcpyDeviceToHost,
+                       c->stream));
+  }
   CK(cudaMemcpyAsync(&c->sc_h->nonfinite, &c->sc_d->nonfinite, sizeof(int), cudaMemcpyDeviceToHost,
                      c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  nlive = c->sc_h->ntail;
+  for (int k = 0; k < 4; k++) c->col_ab[k] = (c->nranks > 1) ? seg[4 + k] : 0;
   NEED(!c->sc_h->nonfinite, OBMD_ERR_NONFINITE, "Non-numeric atom coords - simulation unstable");
-  c->nsorted = nlive;
-  c->nparked = n - nlive;
-  c->nextra = 0;
+  c->nsorted = seg[0];
+  c->nparked = seg[1] - seg[0];
+  c->seg_migL = seg[1];
+  c->seg_migR = seg[2];
+  c->nmigL = seg[2] - seg[1];
+  c->nmigR = seg[3] - seg[2];
+  NEED(c->nranks > 1 || (c->nmigL == 0 && c->nmigR == 0), OBMD_ERR_STATE, "cell build: stray migrants");
+  c->nextra = c->narr = c->nghost = c->nins = 0;
   c->cells_valid = true;
   c->forces_valid = false;
   return OBMD_OK;

@@ -30,8 +30,17 @@ struct Planes {
 // Cell grid: cell size >= max cutoff; linear index (cx*ny + cy)*nz + cz, x slowest, z fastest,
 // so each open-boundary buffer is one contiguous slot range and a z-row of a stencil is contiguous.
 struct Grid {
-  int nx, ny, nz, ncell;
+  int nx, ny, nz, ncell;  // nx = columns stored on this rank (owned + ghost columns)
+  int gnx, cxoff;         // global column count; global index of local column 0
+  int own_a, own_b;       // owned local columns (inclusive); the others hold ghosts only
   double lo[3], hi[3], prd[3], inv[3], half[3];
+};
+
+// Atoms appended after the cell-sorted range [0, base): arrivals from neighbour slabs (mine),
+// ghosts of the neighbour slabs (not mine), atoms inserted by USHER (mine).  They hang off the
+// per-cell extra lists until the next sort.
+struct Extras {
+  int base, narr, nghost, nins;
 };
 
 struct PairTab {
@@ -115,7 +124,20 @@ struct obmd_ctx {
   int n = 0;        // atoms stored (live + parked + extras)
   int nsorted = 0;  // [0,nsorted) cell-sorted live atoms
   int nparked = 0;  // [nsorted, nsorted+nparked) atoms outside the box in x (before pre_exchange)
-  int nextra = 0;   // atoms appended by USHER after the sort: [nsorted, nsorted+nextra)
+  int nextra = 0;   // atoms appended after the sort: [nsorted, nsorted+nextra) = arrivals|ghosts|inserted
+  int narr = 0, nghost = 0, nins = 0;
+  int nmigL = 0, nmigR = 0, seg_migL = 0, seg_migR = 0;  // migrant segments after the sort
+  int ndel_local = 0;
+  int col_ab[4] = {0, 0, 0, 0};  // slot ranges of the first / last owned column (halo source)
+  bool pre_begun = false;
+  // slab decomposition (comm.cu); nranks == 1: whole box, no communication
+  int myrank = 0, nranks = 1;
+  void *nccl = nullptr;        // ncclComm_t
+  int gx0 = 0, gx1 = 0;        // owned global columns [gx0, gx1)
+  double *sendL = nullptr, *sendR = nullptr, *recvL = nullptr, *recvR = nullptr;
+  int comm_cap = 0;            // capacity of each buffer in atoms (8 doubles per atom)
+  double *red_d = nullptr;     // 32 doubles for the packed allreduces
+  double *red_h = nullptr;     // pinned
   bool cells_valid = false;
   bool forces_valid = false;
   Planes cur, alt;
@@ -186,7 +208,7 @@ extern char g_create_err[1024];
 struct ColRange {
   int n;            // number of intervals (0..2)
   int a[2], b[2];   // inclusive column intervals
-  int extras;       // also visit [nsorted, nsorted + nextra)
+  int extras;       // 0: none, 1: the extras this rank owns (arrivals + insertions), 2: all extras
 };
 
 // Sync-free kernel-family timer: records a CUDA event pair on the launching stream and defers
@@ -231,19 +253,43 @@ bool fix_zones(const obmd_ctx *c, ColRange &int_pbc, ColRange &int_pair, ColRang
 int fix_nve_initial(obmd_ctx *c);                               // fix.cu
 int fix_nve_final(obmd_ctx *c);
 int fix_pbc(obmd_ctx *c);
+int fix_pre_begin(obmd_ctx *c);
 int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials);
 int fix_post_force(obmd_ctx *c);
 int fix_reduce_kinetic(obmd_ctx *c, double out[5]);
 int fix_profile_x(obmd_ctx *c, int nbins, double *count, double *mvx);
 int fix_clear_extras(obmd_ctx *c);
 int read_scalars(obmd_ctx *c);  // copies *sc_d to *sc_h and synchronises the stream
+int comm_exchange(obmd_ctx *c);  // comm.cu: migrate + halo + ghost lists
+int comm_allreduce(obmd_ctx *c, double *dev, int nsum, int nmax);  // first nsum: sum, next nmax: max
+int fix_link_extras(obmd_ctx *c, int first, int count, bool sorted_by_cell);
+int fix_compact_extras(obmd_ctx *c);
 
 // ---- small device helpers shared by the TUs --------------------------------------
+static inline Extras extras_of(const obmd_ctx *c)
+{
+  Extras e;
+  e.base = c->nsorted;
+  e.narr = c->narr;
+  e.nghost = c->nghost;
+  e.nins = c->nins;
+  return e;
+}
+
 #ifdef __CUDACC__
+// local column of coordinate x (global column clamped to the box, minus this rank's offset)
 __device__ __forceinline__ int cell_cx(const Grid &g, double x)
 {
   int k = (int) floor((x - g.lo[0]) * g.inv[0]);
-  return min(max(k, 0), g.nx - 1);
+  return min(max(k, 0), g.gnx - 1) - g.cxoff;
+}
+// slot of the q-th extra atom selected by mode (1: mine, 2: all); -1 if q is past the end
+__device__ __forceinline__ int extras_slot(const Extras &e, int mode, int q)
+{
+  if (mode == 2) return q < e.narr + e.nghost + e.nins ? e.base + q : -1;
+  if (q < e.narr) return e.base + q;
+  q -= e.narr;
+  return q < e.nins ? e.base + e.narr + e.nghost + q : -1;
 }
 __device__ __forceinline__ int cell_wrap(int k, int n)
 {

@@ -71,8 +71,7 @@ __device__ __forceinline__ void wrap_dim(double &x, int &image, double lo, doubl
   }
 }
 
-__global__ void k_pbc(Planes p, ColRange cr, int nsorted, int nextra, Grid g,
-                      const int *__restrict__ cell_start)
+__global__ void k_pbc(Planes p, ColRange cr, Extras ex, Grid g, const int *__restrict__ cell_start)
 {
   int gidx = blockIdx.x * blockDim.x + threadIdx.x;
   const int nyz = g.ny * g.nz;
@@ -85,7 +84,7 @@ __global__ void k_pbc(Planes p, ColRange cr, int nsorted, int nextra, Grid g,
     }
     gidx -= e - b;
   }
-  if (i < 0 && cr.extras && gidx >= 0 && gidx < nextra) i = nsorted + gidx;
+  if (i < 0 && cr.extras && gidx >= 0) i = extras_slot(ex, cr.extras, gidx);
   if (i < 0) return;
   double y = p.y[i], z = p.z[i];
   if (y < g.lo[1] || y >= g.hi[1] || z < g.lo[2] || z >= g.hi[2]) {
@@ -121,11 +120,16 @@ int fix_pbc_cols(obmd_ctx *c, const ColRange &cr, cudaStream_t st)
   NEED(c->cells_valid, OBMD_ERR_STATE, "obmd_pbc: cell list is stale (call obmd_build_cells)");
   ScopedTimer t(c, "pbc", st);
   const int n = c->nsorted + c->nextra;
-  if (n > 0) LAUNCH_ON(st, k_pbc, cdiv(n, 256), 256, 0, c->cur, cr, c->nsorted, c->nextra, c->grid, c->cell_start);
+  if (n > 0) LAUNCH_ON(st, k_pbc, cdiv(n, 256), 256, 0, c->cur, cr, extras_of(c), c->grid, c->cell_start);
   return OBMD_OK;
 }
 
-int fix_pbc(obmd_ctx *c) { return fix_pbc_cols(c, all_columns(c), c->stream); }
+int fix_pbc(obmd_ctx *c)
+{
+  ColRange cr = all_columns(c);
+  cr.extras = 2;  // ghosts are wrapped too: they are this rank's private copies
+  return fix_pbc_cols(c, cr, c->stream);
+}
 
 // =====================================================================================
 // pre_exchange, part 1: scan + deletion bookkeeping
@@ -137,14 +141,14 @@ int fix_pbc(obmd_ctx *c) { return fix_pbc_cols(c, all_columns(c), c->stream); }
 // The id pass touches only the two int planes (8 B/atom); positions are read only in the cell
 // columns that overlap the two buffer regions, so the interior can be wrapped and its forces
 // computed on the side stream while this runs (obmd_run).
-__global__ void k_scan_ids(Planes p, int nlive, StepScalars *sc, int *__restrict__ tail_key,
+__global__ void k_scan_ids(Planes p, int nlive, int want_tail, StepScalars *sc, int *__restrict__ tail_key,
                            int *__restrict__ tail_val, int tail_cap)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int mt = 0;
   if (i < nlive) {
     mt = p.tag[i];
-    int li = p.lidx[i];
+    int li = want_tail ? p.lidx[i] : -1;
     if (li >= nlive) {
       int k = atomicAdd(&sc->ntail, 1);
       if (k < tail_cap) {
@@ -157,11 +161,16 @@ __global__ void k_scan_ids(Planes p, int nlive, StepScalars *sc, int *__restrict
   if ((threadIdx.x & 31) == 0 && mt) atomicMax(&sc->maxtag, mt);
 }
 
-__global__ void k_count_regions(Planes p, ColRange cr, Grid g, FixDev fd,
+__global__ void k_count_regions(Planes p, ColRange cr, Extras ex, Grid g, FixDev fd,
                                 const int *__restrict__ cell_start, StepScalars *sc)
 {
   const int nyz = g.ny * g.nz;
   int cl = 0, cright = 0;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < ex.narr + ex.nins; q += gridDim.x * blockDim.x) {
+    int i = extras_slot(ex, 1, q);  // arrivals from neighbour slabs count as owned
+    cl += block_inside(fd.region[0], p.x[i], p.y[i], p.z[i]);
+    cright += block_inside(fd.region[1], p.x[i], p.y[i], p.z[i]);
+  }
   for (int k = 0; k < cr.n; k++) {
     int b = cell_start[cr.a[k] * nyz], e = cell_start[(cr.b[k] + 1) * nyz];
     for (int i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) {
@@ -218,11 +227,11 @@ __device__ void bitonic_desc(int *key, int *val, int npad)
 __global__ void __launch_bounds__(1024)
     k_delete_fixup(Planes p, int nlive, int ndel, int npad_del, int npad_tail, FixDev fd, PairTab pt,
                    StepScalars *sc, int *del_key, int *del_val, int *tail_key, int *tail_val,
-                   int *del_src, double *del_mv)
+                   int *del_src, double *del_mv, int do_walk)
 {
   __shared__ int s_dkey[DEL_SMEM], s_tkey[DEL_SMEM], s_tval[DEL_SMEM], s_src[DEL_SMEM];
   const bool small = (npad_del <= DEL_SMEM && npad_tail <= DEL_SMEM);
-  const int ntail = sc->ntail;
+  const int ntail = do_walk ? sc->ntail : 0;
   // working arrays: shared memory when they fit (the usual few hundred deletions per step)
   int *dkey = small ? s_dkey : del_key, *dval = small ? s_src : del_val;
   int *tkey = small ? s_tkey : tail_key, *tval = small ? s_tval : tail_val;
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(1024)
     if (threadIdx.x < 3) sc->vnewl[comp] = acc;
     else sc->vnewr[comp] = acc;
   }
-  if (threadIdx.x == 32) {  // hole walk, on a different warp than the sums
+  if (threadIdx.x == 32 && do_walk) {  // hole walk, on a different warp than the sums
     const int n = nlive + ndel;  // nlocal before the deletion; nprime = nlive
     int *src = small ? s_src : del_src;  // dval is dead once del_mv is written (small: same array)
     int z = 0;
@@ -315,6 +324,7 @@ struct UsherCfg {
   int nbase;          // local index of the first inserted atom (= nlocal after deletion)
   int nacc_prev;      // accepted trials of the previous round (acc_list entries)
   int natt;
+  int tg0;            // global index of local trial 0 (slab runs: the right rank starts at ntrL)
 };
 
 __device__ __forceinline__ int ranpark_pow(long long n)
@@ -393,7 +403,9 @@ __device__ __forceinline__ void usher_single(int it, int tj, const PairTab &pt, 
 __device__ void usher_energy(const double c[3], int t, const Planes &p, const Grid &g, const PairTab &pt,
                              const FixDev &fd, const int *__restrict__ cell_start, const UsherCfg &u,
                              const int *__restrict__ acc_list, const obmd_trial *__restrict__ prev,
-                             WarpHits &H, StepScalars *sc, double &E, double f[3])
+                             const Extras &ex, const int *__restrict__ extra_head,
+                             const int *__restrict__ extra_next, WarpHits &H, StepScalars *sc, double &E,
+                             double f[3])
 {
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -403,28 +415,35 @@ __device__ void usher_energy(const double c[3], int t, const Planes &p, const Gr
   // turns them into a flat candidate list, and the candidates are then visited 32 at a time with
   // independent loads (two dependent global round trips per energy evaluation instead of 54).
   int cx = cell_cx(g, c[0]), cy = cell_cy(g, c[1]), cz = cell_cz(g, c[2]);
-  int jb = 0, cnt = 0;
+  int jb = 0, cnt = 0, cc = -1, cex = 0;
+  const bool have_extras = (ex.narr + ex.nghost + ex.nins) > 0;  // slab runs: arrivals and ghosts
   if (lane < 27) {
     int ox = lane / 9 - 1, oy = (lane / 3) % 3 - 1, oz = lane % 3 - 1;
     int bx = cx + ox;
     if (bx >= 0 && bx < g.nx) {
-      int cc = (bx * g.ny + cell_wrap(cy + oy, g.ny)) * g.nz + cell_wrap(cz + oz, g.nz);
+      cc = (bx * g.ny + cell_wrap(cy + oy, g.ny)) * g.nz + cell_wrap(cz + oz, g.nz);
       jb = cell_start[cc];
       cnt = cell_start[cc + 1] - jb;
+      if (have_extras)
+        for (int e = extra_head[cc]; e >= 0; e = extra_next[e]) cex++;
     }
   }
-  int off = cnt;
+  int off = cnt + cex;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     int v = __shfl_up_sync(0xffffffffu, off, d);
     if (lane >= d) off += v;
   }
   const int ncand = __shfl_sync(0xffffffffu, off, 31);
-  off -= cnt;  // exclusive
+  off -= cnt + cex;  // exclusive
   if (ncand > USH_CAND) {
     if (lane == 0) sc->usher_error = OBMD_ERR_CAPACITY;
   } else {
     for (int k = 0; k < cnt; k++) H.cand[off + k] = jb + k;
+    if (cex) {
+      int k = cnt;
+      for (int e = extra_head[cc]; e >= 0; e = extra_next[e]) H.cand[off + k++] = ex.base + e;
+    }
   }
   __syncwarp();
   const int nc = ncand > USH_CAND ? 0 : ncand;
@@ -519,8 +538,10 @@ __device__ void usher_energy(const double c[3], int t, const Planes &p, const Gr
 // evaluated (needed by the dirty test of the next round).
 __global__ void __launch_bounds__(USH_WARPS * 32, 8)
     k_usher_eval(const int *__restrict__ list, int nlist, Planes p, Grid g, PairTab pt, FixDev fd,
-                 const int *__restrict__ cell_start, UsherCfg u, const int *__restrict__ acc_list,
-                 const obmd_trial *__restrict__ prev, obmd_trial *__restrict__ cur,
+                 const int *__restrict__ cell_start, UsherCfg u, Extras ex,
+                 const int *__restrict__ extra_head, const int *__restrict__ extra_next,
+                 const int *__restrict__ acc_list, const obmd_trial *__restrict__ prev,
+                 obmd_trial *__restrict__ cur,
                  double *__restrict__ path, int *__restrict__ npts, double *__restrict__ bbox,
                  const int *__restrict__ kfirst, StepScalars *sc)
 {
@@ -529,11 +550,12 @@ __global__ void __launch_bounds__(USH_WARPS * 32, 8)
   const int li = blockIdx.x * USH_WARPS + w;
   if (li >= nlist) return;
   const int t = list ? list[li] : li;
-  const int side = (t < u.ntrL) ? 0 : 1;
+  const int tg = t + u.tg0;  // position of this trial in the (replicated) RanPark stream
+  const int side = (tg < u.ntrL) ? 0 : 1;
   const obmd_block &reg = fd.region[4 + side];
 
   // trial start (:923-927): three consecutive RanPark draws, x then y then z
-  int seed = (int) (((unsigned long long) u.seed0 * (unsigned long long) ranpark_pow(3LL * t)) %
+  int seed = (int) (((unsigned long long) u.seed0 * (unsigned long long) ranpark_pow(3LL * tg)) %
                     2147483647ULL);
   double c[3], start[3];
   for (int d = 0; d < 3; d++) {
@@ -554,7 +576,8 @@ __global__ void __launch_bounds__(USH_WARPS * 32, 8)
   }
   double E = 0.0, f[3];
   while (i < u.natt) {
-    usher_energy(c, t, p, g, pt, fd, cell_start, u, acc_list, prev, hits[w], sc, E, f);
+    usher_energy(c, t, p, g, pt, fd, cell_start, u, acc_list, prev, ex, extra_head, extra_next, hits[w],
+                 sc, E, f);
     if (lane == 0) {
       mypath[np * 3 + 0] = c[0];
       mypath[np * 3 + 1] = c[1];
@@ -730,54 +753,81 @@ __global__ void k_usher_acc(obmd_trial *__restrict__ prev, const obmd_trial *__r
 }
 
 // create_atom + tag/mask/image/v assignment (:1121-1150, atom_vec.cpp:1592-1612), appended after
-// the sorted range; also threads the new atoms into per-cell lists the pair kernel walks.
-__global__ void k_usher_commit(Planes p, int nsorted, int maxtag, int nbase, Grid g, FixDev fd,
+// every other extra atom; the new atoms are then threaded into the per-cell lists the pair kernel
+// walks (fix_link_extras).
+__global__ void k_usher_commit(Planes p, Extras ex, int tag0, Grid g, FixDev fd,
                                obmd_trial *__restrict__ cur, const int *__restrict__ acc_list, int nacc,
-                               int *__restrict__ extra_head, int *__restrict__ extra_next,
-                               int *__restrict__ extra_cell, double *fx, double *fy, double *fz)
+                               double *fx, double *fy, double *fz)
 {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < nacc) {
     obmd_trial &r = cur[acc_list[k]];
-    int s = nsorted + k;
+    int s = ex.base + ex.narr + ex.nghost + k;
     p.x[s] = r.end[0];
     p.y[s] = r.end[1];
     p.z[s] = r.end[2];
     p.vx[s] = p.vy[s] = p.vz[s] = 0.0;
     p.type[s] = fd.ntype;
-    p.tag[s] = maxtag + k + 1;
+    p.tag[s] = tag0 + k + 1;
     p.image[s] = IMG0;
-    p.lidx[s] = nbase + k;
+    p.lidx[s] = s;  // appended: local index == slot (serial runs: nlocal-after-deletion + k)
     fx[s] = fy[s] = fz[s] = 0.0;
-    r.tag = maxtag + k + 1;
-    extra_cell[k] = (cell_cx(g, r.end[0]) * g.ny + cell_cy(g, r.end[1])) * g.nz + cell_cz(g, r.end[2]);
+    r.tag = tag0 + k + 1;
   }
 }
 
-// Per-cell lists of the inserted atoms in ascending k (deterministic): atom k links to the next
-// k' > k in the same cell; the first atom of a cell becomes its head.  One block, cells staged in
-// shared memory, O(nacc) work per thread.
-__global__ void k_extra_link(const int *__restrict__ extra_cell, int nacc, int *__restrict__ extra_head,
-                             int *__restrict__ extra_next)
+// cells of the extra atoms [first, first+count) (indices relative to the extras base)
+__global__ void k_extra_cells(Planes p, int base, int first, int count, Grid g, int *__restrict__ extra_cell)
 {
-  extern __shared__ int cellsh[];
-  for (int k = threadIdx.x; k < nacc; k += blockDim.x) cellsh[k] = extra_cell[k];
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  int s = base + first + k;
+  int lc = cell_cx(g, p.x[s]);
+  lc = min(max(lc, 0), g.nx - 1);
+  extra_cell[first + k] = (lc * g.ny + cell_cy(g, p.y[s])) * g.nz + cell_cz(g, p.z[s]);
+}
+
+// A group that arrives sorted by cell (a neighbour's boundary column): runs of equal cells become
+// the lists.  Precondition: no earlier group has atoms in these cells.
+__global__ void k_link_sorted(const int *__restrict__ extra_cell, int first, int count,
+                              int *__restrict__ extra_head, int *__restrict__ extra_next)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  int e = first + k, cc = extra_cell[e];
+  if (k == 0 || extra_cell[e - 1] != cc) extra_head[cc] = e;
+  extra_next[e] = (k + 1 < count && extra_cell[e + 1] == cc) ? e + 1 : -1;
+}
+
+// An unsorted group (arrivals, a neighbour's own arrivals, USHER insertions): atom k links to the
+// next k' > k of the group in the same cell, the last one to whatever the cell's list held before,
+// and the first becomes the head.  One CTA, cells staged in shared memory, O(count) per thread,
+// deterministic.
+__global__ void k_link_group(const int *__restrict__ extra_cell, int first, int count,
+                             int *__restrict__ extra_head, int *__restrict__ extra_next)
+{
+  extern __shared__ int cellsh[];  // [count] cells, [count] old heads
+  int *oldh = cellsh + count;
+  for (int k = threadIdx.x; k < count; k += blockDim.x) {
+    cellsh[k] = extra_cell[first + k];
+    oldh[k] = extra_head[cellsh[k]];
+  }
   __syncthreads();
-  for (int k = threadIdx.x; k < nacc; k += blockDim.x) {
+  for (int k = threadIdx.x; k < count; k += blockDim.x) {
     int cc = cellsh[k], nxt = -1;
-    for (int q = k + 1; q < nacc; q++)
+    for (int q = k + 1; q < count; q++)
       if (cellsh[q] == cc) {
-        nxt = q;
+        nxt = first + q;
         break;
       }
-    extra_next[k] = nxt;
-    bool first = true;
+    extra_next[first + k] = (nxt >= 0) ? nxt : oldh[k];
+    bool is_first = true;
     for (int q = 0; q < k; q++)
       if (cellsh[q] == cc) {
-        first = false;
+        is_first = false;
         break;
       }
-    if (first) extra_head[cc] = k;
+    if (is_first) extra_head[cc] = first + k;
   }
 }
 
@@ -823,15 +873,16 @@ int read_scalars(obmd_ctx *c)
   return OBMD_OK;
 }
 
-// cell columns overlapped by region block r (one column of slack each side for rounding)
+// local cell columns overlapped by region block r (one column of slack each side for rounding),
+// clipped to the columns this rank owns; e < a when the region misses the slab
 static void region_cols(const obmd_ctx *c, int r, int margin, int &a, int &e)
 {
   const Grid &g = c->grid;
   const obmd_block &b = c->fd.region[r];
-  a = (int) floor((b.lo[0] - g.lo[0]) * g.inv[0]) - 1 - margin;
-  e = (int) floor((b.hi[0] - g.lo[0]) * g.inv[0]) + 1 + margin;
-  a = a < 0 ? 0 : a;
-  e = e > g.nx - 1 ? g.nx - 1 : e;
+  a = (int) floor((b.lo[0] - g.lo[0]) * g.inv[0]) - 1 - margin - g.cxoff;
+  e = (int) floor((b.hi[0] - g.lo[0]) * g.inv[0]) + 1 + margin - g.cxoff;
+  a = a < g.own_a ? g.own_a : a;
+  e = e > g.own_b ? g.own_b : e;
 }
 
 static int merge_intervals(int *lo, int *hi, int n)
@@ -910,6 +961,118 @@ bool fix_zones(const obmd_ctx *c, ColRange &int_pbc, ColRange &int_pair, ColRang
   return true;
 }
 
+#define LINK_MAX 6000  // atoms per unsorted extra group (two int arrays in 48 KB of shared memory)
+
+// cells + per-cell lists for the extra atoms [first, first+count) (relative to the extras base)
+int fix_link_extras(obmd_ctx *c, int first, int count, bool sorted_by_cell)
+{
+  if (count <= 0) return OBMD_OK;
+  LAUNCH(k_extra_cells, cdiv(count, 128), 128, 0, c->cur, c->nsorted, first, count, c->grid, c->extra_cell);
+  if (sorted_by_cell)
+    LAUNCH(k_link_sorted, cdiv(count, 128), 128, 0, c->extra_cell, first, count, c->extra_head, c->extra_next);
+  else {
+    NEED(count <= LINK_MAX, OBMD_ERR_CAPACITY, "more than %d atoms in one unsorted extra group", LINK_MAX);
+    LAUNCH(k_link_group, 1, 512, 2 * sizeof(int) * count, c->extra_cell, first, count, c->extra_head,
+           c->extra_next);
+  }
+  return OBMD_OK;
+}
+
+// copy the 13 per-atom planes of `count` atoms from slot src to slot dst (dst < src) via scratch
+__global__ void k_move_atoms(Planes p, Planes tmp, double *fx, double *fy, double *fz, double *ftmp, int src,
+                             int dst, int count, int phase)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  if (phase == 0) {
+    int s = src + k;
+    tmp.x[k] = p.x[s]; tmp.y[k] = p.y[s]; tmp.z[k] = p.z[s];
+    tmp.vx[k] = p.vx[s]; tmp.vy[k] = p.vy[s]; tmp.vz[k] = p.vz[s];
+    tmp.tag[k] = p.tag[s]; tmp.type[k] = p.type[s]; tmp.image[k] = p.image[s];
+    ftmp[3 * k] = fx[s]; ftmp[3 * k + 1] = fy[s]; ftmp[3 * k + 2] = fz[s];
+  } else {
+    int d = dst + k;
+    p.x[d] = tmp.x[k]; p.y[d] = tmp.y[k]; p.z[d] = tmp.z[k];
+    p.vx[d] = tmp.vx[k]; p.vy[d] = tmp.vy[k]; p.vz[d] = tmp.vz[k];
+    p.tag[d] = tmp.tag[k]; p.type[d] = tmp.type[k]; p.image[d] = tmp.image[k];
+    p.lidx[d] = d;
+    fx[d] = ftmp[3 * k]; fy[d] = ftmp[3 * k + 1]; fz[d] = ftmp[3 * k + 2];
+  }
+}
+
+// Slab runs, after the forces are complete: the ghosts are dead; close the gap they leave between
+// the arrivals and the inserted atoms so that [0, n) is again every atom this rank owns.
+int fix_compact_extras(obmd_ctx *c)
+{
+  if (c->nghost == 0) return OBMD_OK;
+  fix_clear_extras(c);
+  const int src = c->nsorted + c->narr + c->nghost, dst = c->nsorted + c->narr;
+  if (c->nins > 0) {
+    LAUNCH(k_move_atoms, cdiv(c->nins, 128), 128, 0, c->cur, c->alt, c->fx, c->fy, c->fz, c->stage_d, src, dst,
+           c->nins, 0);
+    LAUNCH(k_move_atoms, cdiv(c->nins, 128), 128, 0, c->cur, c->alt, c->fx, c->fy, c->fz, c->stage_d, src, dst,
+           c->nins, 1);
+  }
+  c->n = c->nsorted + c->narr + c->nins;
+  c->nsorted = c->n;  // no longer cell-sorted as a whole, but contiguous; the next sort rebuilds
+  c->narr = c->nghost = c->nins = c->nextra = 0;
+  c->cells_valid = false;
+  return OBMD_OK;
+}
+
+__global__ void k_pack_red(const StepScalars *sc, double *red, int ndel)
+{
+  if (threadIdx.x == 0) {
+    red[0] = sc->cnt_left;
+    red[1] = sc->cnt_right;
+    red[2] = ndel;
+    for (int d = 0; d < 3; d++) {
+      red[3 + d] = sc->vnewl[d];
+      red[6 + d] = sc->vnewr[d];
+    }
+    red[9] = sc->maxtag;  // reduced with max
+  }
+}
+
+// First half of pre_exchange: everything that only needs the atoms parked outside the box
+// (try_deleting :639-865).  Slab runs call it before the halo exchange because the arrivals are
+// stored where the parked atoms sit.
+int fix_pre_begin(obmd_ctx *c)
+{
+  NEED(c->have_fix, OBMD_ERR_STATE, "obmd_pre_exchange: call obmd_fix_create first");
+  NEED(c->cells_valid, OBMD_ERR_STATE, "obmd_pre_exchange: cell list is stale (call obmd_build_cells)");
+  ScopedTimer t(c, "pre_exchange");
+  const int nlive = c->nsorted, ndel = c->nparked;
+  const bool serial = (c->nranks == 1);
+  // zero cnt_left, cnt_right, maxtag, ntail, nonfinite, usher_error, nchanged, ndirty, naccept
+  CK(cudaMemsetAsync(c->sc_d, 0, offsetof(StepScalars, rng_seed), c->stream));
+  CK(cudaMemsetAsync(c->sc_d->vnewl, 0, 6 * sizeof(double), c->stream));
+  if (ndel > c->del_cap) {
+    cudaFree(c->del_key); cudaFree(c->del_val); cudaFree(c->tail_key); cudaFree(c->tail_val);
+    cudaFree(c->del_src); cudaFree(c->del_mv);
+    c->del_cap = next_pow2(ndel + 1024);
+    CK(cudaMalloc(&c->del_src, sizeof(int) * c->del_cap));
+    CK(cudaMalloc(&c->del_mv, sizeof(double) * 4 * c->del_cap));
+    CK(cudaMalloc(&c->del_key, sizeof(int) * c->del_cap));
+    CK(cudaMalloc(&c->del_val, sizeof(int) * c->del_cap));
+    CK(cudaMalloc(&c->tail_key, sizeof(int) * c->del_cap));
+    CK(cudaMalloc(&c->tail_val, sizeof(int) * c->del_cap));
+  }
+  if (serial)  // tags + survivors that will move into holes; slab runs scan after the arrivals are in
+    LAUNCH(k_scan_ids, cdiv(nlive > 0 ? nlive : 1, 256), 256, 0, c->cur, nlive, 1, c->sc_d, c->tail_key,
+           c->tail_val, c->del_cap);
+  if (ndel > 0) {
+    int npad = next_pow2(ndel);
+    LAUNCH(k_delete_fixup, 1, 1024, 0, c->cur, nlive, ndel, npad, npad, c->fd, c->pt, c->sc_d, c->del_key,
+           c->del_val, c->tail_key, c->tail_val, c->del_src, c->del_mv, serial ? 1 : 0);
+  }
+  c->ndel_local = ndel;
+  c->n = nlive;  // the parked atoms are gone
+  c->nparked = 0;
+  c->pre_begun = true;
+  return OBMD_OK;
+}
+
 int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
 {
   NEED(c->have_fix, OBMD_ERR_STATE, "obmd_pre_exchange: call obmd_fix_create first");
@@ -917,128 +1080,162 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
   const obmd_fix_args &fa = c->fa;
   obmd_pre_exchange_report &rep = c->rep;
   memset(&rep, 0, sizeof(rep));
-  const int nlive = c->nsorted, ndel = c->nparked;
+  const bool serial = (c->nranks == 1);
   int rc;
+  if (!c->pre_begun && (rc = fix_pre_begin(c))) return rc;
+  c->pre_begun = false;
+  const int nlive = c->nsorted;
+  int ndel = c->ndel_local, cntL, cntR, maxtag;
+  double vnewl[3], vnewr[3];
   {
     ScopedTimer t(c, "pre_exchange");
-    // zero cnt_left, cnt_right, maxtag, ntail, nonfinite, usher_error, nchanged, ndirty, naccept
-    CK(cudaMemsetAsync(c->sc_d, 0, offsetof(StepScalars, rng_seed), c->stream));
-    CK(cudaMemsetAsync(c->sc_d->vnewl, 0, 6 * sizeof(double), c->stream));
-    if (ndel > c->del_cap) {
-      cudaFree(c->del_key); cudaFree(c->del_val); cudaFree(c->tail_key); cudaFree(c->tail_val);
-      cudaFree(c->del_src); cudaFree(c->del_mv);
-      c->del_cap = next_pow2(ndel + 1024);
-      CK(cudaMalloc(&c->del_src, sizeof(int) * c->del_cap));
-      CK(cudaMalloc(&c->del_mv, sizeof(double) * 4 * c->del_cap));
-      CK(cudaMalloc(&c->del_key, sizeof(int) * c->del_cap));
-      CK(cudaMalloc(&c->del_val, sizeof(int) * c->del_cap));
-      CK(cudaMalloc(&c->tail_key, sizeof(int) * c->del_cap));
-      CK(cudaMalloc(&c->tail_val, sizeof(int) * c->del_cap));
-    }
-    LAUNCH(k_scan_ids, cdiv(nlive > 0 ? nlive : 1, 256), 256, 0, c->cur, nlive, c->sc_d, c->tail_key,
-           c->tail_val, c->del_cap);
+    if (!serial)
+      LAUNCH(k_scan_ids, cdiv(nlive + c->narr > 0 ? nlive + c->narr : 1, 256), 256, 0, c->cur, nlive + c->narr, 0,
+             c->sc_d, c->tail_key, c->tail_val, c->del_cap);
     ColRange bufcols = fix_region_columns(c, 0, 1, 0);
-    LAUNCH(k_count_regions, FB_BLOCKS, FB_THREADS, 0, c->cur, bufcols, c->grid, c->fd, c->cell_start,
-           c->sc_d);
-    if (ndel > 0) {
-      int npad = next_pow2(ndel);
-      LAUNCH(k_delete_fixup, 1, 1024, 0, c->cur, nlive, ndel, npad, npad, c->fd, c->pt, c->sc_d,
-             c->del_key, c->del_val, c->tail_key, c->tail_val, c->del_src, c->del_mv);
+    LAUNCH(k_count_regions, FB_BLOCKS, FB_THREADS, 0, c->cur, bufcols, extras_of(c), c->grid, c->fd,
+           c->cell_start, c->sc_d);
+    if (serial) {
+      if ((rc = read_scalars(c))) return rc;
+      const StepScalars &s = *c->sc_h;
+      NEED(s.usher_error == 0, OBMD_ERR_STATE, "fix obmd: deletion bookkeeping invariant violated");
+      cntL = s.cnt_left; cntR = s.cnt_right; maxtag = s.maxtag;
+      for (int d = 0; d < 3; d++) { vnewl[d] = s.vnewl[d]; vnewr[d] = s.vnewr[d]; }
+    } else {
+      // the ~14 MPI_Allreduce/Scan calls of the reference (:604-605,:677-678, group.cpp:809,
+      // :1868) become one packed sum + one max over NVLink
+      LAUNCH(k_pack_red, 1, 32, 0, c->sc_d, c->red_d, ndel);
+      if ((rc = comm_allreduce(c, c->red_d, 9, 1))) return rc;
+      CK(cudaMemcpyAsync(c->red_h, c->red_d, 10 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      cntL = (int) c->red_h[0]; cntR = (int) c->red_h[1]; ndel = (int) c->red_h[2];
+      for (int d = 0; d < 3; d++) { vnewl[d] = c->red_h[3 + d]; vnewr[d] = c->red_h[6 + d]; }
+      maxtag = (int) c->red_h[9];
     }
-    if ((rc = read_scalars(c))) return rc;
   }
-  const StepScalars &s = *c->sc_h;
-  NEED(s.usher_error == 0, OBMD_ERR_STATE, "fix obmd: deletion bookkeeping invariant violated");
   // try_deleting x2 (:578-579): one uniform() per deleted atom (Q7)
   c->fs.rng_seed = ranpark_skip(c->fs.rng_seed, ndel);
   c->fs.ndeleted += ndel;
-  c->n = nlive;  // the parked atoms are gone
-  c->nparked = 0;
   rep.ndel = ndel;
-  rep.cnt_left = s.cnt_left;
-  rep.cnt_right = s.cnt_right;
-  rep.maxtag = s.maxtag;
+  rep.cnt_left = cntL;
+  rep.cnt_right = cntR;
+  rep.maxtag = maxtag;
   for (int d = 0; d < 3; d++) {
-    rep.vnewl[d] = s.vnewl[d];
-    rep.vnewr[d] = s.vnewr[d];
+    rep.vnewl[d] = vnewl[d];
+    rep.vnewr[d] = vnewr[d];
   }
   // :586-589 (mol_len = 1 in ATOM mode); truncation toward zero
   const double mol_len = 1.0;
-  int stevL = -static_cast<int>((static_cast<double>(s.cnt_left) / mol_len - fa.alpha * fa.nbuf) *
-                                c->dt / fa.tau);
-  int stevR = -static_cast<int>((static_cast<double>(s.cnt_right) / mol_len - fa.alpha * fa.nbuf) *
-                                c->dt / fa.tau);
+  int stevL = -static_cast<int>((static_cast<double>(cntL) / mol_len - fa.alpha * fa.nbuf) * c->dt / fa.tau);
+  int stevR = -static_cast<int>((static_cast<double>(cntR) / mol_len - fa.alpha * fa.nbuf) * c->dt / fa.tau);
   rep.ninsert_left = stevL;
   rep.ninsert_right = stevR;
   const int ntrL = stevL > 0 ? stevL : 0, ntrR = stevR > 0 ? stevR : 0;
   const int ntr = ntrL + ntrR;
+  // slab runs: rank 0 owns the left insertion region, the last rank the right one; both draw from
+  // the same replicated RanPark stream (skip-ahead), so no trial data crosses ranks
+  const bool doL = (c->myrank == 0), doR = (c->myrank == c->nranks - 1);
+  if (!serial) {
+    const Grid &g = c->grid;
+    const double slab_lo = g.lo[0] + c->gx0 / g.inv[0], slab_hi = g.lo[0] + c->gx1 / g.inv[0];
+    NEED(!doL || c->fd.region[4].hi[0] <= slab_hi, OBMD_ERR_ARG,
+         "slab run: region5 (x <= %g) must lie inside the first rank's slab (x < %g)", c->fd.region[4].hi[0],
+         slab_hi);
+    NEED(!doR || c->fd.region[5].lo[0] >= slab_lo, OBMD_ERR_ARG,
+         "slab run: region6 (x >= %g) must lie inside the last rank's slab (x >= %g)", c->fd.region[5].lo[0],
+         slab_lo);
+  }
+  const int ntr_loc = (doL ? ntrL : 0) + (doR ? ntrR : 0);
+  const int tg0 = doL ? 0 : ntrL;
 
-  int nacc = 0;
+  int nacc = 0, naccL = 0, naccR = 0, rounds = 0;
   if (ntr > 0) {
     ScopedTimer t(c, "usher");
     NEED(fa.maxattempt == 1, OBMD_ERR_ARG,
          "fix obmd: maxattempt > 1 is not implemented on the device path (DESIGN.md 5.4)");
-    if ((rc = ensure_trials(c, ntr, fa.nattempt))) return rc;
-    if ((rc = obmd_ensure_capacity(c, nlive + ntr))) return rc;
-    UsherCfg u;
-    u.ntrL = ntrL;
-    u.ntr = ntr;
-    u.seed0 = c->fs.rng_seed;
-    u.nbase = nlive;
-    u.nacc_prev = 0;
-    u.natt = fa.nattempt;
-    const double rsqmax = c->pt.cutmax * c->pt.cutmax * (1.0 + 1e-9);
-    int nlist = ntr;
-    const int *list = nullptr;
-    int round = 0;
-    for (;; round++) {
-      NEED(round <= ntr + 1, OBMD_ERR_STATE, "fix obmd: USHER commit did not converge");
-      LAUNCH(k_usher_eval, cdiv(nlist, USH_WARPS), USH_WARPS * 32, 0, list, nlist, c->cur, c->grid, c->pt,
-             c->fd, c->cell_start, u, c->acc_list, c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts, c->tr_bbox, c->tr_changed + c->tr_cap, c->sc_d);
-      CK(cudaMemsetAsync(&c->sc_d->nchanged, 0, 2 * sizeof(int), c->stream));  // nchanged, ndirty
-      LAUNCH(k_usher_diff, cdiv(ntr, 256), 256, 0, c->tr_prev_d, c->tr_d, ntr, round == 0 ? 1 : 0,
-             c->tr_changed, c->sc_d);
-      LAUNCH(k_usher_dirty, cdiv(ntr, 4), 128, 0, c->tr_prev_d, c->tr_d, ntr, round == 0 ? 1 : 0,
-             c->tr_changed, c->tr_path, c->tr_npts, c->tr_bbox, u.natt, c->grid, c->pt.cutmax * (1.0 + 1e-9),
-             rsqmax, c->tr_list, c->tr_changed + c->tr_cap, c->sc_d);
-      LAUNCH(k_usher_copy, cdiv(ntr, 256), 256, 0, c->tr_prev_d, c->tr_d, ntr);
-      LAUNCH(k_usher_acc, 1, 1024, 0, c->tr_prev_d, c->tr_d, ntr, c->acc_list, c->sc_d);
-      if ((rc = read_scalars(c))) return rc;
-      NEED(c->sc_h->usher_error != OBMD_ERR_USHER, OBMD_ERR_USHER,
-           "fix obmd: USHER force vanished with E above target (the reference would not terminate)");
-      NEED(c->sc_h->usher_error != OBMD_ERR_CAPACITY, OBMD_ERR_CAPACITY,
-           "fix obmd: more than %d neighbours within the cutoff of a USHER point", USH_CAP);
-      nacc = c->sc_h->naccept;
-      if (c->sc_h->nchanged == 0 || c->sc_h->ndirty == 0) break;
-      nlist = c->sc_h->ndirty;
-      list = c->tr_list;
-      u.nacc_prev = nacc;
+    if (ntr_loc > 0) {
+      if ((rc = ensure_trials(c, ntr_loc, fa.nattempt))) return rc;
+      if ((rc = obmd_ensure_capacity(c, nlive + c->nextra + ntr_loc))) return rc;
+      UsherCfg u;
+      u.ntrL = ntrL;
+      u.ntr = ntr;
+      u.seed0 = c->fs.rng_seed;
+      u.nbase = nlive + c->nextra;
+      u.nacc_prev = 0;
+      u.natt = fa.nattempt;
+      u.tg0 = tg0;
+      const Extras ex = extras_of(c);
+      const double rsqmax = c->pt.cutmax * c->pt.cutmax * (1.0 + 1e-9);
+      int nlist = ntr_loc;
+      const int *list = nullptr;
+      int round = 0;
+      for (;; round++) {
+        NEED(round <= ntr_loc + 1, OBMD_ERR_STATE, "fix obmd: USHER commit did not converge");
+        LAUNCH(k_usher_eval, cdiv(nlist, USH_WARPS), USH_WARPS * 32, 0, list, nlist, c->cur, c->grid, c->pt,
+               c->fd, c->cell_start, u, ex, c->extra_head, c->extra_next, c->acc_list, c->tr_prev_d, c->tr_d,
+               c->tr_path, c->tr_npts, c->tr_bbox, c->tr_changed + c->tr_cap, c->sc_d);
+        CK(cudaMemsetAsync(&c->sc_d->nchanged, 0, 2 * sizeof(int), c->stream));  // nchanged, ndirty
+        LAUNCH(k_usher_diff, cdiv(ntr_loc, 256), 256, 0, c->tr_prev_d, c->tr_d, ntr_loc, round == 0 ? 1 : 0,
+               c->tr_changed, c->sc_d);
+        LAUNCH(k_usher_dirty, cdiv(ntr_loc, 4), 128, 0, c->tr_prev_d, c->tr_d, ntr_loc, round == 0 ? 1 : 0,
+               c->tr_changed, c->tr_path, c->tr_npts, c->tr_bbox, u.natt, c->grid,
+               c->pt.cutmax * (1.0 + 1e-9), rsqmax, c->tr_list, c->tr_changed + c->tr_cap, c->sc_d);
+        LAUNCH(k_usher_copy, cdiv(ntr_loc, 256), 256, 0, c->tr_prev_d, c->tr_d, ntr_loc);
+        LAUNCH(k_usher_acc, 1, 1024, 0, c->tr_prev_d, c->tr_d, ntr_loc, c->acc_list, c->sc_d);
+        if ((rc = read_scalars(c))) return rc;
+        NEED(c->sc_h->usher_error != OBMD_ERR_USHER, OBMD_ERR_USHER,
+             "fix obmd: USHER force vanished with E above target (the reference would not terminate)");
+        NEED(c->sc_h->usher_error != OBMD_ERR_CAPACITY, OBMD_ERR_CAPACITY,
+             "fix obmd: more than %d neighbours within the cutoff of a USHER point", USH_CAP);
+        nacc = c->sc_h->naccept;
+        if (c->sc_h->nchanged == 0 || c->sc_h->ndirty == 0) break;
+        nlist = c->sc_h->ndirty;
+        list = c->tr_list;
+        u.nacc_prev = nacc;
+      }
+      rounds = round + 1;
     }
-    rep.usher_rounds = round + 1;
+    naccL = doL ? nacc : 0;  // serial: both sides live in one list, the split is not needed
+    naccR = doR && !doL ? nacc : 0;
+    if (!serial) {  // creation counts of both edge ranks: natoms and the right rank's first new tag
+      double h[2] = {(double) naccL, (double) naccR};
+      CK(cudaMemcpyAsync(c->red_d, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+      if ((rc = comm_allreduce(c, c->red_d, 2, 0))) return rc;
+      CK(cudaMemcpyAsync(c->red_h, c->red_d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      naccL = (int) c->red_h[0];
+      naccR = (int) c->red_h[1];
+    }
+    rep.usher_rounds = rounds;
     c->fs.ntrials += ntr;
-    c->fs.nrounds += round + 1;
+    c->fs.nrounds += rounds;
     // every trial consumes exactly three draws (ATOM mode, uniform distribution, block region)
     c->fs.rng_seed = ranpark_skip(c->fs.rng_seed, 3LL * ntr);
     if (nacc > 0) {
-      LAUNCH(k_usher_commit, cdiv(nacc, 128), 128, 0, c->cur, nlive, s.maxtag, nlive, c->grid, c->fd,
-             c->tr_d, c->acc_list, nacc, c->extra_head, c->extra_next, c->extra_cell, c->fx, c->fy, c->fz);
-      LAUNCH(k_extra_link, 1, 256, sizeof(int) * nacc, c->extra_cell, nacc, c->extra_head, c->extra_next);
+      const int tag0 = maxtag + ((doR && !doL) ? naccL : 0);
+      LAUNCH(k_usher_commit, cdiv(nacc, 128), 128, 0, c->cur, extras_of(c), tag0, c->grid, c->fd, c->tr_d,
+             c->acc_list, nacc, c->fx, c->fy, c->fz);
+      if ((rc = fix_link_extras(c, c->narr + c->nghost, nacc, false))) return rc;
     }
-    if (trials && maxtrials > 0) {
-      int ncopy = ntr < maxtrials ? ntr : maxtrials;
+    if (trials && maxtrials > 0 && ntr_loc > 0) {
+      int ncopy = ntr_loc < maxtrials ? ntr_loc : maxtrials;
       CK(cudaMemcpyAsync(c->tr_h, c->tr_d, sizeof(obmd_trial) * ncopy, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
       memcpy(trials, c->tr_h, sizeof(obmd_trial) * ncopy);
     }
     CK(cudaGetLastError());
   }
-  c->nextra = nacc;
-  c->n = nlive + nacc;
-  c->fs.ninserted += nacc;
+  c->nins = nacc;
+  c->nextra = c->narr + c->nghost + c->nins;
+  c->n = nlive + c->nextra;
+  const int nacc_all = serial ? nacc : naccL + naccR;
+  c->fs.ninserted += nacc_all;
   rep.ntrials = ntr;
-  rep.naccept = nacc;
-  rep.nlocal = c->n;
+  rep.naccept = nacc_all;
+  rep.nlocal = nlive + c->narr + c->nins;
 
+  struct { double vnewl[3], vnewr[3]; } s;
+  for (int d = 0; d < 3; d++) { s.vnewl[d] = vnewl[d]; s.vnewr[d] = vnewr[d]; }
   // :608-630 flux forces
   const double ly = c->boxhi[1] - c->boxlo[1], lz = c->boxhi[2] - c->boxlo[2];
   const double area = ly * lz;
@@ -1117,7 +1314,7 @@ __device__ __forceinline__ double g_par_global_term(const FixDev &fd, double mas
 // regions.  Fixed grid, grid-stride over the contiguous slot ranges, warp-shuffle + block tree,
 // one partial per block: the final value does not depend on scheduling.
 __global__ void __launch_bounds__(FB_THREADS)
-    k_weight_sums(Planes p, int nsorted, int n, Grid g, FixDev fd, PairTab pt, ForceCfg fc,
+    k_weight_sums(Planes p, Extras ex, Grid g, FixDev fd, PairTab pt, ForceCfg fc,
                   const int *__restrict__ cell_start, double *__restrict__ partials)
 {
   double s[4] = {0, 0, 0, 0};
@@ -1127,11 +1324,12 @@ __global__ void __launch_bounds__(FB_THREADS)
     if (iv < fc.nint) {
       b = cell_start[fc.cxa[iv] * nyz];
       e = cell_start[(fc.cxb[iv] + 1) * nyz];
-    } else {  // atoms inserted after the sort
-      b = nsorted;
-      e = n;
+    } else {  // atoms appended after the sort that this rank owns (arrivals, insertions)
+      b = 0;
+      e = ex.narr + ex.nins;
     }
-    for (int i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) {
+    for (int ii = b + blockIdx.x * blockDim.x + threadIdx.x; ii < e; ii += gridDim.x * blockDim.x) {
+      const int i = (iv < fc.nint) ? ii : extras_slot(ex, 1, ii);
       double x = p.x[i], y = p.y[i], z = p.z[i];
       double m = pt.mass[p.type[i]];
 #pragma unroll
@@ -1161,17 +1359,15 @@ __global__ void __launch_bounds__(FB_THREADS)
 // Pass 2 (reg_force :1414-1428, reg_force_perp :1480-1494): f += F * w / G.  Each block first
 // re-reduces the FB_BLOCKS partials in a fixed order (no extra launch, no atomics).
 __global__ void __launch_bounds__(FB_THREADS)
-    k_apply_forces(Planes p, int nsorted, int n, Grid g, FixDev fd, PairTab pt, ForceCfg fc,
-                   const int *__restrict__ cell_start, const double *__restrict__ partials,
+    k_apply_forces(Planes p, Extras ex, Grid g, FixDev fd, PairTab pt, ForceCfg fc,
+                   const int *__restrict__ cell_start, const double *__restrict__ gsum,
                    double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
                    StepScalars *sc)
 {
   __shared__ double G[4];
   if (threadIdx.x < 4) {
-    double v = 0.0;
-    for (int b = 0; b < FB_BLOCKS; b++) v += partials[b * 4 + threadIdx.x];
-    G[threadIdx.x] = v;
-    if (blockIdx.x == 0) sc->gsum[threadIdx.x] = v;
+    G[threadIdx.x] = gsum[threadIdx.x];
+    if (blockIdx.x == 0) sc->gsum[threadIdx.x] = gsum[threadIdx.x];
   }
   __syncthreads();
   const int nyz = g.ny * g.nz;
@@ -1180,11 +1376,12 @@ __global__ void __launch_bounds__(FB_THREADS)
     if (iv < fc.nint) {
       b = cell_start[fc.cxa[iv] * nyz];
       e = cell_start[(fc.cxb[iv] + 1) * nyz];
-    } else {
-      b = nsorted;
-      e = n;
+    } else {  // atoms appended after the sort that this rank owns (arrivals, insertions)
+      b = 0;
+      e = ex.narr + ex.nins;
     }
-    for (int i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) {
+    for (int ii = b + blockIdx.x * blockDim.x + threadIdx.x; ii < e; ii += gridDim.x * blockDim.x) {
+      const int i = (iv < fc.nint) ? ii : extras_slot(ex, 1, ii);
       double x = p.x[i], y = p.y[i], z = p.z[i];
       double m = pt.mass[p.type[i]];
       double ax = fx[i], ay = fy[i], az = fz[i];
@@ -1208,6 +1405,19 @@ __global__ void __launch_bounds__(FB_THREADS)
   }
 }
 
+// fixed-order sum of the per-CTA partials -> gsum[4] (deterministic, no atomics)
+__global__ void k_weight_final(const double *__restrict__ partials, double *__restrict__ gsum)
+{
+  if (threadIdx.x < 4) {
+    double v = 0.0;
+    for (int b = 0; b < FB_BLOCKS; b++) v += partials[b * 4 + threadIdx.x];
+    gsum[threadIdx.x] = v;
+  }
+}
+
+static void region_cols(const obmd_ctx *c, int r, int margin, int &a, int &e);
+static int merge_intervals(int *lo, int *hi, int n);
+
 int fix_post_force(obmd_ctx *c)
 {
   NEED(c->have_fix, OBMD_ERR_STATE, "obmd_post_force: call obmd_fix_create first");
@@ -1218,52 +1428,41 @@ int fix_post_force(obmd_ctx *c)
   memset(&fc, 0, sizeof(fc));
   const double *F[4] = {fs.momentumForce_left, fs.momentumForce_right, fs.shearForce_left,
                         fs.shearForce_right};
-  const Grid &g = c->grid;
-  int lo[4], hi[4], nr = 0;
+  int lo[4], hi[4], nr = 0, nactive = 0;
   for (int r = 0; r < 4; r++) {
     for (int d = 0; d < 3; d++) fc.F[r][d] = F[r][d];
     fc.active[r] = (F[r][0] != 0.0 || F[r][1] != 0.0 || F[r][2] != 0.0);
     if (!fc.active[r]) continue;
-    const obmd_block &b = c->fd.region[r];
-    int a = (int) floor((b.lo[0] - g.lo[0]) * g.inv[0]) - 1;  // one column of slack for rounding
-    int e = (int) floor((b.hi[0] - g.lo[0]) * g.inv[0]) + 1;
-    a = a < 0 ? 0 : a;
-    e = e > g.nx - 1 ? g.nx - 1 : e;
-    if (e < a) {
-      fc.active[r] = 0;
-      continue;
-    }
+    nactive++;
+    int a, e;
+    region_cols(c, r, 0, a, e);  // local columns; empty when the region misses this slab
+    if (e < a) continue;
     lo[nr] = a;
     hi[nr] = e;
     nr++;
   }
-  if (nr == 0) return OBMD_OK;
-  // merge the column intervals into disjoint ones (insertion sort by lo, then sweep)
-  for (int i = 1; i < nr; i++)
-    for (int k = i; k > 0 && lo[k] < lo[k - 1]; k--) {
-      int t1 = lo[k]; lo[k] = lo[k - 1]; lo[k - 1] = t1;
-      t1 = hi[k]; hi[k] = hi[k - 1]; hi[k - 1] = t1;
-    }
-  fc.nint = 0;
-  for (int i = 0; i < nr; i++) {
-    if (fc.nint > 0 && lo[i] <= fc.cxb[fc.nint - 1] + 1) {
-      if (hi[i] > fc.cxb[fc.nint - 1]) fc.cxb[fc.nint - 1] = hi[i];
-    } else {
-      fc.cxa[fc.nint] = lo[i];
-      fc.cxb[fc.nint] = hi[i];
-      fc.nint++;
-    }
+  if (nactive == 0) return OBMD_OK;  // identical on every rank: the forces are replicated
+  nr = merge_intervals(lo, hi, nr);
+  fc.nint = nr;
+  for (int k = 0; k < nr; k++) {
+    fc.cxa[k] = lo[k];
+    fc.cxb[k] = hi[k];
   }
   if (c->partial_cap < FB_BLOCKS * 4) {
     if (c->partials) cudaFree(c->partials);
     c->partial_cap = FB_BLOCKS * 4 + 1024;
     CK(cudaMalloc(&c->partials, sizeof(double) * c->partial_cap));
   }
-  const int n = c->nsorted + c->nextra;
-  LAUNCH(k_weight_sums, FB_BLOCKS, FB_THREADS, 0, c->cur, c->nsorted, n, c->grid, c->fd, c->pt, fc,
-         c->cell_start, c->partials);
-  LAUNCH(k_apply_forces, FB_BLOCKS, FB_THREADS, 0, c->cur, c->nsorted, n, c->grid, c->fd, c->pt, fc,
-         c->cell_start, c->partials, c->fx, c->fy, c->fz, c->sc_d);
+  const Extras ex = extras_of(c);
+  LAUNCH(k_weight_sums, FB_BLOCKS, FB_THREADS, 0, c->cur, ex, c->grid, c->fd, c->pt, fc, c->cell_start,
+         c->partials);
+  LAUNCH(k_weight_final, 1, 32, 0, c->partials, c->red_d);
+  if (c->nranks > 1) {  // a buffer may span slabs: G is a global sum (fix_obmd_merged.cpp:1305,1378)
+    int rc = comm_allreduce(c, c->red_d, 4, 0);
+    if (rc) return rc;
+  }
+  LAUNCH(k_apply_forces, FB_BLOCKS, FB_THREADS, 0, c->cur, ex, c->grid, c->fd, c->pt, fc, c->cell_start,
+         c->red_d, c->fx, c->fy, c->fz, c->sc_d);
   CK(cudaGetLastError());
   return OBMD_OK;
 }

@@ -113,7 +113,7 @@ __device__ __forceinline__ bool pair_screen(const Planes &p, const PairTab &pt, 
 
 // slot of the g-th atom of a column set (intervals in order, then the inserted atoms); -1 if none
 __device__ __forceinline__ int colrange_slot(const ColRange &cr, int gidx, const Grid &g,
-                                             const int *__restrict__ cell_start, int nsorted, int nextra)
+                                             const int *__restrict__ cell_start, const Extras &ex)
 {
   const int nyz = g.ny * g.nz;
   for (int k = 0; k < cr.n; k++) {
@@ -121,19 +121,19 @@ __device__ __forceinline__ int colrange_slot(const ColRange &cr, int gidx, const
     if (gidx < e - b) return b + gidx;
     gidx -= e - b;
   }
-  if (cr.extras && gidx < nextra) return nsorted + gidx;
-  return -1;
+  return cr.extras ? extras_slot(ex, cr.extras, gidx) : -1;
 }
 
 template <bool SINGLE_TYPE, bool TALLY>
 __global__ void __launch_bounds__(PAIR_T)
-    k_pair_dpd(Planes p, ColRange cr, int nsorted, int nextra, Grid g, PairTab pt,
+    k_pair_dpd(Planes p, ColRange cr, Extras ex, Grid g, PairTab pt,
                const int *__restrict__ cell_start, const int *__restrict__ extra_head,
                const int *__restrict__ extra_next, double *__restrict__ fx, double *__restrict__ fy,
                double *__restrict__ fz, unsigned step, int random_on, double *__restrict__ partials)
 {
   __shared__ int hits[PAIR_HCAP * PAIR_T];
-  const int i = colrange_slot(cr, blockIdx.x * PAIR_T + threadIdx.x, g, cell_start, nsorted, nextra);
+  const int i = colrange_slot(cr, blockIdx.x * PAIR_T + threadIdx.x, g, cell_start, ex);
+  const int nextra = ex.narr + ex.nghost + ex.nins;
   int *myhits = hits + threadIdx.x;
   PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (i >= 0) {
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(PAIR_T)
             int bz = cz + oz;
             bz = bz < 0 ? bz + g.nz : (bz >= g.nz ? bz - g.nz : bz);
             for (int e = extra_head[row + bz]; e >= 0; e = extra_next[e]) {
-              int j = nsorted + e;
+              int j = ex.base + e;
               if (j == i) continue;
               if (pair_screen<SINGLE_TYPE>(p, pt, g, j, a))
                 pair_eval<SINGLE_TYPE, TALLY>(p, pt, g, j, a, step, random_on != 0, acc);
@@ -244,7 +244,7 @@ ColRange all_columns(const obmd_ctx *c)
   ColRange cr;
   cr.n = 1;
   cr.a[0] = 0;
-  cr.b[0] = c->grid.nx - 1;
+  cr.b[0] = c->grid.nx - 1;  // ghost columns hold no sorted atoms, so this is every sorted atom
   cr.a[1] = cr.b[1] = 0;
   cr.extras = 1;
   return cr;
@@ -255,7 +255,7 @@ static int colrange_bound(const obmd_ctx *c, const ColRange &cr)
 {
   long long cols = 0;
   for (int k = 0; k < cr.n; k++) cols += cr.b[k] - cr.a[k] + 1;
-  if (cols >= c->grid.nx) return c->nsorted + (cr.extras ? c->nextra : 0);
+  (void) cols;
   // no per-column counts on the host: launch for every sorted atom, surplus threads exit at once
   return c->nsorted + (cr.extras ? c->nextra : 0);
 }
@@ -274,7 +274,7 @@ static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &
     CK(cudaMalloc(&c->partials, sizeof(double) * c->partial_cap));
   }
 #define PAIR_ARGS                                                                             \
-  c->cur, cr, c->nsorted, c->nextra, c->grid, c->pt, c->cell_start, c->extra_head, c->extra_next, \
+  c->cur, cr, extras_of(c), c->grid, c->pt, c->cell_start, c->extra_head, c->extra_next,          \
       c->fx, c->fy, c->fz, (unsigned) step, random_on, c->partials
   if (single && !tally) LAUNCH_ON(st, (k_pair_dpd<true, false>), nb, PAIR_T, 0, PAIR_ARGS);
   else if (single && tally) LAUNCH_ON(st, (k_pair_dpd<true, true>), nb, PAIR_T, 0, PAIR_ARGS);

@@ -1,0 +1,123 @@
+"""Slab-decomposition check, launched as
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 tests/mgpu_check.py
+Every rank owns an x-slab of a tiled box; rank 0 additionally runs the same system on one GPU
+(serial context) and compares: setup forces by tag (1e-9), a deletion-only run (T = 0, deterministic:
+positions by tag 1e-9, same atoms deleted), and a steady-exchange run (atom count, insertion and
+deletion totals within statistical bounds; tags unique across ranks)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+import common_cases as cc  # noqa: E402
+import obmd_b200 as ob  # noqa: E402
+
+
+def make_slab_sim(box, x, v, tag, rank, world, **kw):
+    sim = cc.device_sim(box, device=rank, **kw)
+    uid = [ob.ObmdB200.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    sim.comm_init(rank, world, uid[0])
+    lo, hi = sim.comm_slab()
+    last = rank == world - 1
+    mine = (x[:, 0] >= lo) & ((x[:, 0] < hi) | (last & (x[:, 0] <= box[0, 1])))
+    sim.upload(x[mine], v[mine], np.ones(int(mine.sum()), np.int32), tag[mine], capacity=int(1.5 * mine.sum()) + 50000)
+    return sim, mine
+
+
+def gather_by_tag(sim, keys=("x", "v", "f", "tag")):
+    out = sim.download(keys)
+    objs = [None] * dist.get_world_size()
+    dist.all_gather_object(objs, out)
+    tags = np.concatenate([o["tag"] for o in objs])
+    order = np.argsort(tags)
+    return {k: np.concatenate([o[k] for o in objs])[order] for k in keys}, tags
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo")
+    reps = (2 * world, 1, 1)
+    tag, x, box = cc.tiled(reps)
+    rng = np.random.default_rng(5)
+    v = rng.normal(0, 1, x.shape)
+    B = 0.15 * 33.59462486002239          # fixed physical buffer: fits inside the edge slabs
+    ok = True
+
+    # ---- 1. setup forces, T = 0 -------------------------------------------------------
+    kw = dict(temperature=0.0, alpha=0.7, nbuf=float(int(0.7 * 0.15 * 12637 * 2)), buffer_size=B)
+    sim, mine = make_slab_sim(box, x, v, tag, rank, world, **kw)
+    sim.setup(0)
+    got, tags = gather_by_tag(sim)
+    if rank == 0:
+        ref = cc.device_sim(box, device=0, **kw)
+        ref.upload(x, v, np.ones(len(x), np.int32), tag)
+        ref.setup(0)
+        r = ref.download(("f", "tag"))
+        o = np.argsort(r["tag"])
+        err = cc.mixed_rel_err(got["f"], r["f"][o])
+        print("setup: atoms %d, force err %.3e" % (len(tags), err))
+        ok &= len(tags) == len(x) and err < 1e-9
+    # ---- 2. deletion-only dynamics, deterministic ---------------------------------------
+    nsteps = 30
+    sim.run(1, nsteps)
+    got, tags = gather_by_tag(sim)
+    if rank == 0:
+        ref.run(1, nsteps)
+        r = ref.download(("x", "v", "tag"))
+        o = np.argsort(r["tag"])
+        same = len(tags) == len(o) and np.array_equal(np.sort(tags), r["tag"][o])
+        dx = np.abs(got["x"] - r["x"][o]).max() if same else np.inf
+        st = ref.fix_state()
+        print("run: atoms %d (serial %d), deleted %d, max |dx| %.3e" % (len(tags), len(o), st.ndeleted, dx))
+        ok &= same and dx < 1e-8 and st.ndeleted > 0
+        ref.close()
+    ms = sim.fix_state()
+    sim.close()
+    # ---- 3. steady exchange (USHER on the edge ranks) ----------------------------------------
+    n = len(x)
+    kw = dict(alpha=1.0, nbuf=float(int(0.15 * 12637)), buffer_size=B)
+    sim, mine = make_slab_sim(box, x, np.zeros_like(x), tag, rank, world, **kw)
+    sim.setup(0)
+    sim.run(1, 150)
+    got, tags = gather_by_tag(sim, ("x", "tag"))
+    st = sim.fix_state()
+    k = sim.kinetic()
+    tot = torch.tensor([k[0], k[4]], dtype=torch.float64)
+    dist.all_reduce(tot)
+    if rank == 0:
+        ref = cc.device_sim(box, device=0, **kw)
+        ref.upload(x, np.zeros_like(x), np.ones(n, np.int32), tag, capacity=2 * n)
+        ref.setup(0)
+        ref.run(1, 150)
+        rs = ref.fix_state()
+        rk = ref.kinetic()
+        T = tot[0].item() / (3 * tot[1].item()); Tr = rk[0] / (3 * rk[4])
+        print("R1: atoms %d (serial %d) inserted %d (%d) deleted %d (%d) T %.4f (%.4f) unique tags %s"
+              % (len(tags), int(rk[4]), st.ninserted, rs.ninserted, st.ndeleted, rs.ndeleted, T, Tr,
+                 len(np.unique(tags)) == len(tags)))
+        ok &= len(np.unique(tags)) == len(tags) and int(tot[1].item()) == len(tags)
+        ok &= abs(st.ninserted - rs.ninserted) < 0.25 * max(rs.ninserted, 40)
+        ok &= abs(st.ndeleted - rs.ndeleted) < 0.25 * max(rs.ndeleted, 40)
+        ok &= abs(T - Tr) < 0.03
+        ok &= np.all((got["x"][:, 0] >= 0) & (got["x"][:, 0] <= box[0, 1]))
+        ref.close()
+    sim.comm_finalize()
+    sim.close()
+    flag = torch.tensor([1 if ok else 0])
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MGPU_CHECK", "PASS" if ok else "FAIL")
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
