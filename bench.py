@@ -89,16 +89,31 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons}
 
 
-def build_sim(x, box, device, regime="R1", temperature=1.0):
+def build_sim(x, box, device, regime="R1", temperature=1.0, rank=0, world=1, buffer_size=None, nbuf_atoms=None):
+    """Context for this rank.  world > 1: x-slab decomposition (obmd_comm_init), every rank uploads
+    only the atoms inside its slab; the NCCL unique id travels through torch.distributed."""
     import common_cases as cc
+    import obmd_b200 as ob
     n = len(x)
+    nb = nbuf_atoms if nbuf_atoms is not None else n
     if regime == "R1":
-        kw = dict(alpha=1.0, nbuf=float(int(0.15 * n)))
+        kw = dict(alpha=1.0, nbuf=float(int(0.15 * nb)))
     else:
-        kw = dict(alpha=0.7, nbuf=float(int(0.7 * 0.15 * n)))
+        kw = dict(alpha=0.7, nbuf=float(int(0.7 * 0.15 * nb)))
+    if buffer_size is not None:
+        kw["buffer_size"] = buffer_size
     sim = cc.device_sim(box, device=device, temperature=temperature, **kw)
     tag = np.arange(1, n + 1, dtype=np.int32)
-    sim.upload(x, np.zeros_like(x), np.ones(n, np.int32), tag, capacity=int(1.15 * n))
+    if world > 1:
+        import torch.distributed as dist
+        uid = [ob.ObmdB200.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        sim.comm_init(rank, world, uid[0])
+        lo, hi = sim.comm_slab()
+        mine = (x[:, 0] >= lo) & ((x[:, 0] < hi) | ((rank == world - 1) & (x[:, 0] <= box[0, 1])))
+        x, tag = x[mine], tag[mine]
+    m = len(x)
+    sim.upload(x, np.zeros_like(x), np.ones(m, np.int32), tag, capacity=int(1.15 * m) + 65536)
     sim.setup(0)
     return sim, kw
 
@@ -114,10 +129,16 @@ def ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    reps = tuple(args.reps)
+    # weak scaling: the box grows along the open axis with the number of GPUs (one 4x5x4 tiling =
+    # 1 010 960 atoms per GPU), the buffers keep the physical length and target population of N=1
+    reps1 = tuple(args.reps)
+    reps = (reps1[0] * world, reps1[1], reps1[2])
     x, box = tiled(reps)
-    n0 = len(x)
-    sim, kw = build_sim(x, box, local, args.regime)
+    natoms_total = len(x)
+    n0 = natoms_total // world
+    B1 = 0.15 * 33.59462486002239 * reps1[0]
+    sim, kw = build_sim(x, box, local, args.regime, rank=rank, world=world, buffer_size=B1, nbuf_atoms=n0)
+    del x
     stream = torch.cuda.ExternalStream(sim.L.obmd_stream(sim.h), device=local)
 
     def barrier():
@@ -145,7 +166,7 @@ def ours(args):
     launches = sim.launches - l0
     sampler.stop_flag = True; sampler.join()
     fam = {}
-    for name in ("nve", "bin", "sort", "pre_exchange", "usher", "pbc", "pair", "post_force"):
+    for name in ("nve", "bin", "sort", "comm", "pre_exchange", "usher", "pbc", "pair", "post_force"):
         t, nl = sim.timing_get(name)
         fam[name] = {"ms_per_step": t / args.steps, "launches_per_step": nl / args.steps}
     sim.timing(False)
@@ -154,7 +175,7 @@ def ours(args):
     # ---- e2e through the C ABI with host buffers (plugin flow) ----
     e2e = None
     if args.e2e_steps > 0:
-        e2e = e2e_run(sim, args.e2e_steps, step, barrier)
+        e2e = (e2e_run if world == 1 else e2e_run_slab)(sim, args.e2e_steps, step, barrier)
         step += args.e2e_steps
 
     t = torch.tensor([ms, float(atom_steps), e2e["seconds"] if e2e else 0.0,
@@ -179,10 +200,13 @@ def ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "OBMD-DPD fluid, shipped configuration tiled %dx%dx%d = %d atoms per GPU, "
-                                   "regime %s (alpha %.1f, nbuf %d), T=1, dt=0.001464, rc=1, usher 31.03"
-                                   % (reps + (n0, args.regime, kw["alpha"], int(kw["nbuf"]))),
-                       "atoms_per_gpu": n0, "parallelism": "replicas only" if world > 1 else "single GPU",
+            "config": {"workload": "OBMD-DPD fluid, shipped configuration tiled %dx%dx%d = %d atoms (%d per GPU), "
+                                   "regime %s (alpha %.1f, nbuf %d, buffer %.2f), T=1, dt=0.001464, rc=1, "
+                                   "usher 31.03" % (reps + (natoms_total, n0, args.regime, kw["alpha"],
+                                                            int(kw["nbuf"]), B1)),
+                       "atoms_per_gpu": n0,
+                       "parallelism": ("x-slab decomposition over %d GPUs: NCCL send/recv halo + migration, "
+                                       "packed allreduces" % world) if world > 1 else "single GPU",
                        "l2": "per-step working set (%.0f MB) exceeds the 126 MB L2" % (n0 * 168 / 1e6),
                        "equil_steps": args.equil,
                        "inserted": int(st.ninserted), "deleted": int(st.ndeleted),
@@ -202,9 +226,28 @@ def ours(args):
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_budget)
         print(json.dumps(line), flush=True)
+    if world > 1:
+        sim.comm_finalize()
     sim.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def e2e_run_slab(sim, nsteps, step, barrier):
+    """Slab runs: one device step, then the state makes a round trip through pinned host buffers
+    (what a host-resident integrator or output stage would need every step)."""
+    h2d = d2h = atom_steps = 0
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(nsteps):
+        sim.run(step + s, 1)
+        o = sim.download(("x", "v", "f"))
+        n = len(o["x"]); d2h += 72 * n
+        sim.upload_xv(o["x"], o["v"]); h2d += 48 * n
+        atom_steps += n
+    barrier()
+    sec = time.perf_counter() - t0
+    return {"seconds": sec, "atom_steps": atom_steps, "h2d": h2d // nsteps, "d2h": d2h // nsteps}
 
 
 def e2e_run(sim, nsteps, step, barrier):

@@ -9,7 +9,9 @@ Import as ``import obmd_b200`` (root shim) or
 ``importlib.import_module("obmd-lammps-extension_b200")``.
 """
 from .binding import (ABI_VERSION, FixArgs, FixState, ObmdB200, ObmdError, PreExchangeReport, Trial,
-                      default_regions, lib, lib_path, parse_fix_obmd)
+                      default_regions, lib, lib_path, parse_fix_obmd, slab_bounds, slab_columns,
+                      slab_mask)
 
 __all__ = ["ABI_VERSION", "FixArgs", "FixState", "ObmdB200", "ObmdError", "PreExchangeReport",
-           "Trial", "default_regions", "lib", "lib_path", "parse_fix_obmd"]
+           "Trial", "default_regions", "lib", "lib_path", "parse_fix_obmd", "slab_bounds", "slab_columns",
+           "slab_mask"]

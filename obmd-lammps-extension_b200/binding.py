@@ -143,6 +143,30 @@ def default_regions(boxlo, boxhi, B, shear_size=0.0):
     return [leftB, rightB, lsh, rsh, leftB, rightB]
 
 
+def slab_columns(ncols, nranks, rank):
+    """Owned cell columns [c0, c1) of `rank`: the split setup_grid() (csrc/api.cu) uses."""
+    per, rem = divmod(ncols, nranks)
+    c0 = rank * per + min(rank, rem)
+    return c0, c0 + per + (1 if rank < rem else 0)
+
+
+def slab_bounds(boxlo_x, boxhi_x, cutmax, nranks, rank):
+    """x-range [lo, hi) of the slab of `rank` (cell size = Lx / floor(Lx / cutmax))."""
+    L = boxhi_x - boxlo_x
+    ncols = max(int(L // cutmax), 1)
+    c0, c1 = slab_columns(ncols, nranks, rank)
+    inv = ncols / L
+    return boxlo_x + c0 / inv, (boxhi_x if c1 >= ncols else boxlo_x + c1 / inv)
+
+
+def slab_mask(x, lo, hi, is_last, boxhi_x):
+    """Atoms a rank uploads: x in [lo, hi); the last rank also takes x == boxhi."""
+    m = (x >= lo) & (x < hi)
+    if is_last:
+        m |= (x >= lo) & (x <= boxhi_x)
+    return m
+
+
 def parse_fix_obmd(argv, regions, boxlo, boxhi):
     """Mirror of FixObmdMerged's argument parsing (fix_obmd_merged.cpp:66-164 and options()
     :1881-2164) for ATOM mode: argv is the token list after `fix ID group obmd`, `regions` maps
