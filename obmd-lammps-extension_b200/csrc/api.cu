@@ -71,6 +71,7 @@ extern "C" int obmd_create(obmd_ctx **out, int device)
   memset(&c->cur, 0, sizeof(Planes));
   memset(&c->alt, 0, sizeof(Planes));
   for (int t = 0; t <= MAXT; t++) c->mass[t] = 0.0;
+  if (const char *e2 = getenv("OBMD_B200_OVERLAP")) c->overlap = atoi(e2) != 0;
   snprintf(c->err, sizeof(c->err), "no error");
   *out = c;
   return OBMD_OK;
@@ -95,6 +96,7 @@ extern "C" void obmd_destroy(obmd_ctx *c)
   cudaFree(c->cid); cudaFree(c->rank); cudaFree(c->perm);
   cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->scan_tmp);
   cudaFree(c->extra_head); cudaFree(c->extra_next); cudaFree(c->extra_cell);
+  cudaFree(c->spec_head); cudaFree(c->spec_next); cudaFree(c->spec_cell);
   cudaFree(c->stage_d); cudaFree(c->stage_i);
   cudaFree(c->sc_d); cudaFreeHost(c->sc_h);
   cudaFree(c->red_d); cudaFreeHost(c->red_h);
@@ -104,6 +106,7 @@ extern "C" void obmd_destroy(obmd_ctx *c)
   cudaFree(c->tr_list); cudaFree(c->tr_changed); cudaFree(c->acc_list); cudaFree(c->tr_bbox);
   if (c->tr_h) cudaFreeHost(c->tr_h);
   cudaFree(c->partials);
+  cudaFree(c->redo_flag); cudaFree(c->redo_list); cudaFree(c->redo_count);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   for (auto &p : c->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -209,6 +212,7 @@ extern "C" int obmd_pair_init(obmd_ctx *c, double boltz)
       pt.gamma[j][i] = pt.gamma[i][j];
       pt.sigma[j][i] = pt.sigma[i][j];
       pt.cutsq[i][j] = pt.cutsq[j][i] = pt.cut[i][j] * pt.cut[i][j];
+      pt.cutinv[i][j] = pt.cutinv[j][i] = 1.0 / pt.cut[i][j];
       if (pt.cut[i][j] > pt.cutmax) pt.cutmax = pt.cut[i][j];
     }
   for (int t = 0; t <= MAXT; t++) pt.mass[t] = c->mass[t];
@@ -255,13 +259,16 @@ int setup_grid(obmd_ctx *c)
   g.ncell = g.nx * nn[1] * nn[2];
   if (g.ncell + 6 > c->cell_cap) {
     cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->scan_tmp); cudaFree(c->extra_head);
+    cudaFree(c->spec_head);
     c->cell_cap = g.ncell + 6;
+    CK(cudaMalloc(&c->spec_head, sizeof(int) * c->cell_cap));
     CK(cudaMalloc(&c->cell_count, sizeof(int) * c->cell_cap));
     CK(cudaMalloc(&c->cell_start, sizeof(int) * c->cell_cap));
     CK(cudaMalloc(&c->scan_tmp, sizeof(int) * (c->cell_cap / 4096 + 2)));
     CK(cudaMalloc(&c->extra_head, sizeof(int) * c->cell_cap));
   }
   LAUNCH(k_fill_int, cdiv(c->cell_cap, 256), 256, 0, c->extra_head, c->cell_cap, -1);
+  LAUNCH(k_fill_int, cdiv(c->cell_cap, 256), 256, 0, c->spec_head, c->cell_cap, -1);
   CK(cudaStreamSynchronize(c->stream));
   c->nextra = c->narr = c->nghost = c->nins = 0;
   c->cells_valid = false;
@@ -610,50 +617,58 @@ extern "C" int obmd_comm_slab(const obmd_ctx *c, double *lo, double *hi)
   return OBMD_OK;
 }
 
+// launched from inside fix_pre_exchange, right after USHER round 0 has been enqueued
+static int pair_on_side_stream(obmd_ctx *c)
+{
+  CK(cudaEventRecord(c->ev_sorted, c->stream));
+  CK(cudaStreamWaitEvent(c->stream2, c->ev_sorted, 0));
+  int rc = pair_compute_cols(c, c->hook_step, all_columns(c), c->stream2);
+  if (rc) return rc;
+  CK(cudaEventRecord(c->ev_int, c->stream2));
+  return OBMD_OK;
+}
+
 extern "C" int obmd_run(obmd_ctx *c, long long first_step, int nsteps)
 {
   NEED(c, OBMD_ERR_ARG, "NULL context");
   NEED(c->have_fix && c->pair_ready, OBMD_ERR_STATE, "obmd_run: pair style and fix must be initialised");
   int rc;
-  ColRange ipbc, ipair, opbc, opair;
-  const bool ov = c->overlap && c->nranks == 1 && fix_zones(c, ipbc, ipair, opbc, opair);
   for (int s = 0; s < nsteps; s++) {  // verlet.cpp:229-363
+    const long long step = first_step + s;
     if ((rc = fix_nve_initial(c))) return rc;
     fix_clear_extras(c);
     if ((rc = obmd_ensure_capacity(c, c->n + c->n / 32 + 4096))) return rc;
     if ((rc = cells_build(c))) return rc;
     if (c->nranks > 1) {
       // slab run: deletion sums first (the arrivals reuse the parked slots), then migration + halo
-      // (Comm::exchange / borders), then the rest of pre_exchange with the ghosts in place
+      // (Comm::exchange / borders); the rest of pre_exchange sees the ghosts
       if ((rc = fix_pre_begin(c))) return rc;
       if ((rc = comm_exchange(c))) return rc;
-      if ((rc = fix_pre_exchange(c, nullptr, 0))) return rc;
-      if ((rc = fix_pbc(c))) return rc;
-      if ((rc = pair_compute(c, first_step + s, 0, 0))) return rc;
-      if ((rc = fix_post_force(c))) return rc;
-      if ((rc = fix_compact_extras(c))) return rc;
-      if ((rc = fix_nve_final(c))) return rc;
-      continue;
     }
-    if (ov) {
-      // The interior (columns pre_exchange never reads) is wrapped and its pair forces are
-      // computed on the side stream while the main stream runs the latency-bound USHER rounds.
-      CK(cudaEventRecord(c->ev_sorted, c->stream));
-      CK(cudaStreamWaitEvent(c->stream2, c->ev_sorted, 0));
-      if ((rc = fix_pbc_cols(c, ipbc, c->stream2))) return rc;
-      if ((rc = pair_compute_cols(c, first_step + s, ipair, c->stream2))) return rc;
-      CK(cudaEventRecord(c->ev_int, c->stream2));
-      if ((rc = fix_pre_exchange(c, nullptr, 0))) return rc;
-      if ((rc = fix_pbc_cols(c, opbc, c->stream))) return rc;
+    if (c->overlap) {
+      // PairDPD for every atom this rank owns runs on the side stream.  It starts right behind
+      // USHER round 0 (which fills the machine by itself) and overlaps the re-run rounds, which are
+      // a handful of latency-bound CTAs.  The pair kernel wraps coordinates on the fly, so it does
+      // not need Domain::pbc first; atoms next to an insertion are recomputed afterwards
+      // (fix_redo_pair_near_insertions).
+      c->hook_step = step;
+      c->round0_hook = pair_on_side_stream;
+      c->commit_wait = c->ev_int;
+      rc = fix_pre_exchange(c, nullptr, 0);
+      c->commit_wait = nullptr;
+      if (rc) return rc;
+      NEED(c->round0_hook == nullptr, OBMD_ERR_STATE, "obmd_run: side-stream pair launch was skipped");
       CK(cudaStreamWaitEvent(c->stream, c->ev_int, 0));
-      if ((rc = pair_compute_cols(c, first_step + s, opair, c->stream))) return rc;
+      if ((rc = fix_pbc(c))) return rc;
+      if ((rc = fix_redo_pair_near_insertions(c, step))) return rc;
       c->forces_valid = true;
     } else {
       if ((rc = fix_pre_exchange(c, nullptr, 0))) return rc;
       if ((rc = fix_pbc(c))) return rc;
-      if ((rc = pair_compute(c, first_step + s, 0, 0))) return rc;
+      if ((rc = pair_compute(c, step, 0, 0))) return rc;
     }
     if ((rc = fix_post_force(c))) return rc;
+    if ((rc = fix_compact_extras(c))) return rc;
     if ((rc = fix_nve_final(c))) return rc;
   }
   CK(cudaStreamSynchronize(c->stream));

@@ -46,7 +46,7 @@ struct Extras {
 struct PairTab {
   int ntypes;
   double a0[MAXT + 1][MAXT + 1], gamma[MAXT + 1][MAXT + 1], sigma[MAXT + 1][MAXT + 1];
-  double cut[MAXT + 1][MAXT + 1], cutsq[MAXT + 1][MAXT + 1];
+  double cut[MAXT + 1][MAXT + 1], cutsq[MAXT + 1][MAXT + 1], cutinv[MAXT + 1][MAXT + 1];
   double cutmax;
   double dtinvsqrt;
   unsigned seed;
@@ -90,6 +90,11 @@ struct obmd_ctx {
   cudaStream_t stream = nullptr;   // main stream (high priority): everything the fix orders
   cudaStream_t stream2 = nullptr;  // side stream: interior pbc + PairDPD overlapped with USHER
   cudaEvent_t ev_sorted = nullptr, ev_int = nullptr;
+  cudaEvent_t commit_wait = nullptr;  // if set, pre_exchange waits for it before it links new atoms
+  int (*round0_hook)(obmd_ctx *) = nullptr;  // called once, right after USHER round 0 is enqueued
+  long long hook_step = 0;
+  int *redo_flag = nullptr, *redo_list = nullptr, *redo_count = nullptr;  // pair recompute near insertions
+  int redo_cap = 0, redo_list_cap = 0;
   bool overlap = true;
   char err[1024] = {0};
   long long launches = 0;
@@ -168,6 +173,7 @@ struct obmd_ctx {
   int *tr_list = nullptr;           // trials to evaluate this round
   int *tr_changed = nullptr;        // changed flags
   int *acc_list = nullptr;          // compacted accepted trial ids of the previous round
+  int *spec_head = nullptr, *spec_next = nullptr, *spec_cell = nullptr;  // their per-cell lists
   double *partials = nullptr;       // block partial sums for deterministic reductions
   int partial_cap = 0;
   // last pre_exchange report
@@ -245,6 +251,8 @@ int obmd_ensure_capacity(obmd_ctx *c, int cap);
 int cells_build(obmd_ctx *c);                                   // cells.cu
 int pair_compute(obmd_ctx *c, long long step, int eflag, int vflag);  // pair.cu
 int pair_compute_cols(obmd_ctx *c, long long step, const ColRange &cr, cudaStream_t st);
+int pair_compute_list(obmd_ctx *c, long long step, const int *slot_list, const int *slot_count, int slot_max);
+int fix_redo_pair_near_insertions(obmd_ctx *c, long long step);
 int fix_pbc_cols(obmd_ctx *c, const ColRange &cr, cudaStream_t st);
 ColRange all_columns(const obmd_ctx *c);
 ColRange fix_region_columns(const obmd_ctx *c, int r0, int r1, int margin);

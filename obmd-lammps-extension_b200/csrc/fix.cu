@@ -349,8 +349,8 @@ __device__ __forceinline__ double ranpark_uniform(int &seed)
 struct WarpHits {
   int key[USH_CAP];   // LAMMPS local index of the contributing atom
   int tj[USH_CAP];    // its type
-  double e[USH_CAP], fx[USH_CAP], fy[USH_CAP], fz[USH_CAP];  // pass A: rsq, del; pass B: phi, f
-  int skey[USH_CAP];  // rank-sorted order: slot -> source
+  double e[USH_CAP], fx[USH_CAP], fy[USH_CAP], fz[USH_CAP];  // pass A: rsq, del
+  double se[USH_CAP + 4], sfx[USH_CAP + 4], sfy[USH_CAP + 4], sfz[USH_CAP + 4];  // phi, f by rank
   int cand[USH_CAND]; // storage slots of the atoms in the 27 stencil cells
 };
 
@@ -404,7 +404,8 @@ __device__ void usher_energy(const double c[3], int t, const Planes &p, const Gr
                              const FixDev &fd, const int *__restrict__ cell_start, const UsherCfg &u,
                              const int *__restrict__ acc_list, const obmd_trial *__restrict__ prev,
                              const Extras &ex, const int *__restrict__ extra_head,
-                             const int *__restrict__ extra_next, WarpHits &H, StepScalars *sc, double &E,
+                             const int *__restrict__ extra_next, const int *__restrict__ spec_head,
+                             const int *__restrict__ spec_next, WarpHits &H, StepScalars *sc, double &E,
                              double f[3])
 {
   const int lane = threadIdx.x & 31;
@@ -421,11 +422,18 @@ __device__ void usher_energy(const double c[3], int t, const Planes &p, const Gr
     int ox = lane / 9 - 1, oy = (lane / 3) % 3 - 1, oz = lane % 3 - 1;
     int bx = cx + ox;
     if (bx >= 0 && bx < g.nx) {
-      cc = (bx * g.ny + cell_wrap(cy + oy, g.ny)) * g.nz + cell_wrap(cz + oz, g.nz);
+      int by = cy + oy, bz = cz + oz;  // offsets are +-1: wrap without a division
+      by = by < 0 ? by + g.ny : (by >= g.ny ? by - g.ny : by);
+      bz = bz < 0 ? bz + g.nz : (bz >= g.nz ? bz - g.nz : bz);
+      cc = (bx * g.ny + by) * g.nz + bz;
       jb = cell_start[cc];
       cnt = cell_start[cc + 1] - jb;
       if (have_extras)
         for (int e = extra_head[cc]; e >= 0; e = extra_next[e]) cex++;
+      // atoms accepted by earlier trials of this call (previous round's state) live in their own
+      // per-cell lists, so a point only ever sees the few that share its stencil
+      if (u.nacc_prev > 0)
+        for (int e = spec_head[cc]; e >= 0; e = spec_next[e]) cex += (acc_list[e] < t);
     }
   }
   int off = cnt + cex;
@@ -442,89 +450,106 @@ __device__ void usher_energy(const double c[3], int t, const Planes &p, const Gr
     for (int k = 0; k < cnt; k++) H.cand[off + k] = jb + k;
     if (cex) {
       int k = cnt;
-      for (int e = extra_head[cc]; e >= 0; e = extra_next[e]) H.cand[off + k++] = ex.base + e;
+      if (have_extras)
+        for (int e = extra_head[cc]; e >= 0; e = extra_next[e]) H.cand[off + k++] = ex.base + e;
+      if (u.nacc_prev > 0)
+        for (int e = spec_head[cc]; e >= 0; e = spec_next[e])
+          if (acc_list[e] < t) H.cand[off + k++] = -(e + 1);
     }
   }
   __syncwarp();
   const int nc = ncand > USH_CAND ? 0 : ncand;
-  // pass A over the stencil atoms: cheap screen, hits compacted into the warp's list
-  for (int q0 = 0; q0 < nc; q0 += 32) {
-    int q = q0 + lane;
-    bool hit = false;
-    double rsq = 0, dx = 0, dy = 0, dz = 0;
-    int key = 0, tj = 0;
-    if (q < nc) {
-      int j = H.cand[q];
-      tj = p.type[j];
-      key = p.lidx[j];
-      hit = usher_screen(c, p.x[j], p.y[j], p.z[j], it, tj, g, pt, rsq, dx, dy, dz);
-    }
-    unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (hit) {
-      int s2 = nh + __popc(m & lt);
-      if (s2 < USH_CAP) {
-        H.key[s2] = key;
-        H.tj[s2] = tj;
-        H.e[s2] = rsq;
-        H.fx[s2] = dx;
-        H.fy[s2] = dy;
-        H.fz[s2] = dz;
+  // pass A over the stencil atoms: cheap screen, hits compacted into the warp's list.  Three
+  // candidates per lane per trip (96 covers the usual 81), all loads issued before the first use,
+  // so a trip costs one global round trip instead of three.
+  for (int q0 = 0; q0 < nc; q0 += 96) {
+    double xj[3], yj[3], zj[3];
+    int key[3], tj[3];
+    bool val[3];
+#pragma unroll
+    for (int u2 = 0; u2 < 3; u2++) {
+      const int q = q0 + 32 * u2 + lane;
+      val[u2] = q < nc;
+      key[u2] = 0;
+      tj[u2] = it;
+      xj[u2] = yj[u2] = zj[u2] = 0.0;
+      if (val[u2]) {
+        const int j = H.cand[q];
+        if (j >= 0) {
+          tj[u2] = p.type[j];
+          key[u2] = p.lidx[j];
+          xj[u2] = p.x[j];
+          yj[u2] = p.y[j];
+          zj[u2] = p.z[j];
+        } else {  // created earlier in this call: local index nbase + rank in the accepted list
+          const int e = -j - 1;
+          const obmd_trial &a = prev[acc_list[e]];
+          tj[u2] = fd.ntype;
+          key[u2] = u.nbase + e;
+          xj[u2] = a.end[0];
+          yj[u2] = a.end[1];
+          zj[u2] = a.end[2];
+        }
       }
     }
-    nh += __popc(m);
-  }
-  // ... and over the atoms created by earlier trials of this call (local indices nbase + rank)
-  for (int k0 = 0; k0 < u.nacc_prev; k0 += 32) {
-    int k = k0 + lane;
-    bool hit = false;
-    double rsq = 0, dx = 0, dy = 0, dz = 0;
-    if (k < u.nacc_prev) {
-      int tp = acc_list[k];
-      if (tp < t) {
-        const obmd_trial &q = prev[tp];
-        hit = usher_screen(c, q.end[0], q.end[1], q.end[2], it, fd.ntype, g, pt, rsq, dx, dy, dz);
+#pragma unroll
+    for (int u2 = 0; u2 < 3; u2++) {
+      if (q0 + 32 * u2 >= nc) break;  // warp-uniform
+      double rsq = 0, dx = 0, dy = 0, dz = 0;
+      bool hit = val[u2] && usher_screen(c, xj[u2], yj[u2], zj[u2], it, tj[u2], g, pt, rsq, dx, dy, dz);
+      unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        int s2 = nh + __popc(m & lt);
+        if (s2 < USH_CAP) {
+          H.key[s2] = key[u2];
+          H.tj[s2] = tj[u2];
+          H.e[s2] = rsq;
+          H.fx[s2] = dx;
+          H.fy[s2] = dy;
+          H.fz[s2] = dz;
+        }
       }
+      nh += __popc(m);
     }
-    unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (hit) {
-      int s = nh + __popc(m & lt);
-      if (s < USH_CAP) {
-        H.key[s] = u.nbase + k;
-        H.tj[s] = fd.ntype;
-        H.e[s] = rsq;
-        H.fx[s] = dx;
-        H.fy[s] = dy;
-        H.fz[s] = dz;
-      }
-    }
-    nh += __popc(m);
   }
   if (nh > USH_CAP) {
     if (lane == 0) sc->usher_error = OBMD_ERR_CAPACITY;
     nh = USH_CAP;
   }
   __syncwarp();
-  // pass B (dense: usually a single sweep) + rank sort by key (keys are distinct local indices)
+  // pass B (dense: usually a single sweep): PairDPD::single, then each contribution is stored at
+  // its rank by local index (keys are distinct), zero-padded to a multiple of four
   for (int s = lane; s < nh; s += 32) {
     double e, fx = H.fx[s], fy = H.fy[s], fz = H.fz[s];
     usher_single(it, H.tj[s], pt, H.e[s], e, fx, fy, fz);
-    H.e[s] = e;
-    H.fx[s] = fx;
-    H.fy[s] = fy;
-    H.fz[s] = fz;
     int k = H.key[s], r = 0;
     for (int q = 0; q < nh; q++) r += (H.key[q] < k);
-    H.skey[r] = s;
+    H.se[r] = e;
+    H.sfx[r] = fx;
+    H.sfy[r] = fy;
+    H.sfz[r] = fz;
+  }
+  const int nh4 = (nh + 3) & ~3;
+  if (lane < nh4 - nh) {
+    H.se[nh + lane] = 0.0;
+    H.sfx[nh + lane] = 0.0;
+    H.sfy[nh + lane] = 0.0;
+    H.sfz[nh + lane] = 0.0;
   }
   __syncwarp();
+  // left-to-right sums in ascending local index (the reference's loop order, :1790-1807); adding
+  // the +0.0 padding is exact, and four elements per trip keep the loads ahead of the add chains
   double Es = 0.0, f0 = 0.0, f1 = 0.0, f2 = 0.0;
   if (lane == 0) {
-    for (int r = 0; r < nh; r++) {
-      int s = H.skey[r];
-      Es += H.e[s];
-      f0 += H.fx[s];
-      f1 += H.fy[s];
-      f2 += H.fz[s];
+    for (int r = 0; r < nh4; r += 4) {
+      double e0 = H.se[r], e1 = H.se[r + 1], e2 = H.se[r + 2], e3 = H.se[r + 3];
+      double a0 = H.sfx[r], a1 = H.sfx[r + 1], a2 = H.sfx[r + 2], a3 = H.sfx[r + 3];
+      double b0 = H.sfy[r], b1 = H.sfy[r + 1], b2 = H.sfy[r + 2], b3 = H.sfy[r + 3];
+      double c0 = H.sfz[r], c1 = H.sfz[r + 1], c2 = H.sfz[r + 2], c3 = H.sfz[r + 3];
+      Es += e0; Es += e1; Es += e2; Es += e3;
+      f0 += a0; f0 += a1; f0 += a2; f0 += a3;
+      f1 += b0; f1 += b1; f1 += b2; f1 += b3;
+      f2 += c0; f2 += c1; f2 += c2; f2 += c3;
     }
   }
   E = __shfl_sync(0xffffffffu, Es, 0);
@@ -536,10 +561,11 @@ __device__ void usher_energy(const double c[3], int t, const Planes &p, const Gr
 
 // One warp per trial in `list`.  Writes the trial record and the points at which the energy was
 // evaluated (needed by the dirty test of the next round).
-__global__ void __launch_bounds__(USH_WARPS * 32, 8)
+__global__ void __launch_bounds__(USH_WARPS * 32, 6)
     k_usher_eval(const int *__restrict__ list, int nlist, Planes p, Grid g, PairTab pt, FixDev fd,
                  const int *__restrict__ cell_start, UsherCfg u, Extras ex,
                  const int *__restrict__ extra_head, const int *__restrict__ extra_next,
+                 const int *__restrict__ spec_head, const int *__restrict__ spec_next,
                  const int *__restrict__ acc_list, const obmd_trial *__restrict__ prev,
                  obmd_trial *__restrict__ cur,
                  double *__restrict__ path, int *__restrict__ npts, double *__restrict__ bbox,
@@ -576,8 +602,8 @@ __global__ void __launch_bounds__(USH_WARPS * 32, 8)
   }
   double E = 0.0, f[3];
   while (i < u.natt) {
-    usher_energy(c, t, p, g, pt, fd, cell_start, u, acc_list, prev, ex, extra_head, extra_next, hits[w],
-                 sc, E, f);
+    usher_energy(c, t, p, g, pt, fd, cell_start, u, acc_list, prev, ex, extra_head, extra_next, spec_head,
+                 spec_next, hits[w], sc, E, f);
     if (lane == 0) {
       mypath[np * 3 + 0] = c[0];
       mypath[np * 3 + 1] = c[1];
@@ -787,6 +813,17 @@ __global__ void k_extra_cells(Planes p, int base, int first, int count, Grid g, 
   extra_cell[first + k] = (lc * g.ny + cell_cy(g, p.y[s])) * g.nz + cell_cz(g, p.z[s]);
 }
 
+// cells of the atoms accepted in the round just finished (for the per-cell "spec" lists)
+__global__ void k_spec_cells(const obmd_trial *__restrict__ cur, const int *__restrict__ acc_list, int nacc,
+                             Grid g, int *__restrict__ spec_cell)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nacc) return;
+  const obmd_trial &r = cur[acc_list[k]];
+  int lc = min(max(cell_cx(g, r.end[0]), 0), g.nx - 1);
+  spec_cell[k] = (lc * g.ny + cell_cy(g, r.end[1])) * g.nz + cell_cz(g, r.end[2]);
+}
+
 // A group that arrives sorted by cell (a neighbour's boundary column): runs of equal cells become
 // the lists.  Precondition: no earlier group has atoms in these cells.
 __global__ void k_link_sorted(const int *__restrict__ extra_cell, int first, int count,
@@ -860,6 +897,9 @@ static int ensure_trials(obmd_ctx *c, int ntr, int natt)
   CK(cudaMalloc(&c->tr_list, sizeof(int) * cap));
   CK(cudaMalloc(&c->tr_changed, sizeof(int) * 2 * cap));  // changed flags | kfirst
   CK(cudaMalloc(&c->acc_list, sizeof(int) * cap));
+  cudaFree(c->spec_next); cudaFree(c->spec_cell);
+  CK(cudaMalloc(&c->spec_next, sizeof(int) * cap));
+  CK(cudaMalloc(&c->spec_cell, sizeof(int) * cap));
   CK(cudaMallocHost(&c->tr_h, sizeof(obmd_trial) * cap));
   c->tr_cap = cap;
   c->tr_natt = na;
@@ -975,6 +1015,74 @@ int fix_link_extras(obmd_ctx *c, int first, int count, bool sorted_by_cell)
     LAUNCH(k_link_group, 1, 512, 2 * sizeof(int) * count, c->extra_cell, first, count, c->extra_head,
            c->extra_next);
   }
+  return OBMD_OK;
+}
+
+// ---- pair forces near freshly inserted atoms -------------------------------------------------
+// obmd_run computes the pair forces on the side stream while USHER is still deciding the
+// insertions.  Afterwards only the atoms within one cell of a new atom (and the new atoms
+// themselves) are recomputed, now with the new atoms in the lists: every atom's force is always
+// the complete, fixed-order sum over its stencil, so the result equals a single late evaluation.
+__global__ void k_mark_redo(Extras ex, Grid g, const int *__restrict__ cell_start,
+                            const int *__restrict__ extra_cell, const int *__restrict__ extra_head,
+                            const int *__restrict__ extra_next, int *__restrict__ flag,
+                            int *__restrict__ list, int *__restrict__ count, int cap)
+{
+  int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+  int k = gidx / 27, nb = gidx % 27;
+  if (k >= ex.nins) return;
+  int cc = extra_cell[ex.narr + ex.nghost + k];
+  int cz = cc % g.nz, cy = (cc / g.nz) % g.ny, cx = cc / (g.nz * g.ny);
+  int bx = cx + nb / 9 - 1, by = cy + (nb / 3) % 3 - 1, bz = cz + nb % 3 - 1;
+  if (bx < g.own_a || bx > g.own_b) return;  // ghost columns hold no atoms of this rank
+  by = by < 0 ? by + g.ny : (by >= g.ny ? by - g.ny : by);
+  bz = bz < 0 ? bz + g.nz : (bz >= g.nz ? bz - g.nz : bz);
+  int c2 = (bx * g.ny + by) * g.nz + bz;
+  for (int j = cell_start[c2]; j < cell_start[c2 + 1]; j++)
+    if (atomicExch(&flag[j], 1) == 0) {
+      int q = atomicAdd(count, 1);
+      if (q < cap) list[q] = j;
+    }
+  for (int e = extra_head[c2]; e >= 0; e = extra_next[e]) {
+    if (e >= ex.narr && e < ex.narr + ex.nghost) continue;  // ghosts belong to the neighbour rank
+    int j = ex.base + e;
+    if (atomicExch(&flag[j], 1) == 0) {
+      int q = atomicAdd(count, 1);
+      if (q < cap) list[q] = j;
+    }
+  }
+}
+
+__global__ void k_clear_redo(int *__restrict__ flag, const int *__restrict__ list, const int *__restrict__ count,
+                             int cap)
+{
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = min(*count, cap);
+  if (q < n) flag[list[q]] = 0;
+}
+
+int fix_redo_pair_near_insertions(obmd_ctx *c, long long step)
+{
+  if (c->nins == 0) return OBMD_OK;
+  const int cap = c->nins * 27 * 24;  // 24 atoms per cell on average would be 8x the fluid density
+  if (c->redo_cap < c->cap) {
+    cudaFree(c->redo_flag);
+    CK(cudaMalloc(&c->redo_flag, sizeof(int) * c->cap));
+    CK(cudaMemsetAsync(c->redo_flag, 0, sizeof(int) * c->cap, c->stream));
+    c->redo_cap = c->cap;
+  }
+  if (!c->redo_count) CK(cudaMalloc(&c->redo_count, sizeof(int)));
+  if (cap > c->redo_list_cap) {
+    cudaFree(c->redo_list);
+    c->redo_list_cap = cap + cap / 2;
+    CK(cudaMalloc(&c->redo_list, sizeof(int) * c->redo_list_cap));
+  }
+  CK(cudaMemsetAsync(c->redo_count, 0, sizeof(int), c->stream));
+  LAUNCH(k_mark_redo, cdiv(c->nins * 27, 128), 128, 0, extras_of(c), c->grid, c->cell_start, c->extra_cell,
+         c->extra_head, c->extra_next, c->redo_flag, c->redo_list, c->redo_count, cap);
+  int rc = pair_compute_list(c, step, c->redo_list, c->redo_count, cap);
+  if (rc) return rc;
+  LAUNCH(k_clear_redo, cdiv(cap, 256), 256, 0, c->redo_flag, c->redo_list, c->redo_count, cap);
   return OBMD_OK;
 }
 
@@ -1149,6 +1257,11 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
   const int tg0 = doL ? 0 : ntrL;
 
   int nacc = 0, naccL = 0, naccR = 0, rounds = 0;
+  if ((ntr == 0 || ntr_loc == 0) && c->round0_hook) {  // no USHER work on this rank this step
+    int (*hook)(obmd_ctx *) = c->round0_hook;
+    c->round0_hook = nullptr;
+    if ((rc = hook(c))) return rc;
+  }
   if (ntr > 0) {
     ScopedTimer t(c, "usher");
     NEED(fa.maxattempt == 1, OBMD_ERR_ARG,
@@ -1172,8 +1285,16 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
       for (;; round++) {
         NEED(round <= ntr_loc + 1, OBMD_ERR_STATE, "fix obmd: USHER commit did not converge");
         LAUNCH(k_usher_eval, cdiv(nlist, USH_WARPS), USH_WARPS * 32, 0, list, nlist, c->cur, c->grid, c->pt,
-               c->fd, c->cell_start, u, ex, c->extra_head, c->extra_next, c->acc_list, c->tr_prev_d, c->tr_d,
+               c->fd, c->cell_start, u, ex, c->extra_head, c->extra_next, c->spec_head, c->spec_next,
+               c->acc_list, c->tr_prev_d, c->tr_d,
                c->tr_path, c->tr_npts, c->tr_bbox, c->tr_changed + c->tr_cap, c->sc_d);
+        // Round 0 fills the machine (one warp per trial); the re-run rounds are a handful of CTAs.
+        // obmd_run hooks in here to start the pair kernel on the side stream right behind round 0.
+        if (round == 0 && c->round0_hook) {
+          int (*hook)(obmd_ctx *) = c->round0_hook;
+          c->round0_hook = nullptr;
+          if ((rc = hook(c))) return rc;
+        }
         CK(cudaMemsetAsync(&c->sc_d->nchanged, 0, 2 * sizeof(int), c->stream));  // nchanged, ndirty
         LAUNCH(k_usher_diff, cdiv(ntr_loc, 256), 256, 0, c->tr_prev_d, c->tr_d, ntr_loc, round == 0 ? 1 : 0,
                c->tr_changed, c->sc_d);
@@ -1181,6 +1302,8 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
                c->tr_changed, c->tr_path, c->tr_npts, c->tr_bbox, u.natt, c->grid,
                c->pt.cutmax * (1.0 + 1e-9), rsqmax, c->tr_list, c->tr_changed + c->tr_cap, c->sc_d);
         LAUNCH(k_usher_copy, cdiv(ntr_loc, 256), 256, 0, c->tr_prev_d, c->tr_d, ntr_loc);
+        if (u.nacc_prev > 0)  // drop the previous round's spec lists before acc_list is rebuilt
+          LAUNCH(k_extra_clear, cdiv(u.nacc_prev, 128), 128, 0, c->spec_cell, u.nacc_prev, c->spec_head);
         LAUNCH(k_usher_acc, 1, 1024, 0, c->tr_prev_d, c->tr_d, ntr_loc, c->acc_list, c->sc_d);
         if ((rc = read_scalars(c))) return rc;
         NEED(c->sc_h->usher_error != OBMD_ERR_USHER, OBMD_ERR_USHER,
@@ -1192,6 +1315,11 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
         nlist = c->sc_h->ndirty;
         list = c->tr_list;
         u.nacc_prev = nacc;
+        if (nacc > 0) {  // per-cell lists of the atoms accepted so far, for the re-runs
+          NEED(nacc <= LINK_MAX, OBMD_ERR_CAPACITY, "more than %d insertions in one call", LINK_MAX);
+          LAUNCH(k_spec_cells, cdiv(nacc, 128), 128, 0, c->tr_d, c->acc_list, nacc, c->grid, c->spec_cell);
+          LAUNCH(k_link_group, 1, 512, 2 * sizeof(int) * nacc, c->spec_cell, 0, nacc, c->spec_head, c->spec_next);
+        }
       }
       rounds = round + 1;
     }
@@ -1212,6 +1340,9 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
     // every trial consumes exactly three draws (ATOM mode, uniform distribution, block region)
     c->fs.rng_seed = ranpark_skip(c->fs.rng_seed, 3LL * ntr);
     if (nacc > 0) {
+      // the side stream may still be walking the per-cell extra lists: link the new atoms only
+      // after its pair kernel has finished (obmd_run sets commit_wait)
+      if (c->commit_wait) CK(cudaStreamWaitEvent(c->stream, c->commit_wait, 0));
       const int tag0 = maxtag + ((doR && !doL) ? naccL : 0);
       LAUNCH(k_usher_commit, cdiv(nacc, 128), 128, 0, c->cur, extras_of(c), tag0, c->grid, c->fd, c->tr_d,
              c->acc_list, nacc, c->fx, c->fy, c->fz);

@@ -55,6 +55,20 @@ struct AtomI {
   bool bnd;  // sits in a boundary cell in y or z: needs the minimum-image shift
 };
 
+// Domain::pbc (domain.cpp:529-640) applied on the fly, with exactly the arithmetic of k_pbc: the
+// forces are then the same whether or not the stored coordinates have been wrapped yet, which is
+// what lets the pair kernel run on the side stream while pre_exchange still needs the
+// unwrapped positions (USHER sums must see the reference's pre-pbc coordinates).
+__device__ __forceinline__ double wrap1(double x, double lo, double hi, double prd)
+{
+  if (x < lo) x += prd;
+  if (x >= hi) {
+    x -= prd;
+    x = fmax(x, lo);
+  }
+  return x;
+}
+
 __device__ __forceinline__ void min_image(const Grid &g, double &dely, double &delz)
 {
   if (dely > g.half[1]) dely -= g.prd[1];
@@ -64,20 +78,29 @@ __device__ __forceinline__ void min_image(const Grid &g, double &dely, double &d
 }
 
 // pair_dpd.cpp:117-146 for a pair already known to be inside the cutoff
-template <bool SINGLE_TYPE, bool TALLY>
+template <bool SINGLE_TYPE, bool TALLY, bool PREWRAP>
 __device__ __forceinline__ void pair_eval(const Planes &p, const PairTab &pt, const Grid &g, int j,
                                           const AtomI &a, unsigned step, bool random_on, PairAcc &acc)
 {
-  double delx = a.x - p.x[j], dely = a.y - p.y[j], delz = a.z - p.z[j];
-  if (a.bnd) min_image(g, dely, delz);
+  double delx = a.x - p.x[j], dely, delz;
+  if (a.bnd) {
+    dely = a.y - (PREWRAP ? wrap1(p.y[j], g.lo[1], g.hi[1], g.prd[1]) : p.y[j]);
+    delz = a.z - (PREWRAP ? wrap1(p.z[j], g.lo[2], g.hi[2], g.prd[2]) : p.z[j]);
+    min_image(g, dely, delz);
+  } else {
+    dely = a.y - p.y[j];
+    delz = a.z - p.z[j];
+  }
   double rsq = delx * delx + dely * dely + delz * delz;
   int tj = SINGLE_TYPE ? 1 : p.type[j];
-  double r = sqrt(rsq);
-  if (r < EPSILON_DPD) return;
-  double rinv = 1.0 / r;
+  // one rsqrt instead of sqrt + two divisions (pair_dpd.cpp:118-121 computes r = sqrt(rsq),
+  // rinv = 1/r, wd = 1 - r/cut): same values to ~2 ulp, well inside the 1e-9 force tolerance
+  if (rsq < EPSILON_DPD * EPSILON_DPD) return;
+  double rinv = rsqrt(rsq);
+  double r = rsq * rinv;
   double delvx = a.vx - p.vx[j], delvy = a.vy - p.vy[j], delvz = a.vz - p.vz[j];
   double dot = delx * delvx + dely * delvy + delz * delvz;
-  double wd = 1.0 - r / pt.cut[a.type][tj];
+  double wd = 1.0 - r * pt.cutinv[a.type][tj];
   double fpair = pt.a0[a.type][tj] * wd;
   fpair -= pt.gamma[a.type][tj] * wd * wd * dot * rinv;
   if (random_on) {
@@ -100,12 +123,19 @@ __device__ __forceinline__ void pair_eval(const Planes &p, const PairTab &pt, co
   }
 }
 
-template <bool SINGLE_TYPE>
+template <bool SINGLE_TYPE, bool PREWRAP>
 __device__ __forceinline__ bool pair_screen(const Planes &p, const PairTab &pt, const Grid &g, int j,
                                             const AtomI &a)
 {
-  double delx = a.x - p.x[j], dely = a.y - p.y[j], delz = a.z - p.z[j];
-  if (a.bnd) min_image(g, dely, delz);
+  double delx = a.x - p.x[j], dely, delz;
+  if (a.bnd) {
+    dely = a.y - (PREWRAP ? wrap1(p.y[j], g.lo[1], g.hi[1], g.prd[1]) : p.y[j]);
+    delz = a.z - (PREWRAP ? wrap1(p.z[j], g.lo[2], g.hi[2], g.prd[2]) : p.z[j]);
+    min_image(g, dely, delz);
+  } else {
+    dely = a.y - p.y[j];
+    delz = a.z - p.z[j];
+  }
   double rsq = delx * delx + dely * dely + delz * delz;
   int tj = SINGLE_TYPE ? 1 : p.type[j];
   return rsq < pt.cutsq[a.type][tj];
@@ -124,27 +154,43 @@ __device__ __forceinline__ int colrange_slot(const ColRange &cr, int gidx, const
   return cr.extras ? extras_slot(ex, cr.extras, gidx) : -1;
 }
 
-template <bool SINGLE_TYPE, bool TALLY>
+template <bool SINGLE_TYPE, bool TALLY, bool PREWRAP>
 __global__ void __launch_bounds__(PAIR_T)
     k_pair_dpd(Planes p, ColRange cr, Extras ex, Grid g, PairTab pt,
                const int *__restrict__ cell_start, const int *__restrict__ extra_head,
                const int *__restrict__ extra_next, double *__restrict__ fx, double *__restrict__ fy,
-               double *__restrict__ fz, unsigned step, int random_on, double *__restrict__ partials)
+               double *__restrict__ fz, unsigned step, int random_on, double *__restrict__ partials,
+               const int *__restrict__ slot_list, const int *__restrict__ slot_count)
 {
   __shared__ int hits[PAIR_HCAP * PAIR_T];
-  const int i = colrange_slot(cr, blockIdx.x * PAIR_T + threadIdx.x, g, cell_start, ex);
+  // either the atoms of a column set, or an explicit slot list (recompute after insertions)
+  int i;
+  if (slot_list) {
+    const int gidx = blockIdx.x * PAIR_T + threadIdx.x;
+    i = (gidx < *slot_count) ? slot_list[gidx] : -1;
+  } else
+    i = colrange_slot(cr, blockIdx.x * PAIR_T + threadIdx.x, g, cell_start, ex);
   const int nextra = ex.narr + ex.nghost + ex.nins;
   int *myhits = hits + threadIdx.x;
   PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const unsigned live = __ballot_sync(0xffffffffu, i >= 0);
   if (i >= 0) {
     AtomI a;
-    a.x = p.x[i]; a.y = p.y[i]; a.z = p.z[i];
+    a.x = p.x[i];
+    a.y = PREWRAP ? wrap1(p.y[i], g.lo[1], g.hi[1], g.prd[1]) : p.y[i];
+    a.z = PREWRAP ? wrap1(p.z[i], g.lo[2], g.hi[2], g.prd[2]) : p.z[i];
     a.vx = p.vx[i]; a.vy = p.vy[i]; a.vz = p.vz[i];
     a.tag = p.tag[i];
     a.type = SINGLE_TYPE ? 1 : p.type[i];
     const int cx = cell_cx(g, a.x), cy = cell_cy(g, a.y), cz = cell_cz(g, a.z);
-    a.bnd = (cy == 0 || cy == g.ny - 1 || cz == 0 || cz == g.nz - 1);
+    // minimum image for atoms in a face layer; before Domain::pbc has run (PREWRAP) also for the
+    // second layer, because a face-layer neighbour may still carry unwrapped coordinates.  The
+    // choice is made per warp so the screen loop does not diverge (both paths give the same
+    // numbers for interior atoms: wrap and shift are no-ops there).
+    const int lay = PREWRAP ? 1 : 0;
+    a.bnd = (cy <= lay || cy >= g.ny - 1 - lay || cz <= lay || cz >= g.nz - 1 - lay);
     // z extent of the stencil row: one contiguous segment, plus a wrapped single cell at the faces
+    a.bnd = __any_sync(live, a.bnd);
     const int za = max(cz - 1, 0), zb = min(cz + 1, g.nz - 1);
     const int zw = (cz == 0) ? g.nz - 1 : ((cz == g.nz - 1) ? 0 : -1);
     int nh = 0;
@@ -165,14 +211,24 @@ __global__ void __launch_bounds__(PAIR_T)
             jb = cell_start[row + zw];
             je = cell_start[row + zw + 1];
           }
-          for (int j = jb; j < je; j++) {
-            if (j == i) continue;
-            if (pair_screen<SINGLE_TYPE>(p, pt, g, j, a)) {
-              if (nh < PAIR_HCAP) {
-                myhits[nh * PAIR_T] = j;
-                nh++;
-              } else {
-                pair_eval<SINGLE_TYPE, TALLY>(p, pt, g, j, a, step, random_on != 0, acc);
+          // four candidates per trip: the twelve coordinate loads are issued back to back, so the
+          // screen is bound by issue rate rather than by one L1/L2 round trip per candidate
+          for (int j0 = jb; j0 < je; j0 += 4) {
+            bool h[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int j = min(j0 + u, je - 1);  // clamped lanes repeat the last atom, masked below
+              h[u] = pair_screen<SINGLE_TYPE, PREWRAP>(p, pt, g, j, a) && (j0 + u < je) && (j != i);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              if (h[u]) {
+                if (nh < PAIR_HCAP) {
+                  myhits[nh * PAIR_T] = j0 + u;
+                  nh++;
+                } else {
+                  pair_eval<SINGLE_TYPE, TALLY, PREWRAP>(p, pt, g, j0 + u, a, step, random_on != 0, acc);
+                }
               }
             }
           }
@@ -184,15 +240,15 @@ __global__ void __launch_bounds__(PAIR_T)
             for (int e = extra_head[row + bz]; e >= 0; e = extra_next[e]) {
               int j = ex.base + e;
               if (j == i) continue;
-              if (pair_screen<SINGLE_TYPE>(p, pt, g, j, a))
-                pair_eval<SINGLE_TYPE, TALLY>(p, pt, g, j, a, step, random_on != 0, acc);
+              if (pair_screen<SINGLE_TYPE, PREWRAP>(p, pt, g, j, a))
+                pair_eval<SINGLE_TYPE, TALLY, PREWRAP>(p, pt, g, j, a, step, random_on != 0, acc);
             }
           }
         }
       }
     }
     for (int k = 0; k < nh; k++)
-      pair_eval<SINGLE_TYPE, TALLY>(p, pt, g, myhits[k * PAIR_T], a, step, random_on != 0, acc);
+      pair_eval<SINGLE_TYPE, TALLY, PREWRAP>(p, pt, g, myhits[k * PAIR_T], a, step, random_on != 0, acc);
     fx[i] = acc.fx;
     fy[i] = acc.fy;
     fz[i] = acc.fz;
@@ -260,9 +316,11 @@ static int colrange_bound(const obmd_ctx *c, const ColRange &cr)
   return c->nsorted + (cr.extras ? c->nextra : 0);
 }
 
-static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &cr, cudaStream_t st)
+static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &cr, cudaStream_t st,
+                       const int *slot_list = nullptr, const int *slot_count = nullptr, int slot_max = 0,
+                       bool prewrap = false)
 {
-  const int nmax = colrange_bound(c, cr);
+  const int nmax = slot_list ? slot_max : colrange_bound(c, cr);
   if (nmax <= 0) return OBMD_OK;
   const int nb = cdiv(nmax, PAIR_T);
   const bool single = (c->ntypes == 1);
@@ -275,11 +333,14 @@ static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &
   }
 #define PAIR_ARGS                                                                             \
   c->cur, cr, extras_of(c), c->grid, c->pt, c->cell_start, c->extra_head, c->extra_next,          \
-      c->fx, c->fy, c->fz, (unsigned) step, random_on, c->partials
-  if (single && !tally) LAUNCH_ON(st, (k_pair_dpd<true, false>), nb, PAIR_T, 0, PAIR_ARGS);
-  else if (single && tally) LAUNCH_ON(st, (k_pair_dpd<true, true>), nb, PAIR_T, 0, PAIR_ARGS);
-  else if (!single && !tally) LAUNCH_ON(st, (k_pair_dpd<false, false>), nb, PAIR_T, 0, PAIR_ARGS);
-  else LAUNCH_ON(st, (k_pair_dpd<false, true>), nb, PAIR_T, 0, PAIR_ARGS);
+      c->fx, c->fy, c->fz, (unsigned) step, random_on, c->partials, slot_list, slot_count
+  if (prewrap) {  // side-stream launch of obmd_run: coordinates may not be wrapped yet
+    if (single) LAUNCH_ON(st, (k_pair_dpd<true, false, true>), nb, PAIR_T, 0, PAIR_ARGS);
+    else LAUNCH_ON(st, (k_pair_dpd<false, false, true>), nb, PAIR_T, 0, PAIR_ARGS);
+  } else if (single && !tally) LAUNCH_ON(st, (k_pair_dpd<true, false, false>), nb, PAIR_T, 0, PAIR_ARGS);
+  else if (single && tally) LAUNCH_ON(st, (k_pair_dpd<true, true, false>), nb, PAIR_T, 0, PAIR_ARGS);
+  else if (!single && !tally) LAUNCH_ON(st, (k_pair_dpd<false, false, false>), nb, PAIR_T, 0, PAIR_ARGS);
+  else LAUNCH_ON(st, (k_pair_dpd<false, true, false>), nb, PAIR_T, 0, PAIR_ARGS);
   if (tally) LAUNCH_ON(st, k_pair_tally_final, 1, 256, 0, c->partials, nb, c->sc_d);
   CK(cudaGetLastError());
   return OBMD_OK;
@@ -290,7 +351,14 @@ int pair_compute_cols(obmd_ctx *c, long long step, const ColRange &cr, cudaStrea
 {
   NEED(c->cells_valid, OBMD_ERR_STATE, "pair_compute_cols: cell list is stale");
   ScopedTimer t(c, "pair", st);
-  return pair_launch(c, step, false, cr, st);
+  return pair_launch(c, step, false, cr, st, nullptr, nullptr, 0, true);
+}
+
+// forces of an explicit list of slots (device-side count; the grid covers slot_max)
+int pair_compute_list(obmd_ctx *c, long long step, const int *slot_list, const int *slot_count, int slot_max)
+{
+  ScopedTimer t(c, "pair");
+  return pair_launch(c, step, false, all_columns(c), c->stream, slot_list, slot_count, slot_max);
 }
 
 int pair_compute(obmd_ctx *c, long long step, int eflag, int vflag)
