@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([t.strip() for t in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.rows:
@@ -131,13 +131,24 @@ def ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # weak scaling: the box grows along the open axis with the number of GPUs (one 4x5x4 tiling =
     # 1 010 960 atoms per GPU), the buffers keep the physical length and target population of N=1
-    reps1 = tuple(args.reps)
-    reps = (reps1[0] * world, reps1[1], reps1[2])
+    scaling = "weak"
+    if args.workload == "1m":
+        reps1 = tuple(args.reps)
+        reps = (reps1[0] * world, reps1[1], reps1[2])
+        B1 = 0.15 * 33.59462486002239 * reps1[0]
+    else:
+        # BASELINE configs 3-5: fixed total size, slab-decomposed over the GPUs (strong scaling).
+        # The buffer is 0.15 Lx unless that exceeds what one edge slab can hold.
+        reps = {"4m": (5, 8, 8), "16m": (20, 8, 8)}[args.workload]
+        scaling = "strong"
+        Lx = 33.59462486002239 * reps[0]
+        B1 = min(0.15 * Lx, Lx / world - 2.5)
     x, box = tiled(reps)
     natoms_total = len(x)
     n0 = natoms_total // world
-    B1 = 0.15 * 33.59462486002239 * reps1[0]
-    sim, kw = build_sim(x, box, local, args.regime, rank=rank, world=world, buffer_size=B1, nbuf_atoms=n0)
+    nbuf_atoms = n0 if args.workload == "1m" else int(natoms_total * B1 / (0.15 * box[0, 1]))
+    sim, kw = build_sim(x, box, local, args.regime, rank=rank, world=world, buffer_size=B1,
+                        nbuf_atoms=nbuf_atoms)
     del x
     stream = torch.cuda.ExternalStream(sim.L.obmd_stream(sim.h), device=local)
 
@@ -198,7 +209,7 @@ def ours(args):
         line = {
             "metric": METRIC, "value": atom_steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": "OBMD-DPD fluid, shipped configuration tiled %dx%dx%d = %d atoms (%d per GPU), "
                                    "regime %s (alpha %.1f, nbuf %d, buffer %.2f), T=1, dt=0.001464, rc=1, "
@@ -223,6 +234,8 @@ def ours(args):
             line["e2e"] = {"value": e2e["atom_steps"] / e2e["seconds"], "unit": UNIT,
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                            "steps": args.e2e_steps}
+        if world == 1 and args.lammps_steps > 0:
+            line["e2e_lammps_plugin"] = lammps_plugin_e2e(tuple(args.reps), args.lammps_steps)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_budget)
         print(json.dumps(line), flush=True)
@@ -321,7 +334,7 @@ def ref_binary():
     return p if os.path.exists(p) else None
 
 
-def run_reference(reps, nsteps, regime="R1"):
+def run_reference(reps, nsteps, regime="R1", plugin=None):
     """Run the unmodified reference (oracle/_ref/lmp_serial, 1 core, MPI stubs) on the tiled deck;
     returns (atom_steps, loop_seconds)."""
     x, box = tiled(reps)
@@ -335,7 +348,7 @@ def run_reference(reps, nsteps, regime="R1"):
         np.savetxt(fh, np.column_stack([ids, np.ones(n), x]), fmt="%d %d %.6f %.6f %.6f")
     B = 0.15 * box[0, 1]
     alpha, nbuf = (1.0, int(0.15 * n)) if regime == "R1" else (0.7, int(0.7 * 0.15 * n))
-    deck = DECK.format(data=data, xlB=B, xrB=box[0, 1] - B, xhi=box[0, 1], yhi=box[1, 1], zhi=box[2, 1],
+    deck = ("plugin load %s\n" % plugin if plugin else "") + DECK.format(data=data, xlB=B, xrB=box[0, 1] - B, xhi=box[0, 1], yhi=box[1, 1], zhi=box[2, 1],
                        alpha=alpha, nbuf=nbuf, B=B, nsteps=nsteps)
     inp = os.path.join(wd, "in.ref")
     open(inp, "w").write(deck)
@@ -355,6 +368,18 @@ def run_reference(reps, nsteps, regime="R1"):
         os.remove(f)
     navg = 0.5 * (atoms[0] + atoms[-1]) if atoms else n
     return navg * nsteps, loop
+
+
+def lammps_plugin_e2e(reps, nsteps):
+    """The real drop-in: the unmodified reference LAMMPS binary with `plugin load
+    libobmd_b200_lammps.so` (fix obmd + pair_style dpd on the GPU, FixNVE/pbc/comm on the host)."""
+    plug = os.path.join(ROOT, "obmd-lammps-extension_b200", "libobmd_b200_lammps.so")
+    if ref_binary() is None or not os.path.exists(plug):
+        return {"value": None, "unit": UNIT, "note": "reference binary or plugin not built"}
+    a, loop = run_reference(reps, nsteps, plugin=plug)
+    return {"value": a / loop, "unit": UNIT, "steps": nsteps,
+            "note": "oracle/_ref/lmp_serial + plugin, LAMMPS loop time %.3f s; host FixNVE prints debug "
+                    "lines every step (SURVEY Q8)" % loop}
 
 
 def ref_cost_per_step(n, area_tiles):
@@ -403,7 +428,7 @@ def reference_arm(args):
     x, box = tiled(tuple(args.reps))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * loop / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": "OBMD-DPD fluid, shipped configuration tiled %dx%dx%d = %d atoms, regime R1; "
                                    "reference timed on a bounded sample: tiling %dx%dx%d = %d atoms"
@@ -418,11 +443,15 @@ def reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reps", type=int, nargs=3, default=[4, 5, 4], help="tiling of the shipped box")
+    ap.add_argument("--workload", default="1m", choices=["1m", "4m", "16m"],
+                    help="1m: 1 010 960 atoms per GPU (weak scaling); 4m/16m: fixed total (strong scaling)")
     ap.add_argument("--regime", default="R1", choices=["R0", "R1"])
+    ap.add_argument("--lammps-steps", type=int, default=0,
+                    help="also time the reference LAMMPS binary + plugin (drop-in e2e) for this many steps")
     ap.add_argument("--equil", type=int, default=300, help="untimed equilibration steps from v = 0")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

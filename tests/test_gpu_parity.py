@@ -129,6 +129,36 @@ def test_buffer_force_distribution_vs_reference(shipped, case):
     sim.close()
 
 
+def test_oscillating_flux_vs_oracle(shipped):
+    """BASELINE config 3 in miniature: time-dependent normal and tangential momentum flux
+    (pxy = v_sh, dpxx/freq) fed through obmd_fix_set_flux each step, as the shim does for v_
+    variables (fix_obmd_merged.cpp:563-572, :608-630); forces vs the oracle within 1e-9."""
+    tag, x, box = shipped
+    kw = dict(a0=0.0, gamma=0.0, dpxx=7.0, freq=3.0, shear_size=2.5)
+    sim = cc.device_sim(box, **kw)
+    sim.upload(x, np.zeros_like(x), np.ones(len(x), np.int32), tag)
+    p, a = cc.oracle_sim(box, x, tag=tag, **kw)
+    L = O.lib()
+    dt = 0.001464
+    for s in range(1, 6):
+        sh = 0.5 * np.sin(2 * np.pi * 0.1 * s * dt * 400)      # variable sh equal 0.5*sin(2*PI*0.1*time)
+        p.pxy = sh; p.pxz = -0.25 * sh
+        sim.set_flux(188.0, sh, -0.25 * sh, 7.0, 3.0, 0.7, 0.005, 1327.0)
+        sim.build_cells()
+        rep, _ = sim.pre_exchange()
+        sim.pbc(); sim.pair_compute(s); sim.post_force()
+        L.orc_fix_pre_exchange(C.byref(p), C.byref(a.c), None, 0)
+        a.f[:] = 0.0
+        L.orc_fix_post_force(C.byref(p), C.byref(a.c))
+        f = sim.download(("f",))["f"]
+        assert cc.mixed_rel_err(f, a.view("f")) < FTOL, s
+        st = sim.fix_state()
+        assert tuple(st.shearForce_left) == tuple(p.shearForce_left)
+        assert tuple(st.momentumForce_left) == tuple(p.momentumForce_left)
+    assert np.abs(f[:, 1]).max() > 0 and np.abs(f[:, 2]).max() > 0
+    sim.close()
+
+
 def test_b3_ballistic_bookkeeping(shipped):
     """20 ballistic steps: 234 deletions, 485 insertions; tag-by-local-index order identical to the
     reference; x, v, f to rounding (the weight sum G is a tree reduction here, a serial sum there)."""
