@@ -72,6 +72,7 @@ extern "C" int obmd_create(obmd_ctx **out, int device)
   memset(&c->alt, 0, sizeof(Planes));
   for (int t = 0; t <= MAXT; t++) c->mass[t] = 0.0;
   if (const char *e2 = getenv("OBMD_B200_OVERLAP")) c->overlap = atoi(e2) != 0;
+  if (const char *e3 = getenv("OBMD_B200_TILE")) c->tile_kernel = atoi(e3) != 0;
   snprintf(c->err, sizeof(c->err), "no error");
   *out = c;
   return OBMD_OK;

@@ -96,6 +96,7 @@ struct obmd_ctx {
   int *redo_flag = nullptr, *redo_list = nullptr, *redo_count = nullptr;  // pair recompute near insertions
   int redo_cap = 0, redo_list_cap = 0;
   bool overlap = true;
+  bool tile_kernel = false;  // OBMD_B200_TILE=1: PairDPD through the TMA-staged tiled kernel (pair_tile.cuh)
   char err[1024] = {0};
   long long launches = 0;
   bool timing = false;

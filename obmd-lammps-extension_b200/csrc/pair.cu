@@ -25,7 +25,7 @@
 
 #define EPSILON_DPD 1.0e-10  // pair_dpd.cpp:36
 #define PAIR_T 128           // threads per block
-#define PAIR_HCAP 40         // listed hits per thread (mean 12.6 at rho = 3); overflow is evaluated inline
+#define PAIR_HCAP 32         // listed hits per thread (mean 12.6 at rho = 3); overflow is evaluated inline
 
 __device__ __forceinline__ double dpd_gaussian(int tagi, int tagj, unsigned step, unsigned seed)
 {
@@ -79,17 +79,31 @@ __device__ __forceinline__ void min_image(const Grid &g, double &dely, double &d
 
 // pair_dpd.cpp:117-146 for a pair already known to be inside the cutoff
 template <bool SINGLE_TYPE, bool TALLY, bool PREWRAP>
+__device__ __forceinline__ void pair_eval_xyz(const Planes &p, const PairTab &pt, const Grid &g, int j,
+                                              double xj, double yj, double zj, const AtomI &a, unsigned step,
+                                              bool random_on, PairAcc &acc);
+
+template <bool SINGLE_TYPE, bool TALLY, bool PREWRAP>
 __device__ __forceinline__ void pair_eval(const Planes &p, const PairTab &pt, const Grid &g, int j,
                                           const AtomI &a, unsigned step, bool random_on, PairAcc &acc)
 {
-  double delx = a.x - p.x[j], dely, delz;
+  pair_eval_xyz<SINGLE_TYPE, TALLY, PREWRAP>(p, pt, g, j, p.x[j], p.y[j], p.z[j], a, step, random_on, acc);
+}
+
+// the neighbour's position is passed in (global memory or the tile kernel's shared-memory copy)
+template <bool SINGLE_TYPE, bool TALLY, bool PREWRAP>
+__device__ __forceinline__ void pair_eval_xyz(const Planes &p, const PairTab &pt, const Grid &g, int j,
+                                              double xj, double yj, double zj, const AtomI &a, unsigned step,
+                                              bool random_on, PairAcc &acc)
+{
+  double delx = a.x - xj, dely, delz;
   if (a.bnd) {
-    dely = a.y - (PREWRAP ? wrap1(p.y[j], g.lo[1], g.hi[1], g.prd[1]) : p.y[j]);
-    delz = a.z - (PREWRAP ? wrap1(p.z[j], g.lo[2], g.hi[2], g.prd[2]) : p.z[j]);
+    dely = a.y - (PREWRAP ? wrap1(yj, g.lo[1], g.hi[1], g.prd[1]) : yj);
+    delz = a.z - (PREWRAP ? wrap1(zj, g.lo[2], g.hi[2], g.prd[2]) : zj);
     min_image(g, dely, delz);
   } else {
-    dely = a.y - p.y[j];
-    delz = a.z - p.z[j];
+    dely = a.y - yj;
+    delz = a.z - zj;
   }
   double rsq = delx * delx + dely * dely + delz * delz;
   int tj = SINGLE_TYPE ? 1 : p.type[j];
@@ -154,6 +168,100 @@ __device__ __forceinline__ int colrange_slot(const ColRange &cr, int gidx, const
   return cr.extras ? extras_slot(ex, cr.extras, gidx) : -1;
 }
 
+// ---- one atom against its stencil, straight from global memory (L1/L2) ------------------------
+// Used for explicit slot lists (recompute near insertions), the atoms appended after the sort, the
+// tally variant, and as the fallback of the tiled kernel.  The order in which contributions are
+// accumulated is part of the contract (the tiled kernel reproduces it bit for bit): rows (ox, oy)
+// ascending; inside a row the cells cz-1, cz, cz+1 in that (wrapped) order; hits beyond the list
+// capacity and atoms from the per-cell extra lists are added on the spot, listed hits at the end.
+template <bool SINGLE_TYPE, bool TALLY, bool PREWRAP, typename HitT>
+__device__ __forceinline__ void pair_atom_global(const Planes &p, const Grid &g, const PairTab &pt,
+                                                 const Extras &ex, const int *__restrict__ cell_start,
+                                                 const int *__restrict__ extra_head,
+                                                 const int *__restrict__ extra_next, int i, unsigned live,
+                                                 unsigned step, bool random_on, HitT *myhits, int hstride,
+                                                 PairAcc &acc)
+{
+  const int nextra = ex.narr + ex.nghost + ex.nins;
+  AtomI a;
+  a.x = p.x[i];
+  a.y = PREWRAP ? wrap1(p.y[i], g.lo[1], g.hi[1], g.prd[1]) : p.y[i];
+  a.z = PREWRAP ? wrap1(p.z[i], g.lo[2], g.hi[2], g.prd[2]) : p.z[i];
+  a.vx = p.vx[i]; a.vy = p.vy[i]; a.vz = p.vz[i];
+  a.tag = p.tag[i];
+  a.type = SINGLE_TYPE ? 1 : p.type[i];
+  const int cx = cell_cx(g, a.x), cy = cell_cy(g, a.y), cz = cell_cz(g, a.z);
+  // minimum image for atoms in a face layer; before Domain::pbc has run (PREWRAP) also for the
+  // second layer, because a face-layer neighbour may still carry unwrapped coordinates.  The
+  // choice is made per warp so the screen loop does not diverge (both paths give the same
+  // numbers for interior atoms: wrap and shift are no-ops there).
+  const int lay = PREWRAP ? 1 : 0;
+  a.bnd = (cy <= lay || cy >= g.ny - 1 - lay || cz <= lay || cz >= g.nz - 1 - lay);
+  a.bnd = __any_sync(live, a.bnd);
+  // the three stencil cells of a row in window order; away from the faces they are one segment
+  int segb[3], sege[3], nseg;
+  int nh = 0;
+  for (int ox = -1; ox <= 1; ox++) {
+    const int bx = cx + ox;
+    if (bx < 0 || bx >= g.nx) continue;
+    for (int oy = -1; oy <= 1; oy++) {
+      int by = cy + oy;
+      by = by < 0 ? by + g.ny : (by >= g.ny ? by - g.ny : by);
+      const int row = (bx * g.ny + by) * g.nz;
+      if (cz == 0) {
+        nseg = 2;
+        segb[0] = cell_start[row + g.nz - 1]; sege[0] = cell_start[row + g.nz];
+        segb[1] = cell_start[row]; sege[1] = cell_start[row + 2];
+      } else if (cz == g.nz - 1) {
+        nseg = 2;
+        segb[0] = cell_start[row + cz - 1]; sege[0] = cell_start[row + cz + 1];
+        segb[1] = cell_start[row]; sege[1] = cell_start[row + 1];
+      } else {
+        nseg = 1;
+        segb[0] = cell_start[row + cz - 1]; sege[0] = cell_start[row + cz + 2];
+      }
+      for (int sgi = 0; sgi < nseg; sgi++) {
+        const int jb = segb[sgi], je = sege[sgi];
+        // four candidates per trip: the twelve coordinate loads are issued back to back
+        for (int j0 = jb; j0 < je; j0 += 4) {
+          bool h[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int j = min(j0 + u, je - 1);  // clamped lanes repeat the last atom, masked below
+            h[u] = pair_screen<SINGLE_TYPE, PREWRAP>(p, pt, g, j, a) && (j0 + u < je) && (j != i);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (h[u]) {
+              if (nh < PAIR_HCAP) {
+                myhits[nh * hstride] = (HitT) (j0 + u - i + 32768);  // slot offset from i, biased
+                nh++;
+              } else {
+                pair_eval<SINGLE_TYPE, TALLY, PREWRAP>(p, pt, g, j0 + u, a, step, random_on, acc);
+              }
+            }
+          }
+        }
+      }
+      if (nextra > 0) {  // atoms appended after the sort hang off per-cell lists
+        for (int oz = -1; oz <= 1; oz++) {
+          int bz = cz + oz;
+          bz = bz < 0 ? bz + g.nz : (bz >= g.nz ? bz - g.nz : bz);
+          for (int e = extra_head[row + bz]; e >= 0; e = extra_next[e]) {
+            int j = ex.base + e;
+            if (j == i) continue;
+            if (pair_screen<SINGLE_TYPE, PREWRAP>(p, pt, g, j, a))
+              pair_eval<SINGLE_TYPE, TALLY, PREWRAP>(p, pt, g, j, a, step, random_on, acc);
+          }
+        }
+      }
+    }
+  }
+  for (int k = 0; k < nh; k++)
+    pair_eval<SINGLE_TYPE, TALLY, PREWRAP>(p, pt, g, (int) myhits[k * hstride] - 32768 + i, a, step,
+                                           random_on, acc);
+}
+
 template <bool SINGLE_TYPE, bool TALLY, bool PREWRAP>
 __global__ void __launch_bounds__(PAIR_T)
     k_pair_dpd(Planes p, ColRange cr, Extras ex, Grid g, PairTab pt,
@@ -170,85 +278,12 @@ __global__ void __launch_bounds__(PAIR_T)
     i = (gidx < *slot_count) ? slot_list[gidx] : -1;
   } else
     i = colrange_slot(cr, blockIdx.x * PAIR_T + threadIdx.x, g, cell_start, ex);
-  const int nextra = ex.narr + ex.nghost + ex.nins;
-  int *myhits = hits + threadIdx.x;
   PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const unsigned live = __ballot_sync(0xffffffffu, i >= 0);
   if (i >= 0) {
-    AtomI a;
-    a.x = p.x[i];
-    a.y = PREWRAP ? wrap1(p.y[i], g.lo[1], g.hi[1], g.prd[1]) : p.y[i];
-    a.z = PREWRAP ? wrap1(p.z[i], g.lo[2], g.hi[2], g.prd[2]) : p.z[i];
-    a.vx = p.vx[i]; a.vy = p.vy[i]; a.vz = p.vz[i];
-    a.tag = p.tag[i];
-    a.type = SINGLE_TYPE ? 1 : p.type[i];
-    const int cx = cell_cx(g, a.x), cy = cell_cy(g, a.y), cz = cell_cz(g, a.z);
-    // minimum image for atoms in a face layer; before Domain::pbc has run (PREWRAP) also for the
-    // second layer, because a face-layer neighbour may still carry unwrapped coordinates.  The
-    // choice is made per warp so the screen loop does not diverge (both paths give the same
-    // numbers for interior atoms: wrap and shift are no-ops there).
-    const int lay = PREWRAP ? 1 : 0;
-    a.bnd = (cy <= lay || cy >= g.ny - 1 - lay || cz <= lay || cz >= g.nz - 1 - lay);
-    // z extent of the stencil row: one contiguous segment, plus a wrapped single cell at the faces
-    a.bnd = __any_sync(live, a.bnd);
-    const int za = max(cz - 1, 0), zb = min(cz + 1, g.nz - 1);
-    const int zw = (cz == 0) ? g.nz - 1 : ((cz == g.nz - 1) ? 0 : -1);
-    int nh = 0;
-    for (int ox = -1; ox <= 1; ox++) {
-      const int bx = cx + ox;
-      if (bx < 0 || bx >= g.nx) continue;
-      for (int oy = -1; oy <= 1; oy++) {
-        int by = cy + oy;
-        by = by < 0 ? by + g.ny : (by >= g.ny ? by - g.ny : by);
-        const int row = (bx * g.ny + by) * g.nz;
-        for (int seg = 0; seg < 2; seg++) {
-          int jb, je;
-          if (seg == 0) {
-            jb = cell_start[row + za];
-            je = cell_start[row + zb + 1];
-          } else {
-            if (zw < 0) break;
-            jb = cell_start[row + zw];
-            je = cell_start[row + zw + 1];
-          }
-          // four candidates per trip: the twelve coordinate loads are issued back to back, so the
-          // screen is bound by issue rate rather than by one L1/L2 round trip per candidate
-          for (int j0 = jb; j0 < je; j0 += 4) {
-            bool h[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-              const int j = min(j0 + u, je - 1);  // clamped lanes repeat the last atom, masked below
-              h[u] = pair_screen<SINGLE_TYPE, PREWRAP>(p, pt, g, j, a) && (j0 + u < je) && (j != i);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-              if (h[u]) {
-                if (nh < PAIR_HCAP) {
-                  myhits[nh * PAIR_T] = j0 + u;
-                  nh++;
-                } else {
-                  pair_eval<SINGLE_TYPE, TALLY, PREWRAP>(p, pt, g, j0 + u, a, step, random_on != 0, acc);
-                }
-              }
-            }
-          }
-        }
-        if (nextra > 0) {  // atoms inserted after the sort hang off per-cell lists
-          for (int oz = -1; oz <= 1; oz++) {
-            int bz = cz + oz;
-            bz = bz < 0 ? bz + g.nz : (bz >= g.nz ? bz - g.nz : bz);
-            for (int e = extra_head[row + bz]; e >= 0; e = extra_next[e]) {
-              int j = ex.base + e;
-              if (j == i) continue;
-              if (pair_screen<SINGLE_TYPE, PREWRAP>(p, pt, g, j, a))
-                pair_eval<SINGLE_TYPE, TALLY, PREWRAP>(p, pt, g, j, a, step, random_on != 0, acc);
-            }
-          }
-        }
-      }
-    }
-    for (int k = 0; k < nh; k++)
-      pair_eval<SINGLE_TYPE, TALLY, PREWRAP>(p, pt, g, myhits[k * PAIR_T], a, step, random_on != 0, acc);
+    pair_atom_global<SINGLE_TYPE, TALLY, PREWRAP, int>(p, g, pt, ex, cell_start, extra_head, extra_next, i,
+                                                       live, step, random_on != 0, hits + threadIdx.x,
+                                                       PAIR_T, acc);
     fx[i] = acc.fx;
     fy[i] = acc.fy;
     fz[i] = acc.fz;
@@ -273,6 +308,8 @@ __global__ void __launch_bounds__(PAIR_T)
     }
   }
 }
+
+#include "pair_tile.cuh"
 
 // Fixed-order final reduction of block partials (one block).
 __global__ void k_pair_tally_final(const double *__restrict__ partials, int nblocks, StepScalars *sc)
@@ -320,12 +357,41 @@ static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &
                        const int *slot_list = nullptr, const int *slot_count = nullptr, int slot_max = 0,
                        bool prewrap = false)
 {
-  const int nmax = slot_list ? slot_max : colrange_bound(c, cr);
-  if (nmax <= 0) return OBMD_OK;
-  const int nb = cdiv(nmax, PAIR_T);
   const bool single = (c->ntypes == 1);
   const int random_on = c->temperature > 0.0 ? 1 : 0;
   c->pt.dtinvsqrt = 1.0 / sqrt(c->dt);
+  const Grid &g = c->grid;
+  const bool whole = !slot_list && cr.n == 1 && cr.a[0] == 0 && cr.b[0] == g.nx - 1;
+  if (whole && !tally && c->tile_kernel && c->nsorted > 0) {
+    // cell-sorted atoms: tiled kernel, one CTA per owned (column, row, z-chunk); the atoms appended
+    // after the sort (arrivals, insertions) go through the list kernel below
+    const int nchunk = cdiv(g.nz, P3_ZC), zc = cdiv(g.nz, nchunk);
+    const int ntiles = (g.own_b - g.own_a + 1) * g.ny * nchunk;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CK(cudaFuncSetAttribute(k_pair_tile<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
+      CK(cudaFuncSetAttribute(k_pair_tile<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
+      CK(cudaFuncSetAttribute(k_pair_tile<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
+      CK(cudaFuncSetAttribute(k_pair_tile<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
+      attr_set = true;
+    }
+#define TILE_ARGS                                                                                  \
+  c->cur, extras_of(c), c->grid, c->pt, c->cell_start, c->extra_head, c->extra_next, c->fx, c->fy, \
+      c->fz, (unsigned) step, random_on, nchunk, zc
+    if (single && prewrap) LAUNCH_ON(st, (k_pair_tile<true, true>), ntiles, P3_T, P3_SMEM, TILE_ARGS);
+    else if (single) LAUNCH_ON(st, (k_pair_tile<true, false>), ntiles, P3_T, P3_SMEM, TILE_ARGS);
+    else if (prewrap) LAUNCH_ON(st, (k_pair_tile<false, true>), ntiles, P3_T, P3_SMEM, TILE_ARGS);
+    else LAUNCH_ON(st, (k_pair_tile<false, false>), ntiles, P3_T, P3_SMEM, TILE_ARGS);
+    CK(cudaGetLastError());
+    if (!cr.extras || c->narr + c->nins == 0) return OBMD_OK;
+    ColRange xr;
+    memset(&xr, 0, sizeof(xr));
+    xr.extras = cr.extras;
+    return pair_launch(c, step, false, xr, st, nullptr, nullptr, 0, prewrap);
+  }
+  const int nmax = slot_list ? slot_max : (cr.n == 0 ? c->nextra : colrange_bound(c, cr));
+  if (nmax <= 0) return OBMD_OK;
+  const int nb = cdiv(nmax, PAIR_T);
   if (tally && nb * 7 > c->partial_cap) {
     if (c->partials) cudaFree(c->partials);
     c->partial_cap = nb * 7 + 1024;
