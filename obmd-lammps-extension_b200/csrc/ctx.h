@@ -96,7 +96,9 @@ struct obmd_ctx {
   int *redo_flag = nullptr, *redo_list = nullptr, *redo_count = nullptr;  // pair recompute near insertions
   int redo_cap = 0, redo_list_cap = 0;
   bool overlap = true;
-  bool tile_kernel = false;  // OBMD_B200_TILE=1: PairDPD through the TMA-staged tiled kernel (pair_tile.cuh)
+  bool tile_kernel = true;   // OBMD_B200_TILE=0: PairDPD through the per-atom list kernel instead of pair_row.cuh
+  int row_rows = 0, row_zc = 0, row_threads = 0;  // tuning overrides (OBMD_B200_ROWS, _ZC, _PT); 0 = automatic
+  size_t row_smem_set = 0;
   char err[1024] = {0};
   long long launches = 0;
   bool timing = false;

@@ -41,7 +41,8 @@ __device__ __forceinline__ double dpd_gaussian(int tagi, int tagj, unsigned step
   unsigned h = (unsigned) (z >> 32), l = (unsigned) z;
   float u1 = ((float) h + 1.0f) * 2.3283064365386963e-10f;
   float u2 = (float) l * 2.3283064365386963e-10f;
-  float r = sqrtf(-2.0f * __logf(u1));
+  float r;  // MUFU.SQRT: the default IEEE sqrtf costs a Newton fix-up the Box-Muller radius does not need
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
   return (double) (r * __cosf(6.283185307179586f * u2));
 }
 
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(PAIR_T)
   }
 }
 
-#include "pair_tile.cuh"
+#include "pair_row.cuh"
 
 // Fixed-order final reduction of block partials (one block).
 __global__ void k_pair_tally_final(const double *__restrict__ partials, int nblocks, StepScalars *sc)
@@ -353,6 +354,53 @@ static int colrange_bound(const obmd_ctx *c, const ColRange &cr)
   return c->nsorted + (cr.extras ? c->nextra : 0);
 }
 
+// Tile shape of the row kernel for this box and density: rows per tile R, z-cells per tile zc,
+// threads T, staged-atom capacity.  Chosen to maximise (lanes doing work) x (warps resident per SM,
+// saturating at 16) with a small penalty for the halo redundancy; OBMD_B200_ROWS / _ZC / _PT override.
+struct RowPlan {
+  int R, nchunk, zc, T, cap;
+  size_t smem;
+};
+
+static int pair_row_plan(obmd_ctx *c, bool single, RowPlan &best)
+{
+  const Grid &g = c->grid;
+  const double rho = (double) c->nsorted / ((double) (g.own_b - g.own_a + 1) * g.ny * g.nz);
+  double best_score = -1.0;
+  for (int R = 1; R <= 2; R++) {
+    if (c->row_rows > 0 && R != c->row_rows) continue;
+    const int NR = 3 * (R + 2);
+    for (int nchunk = 1; nchunk <= g.nz; nchunk++) {
+      const int zc = cdiv(g.nz, nchunk);
+      if (zc > PR_MAXZC) continue;
+      if (c->row_zc > 0 && zc != cdiv(g.nz, cdiv(g.nz, c->row_zc))) continue;
+      const double atoms = R * zc * rho;
+      int T = 32 * cdiv((long long) (atoms * 1.03 + 2.0), 32);
+      if (c->row_threads > 0) T = c->row_threads / 32 * 32;
+      if (T < 32) T = 32;
+      if (T > PR_TMAX) continue;
+      const int nw = zc + 2;
+      const int cap = ((int) (NR * nw * rho * 1.08) + 48 + 7) / 8 * 8;
+      const size_t smem = pair_row_smem_bytes(R, cap, nw, T, single);
+      if (smem > 200 * 1024) continue;
+      int ctas = (int) ((227 * 1024) / (smem + 1024));
+      if (ctas > 2048 / T) ctas = 2048 / T;
+      if (ctas > 32) ctas = 32;
+      const double warps = ctas * (T / 32.0);
+      const double passes = ceil(atoms / T);
+      const double lane_eff = atoms / (passes * T);
+      const double redundancy = (double) NR * nw / (R * zc);
+      const double score = lane_eff * (warps < 16.0 ? warps / 16.0 : 1.0) / (1.0 + 0.02 * redundancy);
+      if (score > best_score) {
+        best_score = score;
+        best = {R, nchunk, zc, T, cap, smem};
+      }
+    }
+  }
+  NEED(best_score > 0.0, OBMD_ERR_CAPACITY, "pair_row: no tile shape fits (nz %d, density %.2f)", g.nz, rho);
+  return OBMD_OK;
+}
+
 static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &cr, cudaStream_t st,
                        const int *slot_list = nullptr, const int *slot_count = nullptr, int slot_max = 0,
                        bool prewrap = false)
@@ -361,27 +409,34 @@ static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &
   const int random_on = c->temperature > 0.0 ? 1 : 0;
   c->pt.dtinvsqrt = 1.0 / sqrt(c->dt);
   const Grid &g = c->grid;
-  const bool whole = !slot_list && cr.n == 1 && cr.a[0] == 0 && cr.b[0] == g.nx - 1;
-  if (whole && !tally && c->tile_kernel && c->nsorted > 0) {
-    // cell-sorted atoms: tiled kernel, one CTA per owned (column, row, z-chunk); the atoms appended
-    // after the sort (arrivals, insertions) go through the list kernel below
-    const int nchunk = cdiv(g.nz, P3_ZC), zc = cdiv(g.nz, nchunk);
-    const int ntiles = (g.own_b - g.own_a + 1) * g.ny * nchunk;
-    static bool attr_set = false;
-    if (!attr_set) {
-      CK(cudaFuncSetAttribute(k_pair_tile<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
-      CK(cudaFuncSetAttribute(k_pair_tile<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
-      CK(cudaFuncSetAttribute(k_pair_tile<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
-      CK(cudaFuncSetAttribute(k_pair_tile<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
-      attr_set = true;
+  if (!slot_list && !tally && c->tile_kernel && cr.n > 0 && c->nsorted > 0) {
+    // cell-sorted atoms of the column set: row-tiled kernel (pair_row.cuh), one CTA per
+    // (column, row strip, z-chunk); the atoms appended after the sort go through the list kernel below
+    int ncols = 0;
+    for (int k = 0; k < cr.n; k++) ncols += cr.b[k] - cr.a[k] + 1;
+    RowPlan pl;
+    int rc = pair_row_plan(c, single, pl);
+    if (rc) return rc;
+    if (pl.smem > c->row_smem_set) {
+#define ROW_ATTR(R, S, P) \
+  CK(cudaFuncSetAttribute(k_pair_row<R, S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl.smem))
+      ROW_ATTR(1, true, true); ROW_ATTR(1, true, false); ROW_ATTR(1, false, true); ROW_ATTR(1, false, false);
+      ROW_ATTR(2, true, true); ROW_ATTR(2, true, false); ROW_ATTR(2, false, true); ROW_ATTR(2, false, false);
+      c->row_smem_set = pl.smem;
     }
-#define TILE_ARGS                                                                                  \
-  c->cur, extras_of(c), c->grid, c->pt, c->cell_start, c->extra_head, c->extra_next, c->fx, c->fy, \
-      c->fz, (unsigned) step, random_on, nchunk, zc
-    if (single && prewrap) LAUNCH_ON(st, (k_pair_tile<true, true>), ntiles, P3_T, P3_SMEM, TILE_ARGS);
-    else if (single) LAUNCH_ON(st, (k_pair_tile<true, false>), ntiles, P3_T, P3_SMEM, TILE_ARGS);
-    else if (prewrap) LAUNCH_ON(st, (k_pair_tile<false, true>), ntiles, P3_T, P3_SMEM, TILE_ARGS);
-    else LAUNCH_ON(st, (k_pair_tile<false, false>), ntiles, P3_T, P3_SMEM, TILE_ARGS);
+    const int ntiles = ncols * cdiv(g.ny, pl.R) * pl.nchunk;
+#define ROW_ARGS                                                                                       \
+  c->cur, cr, extras_of(c), c->grid, c->pt, c->cell_start, c->extra_head, c->extra_next, c->fx, c->fy, \
+      c->fz, (unsigned) step, random_on, pl.nchunk, pl.zc, pl.cap
+#define ROW_LAUNCH(R)                                                                                    \
+  do {                                                                                                   \
+    if (single && prewrap) LAUNCH_ON(st, (k_pair_row<R, true, true>), ntiles, pl.T, pl.smem, ROW_ARGS);  \
+    else if (single) LAUNCH_ON(st, (k_pair_row<R, true, false>), ntiles, pl.T, pl.smem, ROW_ARGS);       \
+    else if (prewrap) LAUNCH_ON(st, (k_pair_row<R, false, true>), ntiles, pl.T, pl.smem, ROW_ARGS);      \
+    else LAUNCH_ON(st, (k_pair_row<R, false, false>), ntiles, pl.T, pl.smem, ROW_ARGS);                  \
+  } while (0)
+    if (pl.R == 1) ROW_LAUNCH(1);
+    else ROW_LAUNCH(2);
     CK(cudaGetLastError());
     if (!cr.extras || c->narr + c->nins == 0) return OBMD_OK;
     ColRange xr;

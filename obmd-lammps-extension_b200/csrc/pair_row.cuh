@@ -1,0 +1,389 @@
+// Row-tiled PairDPD kernel (included by pair.cu): the production path for the cell-sorted atoms.
+//
+// A tile is the atoms of R (1 or 2) y-adjacent cell rows of one column over a run of z-cells: R
+// contiguous slot ranges, because z is the fastest cell index.  Its stencil is the 3 x (R+2) rows
+// around it over the same z window plus one cell on either side.  The CTA copies x, v and tag of
+// that window into shared memory ONCE with 8-byte `cp.async` copies (no register staging, every
+// copy in flight at once), in window-cell-major order (w, ry, rx, atom).  In that order the nine
+// stencil cells an atom needs from one window cell are contiguous, and for R = 1 all 27 are, so
+//   phase 1  each thread screens its ~81 candidates in flat loops over shared memory and records
+//            the hits as byte offsets (branch-free push),
+//   phase 2  it evaluates the ~12.6 hits densely (rsqrt, drag, counter RNG), positions, velocities
+//            and tags all from shared memory -- the kernel's only global traffic is the staging
+//            copy (served by L2 after the first touch) and the force store.
+// Periodic images are materialised after the copy lands: a row reached across the y face, or a
+// window cell reached across the z face, is shifted by the box length in shared memory, exactly as
+// the reference's ghost atoms are (comm_brick.cpp:735-760 adds the period once, pair_dpd.cpp:101-104
+// then subtracts plain coordinates).  The inner loops therefore carry no minimum-image logic.
+// Atoms appended after the sort (insertions, slab arrivals and ghosts) hang off per-cell lists; the
+// staging copy folds them into their cells, so they are ordinary candidates too.
+//
+// Accumulation order (fixed by the layout, independent of launch geometry): candidate order
+// (w, ry, rx, slot).  Atoms with more than PR_HCAP neighbours, or a candidate span of more than
+// 256, take a test-and-evaluate loop in the same order.
+#pragma once
+
+#define PR_HCAP 32        // hit slots per thread (mean 12.6 hits at rho = 3); more -> test-and-evaluate path
+#define PR_MAXZC 62       // z-cells per tile at most
+#define PR_TMAX 288
+
+struct RowHdr {
+  int row_base[12];  // first cell index of stencil row r = ry*3 + rx, -1 if it is not needed / does not exist
+  double yshift[12];
+  int tb[2], te[2];  // tile atoms of tile row ty are slots [tb, te)
+  int nstaged;
+};
+
+struct RowSmem {
+  double *pos;          // [cap][3]
+  double *vel;          // [cap][3]
+  int *tag;             // [cap]
+  int *cbeg;            // [NR*nw + 1] staged offset of cell (w, r), index w*NR + r
+  int *gbeg;            // [NR*nw]     first global slot of that cell
+  unsigned char *hits;  // [PR_HCAP][T]
+  unsigned char *type;  // [cap] (multi-type systems only)
+};
+
+// dynamic shared memory of one CTA
+static inline size_t pair_row_smem_bytes(int R, int cap, int nw, int T, bool single_type)
+{
+  const int NR = 3 * (R + 2);
+  size_t b = (size_t) cap * (6 * 8 + 4) + (size_t) 4 * (2 * NR * nw + 2) + (size_t) PR_HCAP * T;
+  if (!single_type) b += (size_t) cap;
+  const size_t fallback = (size_t) T * PAIR_HCAP * 4;  // int hit lists of pair_atom_global
+  if (b < fallback) b = fallback;
+  return (b + 15) / 16 * 16;
+}
+
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src_global)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned) __cvta_generic_to_shared(dst_smem)),
+               "l"(src_global)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src_global)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned) __cvta_generic_to_shared(dst_smem)),
+               "l"(src_global)
+               : "memory");
+}
+
+struct RowAtom {
+  double x, y, z, vx, vy, vz;
+  int tag, type;
+};
+
+// pair_dpd.cpp:117-146 for candidate q of the staged window
+template <bool SINGLE_TYPE>
+__device__ __forceinline__ void pair_row_eval(const RowSmem &S, const PairTab &pt, int q, const RowAtom &a,
+                                              unsigned step, bool random_on, double &fxa, double &fya,
+                                              double &fza)
+{
+  const double *pj = S.pos + 3 * q, *vj = S.vel + 3 * q;
+  const double delx = a.x - pj[0], dely = a.y - pj[1], delz = a.z - pj[2];
+  const double rsq = delx * delx + dely * dely + delz * delz;
+  if (rsq < EPSILON_DPD * EPSILON_DPD) return;  // pair_dpd.cpp:119
+  const int tj = SINGLE_TYPE ? 1 : (int) S.type[q];
+  const double rinv = rsqrt(rsq);
+  const double r = rsq * rinv;
+  const double delvx = a.vx - vj[0], delvy = a.vy - vj[1], delvz = a.vz - vj[2];
+  const double dot = delx * delvx + dely * delvy + delz * delvz;
+  const double wd = 1.0 - r * pt.cutinv[a.type][tj];
+  // fpair = (a0*wd - gamma*wd^2*dot/r + sigma*wd*xi/sqrt(dt)) / r, factored as wd/r * (...)
+  double t = pt.a0[a.type][tj] - pt.gamma[a.type][tj] * wd * dot * rinv;
+  if (random_on) t += pt.sigma[a.type][tj] * pt.dtinvsqrt * dpd_gaussian(a.tag, S.tag[q], step, pt.seed);
+  const double fpair = wd * rinv * t;
+  fxa += delx * fpair;
+  fya += dely * fpair;
+  fza += delz * fpair;
+}
+
+template <bool SINGLE_TYPE>
+__device__ __forceinline__ bool pair_row_hit(const RowSmem &S, const PairTab &pt, int q, const RowAtom &a)
+{
+  const double *pj = S.pos + 3 * q;
+  const double dx = a.x - pj[0], dy = a.y - pj[1], dz = a.z - pj[2];
+  const double rsq = dx * dx + dy * dy + dz * dz;
+  const int tj = SINGLE_TYPE ? 1 : (int) S.type[q];
+  return rsq < pt.cutsq[a.type][tj];
+}
+
+template <int R, bool SINGLE_TYPE, bool PREWRAP>
+__global__ void __launch_bounds__(PR_TMAX, 1)
+    k_pair_row(Planes p, ColRange cr, Extras ex, Grid g, PairTab pt, const int *__restrict__ cell_start,
+               const int *__restrict__ extra_head, const int *__restrict__ extra_next,
+               double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, unsigned step,
+               int random_on, int nchunk, int zc, int cap)
+{
+  constexpr int NR = 3 * (R + 2);  // stencil rows per window cell
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ RowHdr H;
+  const int tid = threadIdx.x, T = blockDim.x;
+
+  // ---- which tile ---------------------------------------------------------------------------
+  const int nstrip = (g.ny + R - 1) / R;
+  const int chunk = blockIdx.x % nchunk;
+  const int rowid = blockIdx.x / nchunk;
+  // odd ny, R = 2: the last strip is shifted back onto rows ny-2, ny-1 and owns only the last one, so
+  // every tile sees all 3 x (R+2) stencil rows (the tail over-read of phase 1 relies on that)
+  int cy = (rowid % nstrip) * R, ty_first = 0;
+  if (cy + R > g.ny) {
+    ty_first = cy + R - g.ny;
+    cy = g.ny - R;
+  }
+  int col = rowid / nstrip, lc = -1;  // col-th column of the set
+  for (int k = 0; k < cr.n; k++) {
+    const int len = cr.b[k] - cr.a[k] + 1;
+    if (lc < 0 && col >= 0 && col < len) lc = cr.a[k] + col;
+    col -= len;
+  }
+  const int z0 = chunk * zc, z1 = min(z0 + zc, g.nz);  // tile cells [z0, z1)
+  if (lc < 0 || z0 >= z1) return;
+  const int nw = z1 - z0 + 2;                          // window cells z0-1 .. z1
+  const int ncw = NR * nw;
+
+  RowSmem S;
+  S.pos = reinterpret_cast<double *>(smem_raw);
+  S.vel = S.pos + 3 * cap;
+  S.tag = reinterpret_cast<int *>(S.vel + 3 * cap);
+  S.cbeg = S.tag + cap;
+  S.gbeg = S.cbeg + ncw + 1;
+  S.hits = reinterpret_cast<unsigned char *>(S.gbeg + ncw);
+  S.type = S.hits + PR_HCAP * T;
+
+  if (tid < NR) {
+    const int ry = tid / 3, rx = tid - 3 * ry;
+    const int bx = lc + rx - 1;
+    int by = cy + ry - 1;
+    double sh = 0.0;
+    if (by < 0) { by += g.ny; sh = -g.prd[1]; }
+    else if (by >= g.ny) { by -= g.ny; sh = g.prd[1]; }
+    H.row_base[tid] = (bx < 0 || bx >= g.nx) ? -1 : (bx * g.ny + by) * g.nz;
+    H.yshift[tid] = sh;
+  }
+  if (tid >= 16 && tid < 16 + 2 * R) {
+    const int k = tid - 16, ty = k >> 1;
+    int v = 0;
+    if (ty >= ty_first) v = cell_start[(lc * g.ny + cy + ty) * g.nz + ((k & 1) ? z1 : z0)];
+    if (k & 1) H.te[ty] = v;
+    else H.tb[ty] = v;
+  }
+  __syncthreads();
+
+  // ---- cell populations of the window (sorted range + appended atoms), then their scan ---------
+  const bool have_extras = (ex.narr + ex.nghost + ex.nins) > 0;
+  const unsigned nw_inv = 65536u / (unsigned) nw + 1u;  // q / nw == (q * nw_inv) >> 16 for q < 65536 / nw
+  for (int q = tid; q < ncw; q += T) {
+    const int r = (int) (((unsigned) q * nw_inv) >> 16), w = q - r * nw;  // threads walk z: coalesced reads
+    int cnt = 0, gb = 0;
+    if (H.row_base[r] >= 0) {
+      int zu = z0 - 1 + w;
+      zu = zu < 0 ? zu + g.nz : (zu >= g.nz ? zu - g.nz : zu);
+      const int cc = H.row_base[r] + zu;
+      gb = cell_start[cc];
+      cnt = cell_start[cc + 1] - gb;
+      if (have_extras)
+        for (int e = extra_head[cc]; e >= 0; e = extra_next[e]) cnt++;
+    }
+    S.cbeg[w * NR + r] = cnt;
+    S.gbeg[w * NR + r] = gb;
+  }
+  __syncthreads();
+  if (tid < 32) {  // exclusive scan of the counts by one warp, a contiguous run per lane
+    const int per = (ncw + 31) / 32, b = tid * per, e = min(b + per, ncw);
+    int s = 0;
+    for (int k = b; k < e; k++) s += S.cbeg[k];
+    int inc = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, d);
+      if (tid >= d) inc += v;
+    }
+    int run = inc - s;
+    for (int k = b; k < e; k++) {
+      const int v = S.cbeg[k];
+      S.cbeg[k] = run;
+      run += v;
+    }
+    if (tid == 31) {
+      S.cbeg[ncw] = inc;
+      H.nstaged = inc;
+    }
+  }
+  __syncthreads();
+  const bool staged = H.nstaged + 4 <= cap;  // 4 slack entries: phase 1 reads up to 3 past a segment
+
+  // ---- staging copy: one thread per staged atom (balanced, consecutive threads copy consecutive
+  // atoms), every copy asynchronous.  The cell of staged index d is found from the estimate
+  // d * cells / atoms and a short probe of the offset table.
+  if (staged) {
+    const float c_per_a = (float) ncw / (float) max(H.nstaged, 1);
+    for (int d = tid; d < H.nstaged; d += T) {
+      int ci = min((int) ((float) d * c_per_a), ncw - 1);
+      while (S.cbeg[ci] > d) ci--;
+      while (S.cbeg[ci + 1] <= d) ci++;
+      const int k = d - S.cbeg[ci];
+      int j = S.gbeg[ci] + k;
+      if (have_extras) {  // atoms appended after the sort sit behind the cell's sorted atoms
+        const int w = ci / NR, r = ci - w * NR;
+        int zu = z0 - 1 + w;
+        zu = zu < 0 ? zu + g.nz : (zu >= g.nz ? zu - g.nz : zu);
+        const int cc = H.row_base[r] + zu;
+        const int ns = cell_start[cc + 1] - S.gbeg[ci];
+        if (k >= ns) {
+          int e = extra_head[cc];
+          for (int m = ns; m < k; m++) e = extra_next[e];
+          j = ex.base + e;
+        }
+      }
+      cp_async8(S.pos + 3 * d, p.x + j);
+      cp_async8(S.pos + 3 * d + 1, p.y + j);
+      cp_async8(S.pos + 3 * d + 2, p.z + j);
+      cp_async8(S.vel + 3 * d, p.vx + j);
+      cp_async8(S.vel + 3 * d + 1, p.vy + j);
+      cp_async8(S.vel + 3 * d + 2, p.vz + j);
+      cp_async4(S.tag + d, p.tag + j);
+      if (!SINGLE_TYPE) S.type[d] = (unsigned char) p.type[j];
+    }
+    if (tid < 4) {  // slack entries read by the last screen group: far away, never a hit
+      const int d = H.nstaged + tid;
+      S.pos[3 * d] = S.pos[3 * d + 1] = S.pos[3 * d + 2] = 1.0e150;
+      if (!SINGLE_TYPE) S.type[d] = 1;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // periodic images (and, before Domain::pbc has run, the wrap itself), fixed up in shared memory
+    for (int ci = tid; ci < ncw; ci += T) {
+      const int w = ci / NR, r = ci - w * NR;
+      if (H.row_base[r] < 0) continue;
+      const int zu = z0 - 1 + w;
+      const double zs = zu < 0 ? -g.prd[2] : (zu >= g.nz ? g.prd[2] : 0.0), ys = H.yshift[r];
+      bool fix = (ys != 0.0) || (zs != 0.0);
+      if (PREWRAP) {  // only face cells can hold coordinates that have not been wrapped yet
+        const int by = cy + r / 3 - 1;
+        fix = fix || by <= 0 || by >= g.ny - 1 || zu <= 0 || zu >= g.nz - 1;
+      }
+      if (!fix) continue;
+      for (int d = S.cbeg[ci]; d < S.cbeg[ci + 1]; d++) {
+        const double yj = S.pos[3 * d + 1], zj = S.pos[3 * d + 2];
+        S.pos[3 * d + 1] = (PREWRAP ? wrap1(yj, g.lo[1], g.hi[1], g.prd[1]) : yj) + ys;
+        S.pos[3 * d + 2] = (PREWRAP ? wrap1(zj, g.lo[2], g.hi[2], g.prd[2]) : zj) + zs;
+      }
+    }
+  }
+  __syncthreads();
+
+  const int n0 = H.te[0] - H.tb[0];
+  const int ntile = n0 + (R > 1 ? H.te[R - 1] - H.tb[R - 1] : 0);
+  for (int k0 = 0; k0 < ntile; k0 += T) {
+    const int k = k0 + tid;
+    const bool mine = k < ntile;
+    const unsigned live = __ballot_sync(0xffffffffu, mine);
+    if (!mine) continue;
+    const int ty = (R > 1 && k >= n0) ? 1 : 0;
+    const int i = ty ? H.tb[R - 1] + (k - n0) : H.tb[0] + k;
+    if (!staged) {  // unusually dense neighbourhood: plain global path
+      PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      pair_atom_global<SINGLE_TYPE, false, PREWRAP, int>(p, g, pt, ex, cell_start, extra_head, extra_next, i,
+                                                         live, step, random_on != 0,
+                                                         reinterpret_cast<int *>(smem_raw) + tid, T, acc);
+      fx[i] = acc.fx;
+      fy[i] = acc.fy;
+      fz[i] = acc.fz;
+      continue;
+    }
+    // window cell of atom i: the own-row cell whose slot range holds i (exact: no coordinate
+    // arithmetic that could disagree with the sort key)
+    const int rc = (ty + 1) * 3 + 1;  // own row, own column
+    int w;
+    {
+      int lo = 1, hi = nw - 2;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (S.gbeg[mid * NR + rc] <= i) lo = mid;
+        else hi = mid - 1;
+      }
+      w = lo;
+    }
+    const int qs = S.cbeg[w * NR + rc] + (i - S.gbeg[w * NR + rc]);
+    RowAtom a;
+    a.x = S.pos[3 * qs]; a.y = S.pos[3 * qs + 1]; a.z = S.pos[3 * qs + 2];
+    a.vx = S.vel[3 * qs]; a.vy = S.vel[3 * qs + 1]; a.vz = S.vel[3 * qs + 2];
+    a.tag = S.tag[qs];
+    a.type = SINGLE_TYPE ? 1 : (int) S.type[qs];
+    // candidate segments: window cells w-1, w, w+1, rows ty..ty+2 (nine cells each); one run for R = 1
+    int sb[3], se[3];
+    if (R == 1) {
+      sb[0] = S.cbeg[(w - 1) * NR];
+      se[0] = S.cbeg[(w + 2) * NR];
+    } else {
+#pragma unroll
+      for (int s = 0; s < 3; s++) {
+        sb[s] = S.cbeg[(w - 1 + s) * NR + ty * 3];
+        se[s] = S.cbeg[(w - 1 + s) * NR + ty * 3 + 9];
+      }
+    }
+    constexpr int NSEG = (R == 1) ? 1 : 3;
+    const int qb = sb[0];
+    double fxa = 0.0, fya = 0.0, fza = 0.0;
+    // hit list: byte offsets from qb, slot k of thread tid at hits[k*T + tid]
+    const unsigned hbase = (unsigned) __cvta_generic_to_shared(S.hits + tid);
+    const unsigned hlim = hbase + (PR_HCAP - 4) * T;
+    unsigned hp = hbase;
+    bool ovf = (se[NSEG - 1] - qb) > 256;
+    if (!ovf) {
+      // ---- phase 1: screen.  The push is branch-free: every candidate's offset is stored at the next
+      // free slot, and the slot only advances on a hit.  A group may run up to 3 candidates past its
+      // segment: what lies there are cells at least one cell width (>= cutoff) away in y or z, or
+      // the far-away slack entries, so the cutoff test itself rejects them -- no tail mask.
+#pragma unroll
+      for (int s = 0; s < NSEG; s++) {
+        const int qe = se[s];
+        for (int q0 = sb[s]; q0 < qe; q0 += 4) {
+          ovf = ovf || (hp > hlim);
+          hp = min(hp, hlim);
+          double rs[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const double *pj = S.pos + 3 * (q0 + u);
+            const double dx = a.x - pj[0], dy = a.y - pj[1], dz = a.z - pj[2];
+            rs[u] = dx * dx + dy * dy + dz * dz;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int tj = SINGLE_TYPE ? 1 : (int) S.type[q0 + u];
+            // store the offset, then advance the slot iff (rsq < cutsq and not myself)
+            asm volatile(
+                "{ .reg .pred p;\n\t"
+                "st.shared.u8 [%0], %1;\n\t"
+                "setp.ne.s32 p, %2, %3;\n\t"
+                "setp.lt.and.f64 p, %4, %5, p;\n\t"
+                "@p add.u32 %0, %0, %6; }"
+                : "+r"(hp)
+                : "r"(q0 + u - qb), "r"(q0 + u), "r"(qs), "d"(rs[u]), "d"(pt.cutsq[a.type][tj]), "r"(T)
+                : "memory");
+          }
+        }
+      }
+    }
+    if (!ovf) {
+      // ---- phase 2: evaluate the listed hits ----------------------------------------------------
+      for (unsigned hq = hbase; hq < hp; hq += T) {
+        unsigned off;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(off) : "r"(hq) : "memory");
+        pair_row_eval<SINGLE_TYPE>(S, pt, qb + (int) off, a, step, random_on != 0, fxa, fya, fza);
+      }
+    } else {
+      // more neighbours than the list holds, or a span beyond a byte: test and evaluate in place
+#pragma unroll
+      for (int s = 0; s < NSEG; s++)
+        for (int q = sb[s]; q < se[s]; q++)
+          if (q != qs && pair_row_hit<SINGLE_TYPE>(S, pt, q, a))
+            pair_row_eval<SINGLE_TYPE>(S, pt, q, a, step, random_on != 0, fxa, fya, fza);
+    }
+    fx[i] = fxa;
+    fy[i] = fya;
+    fz[i] = fza;
+  }
+}
