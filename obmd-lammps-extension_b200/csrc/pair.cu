@@ -380,7 +380,7 @@ static int pair_row_plan(obmd_ctx *c, bool single, RowPlan &best)
       if (T < 32) T = 32;
       if (T > PR_TMAX) continue;
       const int nw = zc + 2;
-      const int cap = ((int) (NR * nw * rho * 1.08) + 48 + 7) / 8 * 8;
+      const int cap = ((int) (NR * nw * rho * 1.04) + 16 + 7) / 8 * 8;
       const size_t smem = pair_row_smem_bytes(R, cap, nw, T, single);
       if (smem > 200 * 1024) continue;
       int ctas = (int) ((227 * 1024) / (smem + 1024));

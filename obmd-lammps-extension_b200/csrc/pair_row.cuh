@@ -6,9 +6,10 @@
 // that window into shared memory ONCE with 8-byte `cp.async` copies (no register staging, every
 // copy in flight at once), in window-cell-major order (w, ry, rx, atom).  In that order the nine
 // stencil cells an atom needs from one window cell are contiguous, and for R = 1 all 27 are, so
-//   phase 1  each thread screens its ~81 candidates in flat loops over shared memory and records
-//            the hits as byte offsets (branch-free push),
-//   phase 2  it evaluates the ~12.6 hits densely (rsqrt, drag, counter RNG), positions, velocities
+//   phase 1  each thread screens its ~81 candidates in flat loops over an fp32 copy of the positions
+//            (one LDS.128 per candidate, conservative margin) and keeps the hits as register bitmasks,
+//   phase 2  it evaluates the ~12.6 hits densely in fp64 (exact cutoff test first, then rsqrt, drag,
+//            counter RNG), positions, velocities
 //            and tags all from shared memory -- the kernel's only global traffic is the staging
 //            copy (served by L2 after the first touch) and the force store.
 // Periodic images are materialised after the copy lands: a row reached across the y face, or a
@@ -19,8 +20,8 @@
 // staging copy folds them into their cells, so they are ordinary candidates too.
 //
 // Accumulation order (fixed by the layout, independent of launch geometry): candidate order
-// (w, ry, rx, slot).  Atoms with more than PR_HCAP neighbours, or a candidate span of more than
-// 256, take a test-and-evaluate loop in the same order.
+// (w, ry, rx, slot).  An atom with more than 64 candidates in one window cell takes a
+// test-and-evaluate loop in the same order.
 #pragma once
 
 #define PR_HCAP 32        // hit slots per thread (mean 12.6 hits at rho = 3); more -> test-and-evaluate path
@@ -32,6 +33,7 @@ struct RowHdr {
   double yshift[12];
   int tb[2], te[2];  // tile atoms of tile row ty are slots [tb, te)
   int nstaged;
+  double org[3];     // low corner of the tile (origin of the fp32 screening copy)
 };
 
 struct RowSmem {
@@ -40,7 +42,8 @@ struct RowSmem {
   int *tag;             // [cap]
   int *cbeg;            // [NR*nw + 1] staged offset of cell (w, r), index w*NR + r
   int *gbeg;            // [NR*nw]     first global slot of that cell
-  unsigned char *hits;  // [PR_HCAP][T]
+  float4 *scr;          // [cap] fp32 copy of pos relative to the tile origin (screening only)
+  unsigned char *hits;  // [PR_HCAP][T] hit list of each thread: byte offsets from its first candidate
   unsigned char *type;  // [cap] (multi-type systems only)
 };
 
@@ -48,7 +51,7 @@ struct RowSmem {
 static inline size_t pair_row_smem_bytes(int R, int cap, int nw, int T, bool single_type)
 {
   const int NR = 3 * (R + 2);
-  size_t b = (size_t) cap * (6 * 8 + 4) + (size_t) 4 * (2 * NR * nw + 2) + (size_t) PR_HCAP * T;
+  size_t b = (size_t) cap * (16 + 6 * 8 + 4) + (size_t) 4 * (2 * NR * nw + 2) + (size_t) PR_HCAP * T;
   if (!single_type) b += (size_t) cap;
   const size_t fallback = (size_t) T * PAIR_HCAP * 4;  // int hit lists of pair_atom_global
   if (b < fallback) b = fallback;
@@ -82,8 +85,9 @@ __device__ __forceinline__ void pair_row_eval(const RowSmem &S, const PairTab &p
   const double *pj = S.pos + 3 * q, *vj = S.vel + 3 * q;
   const double delx = a.x - pj[0], dely = a.y - pj[1], delz = a.z - pj[2];
   const double rsq = delx * delx + dely * dely + delz * delz;
-  if (rsq < EPSILON_DPD * EPSILON_DPD) return;  // pair_dpd.cpp:119
   const int tj = SINGLE_TYPE ? 1 : (int) S.type[q];
+  // the exact cutoff test (pair_dpd.cpp:116; phase 1 screens in fp32 with a margin) and :119
+  if (rsq >= pt.cutsq[a.type][tj] || rsq < EPSILON_DPD * EPSILON_DPD) return;
   const double rinv = rsqrt(rsq);
   const double r = rsq * rinv;
   const double delvx = a.vx - vj[0], delvy = a.vy - vj[1], delvz = a.vz - vj[2];
@@ -96,6 +100,47 @@ __device__ __forceinline__ void pair_row_eval(const RowSmem &S, const PairTab &p
   fxa += delx * fpair;
   fya += dely * fpair;
   fza += delz * fpair;
+}
+
+// Two candidates at once (independent dependency chains: twice the loads in flight and two fp64
+// chains interleaved); `two` == false evaluates only q0.  Contributions are added q0 first, then q1.
+template <bool SINGLE_TYPE>
+__device__ __forceinline__ void pair_row_eval2(const RowSmem &S, const PairTab &pt, int q0, int q1, bool two,
+                                               const RowAtom &a, unsigned step, bool random_on, double &fxa,
+                                               double &fya, double &fza)
+{
+  const double *p0 = S.pos + 3 * q0, *v0 = S.vel + 3 * q0, *p1 = S.pos + 3 * q1, *v1 = S.vel + 3 * q1;
+  const double dx0 = a.x - p0[0], dy0 = a.y - p0[1], dz0 = a.z - p0[2];
+  const double dx1 = a.x - p1[0], dy1 = a.y - p1[1], dz1 = a.z - p1[2];
+  const double du0 = a.vx - v0[0], dv0 = a.vy - v0[1], dw0 = a.vz - v0[2];
+  const double du1 = a.vx - v1[0], dv1 = a.vy - v1[1], dw1 = a.vz - v1[2];
+  const int tg0 = S.tag[q0], tg1 = S.tag[q1];
+  const int t0 = SINGLE_TYPE ? 1 : (int) S.type[q0], t1 = SINGLE_TYPE ? 1 : (int) S.type[q1];
+  const double rsq0 = dx0 * dx0 + dy0 * dy0 + dz0 * dz0, rsq1 = dx1 * dx1 + dy1 * dy1 + dz1 * dz1;
+  // the exact cutoff test (pair_dpd.cpp:116; phase 1 screens in fp32 with a margin) and :119
+  const bool ok0 = rsq0 < pt.cutsq[a.type][t0] && rsq0 >= EPSILON_DPD * EPSILON_DPD;
+  const bool ok1 = two && rsq1 < pt.cutsq[a.type][t1] && rsq1 >= EPSILON_DPD * EPSILON_DPD;
+  const double rinv0 = rsqrt(ok0 ? rsq0 : 1.0), rinv1 = rsqrt(ok1 ? rsq1 : 1.0);
+  const double r0 = rsq0 * rinv0, r1 = rsq1 * rinv1;
+  const double dot0 = dx0 * du0 + dy0 * dv0 + dz0 * dw0, dot1 = dx1 * du1 + dy1 * dv1 + dz1 * dw1;
+  const double wd0 = 1.0 - r0 * pt.cutinv[a.type][t0], wd1 = 1.0 - r1 * pt.cutinv[a.type][t1];
+  double s0 = pt.a0[a.type][t0] - pt.gamma[a.type][t0] * wd0 * dot0 * rinv0;
+  double s1 = pt.a0[a.type][t1] - pt.gamma[a.type][t1] * wd1 * dot1 * rinv1;
+  if (random_on) {
+    s0 += pt.sigma[a.type][t0] * pt.dtinvsqrt * dpd_gaussian(a.tag, tg0, step, pt.seed);
+    s1 += pt.sigma[a.type][t1] * pt.dtinvsqrt * dpd_gaussian(a.tag, tg1, step, pt.seed);
+  }
+  const double fp0 = ok0 ? wd0 * rinv0 * s0 : 0.0, fp1 = ok1 ? wd1 * rinv1 * s1 : 0.0;
+  if (ok0) {
+    fxa += dx0 * fp0;
+    fya += dy0 * fp0;
+    fza += dz0 * fp0;
+  }
+  if (ok1) {
+    fxa += dx1 * fp1;
+    fya += dy1 * fp1;
+    fza += dz1 * fp1;
+  }
 }
 
 template <bool SINGLE_TYPE>
@@ -143,7 +188,8 @@ __global__ void __launch_bounds__(PR_TMAX, 1)
   const int ncw = NR * nw;
 
   RowSmem S;
-  S.pos = reinterpret_cast<double *>(smem_raw);
+  S.scr = reinterpret_cast<float4 *>(smem_raw);
+  S.pos = reinterpret_cast<double *>(S.scr + cap);
   S.vel = S.pos + 3 * cap;
   S.tag = reinterpret_cast<int *>(S.vel + 3 * cap);
   S.cbeg = S.tag + cap;
@@ -161,12 +207,10 @@ __global__ void __launch_bounds__(PR_TMAX, 1)
     H.row_base[tid] = (bx < 0 || bx >= g.nx) ? -1 : (bx * g.ny + by) * g.nz;
     H.yshift[tid] = sh;
   }
-  if (tid >= 16 && tid < 16 + 2 * R) {
-    const int k = tid - 16, ty = k >> 1;
-    int v = 0;
-    if (ty >= ty_first) v = cell_start[(lc * g.ny + cy + ty) * g.nz + ((k & 1) ? z1 : z0)];
-    if (k & 1) H.te[ty] = v;
-    else H.tb[ty] = v;
+  if (tid == 31) {
+    H.org[0] = g.lo[0] + (lc + g.cxoff) * (g.prd[0] / g.gnx);
+    H.org[1] = g.lo[1] + cy * (g.prd[1] / g.ny);
+    H.org[2] = g.lo[2] + z0 * (g.prd[2] / g.nz);
   }
   __syncthreads();
 
@@ -187,6 +231,13 @@ __global__ void __launch_bounds__(PR_TMAX, 1)
     }
     S.cbeg[w * NR + r] = cnt;
     S.gbeg[w * NR + r] = gb;
+  }
+  if (tid >= T - 2 * R) {  // slot ranges of the tile rows (same round trip as the counts)
+    const int k = T - 1 - tid, ty = k >> 1;
+    int v = 0;
+    if (ty >= ty_first) v = cell_start[(lc * g.ny + cy + ty) * g.nz + ((k & 1) ? z1 : z0)];
+    if (k & 1) H.te[ty] = v;
+    else H.tb[ty] = v;
   }
   __syncthreads();
   if (tid < 32) {  // exclusive scan of the counts by one warp, a contiguous run per lane
@@ -214,14 +265,14 @@ __global__ void __launch_bounds__(PR_TMAX, 1)
   const bool staged = H.nstaged + 4 <= cap;  // 4 slack entries: phase 1 reads up to 3 past a segment
 
   // ---- staging copy: one thread per staged atom (balanced, consecutive threads copy consecutive
-  // atoms), every copy asynchronous.  The cell of staged index d is found from the estimate
-  // d * cells / atoms and a short probe of the offset table.
+  // atoms), every copy asynchronous.  The cell of each staged index is first written to a table
+  // (it aliases the tag array: entry d is read by the thread that then issues the copy into tag[d]).
   if (staged) {
-    const float c_per_a = (float) ncw / (float) max(H.nstaged, 1);
+    for (int ci = tid; ci < ncw; ci += T)
+      for (int d = S.cbeg[ci]; d < S.cbeg[ci + 1]; d++) S.tag[d] = ci;
+    __syncthreads();
     for (int d = tid; d < H.nstaged; d += T) {
-      int ci = min((int) ((float) d * c_per_a), ncw - 1);
-      while (S.cbeg[ci] > d) ci--;
-      while (S.cbeg[ci + 1] <= d) ci++;
+      const int ci = S.tag[d];
       const int k = d - S.cbeg[ci];
       int j = S.gbeg[ci] + k;
       if (have_extras) {  // atoms appended after the sort sit behind the cell's sorted atoms
@@ -245,10 +296,9 @@ __global__ void __launch_bounds__(PR_TMAX, 1)
       cp_async4(S.tag + d, p.tag + j);
       if (!SINGLE_TYPE) S.type[d] = (unsigned char) p.type[j];
     }
-    if (tid < 4) {  // slack entries read by the last screen group: far away, never a hit
+    if (tid < 4) {  // slack entries read by the last screen group (masked afterwards): keep them finite
       const int d = H.nstaged + tid;
-      S.pos[3 * d] = S.pos[3 * d + 1] = S.pos[3 * d + 2] = 1.0e150;
-      if (!SINGLE_TYPE) S.type[d] = 1;
+      S.pos[3 * d] = S.pos[3 * d + 1] = S.pos[3 * d + 2] = 1.0e30;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -271,6 +321,13 @@ __global__ void __launch_bounds__(PR_TMAX, 1)
         S.pos[3 * d + 2] = (PREWRAP ? wrap1(zj, g.lo[2], g.hi[2], g.prd[2]) : zj) + zs;
       }
     }
+    __syncthreads();
+    // fp32 screening copy, relative to the tile's low corner (|coordinate| < ~70 cell widths, so the
+    // absolute error is < 1e-5 and the relative margin on cutsq below covers it many times over)
+    const double ox = H.org[0], oy = H.org[1], oz = H.org[2];
+    for (int d = tid; d < H.nstaged + 4; d += T)
+      S.scr[d] = make_float4((float) (S.pos[3 * d] - ox), (float) (S.pos[3 * d + 1] - oy),
+                             (float) (S.pos[3 * d + 2] - oz), 0.0f);
   }
   __syncthreads();
 
@@ -312,75 +369,80 @@ __global__ void __launch_bounds__(PR_TMAX, 1)
     a.vx = S.vel[3 * qs]; a.vy = S.vel[3 * qs + 1]; a.vz = S.vel[3 * qs + 2];
     a.tag = S.tag[qs];
     a.type = SINGLE_TYPE ? 1 : (int) S.type[qs];
-    // candidate segments: window cells w-1, w, w+1, rows ty..ty+2 (nine cells each); one run for R = 1
+    // candidate segments: window cells w-1, w, w+1; in each the rows ty..ty+2 (nine cells) are contiguous
     int sb[3], se[3];
-    if (R == 1) {
-      sb[0] = S.cbeg[(w - 1) * NR];
-      se[0] = S.cbeg[(w + 2) * NR];
-    } else {
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+      sb[s] = S.cbeg[(w - 1 + s) * NR + ty * 3];
+      se[s] = S.cbeg[(w - 1 + s) * NR + ty * 3 + 9];
+    }
+    double fxa = 0.0, fya = 0.0, fza = 0.0;
+    const unsigned hbase = (unsigned) __cvta_generic_to_shared(S.hits + tid);
+    unsigned hp = hbase;  // next free slot of my hit list: hits[k*T + tid]
+    bool fast = (se[0] - sb[0] <= 64) && (se[1] - sb[1] <= 64) && (se[2] - sb[2] <= 64) && (se[2] - sb[0] <= 256);
+    if (fast) {
+      // ---- phase 1: fp32 screen, one LDS.128 per candidate.  The sign of rsq - cut is funnel-shifted
+      // into a word (first candidate highest), the word is bit-reversed so that candidate j sits at
+      // bit j, and its set bits are appended to the hit list as byte offsets from sb[0].  The margin
+      // on the cutoff makes the screen a superset of the exact fp64 test of phase 2.
+      const float4 me = S.scr[qs];
+      const float cut32 = (float) pt.cutmax * (float) pt.cutmax * 1.0001f;
+      int nh = 0;
 #pragma unroll
       for (int s = 0; s < 3; s++) {
-        sb[s] = S.cbeg[(w - 1 + s) * NR + ty * 3];
-        se[s] = S.cbeg[(w - 1 + s) * NR + ty * 3 + 9];
-      }
-    }
-    constexpr int NSEG = (R == 1) ? 1 : 3;
-    const int qb = sb[0];
-    double fxa = 0.0, fya = 0.0, fza = 0.0;
-    // hit list: byte offsets from qb, slot k of thread tid at hits[k*T + tid]
-    const unsigned hbase = (unsigned) __cvta_generic_to_shared(S.hits + tid);
-    const unsigned hlim = hbase + (PR_HCAP - 4) * T;
-    unsigned hp = hbase;
-    bool ovf = (se[NSEG - 1] - qb) > 256;
-    if (!ovf) {
-      // ---- phase 1: screen.  The push is branch-free: every candidate's offset is stored at the next
-      // free slot, and the slot only advances on a hit.  A group may run up to 3 candidates past its
-      // segment: what lies there are cells at least one cell width (>= cutoff) away in y or z, or
-      // the far-away slack entries, so the cutoff test itself rejects them -- no tail mask.
 #pragma unroll
-      for (int s = 0; s < NSEG; s++) {
-        const int qe = se[s];
-        for (int q0 = sb[s]; q0 < qe; q0 += 4) {
-          ovf = ovf || (hp > hlim);
-          hp = min(hp, hlim);
-          double rs[4];
+        for (int half = 0; half < 2; half++) {
+          unsigned word = 0;
+          const int qb = sb[s] + 32 * half, qe = min(se[s], qb + 32);
+          int cnt = 0;
+          for (int q0 = qb; q0 < qe; q0 += 4, cnt += 4) {
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const double *pj = S.pos + 3 * (q0 + u);
-            const double dx = a.x - pj[0], dy = a.y - pj[1], dz = a.z - pj[2];
-            rs[u] = dx * dx + dy * dy + dz * dz;
+            for (int u = 0; u < 4; u++) {
+              const float4 c = S.scr[q0 + u];
+              const float dx = me.x - c.x, dy = me.y - c.y, dz = me.z - c.z;
+              const float rsq = dx * dx + dy * dy + dz * dz;
+              word = __funnelshift_l(__float_as_uint(rsq - cut32), word, 1);
+            }
           }
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const int tj = SINGLE_TYPE ? 1 : (int) S.type[q0 + u];
-            // store the offset, then advance the slot iff (rsq < cutsq and not myself)
-            asm volatile(
-                "{ .reg .pred p;\n\t"
-                "st.shared.u8 [%0], %1;\n\t"
-                "setp.ne.s32 p, %2, %3;\n\t"
-                "setp.lt.and.f64 p, %4, %5, p;\n\t"
-                "@p add.u32 %0, %0, %6; }"
-                : "+r"(hp)
-                : "r"(q0 + u - qb), "r"(q0 + u), "r"(qs), "d"(rs[u]), "d"(pt.cutsq[a.type][tj]), "r"(T)
-                : "memory");
+          word = cnt > 0 ? (__brev(word) >> (32 - cnt)) : 0u;
+          // a group may run up to 3 candidates past the segment: drop those bits
+          const int n = se[s] - qb;  // candidates of this word (<= 0: none)
+          if (n < 32) word &= (n > 0) ? ((1u << n) - 1u) : 0u;
+          if (s == 1) {  // not myself (my own cell is in the middle segment)
+            const int so = qs - qb;
+            if (so >= 0 && so < 32) word &= ~(1u << so);
+          }
+          nh += __popc(word);
+          if (nh <= PR_HCAP) {
+            const int off0 = qb - sb[0];
+            while (word) {
+              const int kbit = __ffs(word) - 1;
+              word &= word - 1u;
+              asm volatile("st.shared.u8 [%0], %1;" ::"r"(hp), "r"(off0 + kbit) : "memory");
+              hp += T;
+            }
           }
         }
       }
-    }
-    if (!ovf) {
-      // ---- phase 2: evaluate the listed hits ----------------------------------------------------
-      for (unsigned hq = hbase; hq < hp; hq += T) {
-        unsigned off;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(off) : "r"(hq) : "memory");
-        pair_row_eval<SINGLE_TYPE>(S, pt, qb + (int) off, a, step, random_on != 0, fxa, fya, fza);
+      fast = nh <= PR_HCAP;
+      if (fast) {
+        // ---- phase 2: evaluate the listed hits in fp64 ---------------------------------------------
+        for (unsigned hq = hbase; hq < hp; hq += 2 * T) {
+          unsigned off0, off1;
+          const bool two = hq + T < hp;
+          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(off0) : "r"(hq) : "memory");
+          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(off1) : "r"(two ? hq + T : hq) : "memory");
+          pair_row_eval2<SINGLE_TYPE>(S, pt, sb[0] + (int) off0, sb[0] + (int) off1, two, a, step, random_on != 0,
+                                      fxa, fya, fza);
+        }
       }
-    } else {
-      // more neighbours than the list holds, or a span beyond a byte: test and evaluate in place
+    }
+    if (!fast) {
+      // an unusually crowded neighbourhood: test and evaluate in place, same order
 #pragma unroll
-      for (int s = 0; s < NSEG; s++)
+      for (int s = 0; s < 3; s++)
         for (int q = sb[s]; q < se[s]; q++)
-          if (q != qs && pair_row_hit<SINGLE_TYPE>(S, pt, q, a))
-            pair_row_eval<SINGLE_TYPE>(S, pt, q, a, step, random_on != 0, fxa, fya, fza);
+          if (q != qs) pair_row_eval<SINGLE_TYPE>(S, pt, q, a, step, random_on != 0, fxa, fya, fza);
     }
     fx[i] = fxa;
     fy[i] = fya;
