@@ -10,8 +10,8 @@ N=1: BASELINE config 2, "OBMD-DPD fluid at equilibrium, 1M particles" = the ship
 configuration tiled 4x5x4 (1 010 960 atoms), steady-exchange regime R1 (alpha 1.0,
 nbuf = int(0.15 N)), see SURVEY 8(d).  value = sum over steps of the atom count / device time
 (CUDA events on the library's stream, max over ranks).  e2e = the same metric through the C ABI
-with HOST buffers: every step uploads x,v from pinned memory, runs the hooks, reads forces (and
-the atom arrays when insertions/deletions changed them) back -- the flow of the LAMMPS plugin.
+with HOST-owned atom arrays: every step uploads x,v from pinned memory (obmd_upload_xv), runs one
+device step (obmd_run) and reads x,v,f,tag,type,image back into pinned memory (obmd_download).
 """
 import argparse
 import json
@@ -186,7 +186,7 @@ def ours(args):
     # ---- e2e through the C ABI with host buffers (plugin flow) ----
     e2e = None
     if args.e2e_steps > 0:
-        e2e = (e2e_run if world == 1 else e2e_run_slab)(sim, args.e2e_steps, step, barrier)
+        e2e = e2e_run(sim, args.e2e_steps, step, barrier)
         step += args.e2e_steps
 
     t = torch.tensor([ms, float(atom_steps), e2e["seconds"] if e2e else 0.0,
@@ -224,7 +224,7 @@ def ours(args):
                        "usher_trials": int(st.ntrials), "usher_rounds": int(st.nrounds)},
             "gpu_launches": int(launches),
             "kernel_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in fam.items()},
-            "roofline": {"kernel": "k_pair_dpd", "bound": "hbm", "achieved": achieved, "peak": hbm,
+            "roofline": {"kernel": "k_pair_row", "bound": "hbm", "achieved": achieved, "peak": hbm,
                          "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic, "peak_source": how,
                          "algorithmic_bytes_per_atom": PAIR_BYTES_PER_ATOM,
                          "note": "fp64-pipe bound, not HBM bound: see DESIGN.md section 6"},
@@ -246,58 +246,26 @@ def ours(args):
         dist.destroy_process_group()
 
 
-def e2e_run_slab(sim, nsteps, step, barrier):
-    """Slab runs: one device step, then the state makes a round trip through pinned host buffers
-    (what a host-resident integrator or output stage would need every step)."""
+def e2e_run(sim, nsteps, step, barrier):
+    """End to end through the C ABI with HOST-owned atom arrays (pinned): every step uploads x, v
+    (obmd_upload_xv, 48 B/atom), runs one device step (obmd_run), and reads x, v, f and -- because
+    the fix inserts and deletes every step -- tag, type, image back (obmd_download, 84 B/atom),
+    so the host copy is current after every step, as a host-resident caller needs it."""
+    import torch
+    n = sim.nlocal
+    cap = int(n * 1.1) + 4096
+    pin = lambda *shape, dt=torch.float64: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+    buf = {"x": pin(cap, 3), "v": pin(cap, 3), "f": pin(cap, 3), "tag": pin(cap, dt=torch.int32),
+           "type": pin(cap, dt=torch.int32), "image": pin(cap, dt=torch.int32)}
+    o = sim.download(out=buf)
     h2d = d2h = atom_steps = 0
     barrier()
     t0 = time.perf_counter()
     for s in range(nsteps):
+        sim.upload_xv(o["x"], o["v"]); h2d += 48 * len(o["x"])
         sim.run(step + s, 1)
-        o = sim.download(("x", "v", "f"))
-        n = len(o["x"]); d2h += 72 * n
-        sim.upload_xv(o["x"], o["v"]); h2d += 48 * n
-        atom_steps += n
-    barrier()
-    sec = time.perf_counter() - t0
-    return {"seconds": sec, "atom_steps": atom_steps, "h2d": h2d // nsteps, "d2h": d2h // nsteps}
-
-
-def e2e_run(sim, nsteps, step, barrier):
-    """Plugin flow: host owns x,v,f (pinned); per step upload x,v, run the device hooks, read f
-    (and the full atom arrays when the fix inserted/deleted) back; the host does the NVE halves as
-    LAMMPS' FixNVE would."""
-    import torch
-    out = sim.download()
-    n = sim.nlocal
-    cap = int(n * 1.1) + 4096
-    pin = lambda *shape, dt=torch.float64: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
-    X, V, F = pin(cap, 3), pin(cap, 3), pin(cap, 3)
-    X[:n], V[:n], F[:n] = out["x"], out["v"], out["f"]
-    dt = 0.001464
-    dtf = 0.5 * dt
-    h2d = d2h = 0
-    atom_steps = 0
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(nsteps):
-        V[:n] += dtf * F[:n]            # FixNVE::initial_integrate on the host (mass 1)
-        X[:n] += dt * V[:n]
-        sim.upload_xv(X[:n], V[:n]); h2d += 48 * n
-        sim.build_cells()
-        rep, _ = sim.pre_exchange()
-        sim.pbc()
-        sim.pair_compute(step + s)
-        sim.post_force()
-        m = sim.nlocal
-        if rep.ndel or rep.naccept:     # atom arrays changed: the shim refreshes the host copy
-            o = sim.download(("x", "v", "f"))
-            X[:m], V[:m], F[:m] = o["x"], o["v"], o["f"]; d2h += 72 * m
-        else:
-            o = sim.download(("x", "f"))
-            X[:m], F[:m] = o["x"], o["f"]; d2h += 48 * m
-        n = m
-        V[:n] += dtf * F[:n]            # FixNVE::final_integrate
+        o = sim.download(out=buf)
+        n = len(o["x"]); d2h += 84 * n
         atom_steps += n
     barrier()
     sec = time.perf_counter() - t0

@@ -355,10 +355,19 @@ class ObmdB200:
         x = np.ascontiguousarray(x, np.float64); v = np.ascontiguousarray(v, np.float64)
         self._ck(self.L.obmd_upload_xv(self.h, len(x), _dptr(x), _dptr(v)))
 
-    def download(self, want=("x", "v", "f", "type", "tag", "image")):
+    def download(self, want=("x", "v", "f", "type", "tag", "image"), out=None):
+        """Atom arrays in LAMMPS local order.  `out` may hold preallocated (e.g. pinned) arrays with
+        room for nlocal rows under the same keys; views of their first nlocal rows are returned."""
         n = self.nlocal
+        arr = {}
+        for k in want:
+            if out is not None and k in out:
+                a = out[k][:n]
+                assert a.flags.c_contiguous and a.dtype == (np.float64 if k in ("x", "v", "f") else np.int32)
+                arr[k] = a
+            else:
+                arr[k] = np.empty((n, 3)) if k in ("x", "v", "f") else np.empty(n, np.int32)
         out = {}
-        arr = {k: (np.empty((n, 3)) if k in ("x", "v", "f") else np.empty(n, np.int32)) for k in want}
         nn = C.c_int()
         self._ck(self.L.obmd_download(self.h, C.byref(nn), _dptr(arr.get("x")), _dptr(arr.get("v")),
                                       _dptr(arr.get("f")), _iptr(arr.get("type")), _iptr(arr.get("tag")),

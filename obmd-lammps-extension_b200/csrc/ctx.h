@@ -255,6 +255,7 @@ int cells_build(obmd_ctx *c);                                   // cells.cu
 int pair_compute(obmd_ctx *c, long long step, int eflag, int vflag);  // pair.cu
 int pair_compute_cols(obmd_ctx *c, long long step, const ColRange &cr, cudaStream_t st);
 int pair_compute_list(obmd_ctx *c, long long step, const int *slot_list, const int *slot_count, int slot_max);
+int pair_add_insertions(obmd_ctx *c, long long step, const int *list, const int *count, int cap);
 int fix_redo_pair_near_insertions(obmd_ctx *c, long long step);
 int fix_pbc_cols(obmd_ctx *c, const ColRange &cr, cudaStream_t st);
 ColRange all_columns(const obmd_ctx *c);

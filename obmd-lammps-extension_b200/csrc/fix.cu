@@ -315,8 +315,8 @@ static int ranpark_skip(int seed, long long n)  // random_park.cpp:43-50 applied
 // =====================================================================================
 
 #define USH_WARPS 4
-#define USH_CAP 96    // contributions per energy evaluation held per warp (mean 13 at rho = 3)
-#define USH_CAND 448  // atoms in the 27 stencil cells of a point (mean 81 at rho = 3)
+#define USH_CAP 64    // contributions per energy evaluation held per warp (mean 13 at rho = 3)
+#define USH_CAND 176  // atoms in the 27 stencil cells of a point (mean 81 at rho = 3)
 
 struct UsherCfg {
   int ntrL, ntr;      // trials for the left region come first (maxattempt == 1)
@@ -349,9 +349,12 @@ __device__ __forceinline__ double ranpark_uniform(int &seed)
 struct WarpHits {
   int key[USH_CAP];   // LAMMPS local index of the contributing atom
   int tj[USH_CAP];    // its type
-  double e[USH_CAP], fx[USH_CAP], fy[USH_CAP], fz[USH_CAP];  // pass A: rsq, del
-  double se[USH_CAP + 4], sfx[USH_CAP + 4], sfy[USH_CAP + 4], sfz[USH_CAP + 4];  // phi, f by rank
-  int cand[USH_CAND]; // storage slots of the atoms in the 27 stencil cells
+  // pass A: rsq, del of each hit; pass B overwrites them with phi, f ordered by local index
+  double e[USH_CAP + 4], fx[USH_CAP + 4], fy[USH_CAP + 4], fz[USH_CAP + 4];
+  // the atoms of the 27 stencil cells of the cell the point is in: gathered once, reused by every
+  // iteration that stays in that cell (a steepest-descent step is a fraction of a cell width)
+  double cx[USH_CAND], cy[USH_CAND], cz[USH_CAND];
+  int ckey[USH_CAND], ctj[USH_CAND];  // LAMMPS local index, type
 };
 
 // Pass A of energy() (:1791-1800): separation with the reference's minimum_image loop
@@ -397,25 +400,21 @@ __device__ __forceinline__ void usher_single(int it, int tj, const PairTab &pt, 
   fz = fforce * fz;
 }
 
-// One warp evaluates E and f at point c: gathers contributions from the 27 cells and from the
-// atoms accepted earlier in this pre_exchange (previous round's state), orders them by LAMMPS
-// local index and sums them left to right -- the reference's summation order (:1790-1807).
-__device__ void usher_energy(const double c[3], int t, const Planes &p, const Grid &g, const PairTab &pt,
-                             const FixDev &fd, const int *__restrict__ cell_start, const UsherCfg &u,
-                             const int *__restrict__ acc_list, const obmd_trial *__restrict__ prev,
-                             const Extras &ex, const int *__restrict__ extra_head,
-                             const int *__restrict__ extra_next, const int *__restrict__ spec_head,
-                             const int *__restrict__ spec_next, WarpHits &H, StepScalars *sc, double &E,
-                             double f[3])
+// One warp gathers the atoms of the 27 cells around cell (cx, cy, cz) into its shared-memory
+// candidate arrays: the sorted atoms of each cell, the atoms appended after the sort (slab runs),
+// and the atoms accepted earlier in this pre_exchange (previous round's state, only those of
+// trials before t).  Returns the number of candidates (0 and an error flag if they do not fit).
+__device__ int usher_gather(int cx, int cy, int cz, int t, const Planes &p, const Grid &g, const FixDev &fd,
+                            const int *__restrict__ cell_start, const UsherCfg &u,
+                            const int *__restrict__ acc_list, const obmd_trial *__restrict__ prev,
+                            const Extras &ex, const int *__restrict__ extra_head,
+                            const int *__restrict__ extra_next, const int *__restrict__ spec_head,
+                            const int *__restrict__ spec_next, WarpHits &H, StepScalars *sc)
 {
   const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
-  const int it = fd.ntype;
-  int nh = 0;
   // Lanes 0..26 each own one stencil cell: one round trip fetches all 27 cell ranges, a warp scan
-  // turns them into a flat candidate list, and the candidates are then visited 32 at a time with
-  // independent loads (two dependent global round trips per energy evaluation instead of 54).
-  int cx = cell_cx(g, c[0]), cy = cell_cy(g, c[1]), cz = cell_cz(g, c[2]);
+  // turns them into a flat candidate list, and the candidates are then loaded 32 at a time with
+  // independent loads (two dependent global round trips per gather).
   int jb = 0, cnt = 0, cc = -1, cex = 0;
   const bool have_extras = (ex.narr + ex.nghost + ex.nins) > 0;  // slab runs: arrivals and ghosts
   if (lane < 27) {
@@ -446,116 +445,132 @@ __device__ void usher_energy(const double c[3], int t, const Planes &p, const Gr
   off -= cnt + cex;  // exclusive
   if (ncand > USH_CAND) {
     if (lane == 0) sc->usher_error = OBMD_ERR_CAPACITY;
-  } else {
-    for (int k = 0; k < cnt; k++) H.cand[off + k] = jb + k;
-    if (cex) {
-      int k = cnt;
-      if (have_extras)
-        for (int e = extra_head[cc]; e >= 0; e = extra_next[e]) H.cand[off + k++] = ex.base + e;
-      if (u.nacc_prev > 0)
-        for (int e = spec_head[cc]; e >= 0; e = spec_next[e])
-          if (acc_list[e] < t) H.cand[off + k++] = -(e + 1);
+    return 0;
+  }
+  // slot of every candidate (ctj doubles as the scratch for it), then the data
+  for (int k = 0; k < cnt; k++) H.ctj[off + k] = jb + k;
+  if (cex) {
+    int k = cnt;
+    if (have_extras)
+      for (int e = extra_head[cc]; e >= 0; e = extra_next[e]) H.ctj[off + k++] = ex.base + e;
+    if (u.nacc_prev > 0)
+      for (int e = spec_head[cc]; e >= 0; e = spec_next[e])
+        if (acc_list[e] < t) H.ctj[off + k++] = -(e + 1);
+  }
+  __syncwarp();
+  for (int q = lane; q < ncand; q += 32) {
+    const int j = H.ctj[q];
+    if (j >= 0) {
+      H.ctj[q] = p.type[j];
+      H.ckey[q] = p.lidx[j];
+      H.cx[q] = p.x[j];
+      H.cy[q] = p.y[j];
+      H.cz[q] = p.z[j];
+    } else {  // created earlier in this call: local index nbase + rank in the accepted list
+      const int e = -j - 1;
+      const obmd_trial &a = prev[acc_list[e]];
+      H.ctj[q] = fd.ntype;
+      H.ckey[q] = u.nbase + e;
+      H.cx[q] = a.end[0];
+      H.cy[q] = a.end[1];
+      H.cz[q] = a.end[2];
     }
   }
   __syncwarp();
-  const int nc = ncand > USH_CAND ? 0 : ncand;
-  // pass A over the stencil atoms: cheap screen, hits compacted into the warp's list.  Three
-  // candidates per lane per trip (96 covers the usual 81), all loads issued before the first use,
-  // so a trip costs one global round trip instead of three.
-  for (int q0 = 0; q0 < nc; q0 += 96) {
-    double xj[3], yj[3], zj[3];
-    int key[3], tj[3];
-    bool val[3];
-#pragma unroll
-    for (int u2 = 0; u2 < 3; u2++) {
-      const int q = q0 + 32 * u2 + lane;
-      val[u2] = q < nc;
-      key[u2] = 0;
-      tj[u2] = it;
-      xj[u2] = yj[u2] = zj[u2] = 0.0;
-      if (val[u2]) {
-        const int j = H.cand[q];
-        if (j >= 0) {
-          tj[u2] = p.type[j];
-          key[u2] = p.lidx[j];
-          xj[u2] = p.x[j];
-          yj[u2] = p.y[j];
-          zj[u2] = p.z[j];
-        } else {  // created earlier in this call: local index nbase + rank in the accepted list
-          const int e = -j - 1;
-          const obmd_trial &a = prev[acc_list[e]];
-          tj[u2] = fd.ntype;
-          key[u2] = u.nbase + e;
-          xj[u2] = a.end[0];
-          yj[u2] = a.end[1];
-          zj[u2] = a.end[2];
-        }
+  return ncand;
+}
+
+// One warp evaluates E and f at point c from the gathered candidates: screens them, orders the
+// contributions by LAMMPS local index and sums them left to right -- the reference's summation
+// order (:1790-1807).
+__device__ void usher_energy(const double c[3], int nc, const Grid &g, const PairTab &pt, const FixDev &fd,
+                             WarpHits &H, StepScalars *sc, double &E, double f[3])
+{
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int it = fd.ntype;
+  int nh = 0;
+  // pass A over the stencil atoms: cheap screen, hits compacted into the warp's list
+  for (int q0 = 0; q0 < nc; q0 += 32) {
+    const int q = q0 + lane;
+    double rsq = 0, dx = 0, dy = 0, dz = 0;
+    int key = 0, tj = it;
+    bool hit = false;
+    if (q < nc) {
+      key = H.ckey[q];
+      tj = H.ctj[q];
+      hit = usher_screen(c, H.cx[q], H.cy[q], H.cz[q], it, tj, g, pt, rsq, dx, dy, dz);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      int s2 = nh + __popc(m & lt);
+      if (s2 < USH_CAP) {
+        H.key[s2] = key;
+        H.tj[s2] = tj;
+        H.e[s2] = rsq;
+        H.fx[s2] = dx;
+        H.fy[s2] = dy;
+        H.fz[s2] = dz;
       }
     }
-#pragma unroll
-    for (int u2 = 0; u2 < 3; u2++) {
-      if (q0 + 32 * u2 >= nc) break;  // warp-uniform
-      double rsq = 0, dx = 0, dy = 0, dz = 0;
-      bool hit = val[u2] && usher_screen(c, xj[u2], yj[u2], zj[u2], it, tj[u2], g, pt, rsq, dx, dy, dz);
-      unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) {
-        int s2 = nh + __popc(m & lt);
-        if (s2 < USH_CAP) {
-          H.key[s2] = key[u2];
-          H.tj[s2] = tj[u2];
-          H.e[s2] = rsq;
-          H.fx[s2] = dx;
-          H.fy[s2] = dy;
-          H.fz[s2] = dz;
-        }
-      }
-      nh += __popc(m);
-    }
+    nh += __popc(m);
   }
   if (nh > USH_CAP) {
     if (lane == 0) sc->usher_error = OBMD_ERR_CAPACITY;
     nh = USH_CAP;
   }
   __syncwarp();
-  // pass B (dense: usually a single sweep): PairDPD::single, then each contribution is stored at
-  // its rank by local index (keys are distinct), zero-padded to a multiple of four
-  for (int s = lane; s < nh; s += 32) {
-    double e, fx = H.fx[s], fy = H.fy[s], fz = H.fz[s];
-    usher_single(it, H.tj[s], pt, H.e[s], e, fx, fy, fz);
-    int k = H.key[s], r = 0;
-    for (int q = 0; q < nh; q++) r += (H.key[q] < k);
-    H.se[r] = e;
-    H.sfx[r] = fx;
-    H.sfy[r] = fy;
-    H.sfz[r] = fz;
-  }
-  const int nh4 = (nh + 3) & ~3;
-  if (lane < nh4 - nh) {
-    H.se[nh + lane] = 0.0;
-    H.sfx[nh + lane] = 0.0;
-    H.sfy[nh + lane] = 0.0;
-    H.sfz[nh + lane] = 0.0;
-  }
-  __syncwarp();
-  // left-to-right sums in ascending local index (the reference's loop order, :1790-1807); adding
-  // the +0.0 padding is exact, and four elements per trip keep the loads ahead of the add chains
-  double Es = 0.0, f0 = 0.0, f1 = 0.0, f2 = 0.0;
-  if (lane == 0) {
-    for (int r = 0; r < nh4; r += 4) {
-      double e0 = H.se[r], e1 = H.se[r + 1], e2 = H.se[r + 2], e3 = H.se[r + 3];
-      double a0 = H.sfx[r], a1 = H.sfx[r + 1], a2 = H.sfx[r + 2], a3 = H.sfx[r + 3];
-      double b0 = H.sfy[r], b1 = H.sfy[r + 1], b2 = H.sfy[r + 2], b3 = H.sfy[r + 3];
-      double c0 = H.sfz[r], c1 = H.sfz[r + 1], c2 = H.sfz[r + 2], c3 = H.sfz[r + 3];
-      Es += e0; Es += e1; Es += e2; Es += e3;
-      f0 += a0; f0 += a1; f0 += a2; f0 += a3;
-      f1 += b0; f1 += b1; f1 += b2; f1 += b3;
-      f2 += c0; f2 += c1; f2 += c2; f2 += c3;
+  // pass B (dense): PairDPD::single, then each contribution is stored at its rank by local index
+  // (keys are distinct) in the same arrays -- every lane holds its (at most two) results in registers
+  // until the whole warp has read its inputs -- zero-padded to a multiple of four
+  double ev[USH_CAP / 32], xv[USH_CAP / 32], yv[USH_CAP / 32], zv[USH_CAP / 32];
+  int rk[USH_CAP / 32];
+#pragma unroll
+  for (int c2 = 0; c2 < USH_CAP / 32; c2++) {
+    const int s = lane + 32 * c2;
+    rk[c2] = -1;
+    if (s < nh) {
+      double e, fx = H.fx[s], fy = H.fy[s], fz = H.fz[s];
+      usher_single(it, H.tj[s], pt, H.e[s], e, fx, fy, fz);
+      int k = H.key[s], r = 0;
+      for (int q = 0; q < nh; q++) r += (H.key[q] < k);
+      rk[c2] = r; ev[c2] = e; xv[c2] = fx; yv[c2] = fy; zv[c2] = fz;
     }
   }
+  __syncwarp();
+#pragma unroll
+  for (int c2 = 0; c2 < USH_CAP / 32; c2++)
+    if (rk[c2] >= 0) {
+      H.e[rk[c2]] = ev[c2];
+      H.fx[rk[c2]] = xv[c2];
+      H.fy[rk[c2]] = yv[c2];
+      H.fz[rk[c2]] = zv[c2];
+    }
+  const int nh4 = (nh + 3) & ~3;
+  if (lane < nh4 - nh) {
+    H.e[nh + lane] = 0.0;
+    H.fx[nh + lane] = 0.0;
+    H.fy[nh + lane] = 0.0;
+    H.fz[nh + lane] = 0.0;
+  }
+  __syncwarp();
+  // left-to-right sums in ascending local index (the reference's loop order, :1790-1807), one lane
+  // per quantity; adding the +0.0 padding is exact, and four elements per trip keep the loads ahead
+  // of the add chain
+  double acc = 0.0;
+  if (lane < 4) {
+    const double *arr = lane == 0 ? H.e : (lane == 1 ? H.fx : (lane == 2 ? H.fy : H.fz));
+    for (int r = 0; r < nh4; r += 4) {
+      const double a0 = arr[r], a1 = arr[r + 1], a2 = arr[r + 2], a3 = arr[r + 3];
+      acc += a0; acc += a1; acc += a2; acc += a3;
+    }
+  }
+  const double Es = acc, f0 = __shfl_sync(0xffffffffu, acc, 1), f1 = __shfl_sync(0xffffffffu, acc, 2),
+               f2 = __shfl_sync(0xffffffffu, acc, 3);
   E = __shfl_sync(0xffffffffu, Es, 0);
-  f[0] = __shfl_sync(0xffffffffu, f0, 0);
-  f[1] = __shfl_sync(0xffffffffu, f1, 0);
-  f[2] = __shfl_sync(0xffffffffu, f2, 0);
+  f[0] = f0;
+  f[1] = f1;
+  f[2] = f2;
   __syncwarp();
 }
 
@@ -601,9 +616,15 @@ __global__ void __launch_bounds__(USH_WARPS * 32, 6)
     c[2] = mypath[3 * i + 2];
   }
   double E = 0.0, f[3];
+  int gx = -1 << 30, gy = 0, gz = 0, nc = 0;  // cell whose stencil is in the candidate arrays
   while (i < u.natt) {
-    usher_energy(c, t, p, g, pt, fd, cell_start, u, acc_list, prev, ex, extra_head, extra_next, spec_head,
-                 spec_next, hits[w], sc, E, f);
+    const int cx = cell_cx(g, c[0]), cy = cell_cy(g, c[1]), cz = cell_cz(g, c[2]);
+    if (cx != gx || cy != gy || cz != gz) {
+      nc = usher_gather(cx, cy, cz, t, p, g, fd, cell_start, u, acc_list, prev, ex, extra_head, extra_next,
+                        spec_head, spec_next, hits[w], sc);
+      gx = cx; gy = cy; gz = cz;
+    }
+    usher_energy(c, nc, g, pt, fd, hits[w], sc, E, f);
     if (lane == 0) {
       mypath[np * 3 + 0] = c[0];
       mypath[np * 3 + 1] = c[1];
@@ -1080,7 +1101,7 @@ int fix_redo_pair_near_insertions(obmd_ctx *c, long long step)
   CK(cudaMemsetAsync(c->redo_count, 0, sizeof(int), c->stream));
   LAUNCH(k_mark_redo, cdiv(c->nins * 27, 128), 128, 0, extras_of(c), c->grid, c->cell_start, c->extra_cell,
          c->extra_head, c->extra_next, c->redo_flag, c->redo_list, c->redo_count, cap);
-  int rc = pair_compute_list(c, step, c->redo_list, c->redo_count, cap);
+  int rc = pair_add_insertions(c, step, c->redo_list, c->redo_count, cap);
   if (rc) return rc;
   LAUNCH(k_clear_redo, cdiv(cap, 256), 256, 0, c->redo_flag, c->redo_list, c->redo_count, cap);
   return OBMD_OK;

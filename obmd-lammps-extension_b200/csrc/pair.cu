@@ -312,6 +312,117 @@ __global__ void __launch_bounds__(PAIR_T)
 
 #include "pair_row.cuh"
 
+// ---- forces after USHER insertions, without recomputing anybody from scratch -----------------
+// obmd_run computes PairDPD on the side stream while USHER is still searching, i.e. without the
+// atoms it is about to create.  Afterwards (a) every new atom gets its full force, one warp per
+// atom: lanes 0..26 own one stencil cell each and the partial sums are combined by a fixed
+// shuffle tree; (b) every old atom in the 27 cells around an insertion (the list k_mark_redo
+// builds) adds the terms of the new atoms in its stencil, in per-cell list order.  Both orders
+// are functions of the data layout only, so the result is deterministic.
+template <bool SINGLE_TYPE>
+__global__ void __launch_bounds__(128)
+    k_pair_new_atoms(Planes p, Extras ex, Grid g, PairTab pt, const int *__restrict__ cell_start,
+                     const int *__restrict__ extra_head, const int *__restrict__ extra_next,
+                     double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, unsigned step,
+                     int random_on)
+{
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (k >= ex.nins) return;
+  const int i = ex.base + ex.narr + ex.nghost + k;
+  AtomI a;
+  a.x = p.x[i]; a.y = p.y[i]; a.z = p.z[i];
+  a.vx = p.vx[i]; a.vy = p.vy[i]; a.vz = p.vz[i];
+  a.tag = p.tag[i];
+  a.type = SINGLE_TYPE ? 1 : p.type[i];
+  a.bnd = true;
+  PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (lane < 27) {
+    const int bx = cell_cx(g, a.x) + lane / 9 - 1;
+    if (bx >= 0 && bx < g.nx) {
+      int by = cell_cy(g, a.y) + (lane / 3) % 3 - 1, bz = cell_cz(g, a.z) + lane % 3 - 1;
+      by = by < 0 ? by + g.ny : (by >= g.ny ? by - g.ny : by);
+      bz = bz < 0 ? bz + g.nz : (bz >= g.nz ? bz - g.nz : bz);
+      const int cc = (bx * g.ny + by) * g.nz + bz;
+      for (int j = cell_start[cc]; j < cell_start[cc + 1]; j++)
+        if (pair_screen<SINGLE_TYPE, false>(p, pt, g, j, a))
+          pair_eval<SINGLE_TYPE, false, false>(p, pt, g, j, a, step, random_on != 0, acc);
+      for (int e = extra_head[cc]; e >= 0; e = extra_next[e]) {
+        const int j = ex.base + e;
+        if (j != i && pair_screen<SINGLE_TYPE, false>(p, pt, g, j, a))
+          pair_eval<SINGLE_TYPE, false, false>(p, pt, g, j, a, step, random_on != 0, acc);
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    acc.fx += __shfl_down_sync(0xffffffffu, acc.fx, d);
+    acc.fy += __shfl_down_sync(0xffffffffu, acc.fy, d);
+    acc.fz += __shfl_down_sync(0xffffffffu, acc.fz, d);
+  }
+  if (lane == 0) {
+    fx[i] = acc.fx;
+    fy[i] = acc.fy;
+    fz[i] = acc.fz;
+  }
+}
+
+template <bool SINGLE_TYPE>
+__global__ void __launch_bounds__(128)
+    k_pair_add_new(Planes p, Extras ex, Grid g, PairTab pt, const int *__restrict__ extra_head,
+                   const int *__restrict__ extra_next, double *__restrict__ fx, double *__restrict__ fy,
+                   double *__restrict__ fz, unsigned step, int random_on, const int *__restrict__ list,
+                   const int *__restrict__ count, int cap)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= min(*count, cap)) return;
+  const int i = list[q], first_new = ex.narr + ex.nghost;
+  if (i >= ex.base + first_new) return;  // the new atoms were done by k_pair_new_atoms
+  AtomI a;
+  a.x = p.x[i]; a.y = p.y[i]; a.z = p.z[i];
+  a.vx = p.vx[i]; a.vy = p.vy[i]; a.vz = p.vz[i];
+  a.tag = p.tag[i];
+  a.type = SINGLE_TYPE ? 1 : p.type[i];
+  a.bnd = true;
+  const int cx = cell_cx(g, a.x), cy = cell_cy(g, a.y), cz = cell_cz(g, a.z);
+  PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int nb = 0; nb < 27; nb++) {
+    const int bx = cx + nb / 9 - 1;
+    if (bx < 0 || bx >= g.nx) continue;
+    int by = cy + (nb / 3) % 3 - 1, bz = cz + nb % 3 - 1;
+    by = by < 0 ? by + g.ny : (by >= g.ny ? by - g.ny : by);
+    bz = bz < 0 ? bz + g.nz : (bz >= g.nz ? bz - g.nz : bz);
+    for (int e = extra_head[(bx * g.ny + by) * g.nz + bz]; e >= 0; e = extra_next[e])
+      if (e >= first_new && pair_screen<SINGLE_TYPE, false>(p, pt, g, ex.base + e, a))
+        pair_eval<SINGLE_TYPE, false, false>(p, pt, g, ex.base + e, a, step, random_on != 0, acc);
+  }
+  fx[i] += acc.fx;
+  fy[i] += acc.fy;
+  fz[i] += acc.fz;
+}
+
+int pair_add_insertions(obmd_ctx *c, long long step, const int *list, const int *count, int cap)
+{
+  ScopedTimer t(c, "pair");
+  if (c->nins == 0) return OBMD_OK;
+  const bool single = (c->ntypes == 1);
+  const int random_on = c->temperature > 0.0 ? 1 : 0;
+  c->pt.dtinvsqrt = 1.0 / sqrt(c->dt);
+  const Extras ex = extras_of(c);
+  if (single) {
+    LAUNCH(k_pair_new_atoms<true>, cdiv(c->nins, 4), 128, 0, c->cur, ex, c->grid, c->pt, c->cell_start,
+           c->extra_head, c->extra_next, c->fx, c->fy, c->fz, (unsigned) step, random_on);
+    LAUNCH(k_pair_add_new<true>, cdiv(cap, 128), 128, 0, c->cur, ex, c->grid, c->pt, c->extra_head,
+           c->extra_next, c->fx, c->fy, c->fz, (unsigned) step, random_on, list, count, cap);
+  } else {
+    LAUNCH(k_pair_new_atoms<false>, cdiv(c->nins, 4), 128, 0, c->cur, ex, c->grid, c->pt, c->cell_start,
+           c->extra_head, c->extra_next, c->fx, c->fy, c->fz, (unsigned) step, random_on);
+    LAUNCH(k_pair_add_new<false>, cdiv(cap, 128), 128, 0, c->cur, ex, c->grid, c->pt, c->extra_head,
+           c->extra_next, c->fx, c->fy, c->fz, (unsigned) step, random_on, list, count, cap);
+  }
+  CK(cudaGetLastError());
+  return OBMD_OK;
+}
+
 // Fixed-order final reduction of block partials (one block).
 __global__ void k_pair_tally_final(const double *__restrict__ partials, int nblocks, StepScalars *sc)
 {
