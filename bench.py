@@ -177,7 +177,8 @@ def ours(args):
     launches = sim.launches - l0
     sampler.stop_flag = True; sampler.join()
     fam = {}
-    for name in ("nve", "bin", "sort", "comm", "pre_exchange", "usher", "pbc", "pair", "post_force"):
+    for name in ("nve", "bin", "sort", "comm", "pre_exchange", "usher", "usher_round0", "usher_rerun",
+                 "usher_commit", "usher_allreduce", "usher_eval0", "usher_evalN", "pbc", "pair", "post_force"):
         t, nl = sim.timing_get(name)
         fam[name] = {"ms_per_step": t / args.steps, "launches_per_step": nl / args.steps}
     sim.timing(False)

@@ -69,9 +69,12 @@ struct StepScalars {
   int ntail;                // survivors with lidx >= nprime found by the scan
   int nonfinite;            // non-numeric coordinate seen while binning
   int usher_error;          // see OBMD_ERR_USHER / capacity
-  int nchanged;             // USHER commit: trials whose state changed this round
-  int ndirty;
-  int naccept;
+  // USHER commit rounds run without host round trips: counters are double-buffered by round parity
+  int nchg2[2];             // trials whose state changed in round r (index r & 1)
+  int ndirty2[2];           // trials to re-run in round r + 1
+  int naccept;              // accepted trials after the latest round
+  int nrounds_work;         // rounds whose evaluation had work to do
+  int trial_cursor;         // next entry of the round's trial list to hand to a warp
   int rng_seed;             // RanPark state after the deletion draws
   double vnewl[3], vnewr[3];
   double gsum[4];           // G_left, G_right, Gperp_left, Gperp_right

@@ -315,6 +315,7 @@ static int ranpark_skip(int seed, long long n)  // random_park.cpp:43-50 applied
 // =====================================================================================
 
 #define USH_WARPS 4
+#define LINK_MAX 6000  // atoms per unsorted extra group (two int arrays in 48 KB of shared memory)
 #define USH_CAP 64    // contributions per energy evaluation held per warp (mean 13 at rho = 3)
 #define USH_CAND 176  // atoms in the 27 stencil cells of a point (mean 81 at rho = 3)
 
@@ -322,7 +323,6 @@ struct UsherCfg {
   int ntrL, ntr;      // trials for the left region come first (maxattempt == 1)
   int seed0;          // RanPark state before the first trial draw
   int nbase;          // local index of the first inserted atom (= nlocal after deletion)
-  int nacc_prev;      // accepted trials of the previous round (acc_list entries)
   int natt;
   int tg0;            // global index of local trial 0 (slab runs: the right rank starts at ntrL)
 };
@@ -389,7 +389,8 @@ __device__ __forceinline__ void usher_single(int it, int tj, const PairTab &pt, 
     phi = 0.0;
   } else {
     double rinv = 1.0 / r;
-    double wd = 1.0 - r / pt.cut[it][tj];
+    const double cut = pt.cut[it][tj];
+    double wd = 1.0 - (cut == 1.0 ? r : r / cut);  // r / 1.0 == r exactly: skip the division
     fforce = pt.a0[it][tj] * wd * 1.0 * rinv;
     phi = 0.5 * pt.a0[it][tj] * pt.cut[it][tj] * wd * wd;
     phi = 1.0 * phi;
@@ -417,6 +418,7 @@ __device__ int usher_gather(int cx, int cy, int cz, int t, const Planes &p, cons
   // independent loads (two dependent global round trips per gather).
   int jb = 0, cnt = 0, cc = -1, cex = 0;
   const bool have_extras = (ex.narr + ex.nghost + ex.nins) > 0;  // slab runs: arrivals and ghosts
+  const bool have_spec = sc->naccept > 0;  // atoms accepted in the previous round (0 during round 0)
   if (lane < 27) {
     int ox = lane / 9 - 1, oy = (lane / 3) % 3 - 1, oz = lane % 3 - 1;
     int bx = cx + ox;
@@ -431,7 +433,7 @@ __device__ int usher_gather(int cx, int cy, int cz, int t, const Planes &p, cons
         for (int e = extra_head[cc]; e >= 0; e = extra_next[e]) cex++;
       // atoms accepted by earlier trials of this call (previous round's state) live in their own
       // per-cell lists, so a point only ever sees the few that share its stencil
-      if (u.nacc_prev > 0)
+      if (have_spec)
         for (int e = spec_head[cc]; e >= 0; e = spec_next[e]) cex += (acc_list[e] < t);
     }
   }
@@ -453,7 +455,7 @@ __device__ int usher_gather(int cx, int cy, int cz, int t, const Planes &p, cons
     int k = cnt;
     if (have_extras)
       for (int e = extra_head[cc]; e >= 0; e = extra_next[e]) H.ctj[off + k++] = ex.base + e;
-    if (u.nacc_prev > 0)
+    if (have_spec)
       for (int e = spec_head[cc]; e >= 0; e = spec_next[e])
         if (acc_list[e] < t) H.ctj[off + k++] = -(e + 1);
   }
@@ -576,20 +578,15 @@ __device__ void usher_energy(const double c[3], int nc, const Grid &g, const Pai
 
 // One warp per trial in `list`.  Writes the trial record and the points at which the energy was
 // evaluated (needed by the dirty test of the next round).
-__global__ void __launch_bounds__(USH_WARPS * 32, 6)
-    k_usher_eval(const int *__restrict__ list, int nlist, Planes p, Grid g, PairTab pt, FixDev fd,
-                 const int *__restrict__ cell_start, UsherCfg u, Extras ex,
-                 const int *__restrict__ extra_head, const int *__restrict__ extra_next,
-                 const int *__restrict__ spec_head, const int *__restrict__ spec_next,
-                 const int *__restrict__ acc_list, const obmd_trial *__restrict__ prev,
-                 obmd_trial *__restrict__ cur,
-                 double *__restrict__ path, int *__restrict__ npts, double *__restrict__ bbox,
-                 const int *__restrict__ kfirst, StepScalars *sc)
+__device__ __forceinline__ void usher_trial(
+    int li, WarpHits *hits, const int *__restrict__ list, const Planes &p, const Grid &g, const PairTab &pt,
+    const FixDev &fd, const int *__restrict__ cell_start, const UsherCfg &u, const Extras &ex,
+    const int *__restrict__ extra_head, const int *__restrict__ extra_next,
+    const int *__restrict__ spec_head, const int *__restrict__ spec_next, const int *__restrict__ acc_list,
+    const obmd_trial *__restrict__ prev, obmd_trial *__restrict__ cur, double *__restrict__ path,
+    int *__restrict__ npts, double *__restrict__ bbox, const int *__restrict__ kfirst, StepScalars *sc)
 {
-  __shared__ WarpHits hits[USH_WARPS];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int li = blockIdx.x * USH_WARPS + w;
-  if (li >= nlist) return;
   const int t = list ? list[li] : li;
   const int tg = t + u.tg0;  // position of this trial in the (replicated) RanPark stream
   const int side = (tg < u.ntrL) ? 0 : 1;
@@ -617,8 +614,27 @@ __global__ void __launch_bounds__(USH_WARPS * 32, 6)
   }
   double E = 0.0, f[3];
   int gx = -1 << 30, gy = 0, gz = 0, nc = 0;  // cell whose stencil is in the candidate arrays
+  // bounding box of the evaluated points (prefilter of the dirty test of the next round; a re-run
+  // keeps the box of its previous path, which contains the unchanged prefix: a superset is fine)
+  double blo[3] = {c[0], c[1], c[2]}, bhi[3] = {c[0], c[1], c[2]};
+  if (list)
+    for (int d = 0; d < 3; d++) {
+      blo[d] = fmin(blo[d], bbox[(size_t) t * 6 + d]);
+      bhi[d] = fmax(bhi[d], bbox[(size_t) t * 6 + 3 + d]);
+    }
   while (i < u.natt) {
-    const int cx = cell_cx(g, c[0]), cy = cell_cy(g, c[1]), cz = cell_cz(g, c[2]);
+    for (int d = 0; d < 3; d++) {
+      blo[d] = fmin(blo[d], c[d]);
+      bhi[d] = fmax(bhi[d], c[d]);
+    }
+    // the point is inside the insertion region, hence inside the box: the cell index is at most one
+    // period off (y == yhi exactly), so the wrap needs no division
+    const int cx = cell_cx(g, c[0]);
+    int cy = (int) floor((c[1] - g.lo[1]) * g.inv[1]), cz = (int) floor((c[2] - g.lo[2]) * g.inv[2]);
+    if (cy < 0 || cy >= 2 * g.ny) cy = cell_wrap(cy, g.ny);
+    else if (cy >= g.ny) cy -= g.ny;
+    if (cz < 0 || cz >= 2 * g.nz) cz = cell_wrap(cz, g.nz);
+    else if (cz >= g.nz) cz -= g.nz;
     if (cx != gx || cy != gy || cz != gz) {
       nc = usher_gather(cx, cy, cz, t, p, g, fd, cell_start, u, acc_list, prev, ex, extra_head, extra_next,
                         spec_head, spec_next, hits[w], sc);
@@ -668,23 +684,46 @@ __global__ void __launch_bounds__(USH_WARPS * 32, 6)
     r.tag = 0;
     cur[t] = r;
     npts[t] = np;
-    // bounding box of the evaluated points (dirty test of the next round)
-    double lo[3] = {mypath[0], mypath[1], mypath[2]}, hi[3] = {mypath[0], mypath[1], mypath[2]};
-    for (int k = 1; k < np; k++)
-      for (int d = 0; d < 3; d++) {
-        lo[d] = fmin(lo[d], mypath[3 * k + d]);
-        hi[d] = fmax(hi[d], mypath[3 * k + d]);
-      }
     for (int d = 0; d < 3; d++) {
-      bbox[(size_t) t * 6 + d] = lo[d];
-      bbox[(size_t) t * 6 + 3 + d] = hi[d];
+      bbox[(size_t) t * 6 + d] = blo[d];
+      bbox[(size_t) t * 6 + 3 + d] = bhi[d];
     }
+  }
+}
+
+// One warp per trial.  Round 0 evaluates every trial (list == nullptr, nlist from the host); the
+// re-run rounds take the list and its length from device memory (ndirty2[par], written by the
+// previous round's k_usher_dirty), so that rounds can be enqueued back to back without a host
+// round trip; a round with nothing to do costs an empty grid.
+__global__ void __launch_bounds__(USH_WARPS * 32, 6)
+    k_usher_eval(const int *__restrict__ list, int nlist, int par, Planes p, Grid g, PairTab pt, FixDev fd,
+                 const int *__restrict__ cell_start, UsherCfg u, Extras ex,
+                 const int *__restrict__ extra_head, const int *__restrict__ extra_next,
+                 const int *__restrict__ spec_head, const int *__restrict__ spec_next,
+                 const int *__restrict__ acc_list, const obmd_trial *__restrict__ prev,
+                 obmd_trial *__restrict__ cur,
+                 double *__restrict__ path, int *__restrict__ npts, double *__restrict__ bbox,
+                 const int *__restrict__ kfirst, StepScalars *sc)
+{
+  __shared__ WarpHits hits[USH_WARPS];
+  const int nl = list ? sc->ndirty2[par] : nlist;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nl > 0) sc->nrounds_work++;
+  // Trials are handed out one at a time from a device counter: their lengths differ widely (a trial
+  // that leaves its region stops at once, most run all nattempt iterations), and with more trials
+  // than resident warps a static assignment would cost a whole second wave.
+  for (;;) {
+    int li = 0;
+    if ((threadIdx.x & 31) == 0) li = atomicAdd(&sc->trial_cursor, 1);
+    li = __shfl_sync(0xffffffffu, li, 0);
+    if (li >= nl) break;
+    usher_trial(li, hits, list, p, g, pt, fd, cell_start, u, ex, extra_head, extra_next, spec_head, spec_next,
+                acc_list, prev, cur, path, npts, bbox, kfirst, sc);
   }
 }
 
 // chg_list = trials whose state (accepted, end) differs between the two latest rounds
 __global__ void k_usher_diff(const obmd_trial *__restrict__ prev, const obmd_trial *__restrict__ cur,
-                             int ntr, int first_round, int *__restrict__ chg_list, StepScalars *sc)
+                             int ntr, int first_round, int par, int *__restrict__ chg_list, StepScalars *sc)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntr) return;
@@ -695,7 +734,7 @@ __global__ void k_usher_diff(const obmd_trial *__restrict__ prev, const obmd_tri
     ch = (a.accepted != b.accepted) ||
         (b.accepted && (a.end[0] != b.end[0] || a.end[1] != b.end[1] || a.end[2] != b.end[2]));
   }
-  if (ch) chg_list[atomicAdd(&sc->nchanged, 1)] = t;
+  if (ch) chg_list[atomicAdd(&sc->nchg2[par], 1)] = t;
 }
 
 // all points involved lie inside the box, so one periodic shift suffices
@@ -729,7 +768,7 @@ __device__ __forceinline__ bool near_bbox(const double *a, const double *bb, con
 // within the cutoff of any point the trial evaluated (a superset test with a small margin).
 // kfirst[t] = index of the first such point: the re-run resumes there.
 __global__ void k_usher_dirty(const obmd_trial *__restrict__ prev, const obmd_trial *__restrict__ cur,
-                              int ntr, int first_round, const int *__restrict__ chg_list,
+                              int ntr, int first_round, int par, const int *__restrict__ chg_list,
                               const double *__restrict__ path, const int *__restrict__ npts,
                               const double *__restrict__ bbox, int natt, Grid g, double rc, double rsqmax,
                               int *__restrict__ list, int *__restrict__ kfirst, StepScalars *sc)
@@ -739,7 +778,7 @@ __global__ void k_usher_dirty(const obmd_trial *__restrict__ prev, const obmd_tr
   if (t >= ntr) return;
   const double *mp = path + (size_t) t * (natt + 1) * 3;
   const double *bb = bbox + (size_t) t * 6;
-  const int np = npts[t], nchg = sc->nchanged;
+  const int np = npts[t], nchg = sc->nchg2[par];
   int kf = np;  // first affected point seen by this lane
   for (int qi = lane; qi < nchg; qi += 32) {
     int q = chg_list[qi];
@@ -758,45 +797,92 @@ __global__ void k_usher_dirty(const obmd_trial *__restrict__ prev, const obmd_tr
   for (int d = 16; d > 0; d >>= 1) kf = min(kf, __shfl_xor_sync(0xffffffffu, kf, d));
   if (kf < np && lane == 0) {
     kfirst[t] = kf;
-    list[atomicAdd(&sc->ndirty, 1)] = t;
+    list[atomicAdd(&sc->ndirty2[par], 1)] = t;
   }
 }
 
-// prev <- cur for every trial (grid copy)
-__global__ void k_usher_copy(obmd_trial *__restrict__ prev, const obmd_trial *__restrict__ cur, int ntr)
+// End of a commit round, one CTA: drops the previous round's per-cell "spec" lists, copies the
+// round's trial states to `prev`, compacts the accepted trials in order into acc_list, threads
+// them into fresh per-cell lists (what the next round's evaluations see of earlier insertions),
+// and zeroes the counters of the next round.  Deterministic: lists are ordered by trial index.
+#define URE_T 1024
+__global__ void __launch_bounds__(URE_T)
+    k_usher_round_end(obmd_trial *__restrict__ prev, const obmd_trial *__restrict__ cur, int ntr, int par,
+                      int *__restrict__ acc_list, int *__restrict__ spec_cell, int *__restrict__ spec_head,
+                      int *__restrict__ spec_next, Grid g, StepScalars *sc)
 {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < ntr) prev[t] = cur[t];
-}
-
-// prev <- cur and the ordered list of accepted trial ids (one block, ordered compaction)
-__global__ void k_usher_acc(obmd_trial *__restrict__ prev, const obmd_trial *__restrict__ cur, int ntr,
-                            int *__restrict__ acc_list, StepScalars *sc)
-{
+  extern __shared__ int cellsh[];  // cells of the accepted trials (at most LINK_MAX)
   __shared__ int base;
-  __shared__ int wsum[32];
-  if (threadIdx.x == 0) base = 0;
+  __shared__ int wsum[URE_T / 32];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int nold = sc->naccept;
+  for (int k = tid; k < nold; k += URE_T) spec_head[spec_cell[k]] = -1;
+  {  // prev <- cur, as a flat copy of doubles (sizeof(obmd_trial) is a multiple of 8)
+    static_assert(sizeof(obmd_trial) % 8 == 0, "obmd_trial must be a whole number of doubles");
+    const double *src = reinterpret_cast<const double *>(cur);
+    double *dst = reinterpret_cast<double *>(prev);
+    const int nd = ntr * (int) (sizeof(obmd_trial) / 8);
+    for (int k = tid; k < nd; k += URE_T) dst[k] = src[k];
+  }
+  if (tid == 0) base = 0;
   __syncthreads();
-  for (int t0 = 0; t0 < ntr; t0 += blockDim.x) {
-    int t = t0 + threadIdx.x;
+  for (int t0 = 0; t0 < ntr; t0 += URE_T) {
+    const int t = t0 + tid;
     int a = 0;
     if (t < ntr) a = cur[t].accepted;
-    unsigned m = __ballot_sync(0xffffffffu, a);
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, a);
     if (lane == 0) wsum[w] = __popc(m);
     __syncthreads();
     int off = base;
     for (int k = 0; k < w; k++) off += wsum[k];
     if (a) acc_list[off + __popc(m & ((1u << lane) - 1u))] = t;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int s = 0;
-      for (int k = 0; k < (int) (blockDim.x >> 5); k++) s += wsum[k];
-      base += s;
+    if (tid == 0) {
+      int s2 = 0;
+      for (int k = 0; k < URE_T / 32; k++) s2 += wsum[k];
+      base += s2;
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) sc->naccept = base;
+  const int nacc = base;
+  if (nacc > LINK_MAX) {
+    if (tid == 0) {
+      sc->usher_error = OBMD_ERR_CAPACITY + 1000;  // reported as "too many insertions in one call"
+      sc->naccept = 0;
+    }
+    return;
+  }
+  for (int k = tid; k < nacc; k += URE_T) {
+    const obmd_trial &r = cur[acc_list[k]];
+    const int lc = min(max(cell_cx(g, r.end[0]), 0), g.nx - 1);
+    const int cc = (lc * g.ny + cell_cy(g, r.end[1])) * g.nz + cell_cz(g, r.end[2]);
+    cellsh[k] = cc;
+    spec_cell[k] = cc;
+  }
+  __syncthreads();
+  for (int k = tid; k < nacc; k += URE_T) {
+    const int cc = cellsh[k];
+    int nxt = -1;
+    for (int q = k + 1; q < nacc; q++)
+      if (cellsh[q] == cc) {
+        nxt = q;
+        break;
+      }
+    spec_next[k] = nxt;
+    bool is_first = true;
+    for (int q = 0; q < k; q++)
+      if (cellsh[q] == cc) {
+        is_first = false;
+        break;
+      }
+    if (is_first) spec_head[cc] = k;
+  }
+  if (tid == 0) {
+    sc->naccept = nacc;
+    sc->nchg2[par ^ 1] = 0;
+    sc->ndirty2[par ^ 1] = 0;
+    sc->trial_cursor = 0;
+  }
 }
 
 // create_atom + tag/mask/image/v assignment (:1121-1150, atom_vec.cpp:1592-1612), appended after
@@ -832,17 +918,6 @@ __global__ void k_extra_cells(Planes p, int base, int first, int count, Grid g, 
   int lc = cell_cx(g, p.x[s]);
   lc = min(max(lc, 0), g.nx - 1);
   extra_cell[first + k] = (lc * g.ny + cell_cy(g, p.y[s])) * g.nz + cell_cz(g, p.z[s]);
-}
-
-// cells of the atoms accepted in the round just finished (for the per-cell "spec" lists)
-__global__ void k_spec_cells(const obmd_trial *__restrict__ cur, const int *__restrict__ acc_list, int nacc,
-                             Grid g, int *__restrict__ spec_cell)
-{
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nacc) return;
-  const obmd_trial &r = cur[acc_list[k]];
-  int lc = min(max(cell_cx(g, r.end[0]), 0), g.nx - 1);
-  spec_cell[k] = (lc * g.ny + cell_cy(g, r.end[1])) * g.nz + cell_cz(g, r.end[2]);
 }
 
 // A group that arrives sorted by cell (a neighbour's boundary column): runs of equal cells become
@@ -1022,7 +1097,6 @@ bool fix_zones(const obmd_ctx *c, ColRange &int_pbc, ColRange &int_pair, ColRang
   return true;
 }
 
-#define LINK_MAX 6000  // atoms per unsorted extra group (two int arrays in 48 KB of shared memory)
 
 // cells + per-cell lists for the extra atoms [first, first+count) (relative to the extras base)
 int fix_link_extras(obmd_ctx *c, int first, int count, bool sorted_by_cell)
@@ -1295,58 +1369,78 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
       u.ntr = ntr;
       u.seed0 = c->fs.rng_seed;
       u.nbase = nlive + c->nextra;
-      u.nacc_prev = 0;
       u.natt = fa.nattempt;
       u.tg0 = tg0;
       const Extras ex = extras_of(c);
       const double rsqmax = c->pt.cutmax * c->pt.cutmax * (1.0 + 1e-9);
-      int nlist = ntr_loc;
-      const int *list = nullptr;
-      int round = 0;
-      for (;; round++) {
-        NEED(round <= ntr_loc + 1, OBMD_ERR_STATE, "fix obmd: USHER commit did not converge");
-        LAUNCH(k_usher_eval, cdiv(nlist, USH_WARPS), USH_WARPS * 32, 0, list, nlist, c->cur, c->grid, c->pt,
-               c->fd, c->cell_start, u, ex, c->extra_head, c->extra_next, c->spec_head, c->spec_next,
-               c->acc_list, c->tr_prev_d, c->tr_d,
-               c->tr_path, c->tr_npts, c->tr_bbox, c->tr_changed + c->tr_cap, c->sc_d);
+      // nchg2, ndirty2, naccept, nrounds_work, trial_cursor
+      CK(cudaMemsetAsync(&c->sc_d->nchg2[0], 0, 7 * sizeof(int), c->stream));
+      // Rounds are enqueued back to back: every count a round needs (how many trials to re-run, how
+      // many atoms were accepted so far) lives in device memory, and a round that finds nothing to
+      // do is a handful of empty launches.  The host looks at the counters only after a batch.
+      const int rerun_grid = ntr_loc < 4 * 2 * NSM ? cdiv(ntr_loc, USH_WARPS) : 2 * NSM;
+      auto enqueue_round = [&](int round) -> int {
+        const int par = round & 1;
+        ScopedTimer t2(c, round == 0 ? "usher_round0" : "usher_rerun");
+        ScopedTimer *t5 = new ScopedTimer(c, round == 0 ? "usher_eval0" : "usher_evalN");
+        if (round == 0)
+          LAUNCH(k_usher_eval, ntr_loc < 6 * NSM * USH_WARPS ? cdiv(ntr_loc, USH_WARPS) : 6 * NSM, USH_WARPS * 32, 0,
+                 (const int *) nullptr, ntr_loc, 0,
+                 c->cur, c->grid, c->pt, c->fd, c->cell_start, u, ex, c->extra_head, c->extra_next,
+                 c->spec_head, c->spec_next, c->acc_list, c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts,
+                 c->tr_bbox, c->tr_changed + c->tr_cap, c->sc_d);
+        else
+          LAUNCH(k_usher_eval, rerun_grid, USH_WARPS * 32, 0, (const int *) c->tr_list, 0, par ^ 1, c->cur,
+                 c->grid, c->pt, c->fd, c->cell_start, u, ex, c->extra_head, c->extra_next, c->spec_head,
+                 c->spec_next, c->acc_list, c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts, c->tr_bbox,
+                 c->tr_changed + c->tr_cap, c->sc_d);
+        delete t5;
         // Round 0 fills the machine (one warp per trial); the re-run rounds are a handful of CTAs.
         // obmd_run hooks in here to start the pair kernel on the side stream right behind round 0.
         if (round == 0 && c->round0_hook) {
           int (*hook)(obmd_ctx *) = c->round0_hook;
           c->round0_hook = nullptr;
-          if ((rc = hook(c))) return rc;
+          int hrc = hook(c);
+          if (hrc) return hrc;
         }
-        CK(cudaMemsetAsync(&c->sc_d->nchanged, 0, 2 * sizeof(int), c->stream));  // nchanged, ndirty
-        LAUNCH(k_usher_diff, cdiv(ntr_loc, 256), 256, 0, c->tr_prev_d, c->tr_d, ntr_loc, round == 0 ? 1 : 0,
+        LAUNCH(k_usher_diff, cdiv(ntr_loc, 256), 256, 0, c->tr_prev_d, c->tr_d, ntr_loc, round == 0 ? 1 : 0, par,
                c->tr_changed, c->sc_d);
-        LAUNCH(k_usher_dirty, cdiv(ntr_loc, 4), 128, 0, c->tr_prev_d, c->tr_d, ntr_loc, round == 0 ? 1 : 0,
+        LAUNCH(k_usher_dirty, cdiv(ntr_loc, 4), 128, 0, c->tr_prev_d, c->tr_d, ntr_loc, round == 0 ? 1 : 0, par,
                c->tr_changed, c->tr_path, c->tr_npts, c->tr_bbox, u.natt, c->grid,
                c->pt.cutmax * (1.0 + 1e-9), rsqmax, c->tr_list, c->tr_changed + c->tr_cap, c->sc_d);
-        LAUNCH(k_usher_copy, cdiv(ntr_loc, 256), 256, 0, c->tr_prev_d, c->tr_d, ntr_loc);
-        if (u.nacc_prev > 0)  // drop the previous round's spec lists before acc_list is rebuilt
-          LAUNCH(k_extra_clear, cdiv(u.nacc_prev, 128), 128, 0, c->spec_cell, u.nacc_prev, c->spec_head);
-        LAUNCH(k_usher_acc, 1, 1024, 0, c->tr_prev_d, c->tr_d, ntr_loc, c->acc_list, c->sc_d);
+        LAUNCH(k_usher_round_end, 1, URE_T, sizeof(int) * LINK_MAX, c->tr_prev_d, c->tr_d, ntr_loc, par,
+               c->acc_list, c->spec_cell, c->spec_head, c->spec_next, c->grid, c->sc_d);
+        return OBMD_OK;
+      };
+      int round = 0;  // rounds enqueued so far
+      int batch = 3;
+      for (;;) {
+        NEED(round <= ntr_loc + 1, OBMD_ERR_STATE, "fix obmd: USHER commit did not converge");
+        for (int k = 0; k < batch; k++, round++)
+          if ((rc = enqueue_round(round))) return rc;
+        batch = 1;
         if ((rc = read_scalars(c))) return rc;
         NEED(c->sc_h->usher_error != OBMD_ERR_USHER, OBMD_ERR_USHER,
              "fix obmd: USHER force vanished with E above target (the reference would not terminate)");
         NEED(c->sc_h->usher_error != OBMD_ERR_CAPACITY, OBMD_ERR_CAPACITY,
-             "fix obmd: more than %d neighbours within the cutoff of a USHER point", USH_CAP);
+             "fix obmd: more than %d neighbours within the cutoff of a USHER point (or %d atoms in its stencil)",
+             USH_CAP, USH_CAND);
+        NEED(c->sc_h->usher_error != OBMD_ERR_CAPACITY + 1000, OBMD_ERR_CAPACITY,
+             "more than %d insertions in one call", LINK_MAX);
         nacc = c->sc_h->naccept;
-        if (c->sc_h->nchanged == 0 || c->sc_h->ndirty == 0) break;
-        nlist = c->sc_h->ndirty;
-        list = c->tr_list;
-        u.nacc_prev = nacc;
-        if (nacc > 0) {  // per-cell lists of the atoms accepted so far, for the re-runs
-          NEED(nacc <= LINK_MAX, OBMD_ERR_CAPACITY, "more than %d insertions in one call", LINK_MAX);
-          LAUNCH(k_spec_cells, cdiv(nacc, 128), 128, 0, c->tr_d, c->acc_list, nacc, c->grid, c->spec_cell);
-          LAUNCH(k_link_group, 1, 512, 2 * sizeof(int) * nacc, c->spec_cell, 0, nacc, c->spec_head, c->spec_next);
-        }
+        const int par = (round - 1) & 1;
+        if (c->sc_h->nchg2[par] == 0 || c->sc_h->ndirty2[par] == 0) break;
       }
-      rounds = round + 1;
+      // the spec lists of the last round are no longer needed
+      if (nacc > 0)
+        LAUNCH(k_extra_clear, cdiv(nacc, 128), 128, 0, c->spec_cell, nacc, c->spec_head);
+      rounds = c->sc_h->nrounds_work;
     }
+
     naccL = doL ? nacc : 0;  // serial: both sides live in one list, the split is not needed
     naccR = doR && !doL ? nacc : 0;
     if (!serial) {  // creation counts of both edge ranks: natoms and the right rank's first new tag
+      ScopedTimer t3(c, "usher_allreduce");
       double h[2] = {(double) naccL, (double) naccR};
       CK(cudaMemcpyAsync(c->red_d, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
       if ((rc = comm_allreduce(c, c->red_d, 2, 0))) return rc;
@@ -1363,6 +1457,7 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
     if (nacc > 0) {
       // the side stream may still be walking the per-cell extra lists: link the new atoms only
       // after its pair kernel has finished (obmd_run sets commit_wait)
+      ScopedTimer t4(c, "usher_commit");
       if (c->commit_wait) CK(cudaStreamWaitEvent(c->stream, c->commit_wait, 0));
       const int tag0 = maxtag + ((doR && !doL) ? naccL : 0);
       LAUNCH(k_usher_commit, cdiv(nacc, 128), 128, 0, c->cur, extras_of(c), tag0, c->grid, c->fd, c->tr_d,
@@ -1558,11 +1653,16 @@ __global__ void __launch_bounds__(FB_THREADS)
 }
 
 // fixed-order sum of the per-CTA partials -> gsum[4] (deterministic, no atomics)
-__global__ void k_weight_final(const double *__restrict__ partials, double *__restrict__ gsum)
+// Fixed-order sum of the per-CTA partials (b = 0, 1, ...): staged through shared memory with one
+// coalesced sweep so the four sequential add chains do not wait on global memory.
+__global__ void __launch_bounds__(256) k_weight_final(const double *__restrict__ partials, double *__restrict__ gsum)
 {
+  __shared__ double sh[FB_BLOCKS * 4];
+  for (int k = threadIdx.x; k < FB_BLOCKS * 4; k += blockDim.x) sh[k] = partials[k];
+  __syncthreads();
   if (threadIdx.x < 4) {
     double v = 0.0;
-    for (int b = 0; b < FB_BLOCKS; b++) v += partials[b * 4 + threadIdx.x];
+    for (int b = 0; b < FB_BLOCKS; b++) v += sh[b * 4 + threadIdx.x];
     gsum[threadIdx.x] = v;
   }
 }
@@ -1608,7 +1708,7 @@ int fix_post_force(obmd_ctx *c)
   const Extras ex = extras_of(c);
   LAUNCH(k_weight_sums, FB_BLOCKS, FB_THREADS, 0, c->cur, ex, c->grid, c->fd, c->pt, fc, c->cell_start,
          c->partials);
-  LAUNCH(k_weight_final, 1, 32, 0, c->partials, c->red_d);
+  LAUNCH(k_weight_final, 1, 256, 0, c->partials, c->red_d);
   if (c->nranks > 1) {  // a buffer may span slabs: G is a global sum (fix_obmd_merged.cpp:1305,1378)
     int rc = comm_allreduce(c, c->red_d, 4, 0);
     if (rc) return rc;
