@@ -24,6 +24,8 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner / INFO lines go to stderr: stdout is one JSON line
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -57,7 +59,11 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons of this rank's GPU during the timed region
+    (B200_PROFILING.md recipe).  Sampled in-process through NVML (nvidia-ml-py): spawning
+    `nvidia-smi` from every rank inside the timed region stalls the driver for milliseconds at a
+    time, which a 1 ms step with several host round trips cannot hide.  Falls back to one
+    nvidia-smi process per sample when NVML is not importable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -65,18 +71,50 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + uuid)
+            self.nvml = pynvml
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def sample_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+        pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        bit = lambda name, alt: getattr(n, name, getattr(n, alt, 0))
+        flags = [bit("nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 bit("nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 bit("nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 bit("nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap")]
+        return [str(sm), str(self.max_sm), str(pw)] + ["Active" if (f and (r & f)) else "Not Active" for f in flags]
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([t.strip() for t in out.split(",")])
+                if self.nvml:
+                    self.rows.append(self.sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                         timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([t.strip() for t in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02 if self.nvml else 0.25)
 
     def summary(self):
         if not self.rows:
@@ -86,7 +124,7 @@ class ClockSampler(threading.Thread):
         reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower() == "active" for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
                 "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows),
-                "reasons": reasons}
+                "reasons": reasons, "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def build_sim(x, box, device, regime="R1", temperature=1.0, rank=0, world=1, buffer_size=None, nbuf_atoms=None):
@@ -183,6 +221,9 @@ def ours(args):
         fam[name] = {"ms_per_step": t / args.steps, "launches_per_step": nl / args.steps}
     sim.timing(False)
     st = sim.fix_state()
+    if world > 1 and os.environ.get("OBMD_BENCH_RANK_TIMERS"):
+        print("rank %d: %.3f ms/step local; %s" % (rank, ms / args.steps, {k: round(v["ms_per_step"], 4)
+              for k, v in fam.items()}), file=sys.stderr, flush=True)
 
     # ---- e2e through the C ABI with host buffers (plugin flow) ----
     e2e = None
@@ -198,6 +239,16 @@ def ours(args):
         ms = tmax[0].item(); atom_steps = tsum[1].item()
         if e2e:
             e2e["seconds"] = tmax[2].item(); e2e["atom_steps"] = tsum[3].item()
+    clocks = sampler.summary()
+    if world > 1:
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        ok = [c for c in allc if c.get("sm_mhz")]
+        if ok:
+            clocks = dict(min(ok, key=lambda c: c["sm_mhz"]))      # the slowest-clocked rank
+            clocks["reasons"] = sorted({r for c in allc for r in c.get("reasons", [])})
+            clocks["power_w_max"] = max(c.get("power_w_max", 0.0) for c in ok)
+            clocks["ranks"] = world
     if rank == 0:
         hbm, how = peaks()
         pair_ms = fam["pair"]["ms_per_step"]
@@ -229,7 +280,7 @@ def ours(args):
                          "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic, "peak_source": how,
                          "algorithmic_bytes_per_atom": PAIR_BYTES_PER_ATOM,
                          "note": "fp64-pipe bound, not HBM bound: see DESIGN.md section 6"},
-            "clocks": sampler.summary(),
+            "clocks": clocks,
         }
         if e2e:
             line["e2e"] = {"value": e2e["atom_steps"] / e2e["seconds"], "unit": UNIT,
