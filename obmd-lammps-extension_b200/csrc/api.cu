@@ -107,7 +107,7 @@ extern "C" void obmd_destroy(obmd_ctx *c)
   cudaFree(c->sendL); cudaFree(c->sendR); cudaFree(c->recvL); cudaFree(c->recvR);
   cudaFree(c->del_key); cudaFree(c->del_val); cudaFree(c->tail_key); cudaFree(c->tail_val); cudaFree(c->del_src); cudaFree(c->del_mv);
   cudaFree(c->tr_d); cudaFree(c->tr_prev_d); cudaFree(c->tr_path); cudaFree(c->tr_npts);
-  cudaFree(c->tr_list); cudaFree(c->tr_changed); cudaFree(c->acc_list); cudaFree(c->tr_bbox);
+  cudaFree(c->tr_list); cudaFree(c->tr_changed); cudaFree(c->tr_chg); cudaFree(c->acc_list); cudaFree(c->tr_bbox);
   if (c->tr_h) cudaFreeHost(c->tr_h);
   cudaFree(c->partials);
   cudaFree(c->redo_flag); cudaFree(c->redo_list); cudaFree(c->redo_count);

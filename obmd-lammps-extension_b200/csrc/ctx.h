@@ -83,6 +83,11 @@ struct StepScalars {
 };
 
 struct PendingTimer;
+// A trial whose state changed in a commit round: old / new atom position (if it was / is accepted)
+struct ChgRec {
+  double o[3], n[3];
+  int q, flags;  // trial index; bit 0: old state was accepted, bit 1: new state is accepted
+};
 struct TimerSlot {
   double ms = 0.0;
   long long launches = 0;
@@ -177,7 +182,8 @@ struct obmd_ctx {
   int *tr_npts = nullptr;
   double *tr_bbox = nullptr;        // [tr_cap][6] bounding box of the evaluated points
   int *tr_list = nullptr;           // trials to evaluate this round
-  int *tr_changed = nullptr;        // changed flags
+  int *tr_changed = nullptr;        // [cap] unused | [cap] kfirst
+  struct ChgRec *tr_chg = nullptr;  // compact records of the trials whose state changed this round
   int *acc_list = nullptr;          // compacted accepted trial ids of the previous round
   int *spec_head = nullptr, *spec_next = nullptr, *spec_cell = nullptr;  // their per-cell lists
   double *partials = nullptr;       // block partial sums for deterministic reductions

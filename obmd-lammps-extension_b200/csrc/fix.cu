@@ -158,7 +158,13 @@ __global__ void k_scan_ids(Planes p, int nlive, int want_tail, StepScalars *sc, 
     }
   }
   for (int d = 16; d > 0; d >>= 1) mt = max(mt, __shfl_down_sync(0xffffffffu, mt, d));
-  if ((threadIdx.x & 31) == 0 && mt) atomicMax(&sc->maxtag, mt);
+  __shared__ int wmax[8];  // one atomic per CTA instead of one per warp (all to the same address)
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = mt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (int) (blockDim.x >> 5); k++) mt = max(mt, wmax[k]);
+    if (mt) atomicMax(&sc->maxtag, mt);
+  }
 }
 
 __global__ void k_count_regions(Planes p, ColRange cr, Extras ex, Grid g, FixDev fd,
@@ -222,7 +228,7 @@ __device__ void bitonic_desc(int *key, int *val, int npad)
 //    the entry created at position p settles at p iff p < nprime.  Only the ndel positions
 //    >= nprime need the walk: src[k] = storage slot of the survivor that ends up in the k-th
 //    effective hole (holes counted downwards, skipping the run of holes at the very top).
-#define DEL_SMEM 2048  // deletions handled entirely in shared memory (more fall back to global)
+#define DEL_SMEM 1024  // deletions handled entirely in shared memory (more fall back to global)
 
 __global__ void __launch_bounds__(1024)
     k_delete_fixup(Planes p, int nlive, int ndel, int npad_del, int npad_tail, FixDev fd, PairTab pt,
@@ -230,7 +236,9 @@ __global__ void __launch_bounds__(1024)
                    int *del_src, double *del_mv, int do_walk)
 {
   __shared__ int s_dkey[DEL_SMEM], s_tkey[DEL_SMEM], s_tval[DEL_SMEM], s_src[DEL_SMEM];
+  __shared__ double s_mv[4 * DEL_SMEM];
   const bool small = (npad_del <= DEL_SMEM && npad_tail <= DEL_SMEM);
+  if (small) del_mv = s_mv;  // the six serial sums below then run out of shared memory
   const int ntail = do_walk ? sc->ntail : 0;
   // working arrays: shared memory when they fit (the usual few hundred deletions per step)
   int *dkey = small ? s_dkey : del_key, *dval = small ? s_src : del_val;
@@ -721,20 +729,31 @@ __global__ void __launch_bounds__(USH_WARPS * 32, 6)
   }
 }
 
-// chg_list = trials whose state (accepted, end) differs between the two latest rounds
+// the trials whose state (accepted, end) differs between the two latest rounds, as compact records
 __global__ void k_usher_diff(const obmd_trial *__restrict__ prev, const obmd_trial *__restrict__ cur,
-                             int ntr, int first_round, int par, int *__restrict__ chg_list, StepScalars *sc)
+                             int ntr, int first_round, int par, ChgRec *__restrict__ chg, StepScalars *sc)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntr) return;
-  int ch;
-  if (first_round) ch = cur[t].accepted;
+  const obmd_trial &b = cur[t];
+  int ch, oldacc = 0;
+  if (first_round) ch = b.accepted;
   else {
-    const obmd_trial &a = prev[t], &b = cur[t];
+    const obmd_trial &a = prev[t];
+    oldacc = a.accepted;
     ch = (a.accepted != b.accepted) ||
         (b.accepted && (a.end[0] != b.end[0] || a.end[1] != b.end[1] || a.end[2] != b.end[2]));
   }
-  if (ch) chg_list[atomicAdd(&sc->nchg2[par], 1)] = t;
+  if (ch) {
+    ChgRec r;
+    for (int d = 0; d < 3; d++) {
+      r.o[d] = oldacc ? prev[t].end[d] : 0.0;
+      r.n[d] = b.end[d];
+    }
+    r.q = t;
+    r.flags = (oldacc ? 1 : 0) | (b.accepted ? 2 : 0);
+    chg[atomicAdd(&sc->nchg2[par], 1)] = r;
+  }
 }
 
 // all points involved lie inside the box, so one periodic shift suffices
@@ -767,8 +786,7 @@ __device__ __forceinline__ bool near_bbox(const double *a, const double *bb, con
 // A trial must be re-run when an earlier trial whose state changed has its old or new atom
 // within the cutoff of any point the trial evaluated (a superset test with a small margin).
 // kfirst[t] = index of the first such point: the re-run resumes there.
-__global__ void k_usher_dirty(const obmd_trial *__restrict__ prev, const obmd_trial *__restrict__ cur,
-                              int ntr, int first_round, int par, const int *__restrict__ chg_list,
+__global__ void k_usher_dirty(int ntr, int par, const ChgRec *__restrict__ chg,
                               const double *__restrict__ path, const int *__restrict__ npts,
                               const double *__restrict__ bbox, int natt, Grid g, double rc, double rsqmax,
                               int *__restrict__ list, int *__restrict__ kfirst, StepScalars *sc)
@@ -780,15 +798,15 @@ __global__ void k_usher_dirty(const obmd_trial *__restrict__ prev, const obmd_tr
   const double *bb = bbox + (size_t) t * 6;
   const int np = npts[t], nchg = sc->nchg2[par];
   int kf = np;  // first affected point seen by this lane
+  if (nchg == 0) return;
   for (int qi = lane; qi < nchg; qi += 32) {
-    int q = chg_list[qi];
-    if (q >= t) continue;
-    bool oldacc = !first_round && prev[q].accepted && near_bbox(prev[q].end, bb, g, rc);
-    bool newacc = cur[q].accepted && near_bbox(cur[q].end, bb, g, rc);
+    const ChgRec r = chg[qi];
+    if (r.q >= t) continue;
+    const bool oldacc = (r.flags & 1) && near_bbox(r.o, bb, g, rc);
+    const bool newacc = (r.flags & 2) && near_bbox(r.n, bb, g, rc);
     if (!oldacc && !newacc) continue;
     for (int k = 0; k < kf; k++) {
-      if ((oldacc && near_pt(prev[q].end, mp + 3 * k, g, rsqmax)) ||
-          (newacc && near_pt(cur[q].end, mp + 3 * k, g, rsqmax))) {
+      if ((oldacc && near_pt(r.o, mp + 3 * k, g, rsqmax)) || (newacc && near_pt(r.n, mp + 3 * k, g, rsqmax))) {
         kf = k;
         break;
       }
@@ -991,7 +1009,9 @@ static int ensure_trials(obmd_ctx *c, int ntr, int natt)
   CK(cudaMalloc(&c->tr_path, sizeof(double) * 3 * (size_t) cap * (na + 1)));
   CK(cudaMalloc(&c->tr_npts, sizeof(int) * cap));
   CK(cudaMalloc(&c->tr_list, sizeof(int) * cap));
-  CK(cudaMalloc(&c->tr_changed, sizeof(int) * 2 * cap));  // changed flags | kfirst
+  CK(cudaMalloc(&c->tr_changed, sizeof(int) * 2 * cap));  // unused | kfirst
+  cudaFree(c->tr_chg);
+  CK(cudaMalloc(&c->tr_chg, sizeof(ChgRec) * cap));
   CK(cudaMalloc(&c->acc_list, sizeof(int) * cap));
   cudaFree(c->spec_next); cudaFree(c->spec_cell);
   CK(cudaMalloc(&c->spec_next, sizeof(int) * cap));
@@ -1404,9 +1424,9 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
           if (hrc) return hrc;
         }
         LAUNCH(k_usher_diff, cdiv(ntr_loc, 256), 256, 0, c->tr_prev_d, c->tr_d, ntr_loc, round == 0 ? 1 : 0, par,
-               c->tr_changed, c->sc_d);
-        LAUNCH(k_usher_dirty, cdiv(ntr_loc, 4), 128, 0, c->tr_prev_d, c->tr_d, ntr_loc, round == 0 ? 1 : 0, par,
-               c->tr_changed, c->tr_path, c->tr_npts, c->tr_bbox, u.natt, c->grid,
+               c->tr_chg, c->sc_d);
+        LAUNCH(k_usher_dirty, cdiv(ntr_loc, 4), 128, 0, ntr_loc, par, c->tr_chg, c->tr_path, c->tr_npts,
+               c->tr_bbox, u.natt, c->grid,
                c->pt.cutmax * (1.0 + 1e-9), rsqmax, c->tr_list, c->tr_changed + c->tr_cap, c->sc_d);
         LAUNCH(k_usher_round_end, 1, URE_T, sizeof(int) * LINK_MAX, c->tr_prev_d, c->tr_d, ntr_loc, par,
                c->acc_list, c->spec_cell, c->spec_head, c->spec_next, c->grid, c->sc_d);

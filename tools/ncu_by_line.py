@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-source-line profile of one kernel: joins `nvdisasm -g` line info of the cubin inside a .so
 with the per-SASS-instruction counts of an .ncu-rep (ncu --set full --import-source on).
-usage: python tools/ncu_by_line.py rep.ncu-rep lib.so <mangled-name substring> <ncu kernel substring> [top N]
+usage: python tools/ncu_by_line.py rep.ncu-rep lib.so <mangled-name substring> <ncu kernel substring> [top N] [launch #]
 The n-th SASS instruction of the function in the cubin is the n-th row of ncu's source page."""
 import csv
 import os
@@ -38,9 +38,10 @@ def sass_lines(so, mangled):
     return out
 
 
-def ncu_rows(rep, kname):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
-                         capture_output=True, text=True).stdout
+def ncu_rows(rep, kname, which=0):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass",
+                          "--launch-skip", str(which), "--launch-count", "1"], capture_output=True, text=True).stdout
+    which = 0
     rows = list(csv.reader(txt.splitlines()))
     cur, blocks = None, []
     for r in rows:
@@ -49,18 +50,19 @@ def ncu_rows(rep, kname):
             blocks.append(cur)
         elif cur is not None:
             cur["rows"].append(r)
-    for b in blocks:
-        if kname in b["name"]:
-            hdr = b["rows"][0]
-            return hdr, [r for r in b["rows"][1:] if len(r) == len(hdr)]
-    raise SystemExit("kernel not found")
+    hits = [b for b in blocks if kname in b["name"]]
+    if which >= len(hits):
+        raise SystemExit("kernel not found (%d launches match)" % len(hits))
+    hdr = hits[which]["rows"][0]
+    return hdr, [r for r in hits[which]["rows"][1:] if len(r) == len(hdr)]
 
 
 def main():
     rep, so, mangled, kname = sys.argv[1:5]
     top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
+    which = int(sys.argv[6]) if len(sys.argv) > 6 else 0  # n-th matching launch in the report
     lines = sass_lines(so, mangled)
-    hdr, rows = ncu_rows(rep, kname)
+    hdr, rows = ncu_rows(rep, kname, which)
     ie, smp = hdr.index("Instructions Executed"), hdr.index("# Samples")
     if len(lines) != len(rows):
         print("warning: %d SASS lines in cubin vs %d in report (different build?)" % (len(lines), len(rows)))
