@@ -13,7 +13,7 @@
 #define EPSILON_FIX 1.0e-6   // fix_obmd_merged.cpp:62
 #define EPSILON_DPD 1.0e-10  // pair_dpd.cpp:36
 #define MY_PI 3.14159265358979323846
-#define FB_BLOCKS (NSM * 2)  // fixed grid of the grid-stride region kernels (2 CTAs per SM)
+#define FB_BLOCKS (NSM * 6)  // fixed grid of the grid-stride region kernels (6 CTAs per SM: ~1 buffer atom per thread at 1 M atoms)
 #define FB_THREADS 256
 
 // =====================================================================================
