@@ -368,3 +368,44 @@ def test_row_tiled_pair_kernel_matches_list_kernel(shipped, monkeypatch):
         scale = np.abs(res[0]).max()
         assert scale > 1.0
         assert np.abs(res[0] - res[1]).max() <= 1e-12 * scale
+
+
+def test_pair_two_types_row_and_list_kernels_vs_oracle(shipped, monkeypatch):
+    """Two atom types with different a0, gamma and cutoffs per type pair (pair_coeff i j a0 gamma rc):
+    the row-tiled kernel screens with the largest cutoff and applies the exact per-pair test in
+    fp64; both kernels must match the oracle's PairDPD::compute (pair_dpd.cpp:66-163) within 1e-9 at
+    T = 0, and each other to 1e-12 with the random term on."""
+    import obmd_b200 as ob
+    tag, x, box = shipped
+    n = len(x)
+    rng = np.random.default_rng(11)
+    v = rng.normal(0, 1, x.shape)
+    typ = (rng.random(n) < 0.4).astype(np.int32) + 1
+    coeff = {(1, 1): (209.6, 4.5, 1.0), (1, 2): (150.0, 3.0, 0.9), (2, 2): (100.0, 6.0, 0.8)}
+    res = {}
+    for temperature in (0.0, 1.0):
+        for tile in ("0", "1"):
+            monkeypatch.setenv("OBMD_B200_TILE", tile)
+            sim = ob.ObmdB200(0)
+            sim.set_box(box[:, 0], box[:, 1]); sim.set_masses([1.0, 2.0]); sim.set_timestep(0.001464)
+            sim.pair_style_dpd(temperature, 1.0, 2616)
+            for (i, j), (a0, gamma, rc) in coeff.items():
+                sim.pair_coeff(i, j, a0, gamma, rc)
+            sim.pair_init(1.0)
+            sim.upload(x, v, typ, tag)
+            sim.build_cells(); sim.pbc(); sim.pair_compute(5)
+            res[(temperature, tile)] = sim.download(("f",))["f"]
+            sim.close()
+    p = O.make_fix(box[:, 0], box[:, 1], ntypes=2, mass=(1.0, 2.0), temperature=0.0)
+    for (i, j), (a0, gamma, rc) in coeff.items():
+        p.a0[i][j] = a0; p.gamma[i][j] = gamma; p.cut[i][j] = rc
+    O.lib().orc_pair_init(C.byref(p))
+    a = O.OracleAtoms(x, v=v, tag=tag, type_=typ)
+    O.lib().orc_pair_compute(C.byref(p), C.byref(a.c), 0, 5, None, None)
+    fr = a.view("f")
+    assert np.abs(fr).max() > 1.0
+    for tile in ("0", "1"):
+        assert cc.mixed_rel_err(res[(0.0, tile)], fr) < FTOL
+    scale = np.abs(res[(1.0, "0")]).max()
+    assert np.abs(res[(1.0, "0")] - res[(1.0, "1")]).max() <= 1e-12 * scale
+    assert np.abs(res[(1.0, "1")] - res[(0.0, "1")]).max() > 1.0   # the random term is on
