@@ -200,6 +200,8 @@ def ours(args):
     for _ in range(args.warmup):
         sim.run(step, 1); step += 1
     sim.timing(True); sim.timing_reset()
+    st0 = sim.fix_state()
+    tr0, rd0, in0, de0 = int(st0.ntrials), int(st0.nrounds), int(st0.ninserted), int(st0.ndeleted)
     sampler = ClockSampler(local); sampler.start()
     barrier()
     l0 = sim.launches
@@ -282,6 +284,20 @@ def ours(args):
                          "note": "fp64-pipe bound, not HBM bound: see DESIGN.md section 6"},
             "clocks": clocks,
         }
+        # USHER is latency-bound (a chain of up to nattempt dependent energy evaluations per trial),
+        # not bandwidth-bound: report its share of the step and its cost per trial instead of a roofline
+        ush = fam["usher"]["ms_per_step"]
+        ntr_step = (int(st.ntrials) - tr0) / args.steps
+        line["usher"] = {"ms_per_step": round(ush, 5), "share_of_step": round(ush / (ms / args.steps), 4),
+                         "eval_ms_per_step": round(fam["usher_eval0"]["ms_per_step"] +
+                                                   fam["usher_evalN"]["ms_per_step"], 5),
+                         "trials_per_step": round(ntr_step, 1),
+                         "rounds_per_step": round((int(st.nrounds) - rd0) / args.steps, 2),
+                         "insertions_per_step": round((int(st.ninserted) - in0) / args.steps, 1),
+                         "deletions_per_step": round((int(st.ndeleted) - de0) / args.steps, 1),
+                         "us_per_trial": round(1e3 * ush / ntr_step, 4) if ntr_step > 0 else None,
+                         "note": "rank 0%s; overlapped with the pair kernel on a side stream" %
+                                 (" (one of the two edge ranks)" if world > 1 else "")}
         if e2e:
             line["e2e"] = {"value": e2e["atom_steps"] / e2e["seconds"], "unit": UNIT,
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
@@ -446,6 +462,7 @@ def reference_arm(args):
     a, loop = run_reference(reps, args.steps)
     val = a / loop
     x, box = tiled(tuple(args.reps))
+    scaling = "weak" if args.workload == "1m" else "strong"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * loop / args.steps,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
