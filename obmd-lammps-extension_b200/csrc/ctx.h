@@ -75,6 +75,7 @@ struct StepScalars {
   int naccept;              // accepted trials after the latest round
   int nrounds_work;         // rounds whose evaluation had work to do
   int trial_cursor;         // next entry of the round's trial list to hand to a warp
+  int nused, nused_prev;    // maxattempt > 1: attempts of the RNG stream the serial loop consumes (a prefix)
   int rng_seed;             // RanPark state after the deletion draws
   double vnewl[3], vnewr[3];
   double gsum[4];           // G_left, G_right, Gperp_left, Gperp_right

@@ -333,6 +333,7 @@ struct UsherCfg {
   int nbase;          // local index of the first inserted atom (= nlocal after deletion)
   int natt;
   int tg0;            // global index of local trial 0 (slab runs: the right rank starts at ntrL)
+  int slots, maxatt;  // maxattempt > 1 (one side per pass): insertions wanted, attempts allowed for each
 };
 
 __device__ __forceinline__ int ranpark_pow(long long n)
@@ -731,18 +732,21 @@ __global__ void __launch_bounds__(USH_WARPS * 32, 6)
 
 // the trials whose state (accepted, end) differs between the two latest rounds, as compact records
 __global__ void k_usher_diff(const obmd_trial *__restrict__ prev, const obmd_trial *__restrict__ cur,
-                             int ntr, int first_round, int par, ChgRec *__restrict__ chg, StepScalars *sc)
+                             int ntr, int first_round, int par, int limit, ChgRec *__restrict__ chg,
+                             StepScalars *sc)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntr) return;
   const obmd_trial &b = cur[t];
+  // maxattempt > 1: only the attempts the serial loop actually makes (t < nused) can insert
+  const int newacc = b.accepted && (!limit || t < sc->nused);
   int ch, oldacc = 0;
-  if (first_round) ch = b.accepted;
+  if (first_round) ch = newacc;
   else {
     const obmd_trial &a = prev[t];
-    oldacc = a.accepted;
-    ch = (a.accepted != b.accepted) ||
-        (b.accepted && (a.end[0] != b.end[0] || a.end[1] != b.end[1] || a.end[2] != b.end[2]));
+    oldacc = a.accepted && (!limit || t < sc->nused_prev);
+    ch = (oldacc != newacc) ||
+        (newacc && (a.end[0] != b.end[0] || a.end[1] != b.end[1] || a.end[2] != b.end[2]));
   }
   if (ch) {
     ChgRec r;
@@ -751,7 +755,7 @@ __global__ void k_usher_diff(const obmd_trial *__restrict__ prev, const obmd_tri
       r.n[d] = b.end[d];
     }
     r.q = t;
-    r.flags = (oldacc ? 1 : 0) | (b.accepted ? 2 : 0);
+    r.flags = (oldacc ? 1 : 0) | (newacc ? 2 : 0);
     chg[atomicAdd(&sc->nchg2[par], 1)] = r;
   }
 }
@@ -819,6 +823,64 @@ __global__ void k_usher_dirty(int ntr, int par, const ChgRec *__restrict__ chg,
   }
 }
 
+// maxattempt > 1 (:912-1172): insertion slot k draws attempts from the RNG stream until one is
+// accepted or maxattempt have failed, then slot k+1 continues where it stopped.  Given the accept
+// flag of every possible attempt, the attempts actually made are a prefix of the stream: a slot
+// boundary sits behind every accepted attempt and behind every maxattempt-th consecutive failure.
+// nused = index of the slots-th boundary + 1.  One CTA, chunked scans.
+__global__ void __launch_bounds__(1024)
+    k_usher_resolve(const obmd_trial *__restrict__ cur, int ntr, int slots, int M, StepScalars *sc)
+{
+  __shared__ int s_last[1024], s_cnt[1024];
+  const int tid = threadIdx.x, per = (ntr + 1023) / 1024, b = tid * per, e = min(b + per, ntr);
+  int last = -1;
+  for (int a = b; a < e; a++)
+    if (cur[a].accepted) last = a;
+  s_last[tid] = last;
+  __syncthreads();
+  if (tid == 0) {  // exclusive running maximum over the chunks
+    int run = -1;
+    for (int k = 0; k < 1024; k++) {
+      const int v = s_last[k];
+      s_last[k] = run;
+      run = max(run, v);
+    }
+  }
+  __syncthreads();
+  int la = s_last[tid], nb = 0;
+  for (int a = b; a < e; a++) {
+    const bool acc = cur[a].accepted != 0;
+    nb += (acc || ((a - la) % M == 0)) ? 1 : 0;
+    if (acc) la = a;
+  }
+  s_cnt[tid] = nb;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int k = 0; k < 1024; k++) {
+      const int v = s_cnt[k];
+      s_cnt[k] = run;
+      run += v;
+    }
+    if (run < slots) sc->nused = ntr;  // cannot happen for ntr == slots * M; keep the state sane
+  }
+  __syncthreads();
+  int c0 = s_cnt[tid];
+  if (c0 < slots && c0 + nb >= slots) {
+    la = s_last[tid];
+    for (int a = b; a < e; a++) {
+      const bool acc = cur[a].accepted != 0;
+      if (acc || ((a - la) % M == 0)) {
+        if (++c0 == slots) {
+          sc->nused = a + 1;
+          break;
+        }
+      }
+      if (acc) la = a;
+    }
+  }
+}
+
 // End of a commit round, one CTA: drops the previous round's per-cell "spec" lists, copies the
 // round's trial states to `prev`, compacts the accepted trials in order into acc_list, threads
 // them into fresh per-cell lists (what the next round's evaluations see of earlier insertions),
@@ -826,7 +888,7 @@ __global__ void k_usher_dirty(int ntr, int par, const ChgRec *__restrict__ chg,
 #define URE_T 1024
 __global__ void __launch_bounds__(URE_T)
     k_usher_round_end(obmd_trial *__restrict__ prev, const obmd_trial *__restrict__ cur, int ntr, int par,
-                      int *__restrict__ acc_list, int *__restrict__ spec_cell, int *__restrict__ spec_head,
+                      int limit, int *__restrict__ acc_list, int *__restrict__ spec_cell, int *__restrict__ spec_head,
                       int *__restrict__ spec_next, Grid g, StepScalars *sc)
 {
   extern __shared__ int cellsh[];  // cells of the accepted trials (at most LINK_MAX)
@@ -834,6 +896,7 @@ __global__ void __launch_bounds__(URE_T)
   __shared__ int wsum[URE_T / 32];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int nold = sc->naccept;
+  const int nlim = limit ? sc->nused : ntr;  // maxattempt > 1: attempts beyond nused are never made
   for (int k = tid; k < nold; k += URE_T) spec_head[spec_cell[k]] = -1;
   {  // prev <- cur, as a flat copy of doubles (sizeof(obmd_trial) is a multiple of 8)
     static_assert(sizeof(obmd_trial) % 8 == 0, "obmd_trial must be a whole number of doubles");
@@ -847,7 +910,7 @@ __global__ void __launch_bounds__(URE_T)
   for (int t0 = 0; t0 < ntr; t0 += URE_T) {
     const int t = t0 + tid;
     int a = 0;
-    if (t < ntr) a = cur[t].accepted;
+    if (t < nlim) a = cur[t].accepted;
     const unsigned m = __ballot_sync(0xffffffffu, a);
     if (lane == 0) wsum[w] = __popc(m);
     __syncthreads();
@@ -900,6 +963,7 @@ __global__ void __launch_bounds__(URE_T)
     sc->nchg2[par ^ 1] = 0;
     sc->ndirty2[par ^ 1] = 0;
     sc->trial_cursor = 0;
+    sc->nused_prev = sc->nused;
   }
 }
 
@@ -913,7 +977,7 @@ __global__ void k_usher_commit(Planes p, Extras ex, int tag0, Grid g, FixDev fd,
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < nacc) {
     obmd_trial &r = cur[acc_list[k]];
-    int s = ex.base + ex.narr + ex.nghost + k;
+    int s = ex.base + ex.narr + ex.nghost + ex.nins + k;  // ex.nins: atoms of an earlier pass
     p.x[s] = r.end[0];
     p.y[s] = r.end[1];
     p.z[s] = r.end[2];
@@ -1371,7 +1435,7 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
   const int ntr_loc = (doL ? ntrL : 0) + (doR ? ntrR : 0);
   const int tg0 = doL ? 0 : ntrL;
 
-  int nacc = 0, naccL = 0, naccR = 0, rounds = 0;
+  int nacc = 0, naccL = 0, naccR = 0, rounds = 0, nused_total = 0, ncopied = 0;
   if ((ntr == 0 || ntr_loc == 0) && c->round0_hook) {  // no USHER work on this rank this step
     int (*hook)(obmd_ctx *) = c->round0_hook;
     c->round0_hook = nullptr;
@@ -1379,117 +1443,155 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
   }
   if (ntr > 0) {
     ScopedTimer t(c, "usher");
-    NEED(fa.maxattempt == 1, OBMD_ERR_ARG,
-         "fix obmd: maxattempt > 1 is not implemented on the device path (DESIGN.md 5.4)");
-    if (ntr_loc > 0) {
-      if ((rc = ensure_trials(c, ntr_loc, fa.nattempt))) return rc;
-      if ((rc = obmd_ensure_capacity(c, nlive + c->nextra + ntr_loc))) return rc;
-      UsherCfg u;
-      u.ntrL = ntrL;
-      u.ntr = ntr;
-      u.seed0 = c->fs.rng_seed;
-      u.nbase = nlive + c->nextra;
-      u.natt = fa.nattempt;
-      u.tg0 = tg0;
-      const Extras ex = extras_of(c);
-      const double rsqmax = c->pt.cutmax * c->pt.cutmax * (1.0 + 1e-9);
-      // nchg2, ndirty2, naccept, nrounds_work, trial_cursor
-      CK(cudaMemsetAsync(&c->sc_d->nchg2[0], 0, 7 * sizeof(int), c->stream));
-      // Rounds are enqueued back to back: every count a round needs (how many trials to re-run, how
-      // many atoms were accepted so far) lives in device memory, and a round that finds nothing to
-      // do is a handful of empty launches.  The host looks at the counters only after a batch.
-      const int rerun_grid = ntr_loc < 4 * 2 * NSM ? cdiv(ntr_loc, USH_WARPS) : 2 * NSM;
-      auto enqueue_round = [&](int round) -> int {
-        const int par = round & 1;
-        ScopedTimer t2(c, round == 0 ? "usher_round0" : "usher_rerun");
-        ScopedTimer *t5 = new ScopedTimer(c, round == 0 ? "usher_eval0" : "usher_evalN");
-        if (round == 0)
-          LAUNCH(k_usher_eval, ntr_loc < 6 * NSM * USH_WARPS ? cdiv(ntr_loc, USH_WARPS) : 6 * NSM, USH_WARPS * 32, 0,
-                 (const int *) nullptr, ntr_loc, 0,
-                 c->cur, c->grid, c->pt, c->fd, c->cell_start, u, ex, c->extra_head, c->extra_next,
-                 c->spec_head, c->spec_next, c->acc_list, c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts,
-                 c->tr_bbox, c->tr_changed + c->tr_cap, c->sc_d);
-        else
-          LAUNCH(k_usher_eval, rerun_grid, USH_WARPS * 32, 0, (const int *) c->tr_list, 0, par ^ 1, c->cur,
-                 c->grid, c->pt, c->fd, c->cell_start, u, ex, c->extra_head, c->extra_next, c->spec_head,
-                 c->spec_next, c->acc_list, c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts, c->tr_bbox,
-                 c->tr_changed + c->tr_cap, c->sc_d);
-        delete t5;
-        // Round 0 fills the machine (one warp per trial); the re-run rounds are a handful of CTAs.
-        // obmd_run hooks in here to start the pair kernel on the side stream right behind round 0.
-        if (round == 0 && c->round0_hook) {
-          int (*hook)(obmd_ctx *) = c->round0_hook;
-          c->round0_hook = nullptr;
-          int hrc = hook(c);
-          if (hrc) return hrc;
-        }
-        LAUNCH(k_usher_diff, cdiv(ntr_loc, 256), 256, 0, c->tr_prev_d, c->tr_d, ntr_loc, round == 0 ? 1 : 0, par,
-               c->tr_chg, c->sc_d);
-        LAUNCH(k_usher_dirty, cdiv(ntr_loc, 4), 128, 0, ntr_loc, par, c->tr_chg, c->tr_path, c->tr_npts,
-               c->tr_bbox, u.natt, c->grid,
-               c->pt.cutmax * (1.0 + 1e-9), rsqmax, c->tr_list, c->tr_changed + c->tr_cap, c->sc_d);
-        LAUNCH(k_usher_round_end, 1, URE_T, sizeof(int) * LINK_MAX, c->tr_prev_d, c->tr_d, ntr_loc, par,
-               c->acc_list, c->spec_cell, c->spec_head, c->spec_next, c->grid, c->sc_d);
-        return OBMD_OK;
-      };
-      int round = 0;  // rounds enqueued so far
-      int batch = 3;
-      for (;;) {
-        NEED(round <= ntr_loc + 1, OBMD_ERR_STATE, "fix obmd: USHER commit did not converge");
-        for (int k = 0; k < batch; k++, round++)
-          if ((rc = enqueue_round(round))) return rc;
-        batch = 1;
-        if ((rc = read_scalars(c))) return rc;
-        NEED(c->sc_h->usher_error != OBMD_ERR_USHER, OBMD_ERR_USHER,
-             "fix obmd: USHER force vanished with E above target (the reference would not terminate)");
-        NEED(c->sc_h->usher_error != OBMD_ERR_CAPACITY, OBMD_ERR_CAPACITY,
-             "fix obmd: more than %d neighbours within the cutoff of a USHER point (or %d atoms in its stencil)",
-             USH_CAP, USH_CAND);
-        NEED(c->sc_h->usher_error != OBMD_ERR_CAPACITY + 1000, OBMD_ERR_CAPACITY,
-             "more than %d insertions in one call", LINK_MAX);
-        nacc = c->sc_h->naccept;
-        const int par = (round - 1) & 1;
-        if (c->sc_h->nchg2[par] == 0 || c->sc_h->ndirty2[par] == 0) break;
-      }
-      // the spec lists of the last round are no longer needed
-      if (nacc > 0)
-        LAUNCH(k_extra_clear, cdiv(nacc, 128), 128, 0, c->spec_cell, nacc, c->spec_head);
-      rounds = c->sc_h->nrounds_work;
+    const int M = fa.maxattempt;
+    NEED(M >= 1, OBMD_ERR_ARG, "fix obmd: maxattempt must be >= 1");
+    NEED(M == 1 || serial, OBMD_ERR_ARG,
+         "fix obmd: maxattempt > 1 in slab runs is not implemented (the right side's position in the RanPark "
+         "stream depends on the left rank's outcomes)");
+    // maxattempt == 1: trial t of either side sits at a fixed place of the RanPark stream, both sides
+    // go through the commit rounds together.  maxattempt > 1: the attempts a side consumes depend on
+    // its outcomes (k_usher_resolve), so the left side is finished and committed first and the right
+    // side starts where it stopped.
+    struct Pass { int nL, nR, slots; };
+    Pass passes[2];
+    int npass = 1;
+    if (M == 1) passes[0] = {ntrL, ntrR, 0};
+    else {
+      passes[0] = {ntrL * M, 0, ntrL};
+      passes[1] = {0, ntrR * M, ntrR};
+      npass = 2;
     }
+    for (int ip = 0; ip < npass; ip++) {
+      const Pass &ps = passes[ip];
+      const int ntr_p = ps.nL + ps.nR;
+      if (ntr_p == 0) continue;
+      const int ntr_loc = (doL ? ps.nL : 0) + (doR ? ps.nR : 0);
+      const int limit = M > 1 ? 1 : 0;
+      int nacc_p = 0, nused_p = ntr_p;
+      if (ntr_loc > 0) {
+        if ((rc = ensure_trials(c, ntr_loc, fa.nattempt))) return rc;
+        if ((rc = obmd_ensure_capacity(c, nlive + c->nextra + ntr_loc))) return rc;
+        UsherCfg u;
+        u.ntrL = ps.nL;
+        u.ntr = ntr_p;
+        u.seed0 = c->fs.rng_seed;
+        u.nbase = nlive + c->nextra;
+        u.natt = fa.nattempt;
+        u.tg0 = doL ? 0 : ps.nL;
+        u.slots = ps.slots;
+        u.maxatt = M;
+        const Extras ex = extras_of(c);
+        const double rsqmax = c->pt.cutmax * c->pt.cutmax * (1.0 + 1e-9);
+        // nchg2, ndirty2, naccept, nrounds_work, trial_cursor, nused, nused_prev
+        CK(cudaMemsetAsync(&c->sc_d->nchg2[0], 0, 9 * sizeof(int), c->stream));
+        // Rounds are enqueued back to back: every count a round needs (how many trials to re-run, how
+        // many atoms were accepted so far) lives in device memory, and a round that finds nothing to
+        // do is a handful of empty launches.  The host looks at the counters only after a batch.
+        const int rerun_grid = ntr_loc < 4 * 2 * NSM ? cdiv(ntr_loc, USH_WARPS) : 2 * NSM;
+        auto enqueue_round = [&](int round) -> int {
+          const int par = round & 1;
+          ScopedTimer t2(c, round == 0 ? "usher_round0" : "usher_rerun");
+          ScopedTimer *t5 = new ScopedTimer(c, round == 0 ? "usher_eval0" : "usher_evalN");
+          if (round == 0)
+            LAUNCH(k_usher_eval, ntr_loc < 6 * NSM * USH_WARPS ? cdiv(ntr_loc, USH_WARPS) : 6 * NSM,
+                   USH_WARPS * 32, 0, (const int *) nullptr, ntr_loc, 0, c->cur, c->grid, c->pt, c->fd,
+                   c->cell_start, u, ex, c->extra_head, c->extra_next, c->spec_head, c->spec_next, c->acc_list,
+                   c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts, c->tr_bbox, c->tr_changed + c->tr_cap,
+                   c->sc_d);
+          else
+            LAUNCH(k_usher_eval, rerun_grid, USH_WARPS * 32, 0, (const int *) c->tr_list, 0, par ^ 1, c->cur,
+                   c->grid, c->pt, c->fd, c->cell_start, u, ex, c->extra_head, c->extra_next, c->spec_head,
+                   c->spec_next, c->acc_list, c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts, c->tr_bbox,
+                   c->tr_changed + c->tr_cap, c->sc_d);
+          delete t5;
+          // Round 0 fills the machine (one warp per trial); the re-run rounds are a handful of CTAs.
+          // obmd_run hooks in here to start the pair kernel on the side stream right behind round 0.
+          if (round == 0 && c->round0_hook) {
+            int (*hook)(obmd_ctx *) = c->round0_hook;
+            c->round0_hook = nullptr;
+            int hrc = hook(c);
+            if (hrc) return hrc;
+          }
+          if (limit) LAUNCH(k_usher_resolve, 1, 1024, 0, c->tr_d, ntr_loc, u.slots, M, c->sc_d);
+          LAUNCH(k_usher_diff, cdiv(ntr_loc, 256), 256, 0, c->tr_prev_d, c->tr_d, ntr_loc, round == 0 ? 1 : 0,
+                 par, limit, c->tr_chg, c->sc_d);
+          LAUNCH(k_usher_dirty, cdiv(ntr_loc, 4), 128, 0, ntr_loc, par, c->tr_chg, c->tr_path, c->tr_npts,
+                 c->tr_bbox, u.natt, c->grid, c->pt.cutmax * (1.0 + 1e-9), rsqmax, c->tr_list,
+                 c->tr_changed + c->tr_cap, c->sc_d);
+          LAUNCH(k_usher_round_end, 1, URE_T, sizeof(int) * LINK_MAX, c->tr_prev_d, c->tr_d, ntr_loc, par, limit,
+                 c->acc_list, c->spec_cell, c->spec_head, c->spec_next, c->grid, c->sc_d);
+          return OBMD_OK;
+        };
+        int round = 0;  // rounds enqueued so far
+        int batch = 3;
+        for (;;) {
+          NEED(round <= ntr_loc + 1, OBMD_ERR_STATE, "fix obmd: USHER commit did not converge");
+          for (int k = 0; k < batch; k++, round++)
+            if ((rc = enqueue_round(round))) return rc;
+          batch = 1;
+          if ((rc = read_scalars(c))) return rc;
+          NEED(c->sc_h->usher_error != OBMD_ERR_USHER, OBMD_ERR_USHER,
+               "fix obmd: USHER force vanished with E above target (the reference would not terminate)");
+          NEED(c->sc_h->usher_error != OBMD_ERR_CAPACITY, OBMD_ERR_CAPACITY,
+               "fix obmd: more than %d neighbours within the cutoff of a USHER point (or %d atoms in its "
+               "stencil)", USH_CAP, USH_CAND);
+          NEED(c->sc_h->usher_error != OBMD_ERR_CAPACITY + 1000, OBMD_ERR_CAPACITY,
+               "more than %d insertions in one call", LINK_MAX);
+          nacc_p = c->sc_h->naccept;
+          const int par = (round - 1) & 1;
+          if (c->sc_h->nchg2[par] == 0 || c->sc_h->ndirty2[par] == 0) break;
+        }
+        if (limit) nused_p = c->sc_h->nused;
+        // the spec lists of the last round are no longer needed
+        if (nacc_p > 0)
+          LAUNCH(k_extra_clear, cdiv(nacc_p, 128), 128, 0, c->spec_cell, nacc_p, c->spec_head);
+        rounds += c->sc_h->nrounds_work;
+      }
 
-    naccL = doL ? nacc : 0;  // serial: both sides live in one list, the split is not needed
-    naccR = doR && !doL ? nacc : 0;
-    if (!serial) {  // creation counts of both edge ranks: natoms and the right rank's first new tag
-      ScopedTimer t3(c, "usher_allreduce");
-      double h[2] = {(double) naccL, (double) naccR};
-      CK(cudaMemcpyAsync(c->red_d, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
-      if ((rc = comm_allreduce(c, c->red_d, 2, 0))) return rc;
-      CK(cudaMemcpyAsync(c->red_h, c->red_d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      naccL = (int) c->red_h[0];
-      naccR = (int) c->red_h[1];
+      if (npass == 1) {
+        naccL = doL ? nacc_p : 0;  // serial: both sides live in one list, the split is not needed
+        naccR = doR && !doL ? nacc_p : 0;
+        if (!serial) {  // creation counts of both edge ranks: natoms and the right rank's first new tag
+          ScopedTimer t3(c, "usher_allreduce");
+          double h[2] = {(double) naccL, (double) naccR};
+          CK(cudaMemcpyAsync(c->red_d, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+          if ((rc = comm_allreduce(c, c->red_d, 2, 0))) return rc;
+          CK(cudaMemcpyAsync(c->red_h, c->red_d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+          CK(cudaStreamSynchronize(c->stream));
+          naccL = (int) c->red_h[0];
+          naccR = (int) c->red_h[1];
+        }
+      }
+      // every attempt made consumes exactly three draws (ATOM mode, uniform distribution, block region)
+      c->fs.rng_seed = ranpark_skip(c->fs.rng_seed, 3LL * nused_p);
+      nused_total += nused_p;
+      if (nacc_p > 0) {
+        // the side stream may still be walking the per-cell extra lists: link the new atoms only
+        // after its pair kernel has finished (obmd_run sets commit_wait)
+        ScopedTimer t4(c, "usher_commit");
+        if (c->commit_wait) CK(cudaStreamWaitEvent(c->stream, c->commit_wait, 0));
+        const int tag0 = maxtag + nacc + ((npass == 1 && doR && !doL) ? naccL : 0);
+        LAUNCH(k_usher_commit, cdiv(nacc_p, 128), 128, 0, c->cur, extras_of(c), tag0, c->grid, c->fd, c->tr_d,
+               c->acc_list, nacc_p, c->fx, c->fy, c->fz);
+        if ((rc = fix_link_extras(c, c->narr + c->nghost + c->nins, nacc_p, false))) return rc;
+      }
+      if (trials && maxtrials > ncopied && ntr_loc > 0) {
+        const int nloc_used = limit ? nused_p : ntr_loc;
+        const int ncopy = nloc_used < maxtrials - ncopied ? nloc_used : maxtrials - ncopied;
+        CK(cudaMemcpyAsync(c->tr_h, c->tr_d, sizeof(obmd_trial) * ncopy, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        memcpy(trials + ncopied, c->tr_h, sizeof(obmd_trial) * ncopy);
+        ncopied += ncopy;
+      }
+      // the next pass sees this pass's atoms as appended atoms (per-cell lists, local indices)
+      nacc += nacc_p;
+      c->nins = nacc;
+      c->nextra = c->narr + c->nghost + c->nins;
+      c->n = nlive + c->nextra;
     }
     rep.usher_rounds = rounds;
-    c->fs.ntrials += ntr;
+    c->fs.ntrials += nused_total;
     c->fs.nrounds += rounds;
-    // every trial consumes exactly three draws (ATOM mode, uniform distribution, block region)
-    c->fs.rng_seed = ranpark_skip(c->fs.rng_seed, 3LL * ntr);
-    if (nacc > 0) {
-      // the side stream may still be walking the per-cell extra lists: link the new atoms only
-      // after its pair kernel has finished (obmd_run sets commit_wait)
-      ScopedTimer t4(c, "usher_commit");
-      if (c->commit_wait) CK(cudaStreamWaitEvent(c->stream, c->commit_wait, 0));
-      const int tag0 = maxtag + ((doR && !doL) ? naccL : 0);
-      LAUNCH(k_usher_commit, cdiv(nacc, 128), 128, 0, c->cur, extras_of(c), tag0, c->grid, c->fd, c->tr_d,
-             c->acc_list, nacc, c->fx, c->fy, c->fz);
-      if ((rc = fix_link_extras(c, c->narr + c->nghost, nacc, false))) return rc;
-    }
-    if (trials && maxtrials > 0 && ntr_loc > 0) {
-      int ncopy = ntr_loc < maxtrials ? ntr_loc : maxtrials;
-      CK(cudaMemcpyAsync(c->tr_h, c->tr_d, sizeof(obmd_trial) * ncopy, cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      memcpy(trials, c->tr_h, sizeof(obmd_trial) * ncopy);
-    }
     CK(cudaGetLastError());
   }
   c->nins = nacc;
@@ -1497,7 +1599,7 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
   c->n = nlive + c->nextra;
   const int nacc_all = serial ? nacc : naccL + naccR;
   c->fs.ninserted += nacc_all;
-  rep.ntrials = ntr;
+  rep.ntrials = nused_total;
   rep.naccept = nacc_all;
   rep.nlocal = nlive + c->narr + c->nins;
 

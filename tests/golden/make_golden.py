@@ -124,11 +124,45 @@ def parse_usher(lines):
     return np.array(out, dtype=np.float64).reshape(-1, 3)
 
 
+def parse_attempts(lines):
+    """USHER verdict lines -> (accepted, E as printed, attempt number within its insertion slot)."""
+    out = []
+    for ln in lines:
+        m = re.match(r"USHER accepts at E = (\S+) in attempt No\. (\d+) with \d+ iterations", ln)
+        if m:
+            out.append((1, float(m.group(1)), int(m.group(2)))); continue
+        m = re.match(r"USHER denies at E = (\S+) at attempt No\. (\d+)", ln)
+        if m:
+            out.append((0, float(m.group(1)), int(m.group(2))))
+    return np.array(out, dtype=np.float64).reshape(-1, 3)
+
+
+def make_b6(wd, n0):
+    """B6: the B1 deck with maxattempt 3 -- pins the slot/attempt bookkeeping of try_inserting
+    (fix_obmd_merged.cpp:912-1172): which draw of the RanPark stream belongs to which slot."""
+    deck = (head() + fix(alpha=1.0, nbuf=2000, maxattempt=3) +
+            "dump d all custom 6 dump.b6 id x y z\ndump_modify d format float %.17g\n"
+            "thermo 1\nthermo_style custom step atoms\nrun 6\n")
+    lines = run_deck("b6", deck, wd)
+    frames = read_dump(os.path.join(wd, "dump.b6"))
+    step, rows = frames[-1]
+    assert step == 6
+    ver = parse_attempts(lines)
+    np.savez_compressed(os.path.join(HERE, "b6_usher_maxattempt3.npz"),
+                        verdicts=ver, final_tag=rows[:, 0].astype(np.int32),
+                        inserted_x=rows[n0:, 1:4].copy(), nsteps=6)
+    print("b6: attempts", len(ver), "accepted", int(ver[:, 0].sum()), "max attempt no.", int(ver[:, 2].max()),
+          "final atoms", len(rows))
+
+
 def main():
     if not os.path.exists(LMP):
         sys.exit("oracle/_ref/lmp_serial missing: run `bash oracle/build_ref.sh` first")
     wd = tempfile.mkdtemp(prefix="obmd_golden_")
     print("working in", wd)
+    if len(sys.argv) > 1 and sys.argv[1] == "b6":   # only the maxattempt fixture (the others are unchanged)
+        make_b6(wd, 12637)
+        return
 
     # ---- shipped configuration (input fixture: ids + coordinates, read_data order) ----
     deck = head() + "dump d all custom 1 dump.in id type x y z\ndump_modify d format float %.17g\nrun 0\n"
@@ -153,6 +187,7 @@ def main():
                         verdicts=ver, final_tag=rows[:, 0].astype(np.int32),
                         inserted_x=rows[n0:, 1:4].copy(), nsteps=12)
     print("b1: trials", len(ver), "accepted", int(ver[:, 0].sum()), "final atoms", len(rows))
+    make_b6(wd, n0)
 
     # ---- B2/B5: normal force distribution, static atoms, pair force zeroed ----
     deck = (head(a0=0.0, gamma=0.0) + fix(dpxx=10.0, freq=5.0) +

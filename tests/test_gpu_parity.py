@@ -409,3 +409,39 @@ def test_pair_two_types_row_and_list_kernels_vs_oracle(shipped, monkeypatch):
     scale = np.abs(res[(1.0, "0")]).max()
     assert np.abs(res[(1.0, "0")] - res[(1.0, "1")]).max() <= 1e-12 * scale
     assert np.abs(res[(1.0, "1")] - res[(0.0, "1")]).max() > 1.0   # the random term is on
+
+
+@pytest.mark.parametrize("maxattempt", [2, 3])
+def test_usher_maxattempt_vs_oracle(shipped, maxattempt):
+    """maxattempt > 1 (fix_obmd_merged.cpp:912-1172): every insertion slot draws up to maxattempt
+    trial positions from the RanPark stream and stops at the first accepted one, so which draw
+    belongs to which slot -- and where the right side starts in the stream -- depends on the
+    outcomes.  Empty buffers give hundreds of slots with same-call interactions; trial stream,
+    counts, tags, final atom order and the RanPark state must equal the serial oracle bit for bit."""
+    tag, x, box = shipped
+    B = 0.15 * box[0, 1]
+    keep = (x[:, 0] > B) & (x[:, 0] < box[0, 1] - B)     # remove every buffer atom
+    xs, ts = x[keep], tag[keep]
+    kw = dict(alpha=1.0, nbuf=1895.0, tau=0.01, maxattempt=maxattempt,
+              usher=(1, 31.03, 1.0, 0.02, 1e4, 1.5, 1.0, 40))
+    sim = cc.device_sim(box, **kw)
+    sim.upload(xs, np.zeros_like(xs), np.ones(len(xs), np.int32), ts, capacity=len(x) * 2)
+    p, a = cc.oracle_sim(box, xs, tag=ts, **kw)
+    L = O.lib()
+    trials = (O.Trial * 16384)()
+    for s in range(3):
+        sim.build_cells()
+        rep, tr = sim.pre_exchange(maxtrials=16384)
+        L.orc_fix_pre_exchange(C.byref(p), C.byref(a.c), trials, 16384)
+        assert rep.ntrials == p.last_ntrials and rep.naccept == p.last_naccept, (s, rep.ntrials, p.last_ntrials)
+        assert rep.ntrials > rep.ninsert_left + rep.ninsert_right > 100   # second attempts were made
+        for k in range(rep.ntrials):
+            assert tuple(tr[k].start) == tuple(trials[k].start), (s, k)
+            assert tuple(tr[k].end) == tuple(trials[k].end), (s, k)
+            assert (tr[k].accepted, tr[k].tag, tr[k].iter, tr[k].side) == \
+                (trials[k].accepted, trials[k].tag, trials[k].iter, trials[k].side), (s, k)
+            assert tr[k].energy == trials[k].energy
+        assert sim.fix_state().rng_seed == p.rng_seed
+    out = sim.download(("x", "tag"))
+    assert np.array_equal(out["tag"], a.view("tag")) and np.array_equal(out["x"], a.view("x"))
+    sim.close()

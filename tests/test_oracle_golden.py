@@ -88,6 +88,37 @@ def test_b1_usher_stream_bit_exact(shipped):
         assert np.array_equal(a.view("x")[len(tag):], g["inserted_x"])  # bit-exact
 
 
+def test_b6_usher_maxattempt3_slot_bookkeeping(shipped):
+    """maxattempt 3 (fix_obmd_merged.cpp:912-1172): verdicts WITH the attempt number inside each
+    insertion slot, accepted positions and tags, 6 steps of the unmodified reference binary."""
+    tag, x, box = shipped
+    L = O.lib()
+    g = load("b6_usher_maxattempt3.npz")
+    p = O.make_fix(box[:, 0], box[:, 1], alpha=1.0, nbuf=2000.0, maxattempt=3)
+    a = O.OracleAtoms(x, tag=tag)
+    trials = (O.Trial * 8192)()
+    ver = []
+    for _ in range(int(g["nsteps"])):
+        L.orc_fix_pre_exchange(C.byref(p), C.byref(a.c), trials, 8192)
+        attempt, side = 0, 0
+        for k in range(p.last_ntrials):
+            t = trials[k]
+            if t.side != side:            # try_inserting is called once per side: slots restart
+                attempt, side = 0, t.side
+            attempt += 1
+            ver.append((t.accepted, sig6(t.energy), attempt))
+            if t.accepted or attempt == 3:
+                attempt = 0
+    ref = g["verdicts"]
+    assert len(ver) == len(ref) and ref[:, 2].max() == 3
+    got = np.array(ver, dtype=np.float64)
+    assert np.array_equal(got[:, 0], ref[:, 0])
+    assert np.array_equal(got[:, 2], ref[:, 2])          # attempt number of every verdict line
+    assert np.allclose(got[:, 1], ref[:, 1], rtol=2e-6, atol=0)
+    assert np.array_equal(a.view("tag"), g["final_tag"])
+    assert np.array_equal(a.view("x")[len(tag):], g["inserted_x"])  # bit-exact
+
+
 def _post_force_once(p, a):
     L = O.lib()
     L.orc_fix_pre_exchange(C.byref(p), C.byref(a.c), None, 0)
