@@ -465,9 +465,9 @@ static int colrange_bound(const obmd_ctx *c, const ColRange &cr)
   return c->nsorted + (cr.extras ? c->nextra : 0);
 }
 
-// Tile shape of the row kernel for this box and density: rows per tile R, z-cells per tile zc,
-// threads T, staged-atom capacity.  Chosen to maximise (lanes doing work) x (warps resident per SM,
-// saturating at 16) with a small penalty for the halo redundancy; OBMD_B200_ROWS / _ZC / _PT override.
+// Tile shape of the row kernel for this box and density: rows per tile R (1, 2, 4), z-cells per tile
+// zc, threads T, staged-atom capacity, ranked by a small cost model fitted to measurements;
+// OBMD_B200_ROWS / _ZC / _PT override.
 struct RowPlan {
   int R, nchunk, zc, T, cap;
   size_t smem;
@@ -478,8 +478,9 @@ static int pair_row_plan(obmd_ctx *c, bool single, RowPlan &best)
   const Grid &g = c->grid;
   const double rho = (double) c->nsorted / ((double) (g.own_b - g.own_a + 1) * g.ny * g.nz);
   double best_score = -1.0;
-  for (int R = 1; R <= 2; R++) {
+  for (int R = 1; R <= 4; R *= 2) {
     if (c->row_rows > 0 && R != c->row_rows) continue;
+    if (R > g.ny) continue;
     const int NR = 3 * (R + 2);
     for (int nchunk = 1; nchunk <= g.nz; nchunk++) {
       const int zc = cdiv(g.nz, nchunk);
@@ -501,7 +502,12 @@ static int pair_row_plan(obmd_ctx *c, bool single, RowPlan &best)
       const double passes = ceil(atoms / T);
       const double lane_eff = atoms / (passes * T);
       const double redundancy = (double) NR * nw / (R * zc);
-      const double score = lane_eff * (warps < 16.0 ? warps / 16.0 : 1.0) / (1.0 + 0.02 * redundancy);
+      // measured on B200 (tools/pair_bench.py, 1 M atoms): lanes doing work x amortisation of the
+      // per-CTA set-up (~40 atoms' worth) x occupancy (saturating at 14 warps/SM), a penalty for the
+      // halo redundancy, and one for CTAs of more than 5 warps (their barriers couple too many warps:
+      // 288-thread tiles ran 40 % slower than 160-thread tiles at the same occupancy)
+      const double score = lane_eff * (atoms / (atoms + 40.0)) * (warps < 14.0 ? warps / 14.0 : 1.0) *
+          (T > 256 ? 0.7 : (T > 192 ? 0.8 : (T > 160 ? 0.9 : 1.0))) / (1.0 + 0.03 * redundancy);
       if (score > best_score) {
         best_score = score;
         best = {R, nchunk, zc, T, cap, smem};
@@ -533,6 +539,7 @@ static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &
   CK(cudaFuncSetAttribute(k_pair_row<R, S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl.smem))
       ROW_ATTR(1, true, true); ROW_ATTR(1, true, false); ROW_ATTR(1, false, true); ROW_ATTR(1, false, false);
       ROW_ATTR(2, true, true); ROW_ATTR(2, true, false); ROW_ATTR(2, false, true); ROW_ATTR(2, false, false);
+      ROW_ATTR(4, true, true); ROW_ATTR(4, true, false); ROW_ATTR(4, false, true); ROW_ATTR(4, false, false);
       c->row_smem_set = pl.smem;
     }
     const int ntiles = ncols * cdiv(g.ny, pl.R) * pl.nchunk;
@@ -547,7 +554,8 @@ static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &
     else LAUNCH_ON(st, (k_pair_row<R, false, false>), ntiles, pl.T, pl.smem, ROW_ARGS);                  \
   } while (0)
     if (pl.R == 1) ROW_LAUNCH(1);
-    else ROW_LAUNCH(2);
+    else if (pl.R == 2) ROW_LAUNCH(2);
+    else ROW_LAUNCH(4);
     CK(cudaGetLastError());
     if (!cr.extras || c->narr + c->nins == 0) return OBMD_OK;
     ColRange xr;

@@ -1,6 +1,6 @@
 // Row-tiled PairDPD kernel (included by pair.cu): the production path for the cell-sorted atoms.
 //
-// A tile is the atoms of R (1 or 2) y-adjacent cell rows of one column over a run of z-cells: R
+// A tile is the atoms of R (1, 2 or 4) y-adjacent cell rows of one column over a run of z-cells: R
 // contiguous slot ranges, because z is the fastest cell index.  Its stencil is the 3 x (R+2) rows
 // around it over the same z window plus one cell on either side.  The CTA copies x, v and tag of
 // that window into shared memory ONCE with 8-byte `cp.async` copies (no register staging, every
@@ -29,9 +29,9 @@
 #define PR_TMAX 288
 
 struct RowHdr {
-  int row_base[12];  // first cell index of stencil row r = ry*3 + rx, -1 if it is not needed / does not exist
-  double yshift[12];
-  int tb[2], te[2];  // tile atoms of tile row ty are slots [tb, te)
+  int row_base[18];  // first cell index of stencil row r = ry*3 + rx (R <= 4), -1 if that column does not exist
+  double yshift[18];
+  int tb[4], te[4];  // tile atoms of tile row ty are slots [tb, te)
   int nstaged;
   double org[3];     // low corner of the tile (origin of the fp32 screening copy)
 };
@@ -331,15 +331,23 @@ __global__ void __launch_bounds__(PR_TMAX, 1)
   }
   __syncthreads();
 
-  const int n0 = H.te[0] - H.tb[0];
-  const int ntile = n0 + (R > 1 ? H.te[R - 1] - H.tb[R - 1] : 0);
+  int ncum[R + 1];  // tile atoms of rows 0..ty-1
+  ncum[0] = 0;
+#pragma unroll
+  for (int ty = 0; ty < R; ty++) ncum[ty + 1] = ncum[ty] + (H.te[ty] - H.tb[ty]);
+  const int ntile = ncum[R];
   for (int k0 = 0; k0 < ntile; k0 += T) {
     const int k = k0 + tid;
     const bool mine = k < ntile;
     const unsigned live = __ballot_sync(0xffffffffu, mine);
     if (!mine) continue;
-    const int ty = (R > 1 && k >= n0) ? 1 : 0;
-    const int i = ty ? H.tb[R - 1] + (k - n0) : H.tb[0] + k;
+    int ty = 0;
+#pragma unroll
+    for (int q = 1; q < R; q++) ty += (k >= ncum[q]) ? 1 : 0;
+    int i = H.tb[0] + k;
+#pragma unroll
+    for (int q = 1; q < R; q++)
+      if (ty == q) i = H.tb[q] + (k - ncum[q]);
     if (!staged) {  // unusually dense neighbourhood: plain global path
       PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
       pair_atom_global<SINGLE_TYPE, false, PREWRAP, int>(p, g, pt, ex, cell_start, extra_head, extra_next, i,

@@ -346,12 +346,13 @@ def test_row_tiled_pair_kernel_matches_list_kernel(shipped, monkeypatch):
     per-atom list kernel that walks global memory with a minimum-image test.  Same pairs, same counter
     RNG, different summation order and image arithmetic: the forces must agree to 1e-12 of the force
     scale, with the random term on, on a box with periodic wraps inside a tile (nz = 11), with tiles
-    split into z-chunks (OBMD_B200_ZC) and with one or two rows per tile (OBMD_B200_ROWS; ny = 11 is
-    odd, so the last strip has a single row), and on the tiled 1 M-atom box (nz = 44, one tile per row)."""
+    split into z-chunks (OBMD_B200_ZC) and with one, two or four rows per tile (OBMD_B200_ROWS; ny = 11 is
+    not a multiple, so the last strip overlaps the previous one), and on the tiled 1 M-atom box (nz = 44, one tile per row)."""
     for reps, n_expected, rows, zc in (((1, 1, 1), 12637, "0", "0"), ((1, 1, 1), 12637, "1", "4"),
                                        ((1, 1, 1), 12637, "2", "11"), ((1, 1, 1), 12637, "2", "3"),
+                                       ((1, 1, 1), 12637, "4", "0"), ((1, 1, 1), 12637, "4", "5"),
                                        ((4, 5, 4), 1010960, "0", "0"), ((4, 5, 4), 1010960, "1", "0"),
-                                       ((1, 2, 5), 126370, "2", "20")):
+                                       ((4, 5, 4), 1010960, "4", "22"), ((1, 2, 5), 126370, "2", "20")):
         tag, x, box = cc.tiled(reps)
         assert len(x) == n_expected
         v = np.random.default_rng(9).normal(0, 1, x.shape)
