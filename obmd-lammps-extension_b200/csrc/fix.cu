@@ -801,22 +801,41 @@ __global__ void k_usher_dirty(int ntr, int par, const ChgRec *__restrict__ chg,
   const double *mp = path + (size_t) t * (natt + 1) * 3;
   const double *bb = bbox + (size_t) t * 6;
   const int np = npts[t], nchg = sc->nchg2[par];
-  int kf = np;  // first affected point seen by this lane
+  int kf = np;  // first affected point found so far
   if (nchg == 0) return;
-  for (int qi = lane; qi < nchg; qi += 32) {
-    const ChgRec r = chg[qi];
-    if (r.q >= t) continue;
-    const bool oldacc = (r.flags & 1) && near_bbox(r.o, bb, g, rc);
-    const bool newacc = (r.flags & 2) && near_bbox(r.n, bb, g, rc);
-    if (!oldacc && !newacc) continue;
-    for (int k = 0; k < kf; k++) {
-      if ((oldacc && near_pt(r.o, mp + 3 * k, g, rsqmax)) || (newacc && near_pt(r.n, mp + 3 * k, g, rsqmax))) {
-        kf = k;
-        break;
+  // lanes prefilter 32 change records at a time against the trial's bounding box; every record that
+  // passes is then tested against all evaluated points by the whole warp (points are read coalesced)
+  for (int q0 = 0; q0 < nchg; q0 += 32) {
+    const int qi = q0 + lane;
+    ChgRec r;
+    r.flags = 0;
+    r.q = 1 << 30;
+    if (qi < nchg) r = chg[qi];
+    const bool oldacc = r.q < t && (r.flags & 1) && near_bbox(r.o, bb, g, rc);
+    const bool newacc = r.q < t && (r.flags & 2) && near_bbox(r.n, bb, g, rc);
+    unsigned m = __ballot_sync(0xffffffffu, oldacc || newacc);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1u;
+      double o[3], n[3];
+      for (int d = 0; d < 3; d++) {
+        o[d] = __shfl_sync(0xffffffffu, r.o[d], src);
+        n[d] = __shfl_sync(0xffffffffu, r.n[d], src);
+      }
+      const bool oa = __shfl_sync(0xffffffffu, (int) oldacc, src) != 0;
+      const bool na = __shfl_sync(0xffffffffu, (int) newacc, src) != 0;
+      for (int k0 = 0; k0 < kf; k0 += 32) {  // kf stays warp-uniform: it is only set from ballots
+        const int k = k0 + lane;
+        const bool hit = k < kf && ((oa && near_pt(o, mp + 3 * k, g, rsqmax)) ||
+                                    (na && near_pt(n, mp + 3 * k, g, rsqmax)));
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (hm) {
+          kf = k0 + __ffs(hm) - 1;
+          break;
+        }
       }
     }
   }
-  for (int d = 16; d > 0; d >>= 1) kf = min(kf, __shfl_xor_sync(0xffffffffu, kf, d));
   if (kf < np && lane == 0) {
     kfirst[t] = kf;
     list[atomicAdd(&sc->ndirty2[par], 1)] = t;
