@@ -75,6 +75,7 @@ extern "C" int obmd_create(obmd_ctx **out, int device)
   if (const char *e3 = getenv("OBMD_B200_TILE")) c->tile_kernel = atoi(e3) != 0;
   if (const char *e4 = getenv("OBMD_B200_ZC")) c->row_zc = atoi(e4);
   if (const char *e6 = getenv("OBMD_B200_ROWS")) c->row_rows = atoi(e6);
+  if (const char *e8 = getenv("OBMD_B200_CAPSCALE")) c->row_capscale = atof(e8);
   if (const char *e5 = getenv("OBMD_B200_PT")) c->row_threads = atoi(e5);
   snprintf(c->err, sizeof(c->err), "no error");
   *out = c;

@@ -108,6 +108,7 @@ struct obmd_ctx {
   bool tile_kernel = true;   // OBMD_B200_TILE=0: PairDPD through the per-atom list kernel instead of pair_row.cuh
   int row_rows = 0, row_zc = 0, row_threads = 0;  // tuning overrides (OBMD_B200_ROWS, _ZC, _PT); 0 = automatic
   size_t row_smem_set = 0;
+  double row_capscale = 1.0;  // OBMD_B200_CAPSCALE (tests): < 1 forces tiles onto the overflow path
   char err[1024] = {0};
   long long launches = 0;
   bool timing = false;

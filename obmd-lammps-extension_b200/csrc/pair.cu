@@ -492,7 +492,11 @@ static int pair_row_plan(obmd_ctx *c, bool single, RowPlan &best)
       if (T < 32) T = 32;
       if (T > PR_TMAX) continue;
       const int nw = zc + 2;
-      const int cap = ((int) (NR * nw * rho * 1.04) + 16 + 7) / 8 * 8;
+      // staged-atom capacity: the mean plus the larger of 4 % + 16 and 3.5 sigma of a Poisson count (a
+      // dense DPD fluid fluctuates far less); a tile that still overflows takes the global-memory path
+      const double nmean = NR * nw * rho;
+      const double slack = fmax(0.04 * nmean + 16.0, 3.5 * sqrt(nmean));
+      const int cap = ((int) ((nmean + slack) * c->row_capscale) + 7) / 8 * 8;
       const size_t smem = pair_row_smem_bytes(R, cap, nw, T, single);
       if (smem > 200 * 1024) continue;
       int ctas = (int) ((227 * 1024) / (smem + 1024));

@@ -369,6 +369,21 @@ def test_row_tiled_pair_kernel_matches_list_kernel(shipped, monkeypatch):
         scale = np.abs(res[0]).max()
         assert scale > 1.0
         assert np.abs(res[0] - res[1]).max() <= 1e-12 * scale
+    # a tile whose window does not fit the shared-memory capacity takes the global-memory path:
+    # shrink the capacity so that every tile (0.5) or only the densest ones (0.99) overflow
+    for capscale in ("0.5", "0.99"):
+        monkeypatch.setenv("OBMD_B200_TILE", "1")
+        monkeypatch.setenv("OBMD_B200_ZC", "0"); monkeypatch.setenv("OBMD_B200_ROWS", "0")
+        monkeypatch.setenv("OBMD_B200_CAPSCALE", capscale)
+        tag, x, box = cc.tiled((1, 2, 5))
+        v = np.random.default_rng(9).normal(0, 1, x.shape)
+        sim = cc.device_sim(box, fix=False)
+        sim.upload(x, v, np.ones(len(x), np.int32), tag)
+        sim.build_cells(); sim.pbc(); sim.pair_compute(3)
+        f = sim.download(("f",))["f"]
+        sim.close()
+        assert np.abs(f - res[1]).max() <= 1e-12 * np.abs(res[1]).max()
+    monkeypatch.delenv("OBMD_B200_CAPSCALE")
 
 
 def test_pair_two_types_row_and_list_kernels_vs_oracle(shipped, monkeypatch):
