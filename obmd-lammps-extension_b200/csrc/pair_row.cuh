@@ -12,8 +12,8 @@
 //            counter RNG), positions, velocities
 //            and tags all from shared memory -- the kernel's only global traffic is the staging
 //            copy (served by L2 after the first touch) and the force store.
-// Periodic images are materialised after the copy lands: a row reached across the y face, or a
-// window cell reached across the z face, is shifted by the box length in shared memory, exactly as
+// Periodic images are materialised while staging: a row reached across the y face, or a
+// window cell reached across the z face, is stored shifted by the box length, exactly as
 // the reference's ghost atoms are (comm_brick.cpp:735-760 adds the period once, pair_dpd.cpp:101-104
 // then subtracts plain coordinates).  The inner loops therefore carry no minimum-image logic.
 // Atoms appended after the sort (insertions, slab arrivals and ghosts) hang off per-cell lists; the
@@ -271,63 +271,71 @@ __global__ void __launch_bounds__(PR_TMAX, 1)
     for (int ci = tid; ci < ncw; ci += T)
       for (int d = S.cbeg[ci]; d < S.cbeg[ci + 1]; d++) S.tag[d] = ci;
     __syncthreads();
-    for (int d = tid; d < H.nstaged; d += T) {
-      const int ci = S.tag[d];
-      const int k = d - S.cbeg[ci];
-      int j = S.gbeg[ci] + k;
-      if (have_extras) {  // atoms appended after the sort sit behind the cell's sorted atoms
+    // Velocities and tags are copied asynchronously as they are.  Positions go through registers: the
+    // thread applies the periodic image shift of the atom's window cell (and, before Domain::pbc has
+    // run, the wrap itself), stores the fp64 position and the fp32 screening copy relative to the
+    // tile's low corner (|coordinate| < ~70 cell widths, so the absolute error is < 1e-5 and the
+    // relative margin on cutsq in phase 1 covers it many times over).  Two atoms per trip keep six
+    // position loads in flight per thread.
+    const double ox = H.org[0], oy = H.org[1], oz = H.org[2];
+    for (int d0 = tid; d0 < H.nstaged; d0 += 2 * T) {
+      int dd[2], jj[2];
+      double ys[2], zs[2];
+      bool on[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int d = d0 + u * T;
+        on[u] = d < H.nstaged;
+        dd[u] = on[u] ? d : d0;
+        const int ci = S.tag[dd[u]];
+        const int k = dd[u] - S.cbeg[ci];
+        int j = S.gbeg[ci] + k;
         const int w = ci / NR, r = ci - w * NR;
-        int zu = z0 - 1 + w;
-        zu = zu < 0 ? zu + g.nz : (zu >= g.nz ? zu - g.nz : zu);
-        const int cc = H.row_base[r] + zu;
-        const int ns = cell_start[cc + 1] - S.gbeg[ci];
-        if (k >= ns) {
-          int e = extra_head[cc];
-          for (int m = ns; m < k; m++) e = extra_next[e];
-          j = ex.base + e;
+        const int zraw = z0 - 1 + w;
+        if (have_extras) {  // atoms appended after the sort sit behind the cell's sorted atoms
+          const int zu = zraw < 0 ? zraw + g.nz : (zraw >= g.nz ? zraw - g.nz : zraw);
+          const int cc = H.row_base[r] + zu;
+          const int ns = cell_start[cc + 1] - S.gbeg[ci];
+          if (k >= ns) {
+            int e = extra_head[cc];
+            for (int m = ns; m < k; m++) e = extra_next[e];
+            j = ex.base + e;
+          }
         }
+        jj[u] = j;
+        ys[u] = H.yshift[r];
+        zs[u] = zraw < 0 ? -g.prd[2] : (zraw >= g.nz ? g.prd[2] : 0.0);
       }
-      cp_async8(S.pos + 3 * d, p.x + j);
-      cp_async8(S.pos + 3 * d + 1, p.y + j);
-      cp_async8(S.pos + 3 * d + 2, p.z + j);
-      cp_async8(S.vel + 3 * d, p.vx + j);
-      cp_async8(S.vel + 3 * d + 1, p.vy + j);
-      cp_async8(S.vel + 3 * d + 2, p.vz + j);
-      cp_async4(S.tag + d, p.tag + j);
-      if (!SINGLE_TYPE) S.type[d] = (unsigned char) p.type[j];
+      double xx[2], yy[2], zz[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        xx[u] = p.x[jj[u]];
+        yy[u] = p.y[jj[u]];
+        zz[u] = p.z[jj[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        if (!on[u]) continue;
+        const int d = dd[u], j = jj[u];
+        cp_async8(S.vel + 3 * d, p.vx + j);
+        cp_async8(S.vel + 3 * d + 1, p.vy + j);
+        cp_async8(S.vel + 3 * d + 2, p.vz + j);
+        cp_async4(S.tag + d, p.tag + j);  // entry d of the cell table was consumed above, by this thread
+        if (!SINGLE_TYPE) S.type[d] = (unsigned char) p.type[j];
+        const double y = (PREWRAP ? wrap1(yy[u], g.lo[1], g.hi[1], g.prd[1]) : yy[u]) + ys[u];
+        const double z = (PREWRAP ? wrap1(zz[u], g.lo[2], g.hi[2], g.prd[2]) : zz[u]) + zs[u];
+        S.pos[3 * d] = xx[u];
+        S.pos[3 * d + 1] = y;
+        S.pos[3 * d + 2] = z;
+        S.scr[d] = make_float4((float) (xx[u] - ox), (float) (y - oy), (float) (z - oz), 0.0f);
+      }
     }
-    if (tid < 4) {  // slack entries read by the last screen group (masked afterwards): keep them finite
+    if (tid < 4) {  // slack entries read by the last screen group (masked afterwards): far away
       const int d = H.nstaged + tid;
-      S.pos[3 * d] = S.pos[3 * d + 1] = S.pos[3 * d + 2] = 1.0e30;
+      S.scr[d] = make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.0f);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    // periodic images (and, before Domain::pbc has run, the wrap itself), fixed up in shared memory
-    for (int ci = tid; ci < ncw; ci += T) {
-      const int w = ci / NR, r = ci - w * NR;
-      if (H.row_base[r] < 0) continue;
-      const int zu = z0 - 1 + w;
-      const double zs = zu < 0 ? -g.prd[2] : (zu >= g.nz ? g.prd[2] : 0.0), ys = H.yshift[r];
-      bool fix = (ys != 0.0) || (zs != 0.0);
-      if (PREWRAP) {  // only face cells can hold coordinates that have not been wrapped yet
-        const int by = cy + r / 3 - 1;
-        fix = fix || by <= 0 || by >= g.ny - 1 || zu <= 0 || zu >= g.nz - 1;
-      }
-      if (!fix) continue;
-      for (int d = S.cbeg[ci]; d < S.cbeg[ci + 1]; d++) {
-        const double yj = S.pos[3 * d + 1], zj = S.pos[3 * d + 2];
-        S.pos[3 * d + 1] = (PREWRAP ? wrap1(yj, g.lo[1], g.hi[1], g.prd[1]) : yj) + ys;
-        S.pos[3 * d + 2] = (PREWRAP ? wrap1(zj, g.lo[2], g.hi[2], g.prd[2]) : zj) + zs;
-      }
-    }
-    __syncthreads();
-    // fp32 screening copy, relative to the tile's low corner (|coordinate| < ~70 cell widths, so the
-    // absolute error is < 1e-5 and the relative margin on cutsq below covers it many times over)
-    const double ox = H.org[0], oy = H.org[1], oz = H.org[2];
-    for (int d = tid; d < H.nstaged + 4; d += T)
-      S.scr[d] = make_float4((float) (S.pos[3 * d] - ox), (float) (S.pos[3 * d + 1] - oy),
-                             (float) (S.pos[3 * d + 2] - oz), 0.0f);
   }
   __syncthreads();
 
