@@ -83,6 +83,10 @@ class ClockSampler(threading.Thread):
                 self.handle = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + uuid)
             self.nvml = pynvml
             self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            # the first queries of a process are slow (tens of ms) and serialise with kernel launches in
+            # the driver: pay for them here, before the timed region starts
+            for _ in range(3):
+                self.sample_nvml()
         except Exception:
             self.nvml = None
 
@@ -114,7 +118,7 @@ class ClockSampler(threading.Thread):
                         self.rows.append([t.strip() for t in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.02 if self.nvml else 0.25)
+            time.sleep(0.05 if self.nvml else 0.25)
 
     def summary(self):
         if not self.rows:
@@ -218,7 +222,7 @@ def ours(args):
     sampler.stop_flag = True; sampler.join()
     fam = {}
     for name in ("nve", "bin", "sort", "comm", "pre_exchange", "usher", "usher_round0", "usher_rerun",
-                 "usher_commit", "usher_allreduce", "usher_eval0", "usher_evalN", "pbc", "pair", "post_force"):
+                 "usher_commit", "usher_allreduce", "usher_eval0", "usher_evalN", "host_wait_scalars", "host_step", "pbc", "pair", "post_force"):
         t, nl = sim.timing_get(name)
         fam[name] = {"ms_per_step": t / args.steps, "launches_per_step": nl / args.steps}
     sim.timing(False)

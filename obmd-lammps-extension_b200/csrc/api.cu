@@ -4,6 +4,8 @@
 #include <cstddef>
 #include <cstdlib>
 
+#include <chrono>
+
 #include "ctx.h"
 
 char g_create_err[1024] = "no error";
@@ -640,6 +642,18 @@ extern "C" int obmd_run(obmd_ctx *c, long long first_step, int nsteps)
   int rc;
   for (int s = 0; s < nsteps; s++) {  // verlet.cpp:229-363
     const long long step = first_step + s;
+    const auto host_t0 = std::chrono::steady_clock::now();
+    struct HostStep {  // host wall time of the step's enqueue work (timing runs only)
+      obmd_ctx *c;
+      std::chrono::steady_clock::time_point t0;
+      ~HostStep()
+      {
+        if (!c->timing) return;
+        TimerSlot &sl = c->timers["host_step"];
+        sl.ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        sl.launches++;
+      }
+    } host_step{c, host_t0};
     if ((rc = fix_nve_initial(c))) return rc;
     fix_clear_extras(c);
     if ((rc = obmd_ensure_capacity(c, c->n + c->n / 32 + 4096))) return rc;

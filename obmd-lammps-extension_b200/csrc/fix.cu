@@ -8,6 +8,8 @@
 //   post_force   (:1229-1240)    -> k_weight_sums, k_apply_forces
 //   FixNVE       (fix_nve.cpp)   -> k_nve_initial, k_nve_final
 //   Domain::pbc  (domain.cpp)    -> k_pbc
+#include <chrono>
+
 #include "ctx.h"
 
 #define EPSILON_FIX 1.0e-6   // fix_obmd_merged.cpp:62
@@ -1107,8 +1109,14 @@ static int ensure_trials(obmd_ctx *c, int ntr, int natt)
 
 int read_scalars(obmd_ctx *c)
 {
+  const auto t0 = std::chrono::steady_clock::now();
   CK(cudaMemcpyAsync(c->sc_h, c->sc_d, sizeof(StepScalars), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  if (c->timing) {  // host wall time spent waiting here (includes the GPU work queued before it)
+    TimerSlot &sl = c->timers["host_wait_scalars"];
+    sl.ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    sl.launches++;
+  }
   return OBMD_OK;
 }
 
