@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(USH_WARPS * 32, 6)
 }
 
 // the trials whose state (accepted, end) differs between the two latest rounds, as compact records
-__global__ void k_usher_diff(const obmd_trial *__restrict__ prev, const obmd_trial *__restrict__ cur,
+__global__ void k_usher_diff(obmd_trial *__restrict__ prev, const obmd_trial *__restrict__ cur,
                              int ntr, int first_round, int par, int limit, ChgRec *__restrict__ chg,
                              StepScalars *sc)
 {
@@ -760,6 +760,9 @@ __global__ void k_usher_diff(const obmd_trial *__restrict__ prev, const obmd_tri
     r.flags = (oldacc ? 1 : 0) | (newacc ? 2 : 0);
     chg[atomicAdd(&sc->nchg2[par], 1)] = r;
   }
+  // prev <- cur: the next round's evaluations read the positions of the atoms accepted so far from
+  // prev, and nothing else reads prev[t] after this point of the round
+  prev[t] = b;
 }
 
 // all points involved lie inside the box, so one periodic shift suffices
@@ -902,14 +905,13 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
-// End of a commit round, one CTA: drops the previous round's per-cell "spec" lists, copies the
-// round's trial states to `prev`, compacts the accepted trials in order into acc_list, threads
-// them into fresh per-cell lists (what the next round's evaluations see of earlier insertions),
+// End of a commit round, one CTA: drops the previous round's per-cell "spec" lists, compacts the
+// accepted trials in order into acc_list, threads them into fresh per-cell lists (what the next round's evaluations see of earlier insertions),
 // and zeroes the counters of the next round.  Deterministic: lists are ordered by trial index.
 #define URE_T 1024
 __global__ void __launch_bounds__(URE_T)
-    k_usher_round_end(obmd_trial *__restrict__ prev, const obmd_trial *__restrict__ cur, int ntr, int par,
-                      int limit, int *__restrict__ acc_list, int *__restrict__ spec_cell, int *__restrict__ spec_head,
+    k_usher_round_end(const obmd_trial *__restrict__ cur, int ntr, int par, int first_round, int limit,
+                      int *__restrict__ acc_list, int *__restrict__ spec_cell, int *__restrict__ spec_head,
                       int *__restrict__ spec_next, Grid g, StepScalars *sc)
 {
   extern __shared__ int cellsh[];  // cells of the accepted trials (at most LINK_MAX)
@@ -918,14 +920,18 @@ __global__ void __launch_bounds__(URE_T)
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int nold = sc->naccept;
   const int nlim = limit ? sc->nused : ntr;  // maxattempt > 1: attempts beyond nused are never made
-  for (int k = tid; k < nold; k += URE_T) spec_head[spec_cell[k]] = -1;
-  {  // prev <- cur, as a flat copy of doubles (sizeof(obmd_trial) is a multiple of 8)
-    static_assert(sizeof(obmd_trial) % 8 == 0, "obmd_trial must be a whole number of doubles");
-    const double *src = reinterpret_cast<const double *>(cur);
-    double *dst = reinterpret_cast<double *>(prev);
-    const int nd = ntr * (int) (sizeof(obmd_trial) / 8);
-    for (int k = tid; k < nd; k += URE_T) dst[k] = src[k];
+  if (!first_round && sc->nchg2[par] == 0) {
+    // nothing changed in this round (a round enqueued ahead of need): the accepted list and its
+    // per-cell lists are still those of the previous round
+    if (tid == 0) {
+      sc->nchg2[par ^ 1] = 0;
+      sc->ndirty2[par ^ 1] = 0;
+      sc->trial_cursor = 0;
+      sc->nused_prev = sc->nused;
+    }
+    return;
   }
+  for (int k = tid; k < nold; k += URE_T) spec_head[spec_cell[k]] = -1;
   if (tid == 0) base = 0;
   __syncthreads();
   for (int t0 = 0; t0 < ntr; t0 += URE_T) {
@@ -1545,8 +1551,8 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
           LAUNCH(k_usher_dirty, cdiv(ntr_loc, 4), 128, 0, ntr_loc, par, c->tr_chg, c->tr_path, c->tr_npts,
                  c->tr_bbox, u.natt, c->grid, c->pt.cutmax * (1.0 + 1e-9), rsqmax, c->tr_list,
                  c->tr_changed + c->tr_cap, c->sc_d);
-          LAUNCH(k_usher_round_end, 1, URE_T, sizeof(int) * LINK_MAX, c->tr_prev_d, c->tr_d, ntr_loc, par, limit,
-                 c->acc_list, c->spec_cell, c->spec_head, c->spec_next, c->grid, c->sc_d);
+          LAUNCH(k_usher_round_end, 1, URE_T, sizeof(int) * LINK_MAX, c->tr_d, ntr_loc, par, round == 0 ? 1 : 0,
+                 limit, c->acc_list, c->spec_cell, c->spec_head, c->spec_next, c->grid, c->sc_d);
           return OBMD_OK;
         };
         int round = 0;  // rounds enqueued so far

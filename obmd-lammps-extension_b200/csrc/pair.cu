@@ -385,16 +385,21 @@ __global__ void __launch_bounds__(128)
   a.bnd = true;
   const int cx = cell_cx(g, a.x), cy = cell_cy(g, a.y), cz = cell_cz(g, a.z);
   PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  // all 27 list heads first (independent loads; almost all of them are empty), then the few lists
+  int head[27];
+#pragma unroll
   for (int nb = 0; nb < 27; nb++) {
     const int bx = cx + nb / 9 - 1;
-    if (bx < 0 || bx >= g.nx) continue;
     int by = cy + (nb / 3) % 3 - 1, bz = cz + nb % 3 - 1;
     by = by < 0 ? by + g.ny : (by >= g.ny ? by - g.ny : by);
     bz = bz < 0 ? bz + g.nz : (bz >= g.nz ? bz - g.nz : bz);
-    for (int e = extra_head[(bx * g.ny + by) * g.nz + bz]; e >= 0; e = extra_next[e])
+    head[nb] = (bx < 0 || bx >= g.nx) ? -1 : extra_head[(bx * g.ny + by) * g.nz + bz];
+  }
+#pragma unroll
+  for (int nb = 0; nb < 27; nb++)
+    for (int e = head[nb]; e >= 0; e = extra_next[e])
       if (e >= first_new && pair_screen<SINGLE_TYPE, false>(p, pt, g, ex.base + e, a))
         pair_eval<SINGLE_TYPE, false, false>(p, pt, g, ex.base + e, a, step, random_on != 0, acc);
-  }
   fx[i] += acc.fx;
   fy[i] += acc.fy;
   fz[i] += acc.fz;
