@@ -77,6 +77,7 @@ extern "C" int obmd_create(obmd_ctx **out, int device)
   if (const char *e3 = getenv("OBMD_B200_TILE")) c->tile_kernel = atoi(e3) != 0;
   if (const char *e4 = getenv("OBMD_B200_ZC")) c->row_zc = atoi(e4);
   if (const char *e6 = getenv("OBMD_B200_ROWS")) c->row_rows = atoi(e6);
+  if (const char *e9 = getenv("OBMD_B200_PAIR_FIRST")) c->pair_first = atoi(e9);
   if (const char *e8 = getenv("OBMD_B200_CAPSCALE")) c->row_capscale = atof(e8);
   if (const char *e5 = getenv("OBMD_B200_PT")) c->row_threads = atoi(e5);
   snprintf(c->err, sizeof(c->err), "no error");
@@ -671,7 +672,12 @@ extern "C" int obmd_run(obmd_ctx *c, long long first_step, int nsteps)
       // not need Domain::pbc first; atoms next to an insertion are recomputed afterwards
       // (fix_redo_pair_near_insertions).
       c->hook_step = step;
-      c->round0_hook = pair_on_side_stream;
+      const bool pair_first = c->pair_first >= 0 ? c->pair_first != 0 : c->nsorted > 3000000;
+      if (pair_first) {  // large systems: the pair kernel is the longer branch, start it at once
+        if ((rc = pair_on_side_stream(c))) return rc;
+        c->round0_hook = nullptr;
+      } else
+        c->round0_hook = pair_on_side_stream;
       c->commit_wait = c->ev_int;
       rc = fix_pre_exchange(c, nullptr, 0);
       c->commit_wait = nullptr;
