@@ -169,6 +169,17 @@ def ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    if world > 1 and not os.environ.get("OBMD_BENCH_NO_PIN"):
+        # one disjoint set of cores per rank (as `numactl`/`taskset` would give each MPI rank): the step
+        # has several host round trips, and rank threads migrating onto each other's cores showed up as
+        # sporadic 30-100 % slow-downs of whole runs on the virtualised GPU hosts
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local * per:(local + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+        except (AttributeError, OSError):
+            pass
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # weak scaling: the box grows along the open axis with the number of GPUs (one 4x5x4 tiling =
@@ -222,7 +233,8 @@ def ours(args):
     sampler.stop_flag = True; sampler.join()
     fam = {}
     for name in ("nve", "bin", "sort", "comm", "pre_exchange", "usher", "usher_round0", "usher_rerun",
-                 "usher_commit", "usher_allreduce", "usher_eval0", "usher_evalN", "host_wait_scalars", "host_step", "pbc", "pair", "post_force"):
+                 "usher_commit", "usher_allreduce", "usher_eval0", "usher_evalN", "host_wait_scalars", "host_step", "host_cells", "host_comm", "host_pre_exchange", "host_usher",
+                 "host_allreduce", "host_post", "host_final_sync", "pbc", "pair", "post_force"):
         t, nl = sim.timing_get(name)
         fam[name] = {"ms_per_step": t / args.steps, "launches_per_step": nl / args.steps}
     sim.timing(False)

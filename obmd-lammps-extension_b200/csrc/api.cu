@@ -658,8 +658,12 @@ extern "C" int obmd_run(obmd_ctx *c, long long first_step, int nsteps)
     if ((rc = fix_nve_initial(c))) return rc;
     fix_clear_extras(c);
     if ((rc = obmd_ensure_capacity(c, c->n + c->n / 32 + 4096))) return rc;
-    if ((rc = cells_build(c))) return rc;
+    {
+      HostTimer hc(c, "host_cells");
+      if ((rc = cells_build(c))) return rc;
+    }
     if (c->nranks > 1) {
+      HostTimer hx(c, "host_comm");
       // slab run: deletion sums first (the arrivals reuse the parked slots), then migration + halo
       // (Comm::exchange / borders); the rest of pre_exchange sees the ghosts
       if ((rc = fix_pre_begin(c))) return rc;
@@ -672,14 +676,22 @@ extern "C" int obmd_run(obmd_ctx *c, long long first_step, int nsteps)
       // not need Domain::pbc first; atoms next to an insertion are recomputed afterwards
       // (fix_redo_pair_near_insertions).
       c->hook_step = step;
-      const bool pair_first = c->pair_first >= 0 ? c->pair_first != 0 : c->nsorted > 3000000;
-      if (pair_first) {  // large systems: the pair kernel is the longer branch, start it at once
+      // The pair kernel starts before pre_exchange's first host round trip: for large systems it is the
+      // longer branch anyway (4 M atoms: 2.42 -> 2.28 ms/step), and for small ones it keeps the GPU busy
+      // while the host reads the counts back and prepares the USHER launches (no difference on a quiet
+      // host, the difference between 1.3 and 1.7 ms/step on a noisy one).  OBMD_B200_PAIR_FIRST=0
+      // launches it right behind USHER round 0 instead.
+      const bool pair_first = c->pair_first != 0;
+      if (pair_first) {
         if ((rc = pair_on_side_stream(c))) return rc;
         c->round0_hook = nullptr;
       } else
         c->round0_hook = pair_on_side_stream;
       c->commit_wait = c->ev_int;
-      rc = fix_pre_exchange(c, nullptr, 0);
+      {
+        HostTimer hp(c, "host_pre_exchange");
+        rc = fix_pre_exchange(c, nullptr, 0);
+      }
       c->commit_wait = nullptr;
       if (rc) return rc;
       NEED(c->round0_hook == nullptr, OBMD_ERR_STATE, "obmd_run: side-stream pair launch was skipped");
@@ -692,11 +704,17 @@ extern "C" int obmd_run(obmd_ctx *c, long long first_step, int nsteps)
       if ((rc = fix_pbc(c))) return rc;
       if ((rc = pair_compute(c, step, 0, 0))) return rc;
     }
-    if ((rc = fix_post_force(c))) return rc;
-    if ((rc = fix_compact_extras(c))) return rc;
-    if ((rc = fix_nve_final(c))) return rc;
+    {
+      HostTimer hf(c, "host_post");
+      if ((rc = fix_post_force(c))) return rc;
+      if ((rc = fix_compact_extras(c))) return rc;
+      if ((rc = fix_nve_final(c))) return rc;
+    }
   }
-  CK(cudaStreamSynchronize(c->stream));
+  {
+    HostTimer hs(c, "host_final_sync");
+    CK(cudaStreamSynchronize(c->stream));
+  }
   return OBMD_OK;
 }
 

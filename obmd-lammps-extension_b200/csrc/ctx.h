@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -105,7 +106,7 @@ struct obmd_ctx {
   int *redo_flag = nullptr, *redo_list = nullptr, *redo_count = nullptr;  // pair recompute near insertions
   int redo_cap = 0, redo_list_cap = 0;
   bool overlap = true;
-  int pair_first = -1;  // side-stream pair kernel before (1) or right behind (0) USHER round 0; -1: by size
+  int pair_first = 1;  // side-stream pair kernel before pre_exchange (1) or right behind USHER round 0 (0)
   bool tile_kernel = true;   // OBMD_B200_TILE=0: PairDPD through the per-atom list kernel instead of pair_row.cuh
   int row_rows = 0, row_zc = 0, row_threads = 0;  // tuning overrides (OBMD_B200_ROWS, _ZC, _PT); 0 = automatic
   size_t row_smem_set = 0;
@@ -256,6 +257,22 @@ struct ScopedTimer {
   ~ScopedTimer()
   {
     if (c->timing && e0) timer_end(c, name, e0, c->launches - l0, st);
+  }
+};
+
+// Host wall-clock time of a scope, accumulated under `name` when timing is on (diagnostics: where the
+// enqueueing thread spends its time, as opposed to the CUDA-event timers above).
+struct HostTimer {
+  obmd_ctx *c;
+  const char *name;
+  std::chrono::steady_clock::time_point t0;
+  HostTimer(obmd_ctx *c_, const char *n) : c(c_), name(n), t0(std::chrono::steady_clock::now()) {}
+  ~HostTimer()
+  {
+    if (!c->timing) return;
+    TimerSlot &sl = c->timers[name];
+    sl.ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    sl.launches++;
   }
 };
 

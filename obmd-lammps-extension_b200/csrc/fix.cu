@@ -1476,6 +1476,7 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
   }
   if (ntr > 0) {
     ScopedTimer t(c, "usher");
+    HostTimer hu(c, "host_usher");
     const int M = fa.maxattempt;
     NEED(M >= 1, OBMD_ERR_ARG, "fix obmd: maxattempt must be >= 1");
     NEED(M == 1 || serial, OBMD_ERR_ARG,
@@ -1586,6 +1587,7 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
         naccR = doR && !doL ? nacc_p : 0;
         if (!serial) {  // creation counts of both edge ranks: natoms and the right rank's first new tag
           ScopedTimer t3(c, "usher_allreduce");
+          HostTimer h3(c, "host_allreduce");
           double h[2] = {(double) naccL, (double) naccR};
           CK(cudaMemcpyAsync(c->red_d, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
           if ((rc = comm_allreduce(c, c->red_d, 2, 0))) return rc;
