@@ -283,14 +283,11 @@ int obmd_ensure_capacity(obmd_ctx *c, int cap);
 int cells_build(obmd_ctx *c);                                   // cells.cu
 int pair_compute(obmd_ctx *c, long long step, int eflag, int vflag);  // pair.cu
 int pair_compute_cols(obmd_ctx *c, long long step, const ColRange &cr, cudaStream_t st);
-int pair_compute_list(obmd_ctx *c, long long step, const int *slot_list, const int *slot_count, int slot_max);
 int pair_add_insertions(obmd_ctx *c, long long step, const int *list, const int *count, int cap);
 int fix_redo_pair_near_insertions(obmd_ctx *c, long long step);
 int fix_pbc_cols(obmd_ctx *c, const ColRange &cr, cudaStream_t st);
 ColRange all_columns(const obmd_ctx *c);
 ColRange fix_region_columns(const obmd_ctx *c, int r0, int r1, int margin);
-bool fix_zones(const obmd_ctx *c, ColRange &int_pbc, ColRange &int_pair, ColRange &out_pbc,
-               ColRange &out_pair);
 int fix_nve_initial(obmd_ctx *c);                               // fix.cu
 int fix_nve_final(obmd_ctx *c);
 int fix_pbc(obmd_ctx *c);

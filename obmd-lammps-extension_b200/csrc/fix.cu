@@ -1176,45 +1176,6 @@ ColRange fix_region_columns(const obmd_ctx *c, int r0, int r1, int margin)
   return cr;
 }
 
-// Split the cell columns into the part pre_exchange reads (buffer regions for the counts,
-// insertion regions +-1 column for USHER) and the largest untouched run [ga, gb].  The interior
-// can be wrapped (columns ga..gb) and its pair forces computed (columns ga+1..gb-1) on the side
-// stream while pre_exchange runs; the rest follows on the main stream.
-bool fix_zones(const obmd_ctx *c, ColRange &int_pbc, ColRange &int_pair, ColRange &out_pbc,
-               ColRange &out_pair)
-{
-  int lo[4], hi[4];
-  region_cols(c, 0, 0, lo[0], hi[0]);
-  region_cols(c, 1, 0, lo[1], hi[1]);
-  region_cols(c, 4, 1, lo[2], hi[2]);
-  region_cols(c, 5, 1, lo[3], hi[3]);
-  int m = merge_intervals(lo, hi, 4);
-  const int nx = c->grid.nx;
-  int ga = 0, gb = -1;
-  for (int k = 0; k <= m; k++) {
-    int a = (k == 0) ? 0 : hi[k - 1] + 1;
-    int b = (k == m) ? nx - 1 : lo[k] - 1;
-    if (b - a > gb - ga) {
-      ga = a;
-      gb = b;
-    }
-  }
-  if (gb - ga + 1 < 6) return false;
-  memset(&int_pbc, 0, sizeof(ColRange));
-  memset(&int_pair, 0, sizeof(ColRange));
-  memset(&out_pbc, 0, sizeof(ColRange));
-  memset(&out_pair, 0, sizeof(ColRange));
-  int_pbc.n = 1; int_pbc.a[0] = ga; int_pbc.b[0] = gb;
-  int_pair.n = 1; int_pair.a[0] = ga + 1; int_pair.b[0] = gb - 1;
-  out_pbc.extras = out_pair.extras = 1;
-  if (ga > 0) { out_pbc.a[out_pbc.n] = 0; out_pbc.b[out_pbc.n] = ga - 1; out_pbc.n++; }
-  if (gb < nx - 1) { out_pbc.a[out_pbc.n] = gb + 1; out_pbc.b[out_pbc.n] = nx - 1; out_pbc.n++; }
-  out_pair.a[0] = 0; out_pair.b[0] = ga; out_pair.n = 1;
-  out_pair.a[1] = gb; out_pair.b[1] = nx - 1; out_pair.n = 2;
-  return true;
-}
-
-
 // cells + per-cell lists for the extra atoms [first, first+count) (relative to the extras base)
 int fix_link_extras(obmd_ctx *c, int first, int count, bool sorted_by_cell)
 {
@@ -1525,7 +1486,8 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
         auto enqueue_round = [&](int round) -> int {
           const int par = round & 1;
           ScopedTimer t2(c, round == 0 ? "usher_round0" : "usher_rerun");
-          ScopedTimer *t5 = new ScopedTimer(c, round == 0 ? "usher_eval0" : "usher_evalN");
+          {
+          ScopedTimer t5(c, round == 0 ? "usher_eval0" : "usher_evalN");
           if (round == 0)
             LAUNCH(k_usher_eval, ntr_loc < 6 * NSM * USH_WARPS ? cdiv(ntr_loc, USH_WARPS) : 6 * NSM,
                    USH_WARPS * 32, 0, (const int *) nullptr, ntr_loc, 0, c->cur, c->grid, c->pt, c->fd,
@@ -1537,7 +1499,7 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
                    c->grid, c->pt, c->fd, c->cell_start, u, ex, c->extra_head, c->extra_next, c->spec_head,
                    c->spec_next, c->acc_list, c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts, c->tr_bbox,
                    c->tr_changed + c->tr_cap, c->sc_d);
-          delete t5;
+          }
           // Round 0 fills the machine (one warp per trial); the re-run rounds are a handful of CTAs.
           // obmd_run hooks in here to start the pair kernel on the side stream right behind round 0.
           if (round == 0 && c->round0_hook) {

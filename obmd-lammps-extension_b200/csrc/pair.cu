@@ -9,18 +9,18 @@
 // symmetric counter-based N(0,1) variate keyed on (min tag, max tag, seed, timestep), identical
 // for the (i,j) and (j,i) evaluations so Newton's third law holds exactly (DESIGN.md "RNG").
 //
-// Kernel shape (v2).  Only ~15 % of the 81 stencil candidates of an atom lie inside the cutoff, so
-// a straight "test then evaluate" loop runs the expensive branch at ~1/3 lane occupancy (ncu, r01:
-// 11.4 active threads per instruction).  Each thread therefore works in two phases:
-//   1. distance screen: walk the 9 stencil rows (the 3 z-cells of a row are one contiguous slot
-//      range because z is the fastest cell index), and push the slots that pass rsq < cutsq into a
-//      per-thread list in shared memory (k-major layout -> conflict free);
-//   2. evaluate the listed pairs densely (sqrt, div, drag, counter RNG), in list order, so the
-//      summation order is fixed by the cell layout alone.
-// The minimum-image correction is applied only by atoms that sit in a boundary cell in y or z.
+// Kernels in this translation unit:
+//   * k_pair_row (pair_row.cuh): the production path for the cell-sorted atoms -- row tiles staged in
+//     shared memory, fp32 screen, fp64 evaluation;
+//   * k_pair_dpd: per-atom kernel that walks global memory (L1/L2) with a minimum-image test: a
+//     distance screen over the 9 stencil rows (the 3 z-cells of a row are one contiguous slot range
+//     because z is the fastest cell index) that pushes the slots inside the cutoff to a per-thread
+//     list, then a dense evaluation of the list.  Used for energy/virial tallies, for the few atoms
+//     appended after the sort, as the overflow path of k_pair_row, and under OBMD_B200_TILE=0;
+//   * k_pair_new_atoms / k_pair_add_new: the incremental update after USHER insertions.
 //
-// Roofline: algorithmic traffic is 80 B/atom (x,v,tag,type in, f out); neighbour reads are
-// served by L1/L2.  The kernel is fp64-pipe/issue bound, not HBM bound.
+// Roofline: algorithmic traffic is 80 B/atom (x,v,tag,type in, f out); neighbour reads are served by
+// shared memory / L2.  The kernels are issue/latency bound in fp64, not HBM bound.
 #include "ctx.h"
 
 #define EPSILON_DPD 1.0e-10  // pair_dpd.cpp:36
@@ -268,17 +268,10 @@ __global__ void __launch_bounds__(PAIR_T)
     k_pair_dpd(Planes p, ColRange cr, Extras ex, Grid g, PairTab pt,
                const int *__restrict__ cell_start, const int *__restrict__ extra_head,
                const int *__restrict__ extra_next, double *__restrict__ fx, double *__restrict__ fy,
-               double *__restrict__ fz, unsigned step, int random_on, double *__restrict__ partials,
-               const int *__restrict__ slot_list, const int *__restrict__ slot_count)
+               double *__restrict__ fz, unsigned step, int random_on, double *__restrict__ partials)
 {
   __shared__ int hits[PAIR_HCAP * PAIR_T];
-  // either the atoms of a column set, or an explicit slot list (recompute after insertions)
-  int i;
-  if (slot_list) {
-    const int gidx = blockIdx.x * PAIR_T + threadIdx.x;
-    i = (gidx < *slot_count) ? slot_list[gidx] : -1;
-  } else
-    i = colrange_slot(cr, blockIdx.x * PAIR_T + threadIdx.x, g, cell_start, ex);
+  const int i = colrange_slot(cr, blockIdx.x * PAIR_T + threadIdx.x, g, cell_start, ex);
   PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const unsigned live = __ballot_sync(0xffffffffu, i >= 0);
   if (i >= 0) {
@@ -528,14 +521,13 @@ static int pair_row_plan(obmd_ctx *c, bool single, RowPlan &best)
 }
 
 static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &cr, cudaStream_t st,
-                       const int *slot_list = nullptr, const int *slot_count = nullptr, int slot_max = 0,
                        bool prewrap = false)
 {
   const bool single = (c->ntypes == 1);
   const int random_on = c->temperature > 0.0 ? 1 : 0;
   c->pt.dtinvsqrt = 1.0 / sqrt(c->dt);
   const Grid &g = c->grid;
-  if (!slot_list && !tally && c->tile_kernel && cr.n > 0 && c->nsorted > 0) {
+  if (!tally && c->tile_kernel && cr.n > 0 && c->nsorted > 0) {
     // cell-sorted atoms of the column set: row-tiled kernel (pair_row.cuh), one CTA per
     // (column, row strip, z-chunk); the atoms appended after the sort go through the list kernel below
     int ncols = 0;
@@ -570,9 +562,9 @@ static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &
     ColRange xr;
     memset(&xr, 0, sizeof(xr));
     xr.extras = cr.extras;
-    return pair_launch(c, step, false, xr, st, nullptr, nullptr, 0, prewrap);
+    return pair_launch(c, step, false, xr, st, prewrap);
   }
-  const int nmax = slot_list ? slot_max : (cr.n == 0 ? c->nextra : colrange_bound(c, cr));
+  const int nmax = cr.n == 0 ? c->nextra : colrange_bound(c, cr);
   if (nmax <= 0) return OBMD_OK;
   const int nb = cdiv(nmax, PAIR_T);
   if (tally && nb * 7 > c->partial_cap) {
@@ -582,7 +574,7 @@ static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &
   }
 #define PAIR_ARGS                                                                             \
   c->cur, cr, extras_of(c), c->grid, c->pt, c->cell_start, c->extra_head, c->extra_next,          \
-      c->fx, c->fy, c->fz, (unsigned) step, random_on, c->partials, slot_list, slot_count
+      c->fx, c->fy, c->fz, (unsigned) step, random_on, c->partials
   if (prewrap) {  // side-stream launch of obmd_run: coordinates may not be wrapped yet
     if (single) LAUNCH_ON(st, (k_pair_dpd<true, false, true>), nb, PAIR_T, 0, PAIR_ARGS);
     else LAUNCH_ON(st, (k_pair_dpd<false, false, true>), nb, PAIR_T, 0, PAIR_ARGS);
@@ -600,14 +592,7 @@ int pair_compute_cols(obmd_ctx *c, long long step, const ColRange &cr, cudaStrea
 {
   NEED(c->cells_valid, OBMD_ERR_STATE, "pair_compute_cols: cell list is stale");
   ScopedTimer t(c, "pair", st);
-  return pair_launch(c, step, false, cr, st, nullptr, nullptr, 0, true);
-}
-
-// forces of an explicit list of slots (device-side count; the grid covers slot_max)
-int pair_compute_list(obmd_ctx *c, long long step, const int *slot_list, const int *slot_count, int slot_max)
-{
-  ScopedTimer t(c, "pair");
-  return pair_launch(c, step, false, all_columns(c), c->stream, slot_list, slot_count, slot_max);
+  return pair_launch(c, step, false, cr, st, true);
 }
 
 int pair_compute(obmd_ctx *c, long long step, int eflag, int vflag)
