@@ -197,12 +197,15 @@ __global__ void k_count_regions(Planes p, ColRange cr, Extras ex, Grid g, FixDev
   }
 }
 
-// In-block bitonic sort (descending by key) of npad = power of two entries in global memory.
-__device__ void bitonic_desc(int *key, int *val, int npad)
+// In-block bitonic sort (descending by key) of two independent (key, value) arrays of npad = power
+// of two entries each, stage by stage together (one barrier per stage for both).
+__device__ void bitonic_desc2(int *key0, int *val0, int *key1, int *val1, int npad)
 {
   for (int k = 2; k <= npad; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+      for (int i2 = threadIdx.x; i2 < 2 * npad; i2 += blockDim.x) {
+        int *key = i2 < npad ? key0 : key1, *val = i2 < npad ? val0 : val1;
+        const int i = i2 < npad ? i2 : i2 - npad;
         int ixj = i ^ j;
         if (ixj > i) {
           bool desc = ((i & k) == 0);
@@ -254,8 +257,7 @@ __global__ void __launch_bounds__(1024)
     tval[k] = (k < ntail) ? tail_val[k] : -1;
   }
   __syncthreads();
-  bitonic_desc(dkey, dval, npad_del);
-  bitonic_desc(tkey, tval, npad_tail);
+  bitonic_desc2(dkey, dval, tkey, tval, npad_del);  // npad_del == npad_tail (fix_pre_begin)
   // momentum contributions m*v of the deleted atoms, in descending local index order
   const double mid = 0.5 * (fd.boxhi[0] + fd.boxlo[0]);
   for (int k = threadIdx.x; k < ndel; k += blockDim.x) {
