@@ -327,9 +327,13 @@ static int ranpark_skip(int seed, long long n)  // random_park.cpp:43-50 applied
 // =====================================================================================
 
 #define USH_WARPS 4
+#ifndef USH_BLOCKS_PER_SM
+#define USH_BLOCKS_PER_SM 5  // resident CTAs per SM the eval kernel is compiled for: measured 4/5/6/7/8 -> eval 0.70/0.66/0.70/0.80/0.88 ms per step (more CTAs = fewer registers = spills)
+#endif
 #define LINK_MAX 6000  // atoms per unsorted extra group (two int arrays in 48 KB of shared memory)
-#define USH_CAP 64    // contributions per energy evaluation held per warp (mean 13 at rho = 3)
-#define USH_CAND 176  // atoms in the 27 stencil cells of a point (mean 81 at rho = 3)
+#define USH_CAP 48    // contributions per energy evaluation held per warp (mean 13 at rho = 3)
+#define USH_CHUNKS ((USH_CAP + 31) / 32)
+#define USH_CAND 144  // atoms in the 27 stencil cells of a point (mean 81 at rho = 3)
 
 struct UsherCfg {
   int ntrL, ntr;      // trials for the left region come first (maxattempt == 1)
@@ -538,10 +542,10 @@ __device__ void usher_energy(const double c[3], int nc, const Grid &g, const Pai
   // pass B (dense): PairDPD::single, then each contribution is stored at its rank by local index
   // (keys are distinct) in the same arrays -- every lane holds its (at most two) results in registers
   // until the whole warp has read its inputs -- zero-padded to a multiple of four
-  double ev[USH_CAP / 32], xv[USH_CAP / 32], yv[USH_CAP / 32], zv[USH_CAP / 32];
-  int rk[USH_CAP / 32];
+  double ev[USH_CHUNKS], xv[USH_CHUNKS], yv[USH_CHUNKS], zv[USH_CHUNKS];
+  int rk[USH_CHUNKS];
 #pragma unroll
-  for (int c2 = 0; c2 < USH_CAP / 32; c2++) {
+  for (int c2 = 0; c2 < USH_CHUNKS; c2++) {
     const int s = lane + 32 * c2;
     rk[c2] = -1;
     if (s < nh) {
@@ -554,7 +558,7 @@ __device__ void usher_energy(const double c[3], int nc, const Grid &g, const Pai
   }
   __syncwarp();
 #pragma unroll
-  for (int c2 = 0; c2 < USH_CAP / 32; c2++)
+  for (int c2 = 0; c2 < USH_CHUNKS; c2++)
     if (rk[c2] >= 0) {
       H.e[rk[c2]] = ev[c2];
       H.fx[rk[c2]] = xv[c2];
@@ -708,7 +712,7 @@ __device__ __forceinline__ void usher_trial(
 // re-run rounds take the list and its length from device memory (ndirty2[par], written by the
 // previous round's k_usher_dirty), so that rounds can be enqueued back to back without a host
 // round trip; a round with nothing to do costs an empty grid.
-__global__ void __launch_bounds__(USH_WARPS * 32, 6)
+__global__ void __launch_bounds__(USH_WARPS * 32, USH_BLOCKS_PER_SM)
     k_usher_eval(const int *__restrict__ list, int nlist, int par, Planes p, Grid g, PairTab pt, FixDev fd,
                  const int *__restrict__ cell_start, UsherCfg u, Extras ex,
                  const int *__restrict__ extra_head, const int *__restrict__ extra_next,
@@ -1491,7 +1495,7 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
           {
           ScopedTimer t5(c, round == 0 ? "usher_eval0" : "usher_evalN");
           if (round == 0)
-            LAUNCH(k_usher_eval, ntr_loc < 6 * NSM * USH_WARPS ? cdiv(ntr_loc, USH_WARPS) : 6 * NSM,
+            LAUNCH(k_usher_eval, ntr_loc < USH_BLOCKS_PER_SM * NSM * USH_WARPS ? cdiv(ntr_loc, USH_WARPS) : USH_BLOCKS_PER_SM * NSM,
                    USH_WARPS * 32, 0, (const int *) nullptr, ntr_loc, 0, c->cur, c->grid, c->pt, c->fd,
                    c->cell_start, u, ex, c->extra_head, c->extra_next, c->spec_head, c->spec_next, c->acc_list,
                    c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts, c->tr_bbox, c->tr_changed + c->tr_cap,
