@@ -226,9 +226,12 @@ def ours(args):
     l0 = sim.launches
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     atom_steps = 0
+    step_wall = []
     e0.record(stream)
     for _ in range(args.steps):
+        tw = time.perf_counter()
         sim.run(step, 1); step += 1
+        step_wall.append(time.perf_counter() - tw)   # obmd_run returns after a stream synchronize
         atom_steps += sim.nlocal
     e1.record(stream)
     barrier()
@@ -253,6 +256,20 @@ def ours(args):
         e2e = e2e_run(sim, args.e2e_steps, step, barrier)
         step += args.e2e_steps
 
+    # ---- the roofline kernel by itself: in the step it shares the GPU with the USHER rounds (side
+    # stream), so its in-step duration measures the overlap, not the kernel.  A few stand-alone launches
+    # on the final configuration, L2 flushed in between, CUDA events on the library's stream.
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    sim.build_cells()
+    sim.timing(True); sim.timing_reset()
+    n_alone = 5
+    for k in range(n_alone):
+        flush.fill_(k & 0xff); torch.cuda.synchronize()
+        sim.pair_compute(step + k)
+    pair_alone_ms = sim.timing_get("pair")[0] / n_alone
+    sim.timing(False)
+    del flush
+
     t = torch.tensor([ms, float(atom_steps), e2e["seconds"] if e2e else 0.0,
                       float(e2e["atom_steps"]) if e2e else 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -274,8 +291,7 @@ def ours(args):
     if rank == 0:
         hbm, how = peaks()
         pair_ms = fam["pair"]["ms_per_step"]
-        natoms_avg = atom_steps / args.steps / world
-        achieved = PAIR_BYTES_PER_ATOM * natoms_avg / (pair_ms * 1e-3) / 1e9 if pair_ms > 0 else 0.0
+        achieved = PAIR_BYTES_PER_ATOM * sim.nlocal / (pair_alone_ms * 1e-3) / 1e9 if pair_alone_ms > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "pair_dram_bytes.json")
         if os.path.exists(tp):
@@ -297,11 +313,19 @@ def ours(args):
                        "inserted": int(st.ninserted), "deleted": int(st.ndeleted),
                        "usher_trials": int(st.ntrials), "usher_rounds": int(st.nrounds)},
             "gpu_launches": int(launches),
+            # host wall time of the individual steps on rank 0 (diagnostics: the GPU hosts are noisy
+            # virtual machines; `ms_per_step` above is the contract's total / K)
+            "ms_per_step_median": round(1e3 * float(np.median(step_wall)), 5),
+            "ms_per_step_p90": round(1e3 * float(np.percentile(step_wall, 90)), 5),
             "kernel_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in fam.items()},
             "roofline": {"kernel": "k_pair_row", "bound": "hbm", "achieved": achieved, "peak": hbm,
                          "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic, "peak_source": how,
                          "algorithmic_bytes_per_atom": PAIR_BYTES_PER_ATOM,
-                         "note": "fp64-pipe bound, not HBM bound: see DESIGN.md section 6"},
+                         "launch_ms": round(pair_alone_ms, 5), "in_step_ms": round(pair_ms, 5),
+                         "note": "launch_ms: %d stand-alone launches on rank 0 after the timed region, L2 flushed "
+                                 "between them; in_step_ms: the same kernel inside the step, where it shares the "
+                                 "GPU with the USHER rounds on the other stream.  Issue/latency bound in fp64, "
+                                 "not HBM bound: DESIGN.md 5.5" % n_alone},
             "clocks": clocks,
         }
         # USHER is latency-bound (a chain of up to nattempt dependent energy evaluations per trial),
