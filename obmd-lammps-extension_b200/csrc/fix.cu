@@ -364,7 +364,7 @@ __device__ __forceinline__ double ranpark_uniform(int &seed)
 }
 
 struct WarpHits {
-  int key[USH_CAP];   // LAMMPS local index of the contributing atom
+  int key[USH_CAP + 4];  // LAMMPS local index of the contributing atom (+ sentinels for the rank loop)
   int tj[USH_CAP];    // its type
   // pass A: rsq, del of each hit; pass B overwrites them with phi, f ordered by local index
   double e[USH_CAP + 4], fx[USH_CAP + 4], fy[USH_CAP + 4], fz[USH_CAP + 4];
@@ -376,28 +376,33 @@ struct WarpHits {
 
 // Pass A of energy() (:1791-1800): separation with the reference's minimum_image loop
 // (domain.cpp:980-1008, y and z periodic) and the cutoff test.
-__device__ __forceinline__ bool usher_screen(const double c[3], double xj, double yj, double zj, int it,
-                                             int tj, const Grid &g, const PairTab &pt, double &rsq,
-                                             double &delx, double &dely, double &delz)
+// `wrap` is false when the 27 gathered cells touch no periodic face (and the box is at least 6 cells
+// wide): every separation is then at most two cell widths, below half the box, so the reference's
+// minimum_image loop would not change it and is skipped.
+__device__ __forceinline__ bool usher_screen(const double c[3], double xj, double yj, double zj, double cutsq,
+                                             bool wrap, const Grid &g, double &rsq, double &delx,
+                                             double &dely, double &delz)
 {
   delx = c[0] - xj;
   dely = c[1] - yj;
   delz = c[2] - zj;
-  while (fabs(dely) > g.half[1]) {
-    if (dely < 0.0) dely += g.prd[1];
-    else dely -= g.prd[1];
-  }
-  while (fabs(delz) > g.half[2]) {
-    if (delz < 0.0) delz += g.prd[2];
-    else delz -= g.prd[2];
+  if (wrap) {
+    while (fabs(dely) > g.half[1]) {
+      if (dely < 0.0) dely += g.prd[1];
+      else dely -= g.prd[1];
+    }
+    while (fabs(delz) > g.half[2]) {
+      if (delz < 0.0) delz += g.prd[2];
+      else delz -= g.prd[2];
+    }
   }
   rsq = delx * delx + dely * dely + delz * delz;
-  return rsq < pt.cutsq[it][tj];
+  return rsq < cutsq;
 }
 
 // Pass B: PairDPD::single (pair_dpd.cpp:401-418, factor_dpd = 1) and fpair*del (:1801-1805)
-__device__ __forceinline__ void usher_single(int it, int tj, const PairTab &pt, double rsq, double &e,
-                                             double &fx, double &fy, double &fz)
+__device__ __forceinline__ void usher_single(double a0, double cut, double rsq, double &e, double &fx,
+                                             double &fy, double &fz)
 {
   double r = sqrt(rsq);
   double fforce, phi;
@@ -406,10 +411,9 @@ __device__ __forceinline__ void usher_single(int it, int tj, const PairTab &pt, 
     phi = 0.0;
   } else {
     double rinv = 1.0 / r;
-    const double cut = pt.cut[it][tj];
     double wd = 1.0 - (cut == 1.0 ? r : r / cut);  // r / 1.0 == r exactly: skip the division
-    fforce = pt.a0[it][tj] * wd * 1.0 * rinv;
-    phi = 0.5 * pt.a0[it][tj] * pt.cut[it][tj] * wd * wd;
+    fforce = a0 * wd * 1.0 * rinv;
+    phi = 0.5 * a0 * cut * wd * wd;
     phi = 1.0 * phi;
   }
   e = phi;
@@ -502,8 +506,10 @@ __device__ int usher_gather(int cx, int cy, int cz, int t, const Planes &p, cons
 // One warp evaluates E and f at point c from the gathered candidates: screens them, orders the
 // contributions by LAMMPS local index and sums them left to right -- the reference's summation
 // order (:1790-1807).
-__device__ void usher_energy(const double c[3], int nc, const Grid &g, const PairTab &pt, const FixDev &fd,
-                             WarpHits &H, StepScalars *sc, double &E, double f[3])
+template <bool ST>  // ST: a single atom type, pair coefficients are the three scalars in `k1`
+__device__ void usher_energy(const double c[3], int nc, bool wrap, const double k1[3], const Grid &g,
+                             const PairTab &pt, const FixDev &fd, WarpHits &H, StepScalars *sc, double &E,
+                             double f[3])
 {
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -517,15 +523,15 @@ __device__ void usher_energy(const double c[3], int nc, const Grid &g, const Pai
     bool hit = false;
     if (q < nc) {
       key = H.ckey[q];
-      tj = H.ctj[q];
-      hit = usher_screen(c, H.cx[q], H.cy[q], H.cz[q], it, tj, g, pt, rsq, dx, dy, dz);
+      if (!ST) tj = H.ctj[q];
+      hit = usher_screen(c, H.cx[q], H.cy[q], H.cz[q], ST ? k1[2] : pt.cutsq[it][tj], wrap, g, rsq, dx, dy, dz);
     }
     unsigned m = __ballot_sync(0xffffffffu, hit);
     if (hit) {
       int s2 = nh + __popc(m & lt);
       if (s2 < USH_CAP) {
         H.key[s2] = key;
-        H.tj[s2] = tj;
+        if (!ST) H.tj[s2] = tj;
         H.e[s2] = rsq;
         H.fx[s2] = dx;
         H.fy[s2] = dy;
@@ -538,6 +544,7 @@ __device__ void usher_energy(const double c[3], int nc, const Grid &g, const Pai
     if (lane == 0) sc->usher_error = OBMD_ERR_CAPACITY;
     nh = USH_CAP;
   }
+  if (lane < 4) H.key[nh + lane] = 0x7fffffff;  // sentinels: the rank loop below runs four keys per trip
   __syncwarp();
   // pass B (dense): PairDPD::single, then each contribution is stored at its rank by local index
   // (keys are distinct) in the same arrays -- every lane holds its (at most two) results in registers
@@ -550,9 +557,11 @@ __device__ void usher_energy(const double c[3], int nc, const Grid &g, const Pai
     rk[c2] = -1;
     if (s < nh) {
       double e, fx = H.fx[s], fy = H.fy[s], fz = H.fz[s];
-      usher_single(it, H.tj[s], pt, H.e[s], e, fx, fy, fz);
+      if (ST) usher_single(k1[0], k1[1], H.e[s], e, fx, fy, fz);
+      else usher_single(pt.a0[it][H.tj[s]], pt.cut[it][H.tj[s]], H.e[s], e, fx, fy, fz);
       int k = H.key[s], r = 0;
-      for (int q = 0; q < nh; q++) r += (H.key[q] < k);
+      for (int q = 0; q < nh; q += 4)
+        r += (H.key[q] < k) + (H.key[q + 1] < k) + (H.key[q + 2] < k) + (H.key[q + 3] < k);
       rk[c2] = r; ev[c2] = e; xv[c2] = fx; yv[c2] = fy; zv[c2] = fz;
     }
   }
@@ -595,6 +604,7 @@ __device__ void usher_energy(const double c[3], int nc, const Grid &g, const Pai
 
 // One warp per trial in `list`.  Writes the trial record and the points at which the energy was
 // evaluated (needed by the dirty test of the next round).
+template <bool ST>
 __device__ __forceinline__ void usher_trial(
     int li, WarpHits *hits, const int *__restrict__ list, const Planes &p, const Grid &g, const PairTab &pt,
     const FixDev &fd, const int *__restrict__ cell_start, const UsherCfg &u, const Extras &ex,
@@ -631,19 +641,10 @@ __device__ __forceinline__ void usher_trial(
   }
   double E = 0.0, f[3];
   int gx = -1 << 30, gy = 0, gz = 0, nc = 0;  // cell whose stencil is in the candidate arrays
-  // bounding box of the evaluated points (prefilter of the dirty test of the next round; a re-run
-  // keeps the box of its previous path, which contains the unchanged prefix: a superset is fine)
-  double blo[3] = {c[0], c[1], c[2]}, bhi[3] = {c[0], c[1], c[2]};
-  if (list)
-    for (int d = 0; d < 3; d++) {
-      blo[d] = fmin(blo[d], bbox[(size_t) t * 6 + d]);
-      bhi[d] = fmax(bhi[d], bbox[(size_t) t * 6 + 3 + d]);
-    }
+  // single type: the three pair coefficients the evaluation needs, read once
+  const double k1[3] = {pt.a0[fd.ntype][fd.ntype], pt.cut[fd.ntype][fd.ntype], pt.cutsq[fd.ntype][fd.ntype]};
+  bool wrap = true;  // does the gathered stencil touch a periodic face?
   while (i < u.natt) {
-    for (int d = 0; d < 3; d++) {
-      blo[d] = fmin(blo[d], c[d]);
-      bhi[d] = fmax(bhi[d], c[d]);
-    }
     // the point is inside the insertion region, hence inside the box: the cell index is at most one
     // period off (y == yhi exactly), so the wrap needs no division
     const int cx = cell_cx(g, c[0]);
@@ -656,8 +657,9 @@ __device__ __forceinline__ void usher_trial(
       nc = usher_gather(cx, cy, cz, t, p, g, fd, cell_start, u, acc_list, prev, ex, extra_head, extra_next,
                         spec_head, spec_next, hits[w], sc);
       gx = cx; gy = cy; gz = cz;
+      wrap = g.ny < 6 || g.nz < 6 || cy == 0 || cy == g.ny - 1 || cz == 0 || cz == g.nz - 1;
     }
-    usher_energy(c, nc, g, pt, fd, hits[w], sc, E, f);
+    usher_energy<ST>(c, nc, wrap, k1, g, pt, fd, hits[w], sc, E, f);
     if (lane == 0) {
       mypath[np * 3 + 0] = c[0];
       mypath[np * 3 + 1] = c[1];
@@ -701,17 +703,34 @@ __device__ __forceinline__ void usher_trial(
     r.tag = 0;
     cur[t] = r;
     npts[t] = np;
+  }
+  // bounding box of the evaluated points (prefilter of the dirty test of the next round): all lanes
+  // read the path (the prefix a re-run kept included) and reduce
+  __syncwarp();
+  double blo[3] = {1e300, 1e300, 1e300}, bhi[3] = {-1e300, -1e300, -1e300};
+  for (int k = lane; k < np; k += 32)
+    for (int d = 0; d < 3; d++) {
+      const double v = mypath[3 * k + d];
+      blo[d] = fmin(blo[d], v);
+      bhi[d] = fmax(bhi[d], v);
+    }
+  for (int d = 0; d < 3; d++)
+    for (int o = 16; o > 0; o >>= 1) {
+      blo[d] = fmin(blo[d], __shfl_xor_sync(0xffffffffu, blo[d], o));
+      bhi[d] = fmax(bhi[d], __shfl_xor_sync(0xffffffffu, bhi[d], o));
+    }
+  if (lane == 0)
     for (int d = 0; d < 3; d++) {
       bbox[(size_t) t * 6 + d] = blo[d];
       bbox[(size_t) t * 6 + 3 + d] = bhi[d];
     }
-  }
 }
 
 // One warp per trial.  Round 0 evaluates every trial (list == nullptr, nlist from the host); the
 // re-run rounds take the list and its length from device memory (ndirty2[par], written by the
 // previous round's k_usher_dirty), so that rounds can be enqueued back to back without a host
 // round trip; a round with nothing to do costs an empty grid.
+template <bool ST>
 __global__ void __launch_bounds__(USH_WARPS * 32, USH_BLOCKS_PER_SM)
     k_usher_eval(const int *__restrict__ list, int nlist, int par, Planes p, Grid g, PairTab pt, FixDev fd,
                  const int *__restrict__ cell_start, UsherCfg u, Extras ex,
@@ -733,7 +752,7 @@ __global__ void __launch_bounds__(USH_WARPS * 32, USH_BLOCKS_PER_SM)
     if ((threadIdx.x & 31) == 0) li = atomicAdd(&sc->trial_cursor, 1);
     li = __shfl_sync(0xffffffffu, li, 0);
     if (li >= nl) break;
-    usher_trial(li, hits, list, p, g, pt, fd, cell_start, u, ex, extra_head, extra_next, spec_head, spec_next,
+    usher_trial<ST>(li, hits, list, p, g, pt, fd, cell_start, u, ex, extra_head, extra_next, spec_head, spec_next,
                 acc_list, prev, cur, path, npts, bbox, kfirst, sc);
   }
 }
@@ -1494,17 +1513,23 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
           ScopedTimer t2(c, round == 0 ? "usher_round0" : "usher_rerun");
           {
           ScopedTimer t5(c, round == 0 ? "usher_eval0" : "usher_evalN");
-          if (round == 0)
-            LAUNCH(k_usher_eval, ntr_loc < USH_BLOCKS_PER_SM * NSM * USH_WARPS ? cdiv(ntr_loc, USH_WARPS) : USH_BLOCKS_PER_SM * NSM,
-                   USH_WARPS * 32, 0, (const int *) nullptr, ntr_loc, 0, c->cur, c->grid, c->pt, c->fd,
-                   c->cell_start, u, ex, c->extra_head, c->extra_next, c->spec_head, c->spec_next, c->acc_list,
-                   c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts, c->tr_bbox, c->tr_changed + c->tr_cap,
-                   c->sc_d);
-          else
-            LAUNCH(k_usher_eval, rerun_grid, USH_WARPS * 32, 0, (const int *) c->tr_list, 0, par ^ 1, c->cur,
-                   c->grid, c->pt, c->fd, c->cell_start, u, ex, c->extra_head, c->extra_next, c->spec_head,
-                   c->spec_next, c->acc_list, c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts, c->tr_bbox,
-                   c->tr_changed + c->tr_cap, c->sc_d);
+          const int grid0 = ntr_loc < USH_BLOCKS_PER_SM * NSM * USH_WARPS ? cdiv(ntr_loc, USH_WARPS)
+                                                                          : USH_BLOCKS_PER_SM * NSM;
+#define USHER_EVAL(ST)                                                                                         \
+  do {                                                                                                         \
+    if (round == 0)                                                                                            \
+      LAUNCH(k_usher_eval<ST>, grid0, USH_WARPS * 32, 0, (const int *) nullptr, ntr_loc, 0, c->cur, c->grid,   \
+             c->pt, c->fd, c->cell_start, u, ex, c->extra_head, c->extra_next, c->spec_head, c->spec_next,     \
+             c->acc_list, c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts, c->tr_bbox, c->tr_changed + c->tr_cap, \
+             c->sc_d);                                                                                         \
+    else                                                                                                       \
+      LAUNCH(k_usher_eval<ST>, rerun_grid, USH_WARPS * 32, 0, (const int *) c->tr_list, 0, par ^ 1, c->cur,    \
+             c->grid, c->pt, c->fd, c->cell_start, u, ex, c->extra_head, c->extra_next, c->spec_head,          \
+             c->spec_next, c->acc_list, c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts, c->tr_bbox,             \
+             c->tr_changed + c->tr_cap, c->sc_d);                                                              \
+  } while (0)
+          if (c->ntypes == 1) USHER_EVAL(true);
+          else USHER_EVAL(false);
           }
           // Round 0 fills the machine (one warp per trial); the re-run rounds are a handful of CTAs.
           // obmd_run hooks in here to start the pair kernel on the side stream right behind round 0.
