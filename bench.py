@@ -218,9 +218,6 @@ def ours(args):
     st0 = sim.fix_state()
     tr0, rd0, in0, de0 = int(st0.ntrials), int(st0.nrounds), int(st0.ninserted), int(st0.ndeleted)
     sampler = ClockSampler(local)
-    if os.environ.get("OBMD_BENCH_SAMPLE_ONCE"):   # diagnostics: one sample before the timed region only
-        sampler.rows.append(sampler.sample_nvml()) if sampler.nvml else None
-        sampler.stop_flag = True
     sampler.start()
     barrier()
     l0 = sim.launches
