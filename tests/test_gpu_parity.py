@@ -461,3 +461,75 @@ def test_usher_maxattempt_vs_oracle(shipped, maxattempt):
     out = sim.download(("x", "tag"))
     assert np.array_equal(out["tag"], a.view("tag")) and np.array_equal(out["x"], a.view("x"))
     sim.close()
+
+
+def test_run_with_many_insertions_matches_hook_sequence(shipped):
+    """obmd_run computes PairDPD on the side stream before the atoms USHER is about to create exist
+    and then updates incrementally (k_pair_new_atoms, k_pair_add_new); the hook sequence computes the
+    pair forces after the insertions, from scratch.  With empty buffers (hundreds of insertions in
+    one step, many of them close to each other) both must give the same atoms and the same forces up
+    to summation order."""
+    tag, x, box = shipped
+    B = 0.15 * box[0, 1]
+    keep = (x[:, 0] > B) & (x[:, 0] < box[0, 1] - B)
+    xs, ts = x[keep], tag[keep]
+    v = np.random.default_rng(21).normal(0, 1, xs.shape)
+    kw = dict(alpha=1.0, nbuf=1895.0, tau=0.01)
+    outs, reps = [], []
+    for mode in (0, 1):
+        sim = cc.device_sim(box, **kw)
+        sim.upload(xs, v, np.ones(len(xs), np.int32), ts, capacity=len(x) * 2)
+        sim.setup(0)
+        for s in range(1, 4):
+            if mode == 0:
+                sim.step(s)
+            else:
+                sim.run(s, 1)
+        outs.append(sim.download())
+        reps.append(sim.fix_state().ninserted)
+        sim.close()
+    assert reps[0] == reps[1] and reps[0] > 100
+    assert np.array_equal(outs[0]["tag"], outs[1]["tag"])
+    fs = np.abs(outs[0]["f"]).max()
+    assert np.abs(outs[0]["f"] - outs[1]["f"]).max() <= 1e-11 * fs
+    assert np.abs(outs[0]["x"] - outs[1]["x"]).max() <= 1e-12
+    assert np.abs(outs[0]["v"] - outs[1]["v"]).max() <= 1e-11 * max(1.0, np.abs(outs[0]["v"]).max())
+
+
+def test_restart_from_downloaded_state(shipped):
+    """Checkpoint / resume: atoms (x, v, f, type, tag, image in LAMMPS local order) plus
+    obmd_fix_get_state (RanPark seed, simulation time, counters) are the whole state -- the pair RNG is
+    keyed on the timestep.  Stop after 10 steps, rebuild a fresh context from the downloaded state and
+    run 10 more: same insertions and deletions, same tags in the same order, trajectories equal up to
+    the summation order inside the cells (the resumed context sorts from a different previous layout)."""
+    tag, x, box = shipped
+    v = np.random.default_rng(31).normal(0, 1, x.shape)
+    kw = dict(alpha=1.0, nbuf=1950.0)
+    a = cc.device_sim(box, **kw)
+    a.upload(x, v, np.ones(len(x), np.int32), tag, capacity=2 * len(x))
+    a.setup(0)
+    a.run(1, 20)
+    ref, ref_state = a.download(), a.fix_state()
+    a.close()
+
+    b = cc.device_sim(box, **kw)
+    b.upload(x, v, np.ones(len(x), np.int32), tag, capacity=2 * len(x))
+    b.setup(0)
+    b.run(1, 10)
+    snap, state = b.download(), b.fix_state()
+    b.close()
+
+    c = cc.device_sim(box, **kw)
+    c.upload(snap["x"], snap["v"], snap["type"], snap["tag"], image=snap["image"], f=snap["f"],
+             capacity=2 * len(x))
+    c.set_fix_state(state)
+    c.run(11, 10)
+    out, out_state = c.download(), c.fix_state()
+    c.close()
+
+    assert (out_state.ninserted, out_state.ndeleted, out_state.rng_seed) == \
+        (ref_state.ninserted, ref_state.ndeleted, ref_state.rng_seed)
+    assert ref_state.ninserted > 0 and ref_state.ndeleted > 0
+    assert np.array_equal(out["tag"], ref["tag"]) and np.array_equal(out["image"], ref["image"])
+    assert np.abs(out["x"] - ref["x"]).max() < 1e-9
+    assert np.abs(out["v"] - ref["v"]).max() < 1e-8
