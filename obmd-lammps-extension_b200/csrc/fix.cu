@@ -257,7 +257,25 @@ __global__ void __launch_bounds__(1024)
     tval[k] = (k < ntail) ? tail_val[k] : -1;
   }
   __syncthreads();
-  bitonic_desc2(dkey, dval, tkey, tval, npad_del);  // npad_del == npad_tail (fix_pre_begin)
+  if (small && npad_del <= 256 && npad_tail <= 256) {
+    // few entries (the usual case): rank sort, two barriers instead of one per bitonic stage.  Rank =
+    // number of larger keys (+ earlier equal ones: only the -1 padding repeats), descending order.
+    const int t = threadIdx.x;
+    int dk = -1, dv = -1, tk = -1, tv = -1, dr = 0, tr = 0;
+    if (t < npad_del) {
+      dk = dkey[t]; dv = dval[t];
+      for (int j = 0; j < npad_del; j++) dr += (dkey[j] > dk) || (dkey[j] == dk && j < t);
+    }
+    if (t < npad_tail) {
+      tk = tkey[t]; tv = tval[t];
+      for (int j = 0; j < npad_tail; j++) tr += (tkey[j] > tk) || (tkey[j] == tk && j < t);
+    }
+    __syncthreads();
+    if (t < npad_del) { dkey[dr] = dk; dval[dr] = dv; }
+    if (t < npad_tail) { tkey[tr] = tk; tval[tr] = tv; }
+    __syncthreads();
+  } else
+    bitonic_desc2(dkey, dval, tkey, tval, npad_del);  // npad_del == npad_tail (fix_pre_begin)
   // momentum contributions m*v of the deleted atoms, in descending local index order
   const double mid = 0.5 * (fd.boxhi[0] + fd.boxlo[0]);
   for (int k = threadIdx.x; k < ndel; k += blockDim.x) {
