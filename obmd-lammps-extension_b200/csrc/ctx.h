@@ -181,7 +181,8 @@ struct obmd_ctx {
   int tr_cap = 0, tr_natt = 0;
   obmd_trial *tr_d = nullptr;       // trial records (state of the latest round)
   obmd_trial *tr_prev_d = nullptr;  // state of the previous round
-  obmd_trial *tr_h = nullptr;       // pinned copy
+  obmd_trial *tr_h = nullptr;       // pinned copy (allocated when a caller asks for the trial records)
+  int tr_h_cap = 0;
   double *tr_path = nullptr;        // [tr_cap][(natt+1)*3]
   int *tr_npts = nullptr;
   double *tr_bbox = nullptr;        // [tr_cap][6] bounding box of the evaluated points

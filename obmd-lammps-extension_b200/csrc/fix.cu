@@ -951,7 +951,7 @@ __global__ void __launch_bounds__(1024)
 // End of a commit round, one CTA: drops the previous round's per-cell "spec" lists, compacts the
 // accepted trials in order into acc_list, threads them into fresh per-cell lists (what the next round's evaluations see of earlier insertions),
 // and zeroes the counters of the next round.  Deterministic: lists are ordered by trial index.
-#define URE_T 1024
+#define URE_T 1024  // 32 warps: the block scan in k_usher_round_end relies on it
 __global__ void __launch_bounds__(URE_T)
     k_usher_round_end(const obmd_trial *__restrict__ cur, int ntr, int par, int first_round, int limit,
                       int *__restrict__ acc_list, int *__restrict__ spec_cell, int *__restrict__ spec_head,
@@ -975,26 +975,36 @@ __global__ void __launch_bounds__(URE_T)
     return;
   }
   for (int k = tid; k < nold; k += URE_T) spec_head[spec_cell[k]] = -1;
-  if (tid == 0) base = 0;
-  __syncthreads();
-  for (int t0 = 0; t0 < ntr; t0 += URE_T) {
-    const int t = t0 + tid;
-    int a = 0;
-    if (t < nlim) a = cur[t].accepted;
-    const unsigned m = __ballot_sync(0xffffffffu, a);
-    if (lane == 0) wsum[w] = __popc(m);
-    __syncthreads();
-    int off = base;
-    for (int k = 0; k < w; k++) off += wsum[k];
-    if (a) acc_list[off + __popc(m & ((1u << lane) - 1u))] = t;
-    __syncthreads();
-    if (tid == 0) {
-      int s2 = 0;
-      for (int k = 0; k < URE_T / 32; k++) s2 += wsum[k];
-      base += s2;
-    }
-    __syncthreads();
+  // ordered compaction of the accepted trials: every thread owns a contiguous run of trials, counts
+  // its accepted ones, a block scan of the counts gives its offset (three barriers in all)
+  const int per = (nlim + URE_T - 1) / URE_T, tb = tid * per, te = min(tb + per, nlim);
+  int cnt = 0;
+  for (int t = tb; t < te; t++) cnt += cur[t].accepted ? 1 : 0;
+  int inc = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += v;
   }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int v = wsum[lane];  // URE_T / 32 == 32 warps
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u2 = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += u2;
+    }
+    wsum[lane] = v;  // inclusive over warps
+    if (lane == 31) base = v;
+  }
+  __syncthreads();
+  {
+    int off = inc - cnt + (w > 0 ? wsum[w - 1] : 0);
+    for (int t = tb; t < te; t++)
+      if (cur[t].accepted) acc_list[off++] = t;
+  }
+  __syncthreads();  // acc_list is read by other threads below
   const int nacc = base;
   if (nacc > LINK_MAX) {
     if (tid == 0) {
@@ -1129,14 +1139,20 @@ int fix_clear_extras(obmd_ctx *c)
   return OBMD_OK;
 }
 
+// Device buffers of the USHER trials.  Regrowing them costs a dozen cudaFree/cudaMalloc pairs (each
+// an implicit device synchronisation) in the middle of a step, so they start at 16 Ki trials and
+// double; the pinned host copy of the trial records is only made when a caller asks for them.
 static int ensure_trials(obmd_ctx *c, int ntr, int natt)
 {
   if (ntr <= c->tr_cap && natt <= c->tr_natt) return OBMD_OK;
-  int cap = ntr > c->tr_cap ? ntr + ntr / 2 + 256 : c->tr_cap;
+  int cap = c->tr_cap;
+  if (ntr > cap) {
+    cap = cap < 16384 ? 16384 : cap;
+    while (cap < ntr) cap *= 2;
+  }
   int na = natt > c->tr_natt ? natt : c->tr_natt;
   cudaFree(c->tr_d); cudaFree(c->tr_prev_d); cudaFree(c->tr_path); cudaFree(c->tr_npts);
   cudaFree(c->tr_list); cudaFree(c->tr_changed); cudaFree(c->acc_list); cudaFree(c->tr_bbox);
-  if (c->tr_h) cudaFreeHost(c->tr_h);
   CK(cudaMalloc(&c->tr_bbox, sizeof(double) * 6 * cap));
   CK(cudaMalloc(&c->tr_d, sizeof(obmd_trial) * cap));
   CK(cudaMalloc(&c->tr_prev_d, sizeof(obmd_trial) * cap));
@@ -1150,9 +1166,20 @@ static int ensure_trials(obmd_ctx *c, int ntr, int natt)
   cudaFree(c->spec_next); cudaFree(c->spec_cell);
   CK(cudaMalloc(&c->spec_next, sizeof(int) * cap));
   CK(cudaMalloc(&c->spec_cell, sizeof(int) * cap));
-  CK(cudaMallocHost(&c->tr_h, sizeof(obmd_trial) * cap));
   c->tr_cap = cap;
   c->tr_natt = na;
+  return OBMD_OK;
+}
+
+static int ensure_trials_host(obmd_ctx *c, int n)
+{
+  if (n <= c->tr_h_cap) return OBMD_OK;
+  if (c->tr_h) cudaFreeHost(c->tr_h);
+  c->tr_h = nullptr;
+  c->tr_h_cap = 0;
+  int cap = n < 4096 ? 4096 : 2 * n;
+  CK(cudaMallocHost(&c->tr_h, sizeof(obmd_trial) * cap));
+  c->tr_h_cap = cap;
   return OBMD_OK;
 }
 
@@ -1290,7 +1317,7 @@ int fix_redo_pair_near_insertions(obmd_ctx *c, long long step)
   if (!c->redo_count) CK(cudaMalloc(&c->redo_count, sizeof(int)));
   if (cap > c->redo_list_cap) {
     cudaFree(c->redo_list);
-    c->redo_list_cap = cap + cap / 2;
+    c->redo_list_cap = 2 * cap < (1 << 20) ? (1 << 20) : 2 * cap;  // regrowing mid-run stalls the step
     CK(cudaMalloc(&c->redo_list, sizeof(int) * c->redo_list_cap));
   }
   CK(cudaMemsetAsync(c->redo_count, 0, sizeof(int), c->stream));
@@ -1624,6 +1651,7 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
       if (trials && maxtrials > ncopied && ntr_loc > 0) {
         const int nloc_used = limit ? nused_p : ntr_loc;
         const int ncopy = nloc_used < maxtrials - ncopied ? nloc_used : maxtrials - ncopied;
+        if ((rc = ensure_trials_host(c, ncopy))) return rc;
         CK(cudaMemcpyAsync(c->tr_h, c->tr_d, sizeof(obmd_trial) * ncopy, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         memcpy(trials + ncopied, c->tr_h, sizeof(obmd_trial) * ncopy);
