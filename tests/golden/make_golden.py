@@ -155,6 +155,30 @@ def make_b6(wd, n0):
           "final atoms", len(rows))
 
 
+def make_p1(wd):
+    """P1: deterministic DPD forces (T = 0) with TWO atom types and per-pair a0, gamma and cutoff
+    (pair_coeff i j a0 gamma rc, pair_dpd.cpp:222-251): pins the oracle's multi-type path."""
+    (xlo, xhi), (ylo, yhi), (zlo, zhi) = BOX
+    deck = ("units lj\nboundary f p p\natom_style atomic\natom_modify sort 0 0\ncomm_modify vel yes\n"
+            "newton on\nread_data %s extra/atom/types 1\nmass 2 2.0\n"
+            "set group all type/fraction 2 0.4 12345\n"
+            "pair_style dpd 0.0 1.0 2616\n"
+            "pair_coeff 1 1 209.6 4.5 1.0\npair_coeff 1 2 150.0 3.0 0.9\npair_coeff 2 2 100.0 6.0 0.8\n"
+            "neighbor 0.4 bin\nneigh_modify delay 0 every 1\ntimestep 0.001464\n"
+            "velocity all create 1.0 4928459 loop geom\n"
+            "dump d all custom 1 dump.p1 id type vx vy vz fx fy fz\ndump_modify d format float %%.17g\n"
+            "thermo_style custom step pe press\nthermo_modify format float %%.15g norm no\nrun 0\n" % DATA)
+    lines = run_deck("p1", deck, wd)
+    (_, rows), = read_dump(os.path.join(wd, "dump.p1"))
+    th = None
+    for k, ln in enumerate(lines):
+        if ln.split()[:2] == ["Step", "PotEng"]:
+            th = np.array(lines[k + 1].split(), dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "p1_pair_two_types_T0.npz"), type=rows[:, 1].astype(np.int32),
+                        v=rows[:, 2:5].copy(), f=rows[:, 5:8].copy(), thermo=th)
+    print("p1: type-2 atoms", int((rows[:, 1] == 2).sum()), "of", len(rows), "thermo", th)
+
+
 def main():
     if not os.path.exists(LMP):
         sys.exit("oracle/_ref/lmp_serial missing: run `bash oracle/build_ref.sh` first")
@@ -162,6 +186,9 @@ def main():
     print("working in", wd)
     if len(sys.argv) > 1 and sys.argv[1] == "b6":   # only the maxattempt fixture (the others are unchanged)
         make_b6(wd, 12637)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "p1":   # only the two-type pair fixture
+        make_p1(wd)
         return
 
     # ---- shipped configuration (input fixture: ids + coordinates, read_data order) ----
@@ -238,6 +265,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "p0_pair_T0.npz"), v=rows[:, 1:4].copy(),
                         f=rows[:, 4:7].copy(), thermo=th)
     print("p0: thermo", th)
+    make_p1(wd)
 
     # ---- RanMars: two static atoms, one Gaussian per step ----
     two = os.path.join(wd, "two.data")

@@ -533,3 +533,25 @@ def test_restart_from_downloaded_state(shipped):
     assert np.array_equal(out["tag"], ref["tag"]) and np.array_equal(out["image"], ref["image"])
     assert np.abs(out["x"] - ref["x"]).max() < 1e-9
     assert np.abs(out["v"] - ref["v"]).max() < 1e-8
+
+
+def test_pair_two_types_T0_vs_reference_fixture(shipped):
+    """Same two-type coefficients, checked directly against the forces of the unmodified reference
+    binary (tests/golden/p1_pair_two_types_T0.npz) through the C ABI, within 1e-9."""
+    import obmd_b200 as ob
+    tag, x, box = shipped
+    g = cc.load("p1_pair_two_types_T0.npz")
+    sim = ob.ObmdB200(0)
+    sim.set_box(box[:, 0], box[:, 1]); sim.set_masses([1.0, 2.0]); sim.set_timestep(0.001464)
+    sim.pair_style_dpd(0.0, 1.0, 2616)
+    for (i, j), (a0, gamma, rc) in {(1, 1): (209.6, 4.5, 1.0), (1, 2): (150.0, 3.0, 0.9),
+                                    (2, 2): (100.0, 6.0, 0.8)}.items():
+        sim.pair_coeff(i, j, a0, gamma, rc)
+    sim.pair_init(1.0)
+    sim.upload(x, g["v"], g["type"], tag)
+    sim.build_cells(); sim.pbc(); sim.pair_compute(0, eflag=1)
+    f = sim.download(("f",))["f"]
+    eng, _ = sim.pair_tallies()
+    sim.close()
+    assert cc.mixed_rel_err(f, g["f"]) < FTOL
+    assert abs(eng - g["thermo"][1]) < 1e-9 * abs(g["thermo"][1])

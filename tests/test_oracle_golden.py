@@ -190,3 +190,26 @@ def test_p0_pair_forces_T0(shipped):
     ke = [np.sum(v[:, i] * v[:, j]) for i, j in ((0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2))]
     pt = [(ke[k] + vir[k]) / vol for k in range(6)]
     assert np.allclose(pt, th[3:9], rtol=1e-9, atol=1e-9)
+
+
+def test_p1_pair_forces_two_types_T0(shipped):
+    """Two atom types with per-pair a0, gamma and cutoff (pair_coeff i j a0 gamma rc,
+    pair_dpd.cpp:222-251, init_one :279-291): forces and energy vs the reference binary.  The GPU
+    test of the same coefficients (test_gpu_parity.py) compares against this oracle path."""
+    tag, x, box = shipped
+    g = load("p1_pair_two_types_T0.npz")
+    L = O.lib()
+    p = O.make_fix(box[:, 0], box[:, 1], ntypes=2, mass=(1.0, 2.0), temperature=0.0)
+    for (i, j), (a0, gamma, rc) in {(1, 1): (209.6, 4.5, 1.0), (1, 2): (150.0, 3.0, 0.9),
+                                    (2, 2): (100.0, 6.0, 0.8)}.items():
+        p.a0[i][j] = a0; p.gamma[i][j] = gamma; p.cut[i][j] = rc
+    L.orc_pair_init(C.byref(p))
+    a = O.OracleAtoms(x, v=g["v"], tag=tag, type_=g["type"])
+    assert 0.3 < (g["type"] == 2).mean() < 0.5
+    eng = C.c_double(); vir = (C.c_double * 6)()
+    L.orc_pair_compute(C.byref(p), C.byref(a.c), 0, 0, C.byref(eng), vir)
+    f = a.view("f"); fr = g["f"]
+    scale = np.maximum(np.abs(fr), np.abs(fr).mean())
+    assert np.max(np.abs(f - fr) / scale) < 1e-9
+    th = g["thermo"]   # step pe press
+    assert abs(eng.value - th[1]) < 1e-9 * abs(th[1])
