@@ -179,6 +179,30 @@ def make_p1(wd):
     print("p1: type-2 atoms", int((rows[:, 1] == 2).sum()), "of", len(rows), "thermo", th)
 
 
+def make_b7(wd, n0):
+    """B7: the B1 USHER deck with two atom types (40 % type 2, per-pair DPD coefficients) and
+    `fix obmd 2 ...` (inserted atoms are type 2): pins the type-dependent branch of energy()/single()."""
+    deck = (head().replace("read_data       %s" % DATA, "read_data       %s extra/atom/types 1\nmass 2 2.0\n"
+                                                       "set group all type/fraction 2 0.4 12345" % DATA)
+            .replace("pair_coeff      * * 209.6 4.5 1.0",
+                     "pair_coeff      1 1 209.6 4.5 1.0\npair_coeff      1 2 150.0 3.0 0.9\n"
+                     "pair_coeff      2 2 100.0 6.0 0.8") +
+            fix(alpha=1.0, nbuf=2000).replace("fix 2 all obmd 1 1 6111", "fix 2 all obmd 2 1 6111") +
+            "dump d all custom 8 dump.b7 id type x y z\ndump_modify d format float %.17g\n"
+            "thermo 1\nthermo_style custom step atoms\nrun 8\n")
+    assert "extra/atom/types" in deck and "pair_coeff      2 2" in deck and "obmd 2 1 6111" in deck
+    lines = run_deck("b7", deck, wd)
+    frames = read_dump(os.path.join(wd, "dump.b7"))
+    step, rows = frames[-1]
+    assert step == 8
+    ver = parse_usher(lines)
+    np.savez_compressed(os.path.join(HERE, "b7_usher_two_types.npz"),
+                        verdicts=ver, final_tag=rows[:, 0].astype(np.int32), final_type=rows[:, 1].astype(np.int32),
+                        inserted_x=rows[n0:, 2:5].copy(), nsteps=8)
+    print("b7: trials", len(ver), "accepted", int(ver[:, 0].sum()), "final atoms", len(rows),
+          "type-2", int((rows[:, 1] == 2).sum()))
+
+
 def main():
     if not os.path.exists(LMP):
         sys.exit("oracle/_ref/lmp_serial missing: run `bash oracle/build_ref.sh` first")
@@ -189,6 +213,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "p1":   # only the two-type pair fixture
         make_p1(wd)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "b7":   # only the two-type USHER fixture
+        make_b7(wd, 12637)
         return
 
     # ---- shipped configuration (input fixture: ids + coordinates, read_data order) ----
@@ -215,6 +242,7 @@ def main():
                         inserted_x=rows[n0:, 1:4].copy(), nsteps=12)
     print("b1: trials", len(ver), "accepted", int(ver[:, 0].sum()), "final atoms", len(rows))
     make_b6(wd, n0)
+    make_b7(wd, n0)
 
     # ---- B2/B5: normal force distribution, static atoms, pair force zeroed ----
     deck = (head(a0=0.0, gamma=0.0) + fix(dpxx=10.0, freq=5.0) +

@@ -555,3 +555,44 @@ def test_pair_two_types_T0_vs_reference_fixture(shipped):
     sim.close()
     assert cc.mixed_rel_err(f, g["f"]) < FTOL
     assert abs(eng - g["thermo"][1]) < 1e-9 * abs(g["thermo"][1])
+
+
+def test_b7_usher_two_types_bit_exact(shipped):
+    """USHER with type-dependent pair coefficients (the multi-type instantiation of the evaluation
+    kernel): 40 % type-2 atoms, `fix obmd 2 ...` inserts type-2 atoms.  Trial stream vs the oracle
+    and final tags / types / inserted positions vs the reference fixture, bit for bit."""
+    import obmd_b200 as ob
+    tag, x, box = shipped
+    g = cc.load("b7_usher_two_types.npz")
+    typ0 = cc.load("p1_pair_two_types_T0.npz")["type"]
+    coeff = {(1, 1): (209.6, 4.5, 1.0), (1, 2): (150.0, 3.0, 0.9), (2, 2): (100.0, 6.0, 0.8)}
+    sim = ob.ObmdB200(0)
+    sim.set_box(box[:, 0], box[:, 1]); sim.set_masses([1.0, 2.0]); sim.set_timestep(0.001464)
+    sim.pair_style_dpd(1.0, 1.0, 2616)
+    for (i, j), (a0, gamma, rc) in coeff.items():
+        sim.pair_coeff(i, j, a0, gamma, rc)
+    sim.pair_init(1.0)
+    sim.fix_obmd(cc.fix_args(box, ntype=2, alpha=1.0, nbuf=2000.0))
+    sim.upload(x, np.zeros_like(x), typ0, tag)
+    p = O.make_fix(box[:, 0], box[:, 1], ntypes=2, mass=(1.0, 2.0), alpha=1.0, nbuf=2000.0, ntype=2)
+    for (i, j), (a0, gamma, rc) in coeff.items():
+        p.a0[i][j] = a0; p.gamma[i][j] = gamma; p.cut[i][j] = rc
+    L = O.lib()
+    L.orc_pair_init(C.byref(p))
+    a = O.OracleAtoms(x, tag=tag, type_=typ0)
+    trials = (O.Trial * 4096)()
+    for s in range(int(g["nsteps"])):
+        sim.build_cells()
+        rep, tr = sim.pre_exchange(maxtrials=4096)
+        L.orc_fix_pre_exchange(C.byref(p), C.byref(a.c), trials, 4096)
+        assert rep.ntrials == p.last_ntrials and rep.naccept == p.last_naccept, s
+        for k in range(rep.ntrials):
+            t, o = tr[k], trials[k]
+            assert tuple(t.start) == tuple(o.start) and tuple(t.end) == tuple(o.end), (s, k)
+            assert t.energy == o.energy and t.iter == o.iter, (s, k)
+            assert (t.accepted, t.side, t.tag) == (o.accepted, o.side, o.tag), (s, k)
+    out = sim.download(("x", "tag", "type"))
+    assert np.array_equal(out["tag"], g["final_tag"]) and np.array_equal(out["type"], g["final_type"])
+    assert np.array_equal(out["x"][len(tag):], g["inserted_x"])
+    assert (out["type"][len(tag):] == 2).all() and len(out["tag"]) - len(tag) > 100
+    sim.close()

@@ -213,3 +213,43 @@ def test_p1_pair_forces_two_types_T0(shipped):
     assert np.max(np.abs(f - fr) / scale) < 1e-9
     th = g["thermo"]   # step pe press
     assert abs(eng.value - th[1]) < 1e-9 * abs(th[1])
+
+
+TWO_TYPE_COEFF = {(1, 1): (209.6, 4.5, 1.0), (1, 2): (150.0, 3.0, 0.9), (2, 2): (100.0, 6.0, 0.8)}
+
+
+def two_type_fix(box, **kw):
+    p = O.make_fix(box[:, 0], box[:, 1], ntypes=2, mass=(1.0, 2.0), **kw)
+    for (i, j), (a0, gamma, rc) in TWO_TYPE_COEFF.items():
+        p.a0[i][j] = a0; p.gamma[i][j] = gamma; p.cut[i][j] = rc
+    O.lib().orc_pair_init(C.byref(p))
+    return p
+
+
+def test_b7_usher_two_types_insert_type_2(shipped):
+    """USHER with type-dependent pair coefficients: 40 % of the atoms are type 2 and `fix obmd 2 ...`
+    inserts type-2 atoms (energy()/single() use a0, cut of the (2, j) pairs, fix_obmd_merged.cpp:1774-1810).
+    Verdicts, accepted positions, tags and types vs 8 steps of the unmodified reference binary."""
+    tag, x, box = shipped
+    g = load("b7_usher_two_types.npz")
+    typ0 = load("p1_pair_two_types_T0.npz")["type"]      # same `set type/fraction 2 0.4 12345`
+    assert np.array_equal(typ0, g["final_type"][:len(tag)])
+    L = O.lib()
+    p = two_type_fix(box, alpha=1.0, nbuf=2000.0, ntype=2)
+    a = O.OracleAtoms(x, tag=tag, type_=typ0)
+    trials = (O.Trial * 4096)()
+    ver = []
+    for _ in range(int(g["nsteps"])):
+        L.orc_fix_pre_exchange(C.byref(p), C.byref(a.c), trials, 4096)
+        for k in range(p.last_ntrials):
+            t = trials[k]
+            ver.append((t.accepted, sig6(t.energy), t.iter if t.accepted else -1))
+    ref = g["verdicts"]
+    assert len(ver) == len(ref) and ref[:, 0].sum() > 100
+    got = np.array(ver, dtype=np.float64)
+    assert np.array_equal(got[:, 0], ref[:, 0])
+    assert np.array_equal(got[:, 2], ref[:, 2])
+    assert np.allclose(got[:, 1], ref[:, 1], rtol=2e-6, atol=0)
+    assert np.array_equal(a.view("tag"), g["final_tag"])
+    assert np.array_equal(a.view("type"), g["final_type"])
+    assert np.array_equal(a.view("x")[len(tag):], g["inserted_x"])  # bit-exact
