@@ -203,6 +203,32 @@ def make_b7(wd, n0):
           "type-2", int((rows[:, 1] == 2).sum()))
 
 
+def make_b8(wd):
+    """B8: the ballistic bookkeeping deck with two atom types of mass 1 and 2 and tangential flux on
+    2.5-wide shear regions: pins every mass-dependent path (FixNVE dtf/m, momentum of the deleted atoms,
+    mass-weighted g_perp, fix_obmd_merged.cpp:827-837, :1344-1381, :1452-1514)."""
+    deck = (head(a0=0.0, gamma=0.0, dt=0.01, shear=2.5)
+            .replace("read_data       %s" % DATA, "read_data       %s extra/atom/types 1\nmass 2 2.0\n"
+                                                  "set group all type/fraction 2 0.4 12345" % DATA) +
+            "velocity all create 25.0 4928459 loop geom\nfix 1 all nve\n" +
+            fix(alpha=1.0, tau=0.05, nbuf=2000, pxy=2.0, pxz=-1.0) +
+            "dump d all custom 20 dump.b8 id type x y z vx vy vz fx fy fz\n"
+            "dump_modify d format float %.17g\nrun 20\n")
+    assert "extra/atom/types" in deck
+    lines = run_deck("b8", deck, wd)
+    frames = read_dump(os.path.join(wd, "dump.b8"))
+    (s0, r0), (s1, r1) = frames
+    assert (s0, s1) == (0, 20)
+    ndel = sum(1 for ln in lines if ln.startswith("Deleting"))
+    ver = parse_usher(lines)
+    np.savez_compressed(os.path.join(HERE, "b8_ballistic_two_masses.npz"),
+                        type0=r0[:, 1].astype(np.int32), v0=r0[:, 5:8].copy(),
+                        tag20=r1[:, 0].astype(np.int32), type20=r1[:, 1].astype(np.int32),
+                        x20=r1[:, 2:5].copy(), v20=r1[:, 5:8].copy(), f20=r1[:, 8:11].copy(),
+                        ndel=ndel, nins=int(ver[:, 0].sum()))
+    print("b8: deletions", ndel, "insertions", int(ver[:, 0].sum()), "atoms", len(r1))
+
+
 def main():
     if not os.path.exists(LMP):
         sys.exit("oracle/_ref/lmp_serial missing: run `bash oracle/build_ref.sh` first")
@@ -213,6 +239,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "p1":   # only the two-type pair fixture
         make_p1(wd)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "b8":   # only the two-mass ballistic fixture
+        make_b8(wd)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "b7":   # only the two-type USHER fixture
         make_b7(wd, 12637)
@@ -243,6 +272,7 @@ def main():
     print("b1: trials", len(ver), "accepted", int(ver[:, 0].sum()), "final atoms", len(rows))
     make_b6(wd, n0)
     make_b7(wd, n0)
+    make_b8(wd)
 
     # ---- B2/B5: normal force distribution, static atoms, pair force zeroed ----
     deck = (head(a0=0.0, gamma=0.0) + fix(dpxx=10.0, freq=5.0) +

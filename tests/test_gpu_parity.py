@@ -596,3 +596,27 @@ def test_b7_usher_two_types_bit_exact(shipped):
     assert np.array_equal(out["x"][len(tag):], g["inserted_x"])
     assert (out["type"][len(tag):] == 2).all() and len(out["tag"]) - len(tag) > 100
     sim.close()
+
+
+def test_b8_ballistic_two_masses(shipped):
+    """20 ballistic steps with atom types of mass 1 and 2 and tangential flux on shear regions
+    (mass-dependent FixNVE, deleted momentum, mass-weighted tangential weights): tag order and types
+    identical to the reference binary; x, v, f to rounding."""
+    tag, x, box = shipped
+    g = cc.load("b8_ballistic_two_masses.npz")
+    kw = dict(a0=0.0, gamma=0.0, dt=0.01, alpha=1.0, tau=0.05, nbuf=2000.0, pxy=2.0, pxz=-1.0,
+              shear_size=2.5, masses=(1.0, 2.0))
+    sim = cc.device_sim(box, **kw)
+    sim.upload(x, g["v0"], g["type0"], tag)
+    sim.setup(0)
+    ndel = nins = 0
+    for s in range(1, 21):
+        rep, _ = sim.step(s)
+        ndel += rep.ndel; nins += rep.naccept
+    assert (ndel, nins) == (int(g["ndel"]), int(g["nins"]))
+    out = sim.download()
+    assert np.array_equal(out["tag"], g["tag20"]) and np.array_equal(out["type"], g["type20"])
+    assert np.allclose(out["x"], g["x20"], rtol=0, atol=1e-11)
+    assert np.allclose(out["v"], g["v20"], rtol=0, atol=1e-10)
+    assert cc.mixed_rel_err(out["f"], g["f20"]) < FTOL
+    sim.close()

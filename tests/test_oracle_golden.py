@@ -253,3 +253,25 @@ def test_b7_usher_two_types_insert_type_2(shipped):
     assert np.array_equal(a.view("tag"), g["final_tag"])
     assert np.array_equal(a.view("type"), g["final_type"])
     assert np.array_equal(a.view("x")[len(tag):], g["inserted_x"])  # bit-exact
+
+
+def test_b8_ballistic_two_masses_bit_exact(shipped):
+    """20 ballistic steps with atom types of mass 1 and 2 and tangential flux on shear regions: FixNVE
+    with dtf/m, momentum of the deleted atoms, mass-weighted tangential weights, type of the inserted
+    atoms -- order, x, v, f bit for bit vs the reference binary."""
+    tag, x, box = shipped
+    g = load("b8_ballistic_two_masses.npz")
+    L = O.lib()
+    p = O.make_fix(box[:, 0], box[:, 1], ntypes=2, mass=(1.0, 2.0), a0=0.0, gamma=0.0, dt=0.01, alpha=1.0,
+                   tau=0.05, nbuf=2000.0, pxy=2.0, pxz=-1.0, shear_size=2.5)
+    a = O.OracleAtoms(x, v=g["v0"], tag=tag, type_=g["type0"])
+    trials = (O.Trial * 4096)()
+    ndel = nins = 0
+    for s in range(1, 21):
+        L.orc_step(C.byref(p), C.byref(a.c), 0, s, trials, 4096)
+        ndel += p.last_ndel; nins += p.last_naccept
+    assert (ndel, nins) == (int(g["ndel"]), int(g["nins"]))
+    assert np.array_equal(a.view("tag"), g["tag20"]) and np.array_equal(a.view("type"), g["type20"])
+    assert np.array_equal(a.view("x"), g["x20"])
+    assert np.array_equal(a.view("v"), g["v20"])
+    assert np.array_equal(a.view("f"), g["f20"])
