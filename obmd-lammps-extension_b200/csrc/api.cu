@@ -80,6 +80,14 @@ extern "C" int obmd_create(obmd_ctx **out, int device)
   if (const char *e9 = getenv("OBMD_B200_PAIR_FIRST")) c->pair_first = atoi(e9);
   if (const char *e8 = getenv("OBMD_B200_CAPSCALE")) c->row_capscale = atof(e8);
   if (const char *e5 = getenv("OBMD_B200_PT")) c->row_threads = atoi(e5);
+  if (const char *e10 = getenv("OBMD_B200_USH_G")) {
+    const int gsz = atoi(e10);
+    if (gsz == 8 || gsz == 16 || gsz == 32) c->ush_group = gsz;
+  }
+  if (const char *e11 = getenv("OBMD_B200_USH_CTAS")) {
+    const int v = atoi(e11);
+    if (v >= 1 && v <= 16) c->ush_ctas_per_sm = v;
+  }
   snprintf(c->err, sizeof(c->err), "no error");
   *out = c;
   return OBMD_OK;
@@ -110,8 +118,9 @@ extern "C" void obmd_destroy(obmd_ctx *c)
   cudaFree(c->red_d); cudaFreeHost(c->red_h);
   cudaFree(c->sendL); cudaFree(c->sendR); cudaFree(c->recvL); cudaFree(c->recvR);
   cudaFree(c->del_key); cudaFree(c->del_val); cudaFree(c->tail_key); cudaFree(c->tail_val); cudaFree(c->del_src); cudaFree(c->del_mv);
-  cudaFree(c->tr_d); cudaFree(c->tr_prev_d); cudaFree(c->tr_path); cudaFree(c->tr_npts);
-  cudaFree(c->tr_list); cudaFree(c->tr_changed); cudaFree(c->tr_chg); cudaFree(c->acc_list); cudaFree(c->tr_bbox);
+  cudaFree(c->tr_d); cudaFree(c->tr_path); cudaFree(c->tr_npts);
+  cudaFree(c->tr_list); cudaFree(c->tr_kfirst); cudaFree(c->tr_chg); cudaFree(c->acc_list); cudaFree(c->tr_bbox);
+  cudaFree(c->spec_trial); cudaFree(c->spec_of_trial); cudaFree(c->spec_pos);
   if (c->tr_h) cudaFreeHost(c->tr_h);
   cudaFree(c->partials);
   cudaFree(c->redo_flag); cudaFree(c->redo_list); cudaFree(c->redo_count);

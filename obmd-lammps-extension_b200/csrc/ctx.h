@@ -77,6 +77,7 @@ struct StepScalars {
   int nrounds_work;         // rounds whose evaluation had work to do
   int trial_cursor;         // next entry of the round's trial list to hand to a warp
   int nused, nused_prev;    // maxattempt > 1: attempts of the RNG stream the serial loop consumes (a prefix)
+  int nspec;                // accepted-atom entries published so far in this call (usher.cu)
   int rng_seed;             // RanPark state after the deletion draws
   double vnewl[3], vnewr[3];
   double gsum[4];           // G_left, G_right, Gperp_left, Gperp_right
@@ -180,17 +181,21 @@ struct obmd_ctx {
   // USHER scratch
   int tr_cap = 0, tr_natt = 0;
   obmd_trial *tr_d = nullptr;       // trial records (state of the latest round)
-  obmd_trial *tr_prev_d = nullptr;  // state of the previous round
   obmd_trial *tr_h = nullptr;       // pinned copy (allocated when a caller asks for the trial records)
   int tr_h_cap = 0;
   double *tr_path = nullptr;        // [tr_cap][(natt+1)*3]
   int *tr_npts = nullptr;
-  double *tr_bbox = nullptr;        // [tr_cap][6] bounding box of the evaluated points
-  int *tr_list = nullptr;           // trials to evaluate this round
-  int *tr_changed = nullptr;        // [cap] unused | [cap] kfirst
+  float *tr_bbox = nullptr;         // [tr_cap][6] bounding box of the evaluated points (rounded outwards)
+  int *tr_list = nullptr;           // trials to re-run this round
+  int *tr_kfirst = nullptr;         // first evaluation point of a listed trial that must be redone
   struct ChgRec *tr_chg = nullptr;  // compact records of the trials whose state changed this round
-  int *acc_list = nullptr;          // compacted accepted trial ids of the previous round
-  int *spec_head = nullptr, *spec_next = nullptr, *spec_cell = nullptr;  // their per-cell lists
+  int *acc_list = nullptr;          // accepted trial ids in order (final)
+  // atoms accepted so far in this call: append-only entries threaded into per-cell lists
+  int *spec_head = nullptr, *spec_next = nullptr, *spec_cell = nullptr, *spec_trial = nullptr;
+  int *spec_of_trial = nullptr;     // [tr_cap] entry of trial t's accepted atom, -1 if none
+  double *spec_pos = nullptr;
+  int ush_group = 32;               // lanes per trial in round 0 (OBMD_B200_USH_G: 8, 16, 32)
+  int ush_ctas_per_sm = 6;          // persistent grid of round 0 (OBMD_B200_USH_CTAS)
   double *partials = nullptr;       // block partial sums for deterministic reductions
   int partial_cap = 0;
   // last pre_exchange report
@@ -303,6 +308,19 @@ int comm_exchange(obmd_ctx *c);  // comm.cu: migrate + halo + ghost lists
 int comm_allreduce(obmd_ctx *c, double *dev, int nsum, int nmax);  // first nsum: sum, next nmax: max
 int fix_link_extras(obmd_ctx *c, int first, int count, bool sorted_by_cell);
 int fix_compact_extras(obmd_ctx *c);
+struct UsherCfg {
+  int ntrL, ntr;      // trials for the left region come first (maxattempt == 1)
+  int seed0;          // RanPark state before the first trial draw
+  int nbase;          // local index of the first inserted atom (= nlocal after deletion)
+  int natt;
+  int tg0;            // global index of local trial 0 (slab runs: the right rank starts at ntrL)
+  int slots, maxatt;  // maxattempt > 1 (one side per pass): insertions wanted, attempts allowed for each
+};
+
+int usher_pass(obmd_ctx *c, const UsherCfg &u, int ntr_loc, int limit, int *nacc_out, int *nused_out,
+               int *rounds_out);
+int usher_commit(obmd_ctx *c, int tag0, int nacc);
+int usher_trials_to_host(obmd_ctx *c, obmd_trial *dst, int ncopy);
 
 // ---- small device helpers shared by the TUs --------------------------------------
 static inline Extras extras_of(const obmd_ctx *c)

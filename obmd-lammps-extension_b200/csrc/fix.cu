@@ -3,8 +3,7 @@
 // trial coordinates, weights, integrator) must not be contracted into FMAs, because the
 // reference is an x86-64 build without FMA.
 //
-//   pre_exchange (:550-633)      -> k_scan_atoms, k_delete_fixup, k_usher_eval/_diff/_dirty/_acc,
-//                                   k_usher_commit
+//   pre_exchange (:550-633)      -> k_scan_ids, k_count_regions, k_delete_fixup; batched USHER in usher.cu
 //   post_force   (:1229-1240)    -> k_weight_sums, k_apply_forces
 //   FixNVE       (fix_nve.cpp)   -> k_nve_initial, k_nve_final
 //   Domain::pbc  (domain.cpp)    -> k_pbc
@@ -339,737 +338,9 @@ static int ranpark_skip(int seed, long long n)  // random_park.cpp:43-50 applied
   return (int) (((unsigned long long) seed * r) % m);
 }
 
-// =====================================================================================
-// pre_exchange, part 2: batched USHER (try_inserting :869-1225, usher :1518-1616,
-// energy :1774-1810, PairDPD::single pair_dpd.cpp:401-418)
-// =====================================================================================
+// pre_exchange, part 2 (batched USHER: try_inserting :869-1225, usher :1518-1616) lives in usher.cu.
 
-#define USH_WARPS 4
-#ifndef USH_BLOCKS_PER_SM
-#define USH_BLOCKS_PER_SM 5  // resident CTAs per SM the eval kernel is compiled for: measured 4/5/6/7/8 -> eval 0.70/0.66/0.70/0.80/0.88 ms per step (more CTAs = fewer registers = spills)
-#endif
 #define LINK_MAX 6000  // atoms per unsorted extra group (two int arrays in 48 KB of shared memory)
-#define USH_CAP 48    // contributions per energy evaluation held per warp (mean 13 at rho = 3)
-#define USH_CHUNKS ((USH_CAP + 31) / 32)
-#define USH_CAND 144  // atoms in the 27 stencil cells of a point (mean 81 at rho = 3)
-
-struct UsherCfg {
-  int ntrL, ntr;      // trials for the left region come first (maxattempt == 1)
-  int seed0;          // RanPark state before the first trial draw
-  int nbase;          // local index of the first inserted atom (= nlocal after deletion)
-  int natt;
-  int tg0;            // global index of local trial 0 (slab runs: the right rank starts at ntrL)
-  int slots, maxatt;  // maxattempt > 1 (one side per pass): insertions wanted, attempts allowed for each
-};
-
-__device__ __forceinline__ int ranpark_pow(long long n)
-{
-  unsigned long long m = 2147483647ULL, a = 16807ULL, r = 1ULL;
-  while (n > 0) {
-    if (n & 1) r = (r * a) % m;
-    a = (a * a) % m;
-    n >>= 1;
-  }
-  return (int) r;
-}
-
-__device__ __forceinline__ double ranpark_uniform(int &seed)
-{
-  int k = seed / 127773;
-  seed = 16807 * (seed - k * 127773) - 2836 * k;
-  if (seed < 0) seed += 2147483647;
-  return (1.0 / 2147483647) * seed;
-}
-
-struct WarpHits {
-  int key[USH_CAP + 4];  // LAMMPS local index of the contributing atom (+ sentinels for the rank loop)
-  int tj[USH_CAP];    // its type
-  // pass A: rsq, del of each hit; pass B overwrites them with phi, f ordered by local index
-  double e[USH_CAP + 4], fx[USH_CAP + 4], fy[USH_CAP + 4], fz[USH_CAP + 4];
-  // the atoms of the 27 stencil cells of the cell the point is in: gathered once, reused by every
-  // iteration that stays in that cell (a steepest-descent step is a fraction of a cell width)
-  double cx[USH_CAND], cy[USH_CAND], cz[USH_CAND];
-  int ckey[USH_CAND], ctj[USH_CAND];  // LAMMPS local index, type
-};
-
-// Pass A of energy() (:1791-1800): separation with the reference's minimum_image loop
-// (domain.cpp:980-1008, y and z periodic) and the cutoff test.
-// `wrap` is false when the 27 gathered cells touch no periodic face (and the box is at least 6 cells
-// wide): every separation is then at most two cell widths, below half the box, so the reference's
-// minimum_image loop would not change it and is skipped.
-__device__ __forceinline__ bool usher_screen(const double c[3], double xj, double yj, double zj, double cutsq,
-                                             bool wrap, const Grid &g, double &rsq, double &delx,
-                                             double &dely, double &delz)
-{
-  delx = c[0] - xj;
-  dely = c[1] - yj;
-  delz = c[2] - zj;
-  if (wrap) {
-    while (fabs(dely) > g.half[1]) {
-      if (dely < 0.0) dely += g.prd[1];
-      else dely -= g.prd[1];
-    }
-    while (fabs(delz) > g.half[2]) {
-      if (delz < 0.0) delz += g.prd[2];
-      else delz -= g.prd[2];
-    }
-  }
-  rsq = delx * delx + dely * dely + delz * delz;
-  return rsq < cutsq;
-}
-
-// Pass B: PairDPD::single (pair_dpd.cpp:401-418, factor_dpd = 1) and fpair*del (:1801-1805)
-__device__ __forceinline__ void usher_single(double a0, double cut, double rsq, double &e, double &fx,
-                                             double &fy, double &fz)
-{
-  double r = sqrt(rsq);
-  double fforce, phi;
-  if (r < EPSILON_DPD) {
-    fforce = 0.0;
-    phi = 0.0;
-  } else {
-    double rinv = 1.0 / r;
-    double wd = 1.0 - (cut == 1.0 ? r : r / cut);  // r / 1.0 == r exactly: skip the division
-    fforce = a0 * wd * 1.0 * rinv;
-    phi = 0.5 * a0 * cut * wd * wd;
-    phi = 1.0 * phi;
-  }
-  e = phi;
-  fx = fforce * fx;
-  fy = fforce * fy;
-  fz = fforce * fz;
-}
-
-// One warp gathers the atoms of the 27 cells around cell (cx, cy, cz) into its shared-memory
-// candidate arrays: the sorted atoms of each cell, the atoms appended after the sort (slab runs),
-// and the atoms accepted earlier in this pre_exchange (previous round's state, only those of
-// trials before t).  Returns the number of candidates (0 and an error flag if they do not fit).
-__device__ int usher_gather(int cx, int cy, int cz, int t, const Planes &p, const Grid &g, const FixDev &fd,
-                            const int *__restrict__ cell_start, const UsherCfg &u,
-                            const int *__restrict__ acc_list, const obmd_trial *__restrict__ prev,
-                            const Extras &ex, const int *__restrict__ extra_head,
-                            const int *__restrict__ extra_next, const int *__restrict__ spec_head,
-                            const int *__restrict__ spec_next, WarpHits &H, StepScalars *sc)
-{
-  const int lane = threadIdx.x & 31;
-  // Lanes 0..26 each own one stencil cell: one round trip fetches all 27 cell ranges, a warp scan
-  // turns them into a flat candidate list, and the candidates are then loaded 32 at a time with
-  // independent loads (two dependent global round trips per gather).
-  int jb = 0, cnt = 0, cc = -1, cex = 0;
-  const bool have_extras = (ex.narr + ex.nghost + ex.nins) > 0;  // slab runs: arrivals and ghosts
-  const bool have_spec = sc->naccept > 0;  // atoms accepted in the previous round (0 during round 0)
-  if (lane < 27) {
-    int ox = lane / 9 - 1, oy = (lane / 3) % 3 - 1, oz = lane % 3 - 1;
-    int bx = cx + ox;
-    if (bx >= 0 && bx < g.nx) {
-      int by = cy + oy, bz = cz + oz;  // offsets are +-1: wrap without a division
-      by = by < 0 ? by + g.ny : (by >= g.ny ? by - g.ny : by);
-      bz = bz < 0 ? bz + g.nz : (bz >= g.nz ? bz - g.nz : bz);
-      cc = (bx * g.ny + by) * g.nz + bz;
-      jb = cell_start[cc];
-      cnt = cell_start[cc + 1] - jb;
-      if (have_extras)
-        for (int e = extra_head[cc]; e >= 0; e = extra_next[e]) cex++;
-      // atoms accepted by earlier trials of this call (previous round's state) live in their own
-      // per-cell lists, so a point only ever sees the few that share its stencil
-      if (have_spec)
-        for (int e = spec_head[cc]; e >= 0; e = spec_next[e]) cex += (acc_list[e] < t);
-    }
-  }
-  int off = cnt + cex;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, off, d);
-    if (lane >= d) off += v;
-  }
-  const int ncand = __shfl_sync(0xffffffffu, off, 31);
-  off -= cnt + cex;  // exclusive
-  if (ncand > USH_CAND) {
-    if (lane == 0) sc->usher_error = OBMD_ERR_CAPACITY;
-    return 0;
-  }
-  // slot of every candidate (ctj doubles as the scratch for it), then the data
-  for (int k = 0; k < cnt; k++) H.ctj[off + k] = jb + k;
-  if (cex) {
-    int k = cnt;
-    if (have_extras)
-      for (int e = extra_head[cc]; e >= 0; e = extra_next[e]) H.ctj[off + k++] = ex.base + e;
-    if (have_spec)
-      for (int e = spec_head[cc]; e >= 0; e = spec_next[e])
-        if (acc_list[e] < t) H.ctj[off + k++] = -(e + 1);
-  }
-  __syncwarp();
-  for (int q = lane; q < ncand; q += 32) {
-    const int j = H.ctj[q];
-    if (j >= 0) {
-      H.ctj[q] = p.type[j];
-      H.ckey[q] = p.lidx[j];
-      H.cx[q] = p.x[j];
-      H.cy[q] = p.y[j];
-      H.cz[q] = p.z[j];
-    } else {  // created earlier in this call: local index nbase + rank in the accepted list
-      const int e = -j - 1;
-      const obmd_trial &a = prev[acc_list[e]];
-      H.ctj[q] = fd.ntype;
-      H.ckey[q] = u.nbase + e;
-      H.cx[q] = a.end[0];
-      H.cy[q] = a.end[1];
-      H.cz[q] = a.end[2];
-    }
-  }
-  __syncwarp();
-  return ncand;
-}
-
-// One warp evaluates E and f at point c from the gathered candidates: screens them, orders the
-// contributions by LAMMPS local index and sums them left to right -- the reference's summation
-// order (:1790-1807).
-template <bool ST>  // ST: a single atom type, pair coefficients are the three scalars in `k1`
-__device__ void usher_energy(const double c[3], int nc, bool wrap, const double k1[3], const Grid &g,
-                             const PairTab &pt, const FixDev &fd, WarpHits &H, StepScalars *sc, double &E,
-                             double f[3])
-{
-  const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
-  const int it = fd.ntype;
-  int nh = 0;
-  // pass A over the stencil atoms: cheap screen, hits compacted into the warp's list
-  for (int q0 = 0; q0 < nc; q0 += 32) {
-    const int q = q0 + lane;
-    double rsq = 0, dx = 0, dy = 0, dz = 0;
-    int key = 0, tj = it;
-    bool hit = false;
-    if (q < nc) {
-      key = H.ckey[q];
-      if (!ST) tj = H.ctj[q];
-      hit = usher_screen(c, H.cx[q], H.cy[q], H.cz[q], ST ? k1[2] : pt.cutsq[it][tj], wrap, g, rsq, dx, dy, dz);
-    }
-    unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (hit) {
-      int s2 = nh + __popc(m & lt);
-      if (s2 < USH_CAP) {
-        H.key[s2] = key;
-        if (!ST) H.tj[s2] = tj;
-        H.e[s2] = rsq;
-        H.fx[s2] = dx;
-        H.fy[s2] = dy;
-        H.fz[s2] = dz;
-      }
-    }
-    nh += __popc(m);
-  }
-  if (nh > USH_CAP) {
-    if (lane == 0) sc->usher_error = OBMD_ERR_CAPACITY;
-    nh = USH_CAP;
-  }
-  if (lane < 4) H.key[nh + lane] = 0x7fffffff;  // sentinels: the rank loop below runs four keys per trip
-  __syncwarp();
-  // pass B (dense): PairDPD::single, then each contribution is stored at its rank by local index
-  // (keys are distinct) in the same arrays -- every lane holds its (at most two) results in registers
-  // until the whole warp has read its inputs -- zero-padded to a multiple of four
-  double ev[USH_CHUNKS], xv[USH_CHUNKS], yv[USH_CHUNKS], zv[USH_CHUNKS];
-  int rk[USH_CHUNKS];
-#pragma unroll
-  for (int c2 = 0; c2 < USH_CHUNKS; c2++) {
-    const int s = lane + 32 * c2;
-    rk[c2] = -1;
-    if (s < nh) {
-      double e, fx = H.fx[s], fy = H.fy[s], fz = H.fz[s];
-      if (ST) usher_single(k1[0], k1[1], H.e[s], e, fx, fy, fz);
-      else usher_single(pt.a0[it][H.tj[s]], pt.cut[it][H.tj[s]], H.e[s], e, fx, fy, fz);
-      int k = H.key[s], r = 0;
-      for (int q = 0; q < nh; q += 4)
-        r += (H.key[q] < k) + (H.key[q + 1] < k) + (H.key[q + 2] < k) + (H.key[q + 3] < k);
-      rk[c2] = r; ev[c2] = e; xv[c2] = fx; yv[c2] = fy; zv[c2] = fz;
-    }
-  }
-  __syncwarp();
-#pragma unroll
-  for (int c2 = 0; c2 < USH_CHUNKS; c2++)
-    if (rk[c2] >= 0) {
-      H.e[rk[c2]] = ev[c2];
-      H.fx[rk[c2]] = xv[c2];
-      H.fy[rk[c2]] = yv[c2];
-      H.fz[rk[c2]] = zv[c2];
-    }
-  const int nh4 = (nh + 3) & ~3;
-  if (lane < nh4 - nh) {
-    H.e[nh + lane] = 0.0;
-    H.fx[nh + lane] = 0.0;
-    H.fy[nh + lane] = 0.0;
-    H.fz[nh + lane] = 0.0;
-  }
-  __syncwarp();
-  // left-to-right sums in ascending local index (the reference's loop order, :1790-1807), one lane
-  // per quantity; adding the +0.0 padding is exact, and four elements per trip keep the loads ahead
-  // of the add chain
-  double acc = 0.0;
-  if (lane < 4) {
-    const double *arr = lane == 0 ? H.e : (lane == 1 ? H.fx : (lane == 2 ? H.fy : H.fz));
-    for (int r = 0; r < nh4; r += 4) {
-      const double a0 = arr[r], a1 = arr[r + 1], a2 = arr[r + 2], a3 = arr[r + 3];
-      acc += a0; acc += a1; acc += a2; acc += a3;
-    }
-  }
-  const double Es = acc, f0 = __shfl_sync(0xffffffffu, acc, 1), f1 = __shfl_sync(0xffffffffu, acc, 2),
-               f2 = __shfl_sync(0xffffffffu, acc, 3);
-  E = __shfl_sync(0xffffffffu, Es, 0);
-  f[0] = f0;
-  f[1] = f1;
-  f[2] = f2;
-  __syncwarp();
-}
-
-// One warp per trial in `list`.  Writes the trial record and the points at which the energy was
-// evaluated (needed by the dirty test of the next round).
-template <bool ST>
-__device__ __forceinline__ void usher_trial(
-    int li, WarpHits *hits, const int *__restrict__ list, const Planes &p, const Grid &g, const PairTab &pt,
-    const FixDev &fd, const int *__restrict__ cell_start, const UsherCfg &u, const Extras &ex,
-    const int *__restrict__ extra_head, const int *__restrict__ extra_next,
-    const int *__restrict__ spec_head, const int *__restrict__ spec_next, const int *__restrict__ acc_list,
-    const obmd_trial *__restrict__ prev, obmd_trial *__restrict__ cur, double *__restrict__ path,
-    int *__restrict__ npts, double *__restrict__ bbox, const int *__restrict__ kfirst, StepScalars *sc)
-{
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = list ? list[li] : li;
-  const int tg = t + u.tg0;  // position of this trial in the (replicated) RanPark stream
-  const int side = (tg < u.ntrL) ? 0 : 1;
-  const obmd_block &reg = fd.region[4 + side];
-
-  // trial start (:923-927): three consecutive RanPark draws, x then y then z
-  int seed = (int) (((unsigned long long) u.seed0 * (unsigned long long) ranpark_pow(3LL * tg)) %
-                    2147483647ULL);
-  double c[3], start[3];
-  for (int d = 0; d < 3; d++) {
-    c[d] = reg.lo[d] + ranpark_uniform(seed) * (reg.hi[d] - reg.lo[d]);
-    start[d] = c[d];
-  }
-
-  double *mypath = path + (size_t) t * (u.natt + 1) * 3;
-  int i = 0, np = 0;
-  if (list) {
-    // Re-run of a trial whose neighbourhood changed: everything before the first affected
-    // evaluation point is unchanged, so resume there (the state at the top of iteration k is
-    // exactly (path[k], i = k)).
-    i = np = kfirst[t];
-    c[0] = mypath[3 * i];
-    c[1] = mypath[3 * i + 1];
-    c[2] = mypath[3 * i + 2];
-  }
-  double E = 0.0, f[3];
-  int gx = -1 << 30, gy = 0, gz = 0, nc = 0;  // cell whose stencil is in the candidate arrays
-  // single type: the three pair coefficients the evaluation needs, read once
-  const double k1[3] = {pt.a0[fd.ntype][fd.ntype], pt.cut[fd.ntype][fd.ntype], pt.cutsq[fd.ntype][fd.ntype]};
-  bool wrap = true;  // does the gathered stencil touch a periodic face?
-  while (i < u.natt) {
-    // the point is inside the insertion region, hence inside the box: the cell index is at most one
-    // period off (y == yhi exactly), so the wrap needs no division
-    const int cx = cell_cx(g, c[0]);
-    int cy = (int) floor((c[1] - g.lo[1]) * g.inv[1]), cz = (int) floor((c[2] - g.lo[2]) * g.inv[2]);
-    if (cy < 0 || cy >= 2 * g.ny) cy = cell_wrap(cy, g.ny);
-    else if (cy >= g.ny) cy -= g.ny;
-    if (cz < 0 || cz >= 2 * g.nz) cz = cell_wrap(cz, g.nz);
-    else if (cz >= g.nz) cz -= g.nz;
-    if (cx != gx || cy != gy || cz != gz) {
-      nc = usher_gather(cx, cy, cz, t, p, g, fd, cell_start, u, acc_list, prev, ex, extra_head, extra_next,
-                        spec_head, spec_next, hits[w], sc);
-      gx = cx; gy = cy; gz = cz;
-      wrap = g.ny < 6 || g.nz < 6 || cy == 0 || cy == g.ny - 1 || cz == 0 || cz == g.nz - 1;
-    }
-    usher_energy<ST>(c, nc, wrap, k1, g, pt, fd, hits[w], sc, E, f);
-    if (lane == 0) {
-      mypath[np * 3 + 0] = c[0];
-      mypath[np * 3 + 1] = c[1];
-      mypath[np * 3 + 2] = c[2];
-    }
-    np++;
-    if (E < fd.etarget + EPSILON_FIX) break;
-    double fabs_ = sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
-    if (fabs_ < EPSILON_FIX) {  // the reference `continue`s without progress: report it
-      if (lane == 0) sc->usher_error = OBMD_ERR_USHER;
-      break;
-    }
-    double ds;
-    if (E > fd.uovlp) ds = fd.dsovlp - pow(4 * fd.eps / E, 1.0 / 12.0);
-    else ds = fmin((E - fd.etarget) / fabs_, fd.ds0);
-    c[0] += f[0] / fabs_ * ds;
-    c[1] += f[1] / fabs_ * ds;
-    c[2] += f[2] / fabs_ * ds;
-    if (!block_inside(reg, c[0], c[1], c[2])) break;  // check_mol_region (:1700-1712)
-    i += 1;
-  }
-  bool ok = (E < fd.etarget + EPSILON_FIX);
-  // check_mol_proc / check_proc (:1645-1696) on the owning rank: half-open box in x,y; the top z
-  // face belongs to the last processor
-  if (ok) {
-    bool in = c[0] >= fd.boxlo[0] && c[0] < fd.boxhi[0] && c[1] >= fd.boxlo[1] && c[1] < fd.boxhi[1] &&
-        c[2] >= fd.boxlo[2];
-    if (!in) ok = false;
-  }
-  if (ok && !block_inside(reg, c[0], c[1], c[2])) ok = false;  // :1107-1108
-  if (lane == 0) {
-    obmd_trial r;
-    for (int d = 0; d < 3; d++) {
-      r.start[d] = start[d];
-      r.end[d] = c[d];
-    }
-    r.energy = E;
-    r.iter = i;
-    r.accepted = ok ? 1 : 0;
-    r.side = side;
-    r.tag = 0;
-    cur[t] = r;
-    npts[t] = np;
-  }
-  // bounding box of the evaluated points (prefilter of the dirty test of the next round): all lanes
-  // read the path (the prefix a re-run kept included) and reduce
-  __syncwarp();
-  double blo[3] = {1e300, 1e300, 1e300}, bhi[3] = {-1e300, -1e300, -1e300};
-  for (int k = lane; k < np; k += 32)
-    for (int d = 0; d < 3; d++) {
-      const double v = mypath[3 * k + d];
-      blo[d] = fmin(blo[d], v);
-      bhi[d] = fmax(bhi[d], v);
-    }
-  for (int d = 0; d < 3; d++)
-    for (int o = 16; o > 0; o >>= 1) {
-      blo[d] = fmin(blo[d], __shfl_xor_sync(0xffffffffu, blo[d], o));
-      bhi[d] = fmax(bhi[d], __shfl_xor_sync(0xffffffffu, bhi[d], o));
-    }
-  if (lane == 0)
-    for (int d = 0; d < 3; d++) {
-      bbox[(size_t) t * 6 + d] = blo[d];
-      bbox[(size_t) t * 6 + 3 + d] = bhi[d];
-    }
-}
-
-// One warp per trial.  Round 0 evaluates every trial (list == nullptr, nlist from the host); the
-// re-run rounds take the list and its length from device memory (ndirty2[par], written by the
-// previous round's k_usher_dirty), so that rounds can be enqueued back to back without a host
-// round trip; a round with nothing to do costs an empty grid.
-template <bool ST>
-__global__ void __launch_bounds__(USH_WARPS * 32, USH_BLOCKS_PER_SM)
-    k_usher_eval(const int *__restrict__ list, int nlist, int par, Planes p, Grid g, PairTab pt, FixDev fd,
-                 const int *__restrict__ cell_start, UsherCfg u, Extras ex,
-                 const int *__restrict__ extra_head, const int *__restrict__ extra_next,
-                 const int *__restrict__ spec_head, const int *__restrict__ spec_next,
-                 const int *__restrict__ acc_list, const obmd_trial *__restrict__ prev,
-                 obmd_trial *__restrict__ cur,
-                 double *__restrict__ path, int *__restrict__ npts, double *__restrict__ bbox,
-                 const int *__restrict__ kfirst, StepScalars *sc)
-{
-  __shared__ WarpHits hits[USH_WARPS];
-  const int nl = list ? sc->ndirty2[par] : nlist;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && nl > 0) sc->nrounds_work++;
-  // Trials are handed out one at a time from a device counter: their lengths differ widely (a trial
-  // that leaves its region stops at once, most run all nattempt iterations), and with more trials
-  // than resident warps a static assignment would cost a whole second wave.
-  for (;;) {
-    int li = 0;
-    if ((threadIdx.x & 31) == 0) li = atomicAdd(&sc->trial_cursor, 1);
-    li = __shfl_sync(0xffffffffu, li, 0);
-    if (li >= nl) break;
-    usher_trial<ST>(li, hits, list, p, g, pt, fd, cell_start, u, ex, extra_head, extra_next, spec_head, spec_next,
-                acc_list, prev, cur, path, npts, bbox, kfirst, sc);
-  }
-}
-
-// the trials whose state (accepted, end) differs between the two latest rounds, as compact records
-__global__ void k_usher_diff(obmd_trial *__restrict__ prev, const obmd_trial *__restrict__ cur,
-                             int ntr, int first_round, int par, int limit, ChgRec *__restrict__ chg,
-                             StepScalars *sc)
-{
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ntr) return;
-  const obmd_trial &b = cur[t];
-  // maxattempt > 1: only the attempts the serial loop actually makes (t < nused) can insert
-  const int newacc = b.accepted && (!limit || t < sc->nused);
-  int ch, oldacc = 0;
-  if (first_round) ch = newacc;
-  else {
-    const obmd_trial &a = prev[t];
-    oldacc = a.accepted && (!limit || t < sc->nused_prev);
-    ch = (oldacc != newacc) ||
-        (newacc && (a.end[0] != b.end[0] || a.end[1] != b.end[1] || a.end[2] != b.end[2]));
-  }
-  if (ch) {
-    ChgRec r;
-    for (int d = 0; d < 3; d++) {
-      r.o[d] = oldacc ? prev[t].end[d] : 0.0;
-      r.n[d] = b.end[d];
-    }
-    r.q = t;
-    r.flags = (oldacc ? 1 : 0) | (newacc ? 2 : 0);
-    chg[atomicAdd(&sc->nchg2[par], 1)] = r;
-  }
-  // prev <- cur: the next round's evaluations read the positions of the atoms accepted so far from
-  // prev, and nothing else reads prev[t] after this point of the round
-  prev[t] = b;
-}
-
-// all points involved lie inside the box, so one periodic shift suffices
-__device__ __forceinline__ bool near_pt(const double *a, const double *b, const Grid &g, double rsqmax)
-{
-  double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
-  if (dy > g.half[1]) dy -= g.prd[1];
-  else if (dy < -g.half[1]) dy += g.prd[1];
-  if (dz > g.half[2]) dz -= g.prd[2];
-  else if (dz < -g.half[2]) dz += g.prd[2];
-  return dx * dx + dy * dy + dz * dz <= rsqmax;
-}
-
-// is coordinate v (or a periodic image) within rc of the interval [lo, hi]?
-__device__ __forceinline__ bool axis_near(double v, double lo, double hi, double rc, double L, bool periodic)
-{
-  lo -= rc;
-  hi += rc;
-  if (v >= lo && v <= hi) return true;
-  if (!periodic) return false;
-  return (v + L >= lo && v + L <= hi) || (v - L >= lo && v - L <= hi);
-}
-
-__device__ __forceinline__ bool near_bbox(const double *a, const double *bb, const Grid &g, double rc)
-{
-  return axis_near(a[0], bb[0], bb[3], rc, 0.0, false) && axis_near(a[1], bb[1], bb[4], rc, g.prd[1], true) &&
-      axis_near(a[2], bb[2], bb[5], rc, g.prd[2], true);
-}
-
-// A trial must be re-run when an earlier trial whose state changed has its old or new atom
-// within the cutoff of any point the trial evaluated (a superset test with a small margin).
-// kfirst[t] = index of the first such point: the re-run resumes there.
-__global__ void k_usher_dirty(int ntr, int par, const ChgRec *__restrict__ chg,
-                              const double *__restrict__ path, const int *__restrict__ npts,
-                              const double *__restrict__ bbox, int natt, Grid g, double rc, double rsqmax,
-                              int *__restrict__ list, int *__restrict__ kfirst, StepScalars *sc)
-{
-  int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  int lane = threadIdx.x & 31;
-  if (t >= ntr) return;
-  const double *mp = path + (size_t) t * (natt + 1) * 3;
-  const double *bb = bbox + (size_t) t * 6;
-  const int np = npts[t], nchg = sc->nchg2[par];
-  int kf = np;  // first affected point found so far
-  if (nchg == 0) return;
-  // lanes prefilter 32 change records at a time against the trial's bounding box; every record that
-  // passes is then tested against all evaluated points by the whole warp (points are read coalesced)
-  for (int q0 = 0; q0 < nchg; q0 += 32) {
-    const int qi = q0 + lane;
-    ChgRec r;
-    r.flags = 0;
-    r.q = 1 << 30;
-    if (qi < nchg) r = chg[qi];
-    const bool oldacc = r.q < t && (r.flags & 1) && near_bbox(r.o, bb, g, rc);
-    const bool newacc = r.q < t && (r.flags & 2) && near_bbox(r.n, bb, g, rc);
-    unsigned m = __ballot_sync(0xffffffffu, oldacc || newacc);
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1u;
-      double o[3], n[3];
-      for (int d = 0; d < 3; d++) {
-        o[d] = __shfl_sync(0xffffffffu, r.o[d], src);
-        n[d] = __shfl_sync(0xffffffffu, r.n[d], src);
-      }
-      const bool oa = __shfl_sync(0xffffffffu, (int) oldacc, src) != 0;
-      const bool na = __shfl_sync(0xffffffffu, (int) newacc, src) != 0;
-      for (int k0 = 0; k0 < kf; k0 += 32) {  // kf stays warp-uniform: it is only set from ballots
-        const int k = k0 + lane;
-        const bool hit = k < kf && ((oa && near_pt(o, mp + 3 * k, g, rsqmax)) ||
-                                    (na && near_pt(n, mp + 3 * k, g, rsqmax)));
-        const unsigned hm = __ballot_sync(0xffffffffu, hit);
-        if (hm) {
-          kf = k0 + __ffs(hm) - 1;
-          break;
-        }
-      }
-    }
-  }
-  if (kf < np && lane == 0) {
-    kfirst[t] = kf;
-    list[atomicAdd(&sc->ndirty2[par], 1)] = t;
-  }
-}
-
-// maxattempt > 1 (:912-1172): insertion slot k draws attempts from the RNG stream until one is
-// accepted or maxattempt have failed, then slot k+1 continues where it stopped.  Given the accept
-// flag of every possible attempt, the attempts actually made are a prefix of the stream: a slot
-// boundary sits behind every accepted attempt and behind every maxattempt-th consecutive failure.
-// nused = index of the slots-th boundary + 1.  One CTA, chunked scans.
-__global__ void __launch_bounds__(1024)
-    k_usher_resolve(const obmd_trial *__restrict__ cur, int ntr, int slots, int M, StepScalars *sc)
-{
-  __shared__ int s_last[1024], s_cnt[1024];
-  const int tid = threadIdx.x, per = (ntr + 1023) / 1024, b = tid * per, e = min(b + per, ntr);
-  int last = -1;
-  for (int a = b; a < e; a++)
-    if (cur[a].accepted) last = a;
-  s_last[tid] = last;
-  __syncthreads();
-  if (tid == 0) {  // exclusive running maximum over the chunks
-    int run = -1;
-    for (int k = 0; k < 1024; k++) {
-      const int v = s_last[k];
-      s_last[k] = run;
-      run = max(run, v);
-    }
-  }
-  __syncthreads();
-  int la = s_last[tid], nb = 0;
-  for (int a = b; a < e; a++) {
-    const bool acc = cur[a].accepted != 0;
-    nb += (acc || ((a - la) % M == 0)) ? 1 : 0;
-    if (acc) la = a;
-  }
-  s_cnt[tid] = nb;
-  __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int k = 0; k < 1024; k++) {
-      const int v = s_cnt[k];
-      s_cnt[k] = run;
-      run += v;
-    }
-    if (run < slots) sc->nused = ntr;  // cannot happen for ntr == slots * M; keep the state sane
-  }
-  __syncthreads();
-  int c0 = s_cnt[tid];
-  if (c0 < slots && c0 + nb >= slots) {
-    la = s_last[tid];
-    for (int a = b; a < e; a++) {
-      const bool acc = cur[a].accepted != 0;
-      if (acc || ((a - la) % M == 0)) {
-        if (++c0 == slots) {
-          sc->nused = a + 1;
-          break;
-        }
-      }
-      if (acc) la = a;
-    }
-  }
-}
-
-// End of a commit round, one CTA: drops the previous round's per-cell "spec" lists, compacts the
-// accepted trials in order into acc_list, threads them into fresh per-cell lists (what the next round's evaluations see of earlier insertions),
-// and zeroes the counters of the next round.  Deterministic: lists are ordered by trial index.
-#define URE_T 1024  // 32 warps: the block scan in k_usher_round_end relies on it
-__global__ void __launch_bounds__(URE_T)
-    k_usher_round_end(const obmd_trial *__restrict__ cur, int ntr, int par, int first_round, int limit,
-                      int *__restrict__ acc_list, int *__restrict__ spec_cell, int *__restrict__ spec_head,
-                      int *__restrict__ spec_next, Grid g, StepScalars *sc)
-{
-  extern __shared__ int cellsh[];  // cells of the accepted trials (at most LINK_MAX)
-  __shared__ int base;
-  __shared__ int wsum[URE_T / 32];
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int nold = sc->naccept;
-  const int nlim = limit ? sc->nused : ntr;  // maxattempt > 1: attempts beyond nused are never made
-  if (!first_round && sc->nchg2[par] == 0) {
-    // nothing changed in this round (a round enqueued ahead of need): the accepted list and its
-    // per-cell lists are still those of the previous round
-    if (tid == 0) {
-      sc->nchg2[par ^ 1] = 0;
-      sc->ndirty2[par ^ 1] = 0;
-      sc->trial_cursor = 0;
-      sc->nused_prev = sc->nused;
-    }
-    return;
-  }
-  for (int k = tid; k < nold; k += URE_T) spec_head[spec_cell[k]] = -1;
-  // ordered compaction of the accepted trials: every thread owns a contiguous run of trials, counts
-  // its accepted ones, a block scan of the counts gives its offset (three barriers in all)
-  const int per = (nlim + URE_T - 1) / URE_T, tb = tid * per, te = min(tb + per, nlim);
-  int cnt = 0;
-  for (int t = tb; t < te; t++) cnt += cur[t].accepted ? 1 : 0;
-  int inc = cnt;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc += v;
-  }
-  if (lane == 31) wsum[w] = inc;
-  __syncthreads();
-  if (w == 0) {
-    int v = wsum[lane];  // URE_T / 32 == 32 warps
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int u2 = __shfl_up_sync(0xffffffffu, v, d);
-      if (lane >= d) v += u2;
-    }
-    wsum[lane] = v;  // inclusive over warps
-    if (lane == 31) base = v;
-  }
-  __syncthreads();
-  {
-    int off = inc - cnt + (w > 0 ? wsum[w - 1] : 0);
-    for (int t = tb; t < te; t++)
-      if (cur[t].accepted) acc_list[off++] = t;
-  }
-  __syncthreads();  // acc_list is read by other threads below
-  const int nacc = base;
-  if (nacc > LINK_MAX) {
-    if (tid == 0) {
-      sc->usher_error = OBMD_ERR_CAPACITY + 1000;  // reported as "too many insertions in one call"
-      sc->naccept = 0;
-    }
-    return;
-  }
-  for (int k = tid; k < nacc; k += URE_T) {
-    const obmd_trial &r = cur[acc_list[k]];
-    const int lc = min(max(cell_cx(g, r.end[0]), 0), g.nx - 1);
-    const int cc = (lc * g.ny + cell_cy(g, r.end[1])) * g.nz + cell_cz(g, r.end[2]);
-    cellsh[k] = cc;
-    spec_cell[k] = cc;
-  }
-  __syncthreads();
-  for (int k = tid; k < nacc; k += URE_T) {
-    const int cc = cellsh[k];
-    int nxt = -1;
-    for (int q = k + 1; q < nacc; q++)
-      if (cellsh[q] == cc) {
-        nxt = q;
-        break;
-      }
-    spec_next[k] = nxt;
-    bool is_first = true;
-    for (int q = 0; q < k; q++)
-      if (cellsh[q] == cc) {
-        is_first = false;
-        break;
-      }
-    if (is_first) spec_head[cc] = k;
-  }
-  if (tid == 0) {
-    sc->naccept = nacc;
-    sc->nchg2[par ^ 1] = 0;
-    sc->ndirty2[par ^ 1] = 0;
-    sc->trial_cursor = 0;
-    sc->nused_prev = sc->nused;
-  }
-}
-
-// create_atom + tag/mask/image/v assignment (:1121-1150, atom_vec.cpp:1592-1612), appended after
-// every other extra atom; the new atoms are then threaded into the per-cell lists the pair kernel
-// walks (fix_link_extras).
-__global__ void k_usher_commit(Planes p, Extras ex, int tag0, Grid g, FixDev fd,
-                               obmd_trial *__restrict__ cur, const int *__restrict__ acc_list, int nacc,
-                               double *fx, double *fy, double *fz)
-{
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < nacc) {
-    obmd_trial &r = cur[acc_list[k]];
-    int s = ex.base + ex.narr + ex.nghost + ex.nins + k;  // ex.nins: atoms of an earlier pass
-    p.x[s] = r.end[0];
-    p.y[s] = r.end[1];
-    p.z[s] = r.end[2];
-    p.vx[s] = p.vy[s] = p.vz[s] = 0.0;
-    p.type[s] = fd.ntype;
-    p.tag[s] = tag0 + k + 1;
-    p.image[s] = IMG0;
-    p.lidx[s] = s;  // appended: local index == slot (serial runs: nlocal-after-deletion + k)
-    fx[s] = fy[s] = fz[s] = 0.0;
-    r.tag = tag0 + k + 1;
-  }
-}
 
 // cells of the extra atoms [first, first+count) (indices relative to the extras base)
 __global__ void k_extra_cells(Planes p, int base, int first, int count, Grid g, int *__restrict__ extra_cell)
@@ -1136,50 +407,6 @@ int fix_clear_extras(obmd_ctx *c)
 {
   if (c->nextra > 0)
     LAUNCH(k_extra_clear, cdiv(c->nextra, 128), 128, 0, c->extra_cell, c->nextra, c->extra_head);
-  return OBMD_OK;
-}
-
-// Device buffers of the USHER trials.  Regrowing them costs a dozen cudaFree/cudaMalloc pairs (each
-// an implicit device synchronisation) in the middle of a step, so they start at 16 Ki trials and
-// double; the pinned host copy of the trial records is only made when a caller asks for them.
-static int ensure_trials(obmd_ctx *c, int ntr, int natt)
-{
-  if (ntr <= c->tr_cap && natt <= c->tr_natt) return OBMD_OK;
-  int cap = c->tr_cap;
-  if (ntr > cap) {
-    cap = cap < 16384 ? 16384 : cap;
-    while (cap < ntr) cap *= 2;
-  }
-  int na = natt > c->tr_natt ? natt : c->tr_natt;
-  cudaFree(c->tr_d); cudaFree(c->tr_prev_d); cudaFree(c->tr_path); cudaFree(c->tr_npts);
-  cudaFree(c->tr_list); cudaFree(c->tr_changed); cudaFree(c->acc_list); cudaFree(c->tr_bbox);
-  CK(cudaMalloc(&c->tr_bbox, sizeof(double) * 6 * cap));
-  CK(cudaMalloc(&c->tr_d, sizeof(obmd_trial) * cap));
-  CK(cudaMalloc(&c->tr_prev_d, sizeof(obmd_trial) * cap));
-  CK(cudaMalloc(&c->tr_path, sizeof(double) * 3 * (size_t) cap * (na + 1)));
-  CK(cudaMalloc(&c->tr_npts, sizeof(int) * cap));
-  CK(cudaMalloc(&c->tr_list, sizeof(int) * cap));
-  CK(cudaMalloc(&c->tr_changed, sizeof(int) * 2 * cap));  // unused | kfirst
-  cudaFree(c->tr_chg);
-  CK(cudaMalloc(&c->tr_chg, sizeof(ChgRec) * cap));
-  CK(cudaMalloc(&c->acc_list, sizeof(int) * cap));
-  cudaFree(c->spec_next); cudaFree(c->spec_cell);
-  CK(cudaMalloc(&c->spec_next, sizeof(int) * cap));
-  CK(cudaMalloc(&c->spec_cell, sizeof(int) * cap));
-  c->tr_cap = cap;
-  c->tr_natt = na;
-  return OBMD_OK;
-}
-
-static int ensure_trials_host(obmd_ctx *c, int n)
-{
-  if (n <= c->tr_h_cap) return OBMD_OK;
-  if (c->tr_h) cudaFreeHost(c->tr_h);
-  c->tr_h = nullptr;
-  c->tr_h_cap = 0;
-  int cap = n < 4096 ? 4096 : 2 * n;
-  CK(cudaMallocHost(&c->tr_h, sizeof(obmd_trial) * cap));
-  c->tr_h_cap = cap;
   return OBMD_OK;
 }
 
@@ -1534,7 +761,6 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
       const int limit = M > 1 ? 1 : 0;
       int nacc_p = 0, nused_p = ntr_p;
       if (ntr_loc > 0) {
-        if ((rc = ensure_trials(c, ntr_loc, fa.nattempt))) return rc;
         if ((rc = obmd_ensure_capacity(c, nlive + c->nextra + ntr_loc))) return rc;
         UsherCfg u;
         u.ntrL = ps.nL;
@@ -1545,79 +771,11 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
         u.tg0 = doL ? 0 : ps.nL;
         u.slots = ps.slots;
         u.maxatt = M;
-        const Extras ex = extras_of(c);
-        const double rsqmax = c->pt.cutmax * c->pt.cutmax * (1.0 + 1e-9);
-        // nchg2, ndirty2, naccept, nrounds_work, trial_cursor, nused, nused_prev
-        CK(cudaMemsetAsync(&c->sc_d->nchg2[0], 0, 9 * sizeof(int), c->stream));
-        // Rounds are enqueued back to back: every count a round needs (how many trials to re-run, how
-        // many atoms were accepted so far) lives in device memory, and a round that finds nothing to
-        // do is a handful of empty launches.  The host looks at the counters only after a batch.
-        const int rerun_grid = ntr_loc < 4 * 2 * NSM ? cdiv(ntr_loc, USH_WARPS) : 2 * NSM;
-        auto enqueue_round = [&](int round) -> int {
-          const int par = round & 1;
-          ScopedTimer t2(c, round == 0 ? "usher_round0" : "usher_rerun");
-          {
-          ScopedTimer t5(c, round == 0 ? "usher_eval0" : "usher_evalN");
-          const int grid0 = ntr_loc < USH_BLOCKS_PER_SM * NSM * USH_WARPS ? cdiv(ntr_loc, USH_WARPS)
-                                                                          : USH_BLOCKS_PER_SM * NSM;
-#define USHER_EVAL(ST)                                                                                         \
-  do {                                                                                                         \
-    if (round == 0)                                                                                            \
-      LAUNCH(k_usher_eval<ST>, grid0, USH_WARPS * 32, 0, (const int *) nullptr, ntr_loc, 0, c->cur, c->grid,   \
-             c->pt, c->fd, c->cell_start, u, ex, c->extra_head, c->extra_next, c->spec_head, c->spec_next,     \
-             c->acc_list, c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts, c->tr_bbox, c->tr_changed + c->tr_cap, \
-             c->sc_d);                                                                                         \
-    else                                                                                                       \
-      LAUNCH(k_usher_eval<ST>, rerun_grid, USH_WARPS * 32, 0, (const int *) c->tr_list, 0, par ^ 1, c->cur,    \
-             c->grid, c->pt, c->fd, c->cell_start, u, ex, c->extra_head, c->extra_next, c->spec_head,          \
-             c->spec_next, c->acc_list, c->tr_prev_d, c->tr_d, c->tr_path, c->tr_npts, c->tr_bbox,             \
-             c->tr_changed + c->tr_cap, c->sc_d);                                                              \
-  } while (0)
-          if (c->ntypes == 1) USHER_EVAL(true);
-          else USHER_EVAL(false);
-          }
-          // Round 0 fills the machine (one warp per trial); the re-run rounds are a handful of CTAs.
-          // obmd_run hooks in here to start the pair kernel on the side stream right behind round 0.
-          if (round == 0 && c->round0_hook) {
-            int (*hook)(obmd_ctx *) = c->round0_hook;
-            c->round0_hook = nullptr;
-            int hrc = hook(c);
-            if (hrc) return hrc;
-          }
-          if (limit) LAUNCH(k_usher_resolve, 1, 1024, 0, c->tr_d, ntr_loc, u.slots, M, c->sc_d);
-          LAUNCH(k_usher_diff, cdiv(ntr_loc, 256), 256, 0, c->tr_prev_d, c->tr_d, ntr_loc, round == 0 ? 1 : 0,
-                 par, limit, c->tr_chg, c->sc_d);
-          LAUNCH(k_usher_dirty, cdiv(ntr_loc, 4), 128, 0, ntr_loc, par, c->tr_chg, c->tr_path, c->tr_npts,
-                 c->tr_bbox, u.natt, c->grid, c->pt.cutmax * (1.0 + 1e-9), rsqmax, c->tr_list,
-                 c->tr_changed + c->tr_cap, c->sc_d);
-          LAUNCH(k_usher_round_end, 1, URE_T, sizeof(int) * LINK_MAX, c->tr_d, ntr_loc, par, round == 0 ? 1 : 0,
-                 limit, c->acc_list, c->spec_cell, c->spec_head, c->spec_next, c->grid, c->sc_d);
-          return OBMD_OK;
-        };
-        int round = 0;  // rounds enqueued so far
-        int batch = 4;  // 3.3 rounds on average at 1 M atoms: one host round trip per call in ~90 % of the calls
-        for (;;) {
-          NEED(round <= ntr_loc + 1, OBMD_ERR_STATE, "fix obmd: USHER commit did not converge");
-          for (int k = 0; k < batch; k++, round++)
-            if ((rc = enqueue_round(round))) return rc;
-          batch = 1;
-          if ((rc = read_scalars(c))) return rc;
-          NEED(c->sc_h->usher_error != OBMD_ERR_USHER, OBMD_ERR_USHER,
-               "fix obmd: USHER force vanished with E above target (the reference would not terminate)");
-          NEED(c->sc_h->usher_error != OBMD_ERR_CAPACITY, OBMD_ERR_CAPACITY,
-               "fix obmd: more than %d neighbours within the cutoff of a USHER point (or %d atoms in its "
-               "stencil)", USH_CAP, USH_CAND);
-          NEED(c->sc_h->usher_error != OBMD_ERR_CAPACITY + 1000, OBMD_ERR_CAPACITY,
-               "more than %d insertions in one call", LINK_MAX);
-          nacc_p = c->sc_h->naccept;
-          const int par = (round - 1) & 1;
-          if (c->sc_h->nchg2[par] == 0 || c->sc_h->ndirty2[par] == 0) break;
-        }
-        if (limit) nused_p = c->sc_h->nused;
-        // the spec lists of the last round are no longer needed
-        if (nacc_p > 0)
-          LAUNCH(k_extra_clear, cdiv(nacc_p, 128), 128, 0, c->spec_cell, nacc_p, c->spec_head);
-        rounds += c->sc_h->nrounds_work;
+        // round 0, the first diff / dirty test and the fix-up kernel that runs every re-run round are
+        // enqueued back to back; the outcome is read back once (usher.cu)
+        int rounds_p = 0;
+        if ((rc = usher_pass(c, u, ntr_loc, limit, &nacc_p, &nused_p, &rounds_p))) return rc;
+        rounds += rounds_p;
       }
 
       if (npass == 1) {
@@ -1644,17 +802,13 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
         ScopedTimer t4(c, "usher_commit");
         if (c->commit_wait) CK(cudaStreamWaitEvent(c->stream, c->commit_wait, 0));
         const int tag0 = maxtag + nacc + ((npass == 1 && doR && !doL) ? naccL : 0);
-        LAUNCH(k_usher_commit, cdiv(nacc_p, 128), 128, 0, c->cur, extras_of(c), tag0, c->grid, c->fd, c->tr_d,
-               c->acc_list, nacc_p, c->fx, c->fy, c->fz);
+        if ((rc = usher_commit(c, tag0, nacc_p))) return rc;
         if ((rc = fix_link_extras(c, c->narr + c->nghost + c->nins, nacc_p, false))) return rc;
       }
       if (trials && maxtrials > ncopied && ntr_loc > 0) {
         const int nloc_used = limit ? nused_p : ntr_loc;
         const int ncopy = nloc_used < maxtrials - ncopied ? nloc_used : maxtrials - ncopied;
-        if ((rc = ensure_trials_host(c, ncopy))) return rc;
-        CK(cudaMemcpyAsync(c->tr_h, c->tr_d, sizeof(obmd_trial) * ncopy, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        memcpy(trials + ncopied, c->tr_h, sizeof(obmd_trial) * ncopy);
+        if ((rc = usher_trials_to_host(c, trials + ncopied, ncopy))) return rc;
         ncopied += ncopy;
       }
       // the next pass sees this pass's atoms as appended atoms (per-cell lists, local indices)

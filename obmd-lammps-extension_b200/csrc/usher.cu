@@ -1,0 +1,1012 @@
+// Batched USHER on the device: try_inserting (fix_obmd_merged.cpp:869-1225), usher (:1518-1616),
+// energy (:1774-1810), PairDPD::single (pair_dpd.cpp:401-418).  Compiled with -fmad=false: every
+// sum, product and quotient that reaches a trial coordinate is evaluated exactly as the x86-64
+// reference build evaluates it (no FMA contraction, IEEE sqrt and division, contributions summed
+// in ascending LAMMPS local index).
+//
+// The reference inserts serially: trial t sees the atoms accepted by trials < t.  Here
+//   round 0   k_usher_eval evaluates every trial of the call speculatively against the
+//             pre-insertion configuration, one lane group (8, 16 or 32 lanes) per trial;
+//   k_usher_diff / k_usher_dirty find the trials whose evaluation points lie within the cutoff of an
+//             atom accepted by an earlier trial;
+//   k_usher_fix (one thread-block cluster, no host round trips) re-runs those trials from the first
+//             affected point, with the accepted atoms visible through per-cell lists, and repeats
+//             diff -> dirty -> re-run until nothing changes.  Trial t depends only on trials < t, so
+//             the fixed point equals the serial result bit for bit.
+//
+// One energy evaluation: the group keeps an fp32 copy (relative to the corner of the point's cell,
+// periodic image already chosen) of the atoms of the 27 surrounding cells in shared memory and
+// refreshes it only when the point changes cell.  Candidates are screened in fp32 against a widened
+// cutoff (a superset of the exact test), the few survivors are evaluated in fp64 with the
+// reference's expressions (minimum-image loop, exact cutoff test, sqrt, division), ranked by local
+// index and summed left to right by one lane per quantity.
+#include <cooperative_groups.h>
+
+#include "ctx.h"
+
+namespace cg = cooperative_groups;
+
+#define EPSILON_FIX 1.0e-6   // fix_obmd_merged.cpp:62
+#define EPSILON_DPD 1.0e-10  // pair_dpd.cpp:36
+
+#define USH_CAND 144  // atoms in the 27 stencil cells of a point (mean 81 at rho = 3)
+#define USH_CAP 48    // fp32-screened neighbours of a point (mean 13 at rho = 3)
+#define USH_T 128     // threads per CTA of the round-0 kernel
+#define FIX_CL 8      // CTAs in the cluster of the fix-up kernel
+#define FIX_T 512     // threads per CTA there (one warp per re-run trial: 128 trials at a time)
+#define KEY_DROP 0x7fffff00  // keys of screened candidates that fail the exact cutoff test (+ slot)
+
+// per lane group: the stencil of the cell the point is in, and the scratch of one energy evaluation
+struct __align__(16) UGroup {
+  uint4 scr[USH_CAND];  // x, y, z (fp32 bits, relative to the cell corner), w = slot (>= 0) or -(entry + 1)
+  double e[USH_CAP], fx[USH_CAP], fy[USH_CAP], fz[USH_CAP];
+  int key[USH_CAP];              // LAMMPS local index of the contributing atom
+  unsigned short hq[USH_CAP];    // candidate index of each screened neighbour
+  unsigned char inv[USH_CAP];    // inv[rank by key] = position in the arrays above
+};
+
+struct UsherArgs {
+  Planes p;
+  Grid g;
+  FixDev fd;
+  UsherCfg u;
+  Extras ex;
+  const int *cell_start, *extra_head, *extra_next;
+  // atoms accepted so far in this call ("spec" entries, append-only; a dead entry has trial INT_MAX)
+  int *spec_head, *spec_next, *spec_cell, *spec_trial, *spec_of_trial;
+  double *spec_pos;
+  int spec_cap;
+  obmd_trial *cur;
+  double *path;
+  int *npts;
+  float *bbox;
+  int *kfirst, *list;
+  ChgRec *chg;
+  int *acc_list;
+  StepScalars *sc;
+  int ntr, limit;
+  double rc, rsqmax;  // dirty test: cutoff with a small margin
+};
+
+__device__ __forceinline__ int ranpark_pow(long long n)
+{
+  unsigned long long m = 2147483647ULL, a = 16807ULL, r = 1ULL;
+  while (n > 0) {
+    if (n & 1) r = (r * a) % m;
+    a = (a * a) % m;
+    n >>= 1;
+  }
+  return (int) r;
+}
+
+__device__ __forceinline__ double ranpark_uniform(int &seed)  // random_park.cpp:43-50
+{
+  int k = seed / 127773;
+  seed = 16807 * (seed - k * 127773) - 2836 * k;
+  if (seed < 0) seed += 2147483647;
+  return (1.0 / 2147483647) * seed;
+}
+
+// PairDPD::single (pair_dpd.cpp:401-418, factor_dpd = 1) and fpair*del (:1801-1805)
+__device__ __forceinline__ void usher_single(double a0, double cut, double rsq, double &e, double &fx,
+                                             double &fy, double &fz)
+{
+  double r = sqrt(rsq);
+  double fforce, phi;
+  if (r < EPSILON_DPD) {
+    fforce = 0.0;
+    phi = 0.0;
+  } else {
+    double rinv = 1.0 / r;
+    double wd = 1.0 - (cut == 1.0 ? r : r / cut);  // r / 1.0 == r exactly: skip the division
+    fforce = a0 * wd * 1.0 * rinv;
+    phi = 0.5 * a0 * cut * wd * wd;
+    phi = 1.0 * phi;
+  }
+  e = phi;
+  fx = fforce * fx;
+  fy = fforce * fy;
+  fz = fforce * fz;
+}
+
+// ---- stencil gather -------------------------------------------------------------------------------
+// The lanes of a group own the 27 cells around (cx, cy, cz): cell ranges of the sorted atoms, the
+// atoms appended after the sort (slab runs, earlier passes) and the atoms accepted earlier in this
+// call by trials < t.  A group scan turns the counts into a flat candidate list (slot codes first,
+// then one balanced pass loads the coordinates and stores the fp32 screening copy).
+template <int G>
+__device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroup &S, int cx, int cy, int cz, int t,
+                                            double ox, double oy, double oz, int gl, unsigned gmask,
+                                            bool have_extras, bool have_spec)
+{
+  constexpr int NCL = (27 + G - 1) / G;
+  const Grid &g = A.g;
+  int jb[NCL], cnt[NCL], cc[NCL], oyz[NCL];
+  int tot = 0;
+#pragma unroll
+  for (int s = 0; s < NCL; s++) {
+    const int n = gl + s * G;
+    cc[s] = -1;
+    jb[s] = 0;
+    cnt[s] = 0;
+    oyz[s] = 0;
+    if (n < 27) {
+      const int a = (n * 11) >> 5;  // n / 3 for n < 32
+      const int oz_ = n - 3 * a - 1;
+      const int b = (a * 11) >> 5;  // n / 9
+      const int oy_ = a - 3 * b - 1, ox_ = b - 1;
+      const int bx = cx + ox_;
+      if (bx >= 0 && bx < g.nx) {
+        int by = cy + oy_, bz = cz + oz_;  // offsets are +-1: wrap without a division
+        by = by < 0 ? by + g.ny : (by >= g.ny ? by - g.ny : by);
+        bz = bz < 0 ? bz + g.nz : (bz >= g.nz ? bz - g.nz : bz);
+        const int c2 = (bx * g.ny + by) * g.nz + bz;
+        cc[s] = c2;
+        jb[s] = __ldg(A.cell_start + c2);
+        cnt[s] = __ldg(A.cell_start + c2 + 1) - jb[s];
+        oyz[s] = (oy_ + 1) | ((oz_ + 1) << 2);
+        tot += cnt[s];
+        if (have_extras)
+          for (int e = __ldg(A.extra_head + c2); e >= 0; e = __ldg(A.extra_next + e)) tot++;
+        if (have_spec)
+          for (int e = __ldcg(A.spec_head + c2); e >= 0; e = __ldcg(A.spec_next + e))
+            tot += (__ldcg(A.spec_trial + e) < t) ? 1 : 0;
+      }
+    }
+  }
+  int inc = tot;
+#pragma unroll
+  for (int d = 1; d < G; d <<= 1) {
+    const int v = __shfl_up_sync(gmask, inc, d, G);
+    if (gl >= d) inc += v;
+  }
+  const int ncand = __shfl_sync(gmask, inc, G - 1, G);
+  if (ncand > USH_CAND) {
+    if (gl == 0) A.sc->usher_error = OBMD_ERR_CAPACITY;
+    return 0;
+  }
+  int off = inc - tot;  // exclusive
+  int2 *codes = reinterpret_cast<int2 *>(S.scr);  // candidate q: {slot code, (oy+1) | (oz+1) << 2} in .z/.w
+#pragma unroll
+  for (int s = 0; s < NCL; s++) {
+    if (cc[s] < 0) continue;
+    for (int k = 0; k < cnt[s]; k++) codes[2 * (off++) + 1] = make_int2(jb[s] + k, oyz[s]);
+    if (have_extras)
+      for (int e = __ldg(A.extra_head + cc[s]); e >= 0; e = __ldg(A.extra_next + e))
+        codes[2 * (off++) + 1] = make_int2(A.ex.base + e, oyz[s]);
+    if (have_spec)
+      for (int e = __ldcg(A.spec_head + cc[s]); e >= 0; e = __ldcg(A.spec_next + e))
+        if (__ldcg(A.spec_trial + e) < t) codes[2 * (off++) + 1] = make_int2(-(e + 1), oyz[s]);
+  }
+  __syncwarp(gmask);
+  const float wy = (float) (g.prd[1] / g.ny), wz = (float) (g.prd[2] / g.nz);
+  const float py = (float) g.prd[1], pz = (float) g.prd[2];
+  const float ipy = 1.0f / py, ipz = 1.0f / pz;
+  for (int q = gl; q < ncand; q += G) {
+    const int2 cd = codes[2 * q + 1];
+    double xj, yj, zj;
+    if (cd.x >= 0) {
+      xj = __ldg(A.p.x + cd.x);
+      yj = __ldg(A.p.y + cd.x);
+      zj = __ldg(A.p.z + cd.x);
+    } else {  // accepted earlier in this call
+      const double *sp = A.spec_pos + 3 * (size_t) (-cd.x - 1);
+      xj = __ldcg(sp);
+      yj = __ldcg(sp + 1);
+      zj = __ldcg(sp + 2);
+    }
+    const float rx = (float) (xj - ox);
+    float ry = (float) (yj - oy), rz = (float) (zj - oz);
+    // periodic image next to the centre cell (also covers coordinates Domain::pbc has not wrapped
+    // yet): the candidate's cell is at offset o, its centre at (o + 0.5) cell widths
+    const float ty = ((float) (cd.y & 3) - 0.5f) * wy, tz = ((float) (cd.y >> 2) - 0.5f) * wz;
+    ry -= py * rintf((ry - ty) * ipy);
+    rz -= pz * rintf((rz - tz) * ipz);
+    S.scr[q] = make_uint4(__float_as_uint(rx), __float_as_uint(ry), __float_as_uint(rz), (unsigned) cd.x);
+  }
+  __syncwarp(gmask);
+  return ncand;
+}
+
+// ---- one energy evaluation (:1774-1810) -------------------------------------------------------------
+// Returns E and f in every lane of the group.
+template <bool ST, int G>
+__device__ __forceinline__ void usher_energy(const UsherArgs &A, const PairTab &pt, UGroup &S, const double c[3],
+                                             double ox, double oy, double oz, int nc, bool wrap,
+                                             const double k1[3], int gl, int gbase, unsigned gmask,
+                                             double &E, double f[3])
+{
+  constexpr unsigned GM = (G == 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+  const Grid &g = A.g;
+  const int it = A.fd.ntype;
+  // fp32 screen: a superset of the exact test (coordinates relative to the cell corner are below three
+  // cell widths, so the absolute error of rsq is ~1e-6; the margin is 1e-3)
+  const float px = (float) (c[0] - ox), py = (float) (c[1] - oy), pz = (float) (c[2] - oz);
+  const float cut32 = (float) pt.cutmax * (float) pt.cutmax * 1.001f;
+  int nh = 0;
+  for (int q0 = 0; q0 < nc; q0 += G) {
+    const int q = q0 + gl;
+    bool hit = false;
+    if (q < nc) {
+      const uint4 s = S.scr[q];
+      const float dx = px - __uint_as_float(s.x), dy = py - __uint_as_float(s.y), dz = pz - __uint_as_float(s.z);
+      hit = dx * dx + dy * dy + dz * dz < cut32;
+    }
+    const unsigned m = (__ballot_sync(gmask, hit) >> gbase) & GM;
+    if (hit) {
+      const int s2 = nh + __popc(m & ((1u << gl) - 1u));
+      if (s2 < USH_CAP) S.hq[s2] = (unsigned short) q;
+    }
+    nh += __popc(m);
+  }
+  if (nh > USH_CAP) {
+    if (gl == 0) A.sc->usher_error = OBMD_ERR_CAPACITY;
+    nh = USH_CAP;
+  }
+  __syncwarp(gmask);
+  // exact evaluation of the screened candidates: separation with the reference's minimum_image loop
+  // (domain.cpp:980-1008, y and z periodic; skipped when the stencil touches no periodic face, where
+  // it cannot change anything), exact cutoff test, PairDPD::single
+  for (int k = gl; k < nh; k += G) {
+    const int code = (int) S.scr[S.hq[k]].w;
+    double xj, yj, zj;
+    int key, tj = it;
+    if (code >= 0) {
+      xj = __ldg(A.p.x + code);
+      yj = __ldg(A.p.y + code);
+      zj = __ldg(A.p.z + code);
+      key = __ldg(A.p.lidx + code);
+      if (!ST) tj = __ldg(A.p.type + code);
+    } else {  // created earlier in this call: local index nbase + (rank among the accepted trials);
+              // the trial index orders the created atoms the same way
+      const int e = -code - 1;
+      const double *sp = A.spec_pos + 3 * (size_t) e;
+      xj = __ldcg(sp);
+      yj = __ldcg(sp + 1);
+      zj = __ldcg(sp + 2);
+      key = A.u.nbase + __ldcg(A.spec_trial + e);
+    }
+    double delx = c[0] - xj, dely = c[1] - yj, delz = c[2] - zj;
+    if (wrap) {
+      while (fabs(dely) > g.half[1]) {
+        if (dely < 0.0) dely += g.prd[1];
+        else dely -= g.prd[1];
+      }
+      while (fabs(delz) > g.half[2]) {
+        if (delz < 0.0) delz += g.prd[2];
+        else delz -= g.prd[2];
+      }
+    }
+    const double rsq = delx * delx + dely * dely + delz * delz;
+    double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+    if (rsq < (ST ? k1[2] : pt.cutsq[it][tj])) {
+      fx = delx;
+      fy = dely;
+      fz = delz;
+      if (ST) usher_single(k1[0], k1[1], rsq, e, fx, fy, fz);
+      else usher_single(pt.a0[it][tj], pt.cut[it][tj], rsq, e, fx, fy, fz);
+    } else
+      key = KEY_DROP + k;  // outside the exact cutoff: contributes +0.0 behind every real term
+    S.key[k] = key;
+    S.e[k] = e;
+    S.fx[k] = fx;
+    S.fy[k] = fy;
+    S.fz[k] = fz;
+  }
+  __syncwarp(gmask);
+  // rank by local index (keys are distinct), then left-to-right sums in ascending local index, one
+  // lane per quantity -- the reference's loop order (:1790-1807)
+  for (int k = gl; k < nh; k += G) {
+    const int key = S.key[k];
+    int r = 0;
+    for (int k2 = 0; k2 < nh; k2++) r += (S.key[k2] < key) ? 1 : 0;
+    S.inv[r] = (unsigned char) k;
+  }
+  __syncwarp(gmask);
+  double acc = 0.0;
+  if (gl < 4) {
+    const double *arr = gl == 0 ? S.e : (gl == 1 ? S.fx : (gl == 2 ? S.fy : S.fz));
+    int r = 0;
+    for (; r + 4 <= nh; r += 4) {
+      const double a0 = arr[S.inv[r]], a1 = arr[S.inv[r + 1]], a2 = arr[S.inv[r + 2]], a3 = arr[S.inv[r + 3]];
+      acc += a0;
+      acc += a1;
+      acc += a2;
+      acc += a3;
+    }
+    for (; r < nh; r++) acc += arr[S.inv[r]];
+  }
+  E = __shfl_sync(gmask, acc, 0, G);
+  f[0] = __shfl_sync(gmask, acc, 1, G);
+  f[1] = __shfl_sync(gmask, acc, 2, G);
+  f[2] = __shfl_sync(gmask, acc, 3, G);
+}
+
+// ---- trials ------------------------------------------------------------------------------------
+// Every group of G lanes runs whole trials.  `list` == nullptr: trial li is li (round 0, handed out
+// from a device counter because trial lengths differ widely); otherwise the trials of `list` are
+// re-run from their first affected evaluation point (static assignment: group first, first + stride ...).
+template <bool ST, int G>
+__device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &pt, UGroup *groups,
+                                             const int *list, int nl, int *cursor, int first, int stride)
+{
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1), gbase = lane & ~(G - 1);
+  constexpr unsigned GM = (G == 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+  const unsigned gmask = GM << gbase;
+  UGroup &S = groups[(threadIdx.x >> 5) * (32 / G) + (lane / G)];
+  const Grid &g = A.g;
+  const FixDev &fd = A.fd;
+  const UsherCfg &u = A.u;
+  const double k1[3] = {pt.a0[fd.ntype][fd.ntype], pt.cut[fd.ntype][fd.ntype], pt.cutsq[fd.ntype][fd.ntype]};
+  const bool have_extras = (A.ex.narr + A.ex.nghost + A.ex.nins) > 0;
+  const bool have_spec = list != nullptr;  // nothing has been accepted yet in round 0
+  const double wx = g.prd[0] / g.gnx, wy = g.prd[1] / g.ny, wz = g.prd[2] / g.nz;
+
+  bool active = false, more = true;
+  int t = 0, side = 0, i = 0, np = 0, nc = 0, gx = 0, gy = 0, gz = 0, nextli = first;
+  bool wrap = true;
+  double c[3] = {0, 0, 0}, start[3] = {0, 0, 0}, E = 0.0, ox = 0.0, oy = 0.0, oz = 0.0;
+  float blo[3] = {0, 0, 0}, bhi[3] = {0, 0, 0};
+  double *mypath = A.path;
+  for (;;) {
+    if (!active && more) {
+      int li;
+      if (cursor) {
+        li = 0;
+        if (gl == 0) li = atomicAdd(cursor, 1);
+        li = __shfl_sync(gmask, li, 0, G);
+      } else {
+        li = nextli;
+        nextli += stride;
+      }
+      if (li < nl) {
+        t = list ? __ldcg(list + li) : li;
+        const int tg = t + u.tg0;  // position of this trial in the (replicated) RanPark stream
+        side = (tg < u.ntrL) ? 0 : 1;
+        const obmd_block &reg = fd.region[4 + side];
+        // trial start (:923-927): three consecutive RanPark draws, x then y then z
+        int seed = (int) (((unsigned long long) u.seed0 * (unsigned long long) ranpark_pow(3LL * tg)) %
+                          2147483647ULL);
+        for (int d = 0; d < 3; d++) {
+          c[d] = reg.lo[d] + ranpark_uniform(seed) * (reg.hi[d] - reg.lo[d]);
+          start[d] = c[d];
+        }
+        mypath = A.path + (size_t) t * (u.natt + 1) * 3;
+        i = np = 0;
+        for (int d = 0; d < 3; d++) {
+          blo[d] = 3.0e38f;
+          bhi[d] = -3.0e38f;
+        }
+        if (list) {
+          // Re-run of a trial whose neighbourhood changed: everything before the first affected
+          // evaluation point is unchanged, so resume there (the state at the top of iteration k is
+          // exactly (path[k], i = k)).  The stored bounding box already covers the kept prefix.
+          i = np = __ldcg(A.kfirst + t);
+          for (int d = 0; d < 3; d++) {
+            c[d] = __ldcg(mypath + 3 * i + d);
+            blo[d] = __ldcg(A.bbox + (size_t) t * 6 + d);
+            bhi[d] = __ldcg(A.bbox + (size_t) t * 6 + 3 + d);
+          }
+        }
+        gx = -(1 << 30);
+        E = 0.0;
+        active = true;
+      } else
+        more = false;
+    }
+    if (!__any_sync(0xffffffffu, active)) break;
+    if (!active) continue;
+
+    const obmd_block &reg = fd.region[4 + side];
+    // the point is inside the insertion region, hence inside the box: the cell index is at most one
+    // period off (y == yhi exactly), so the wrap needs no division
+    const int cx = cell_cx(g, c[0]);
+    int cy = (int) floor((c[1] - g.lo[1]) * g.inv[1]), cz = (int) floor((c[2] - g.lo[2]) * g.inv[2]);
+    if (cy < 0 || cy >= 2 * g.ny) cy = cell_wrap(cy, g.ny);
+    else if (cy >= g.ny) cy -= g.ny;
+    if (cz < 0 || cz >= 2 * g.nz) cz = cell_wrap(cz, g.nz);
+    else if (cz >= g.nz) cz -= g.nz;
+    if (cx != gx || cy != gy || cz != gz) {
+      ox = g.lo[0] + (cx + g.cxoff) * wx;
+      oy = g.lo[1] + cy * wy;
+      oz = g.lo[2] + cz * wz;
+      nc = usher_gather<G>(A, S, cx, cy, cz, t, ox, oy, oz, gl, gmask, have_extras, have_spec);
+      gx = cx;
+      gy = cy;
+      gz = cz;
+      // pre_exchange runs before Domain::pbc: an atom that has just left through a periodic face still
+      // carries its unwrapped coordinate and sits in a face cell, so stencils reaching the face layer
+      // (points in the two outermost layers) need the reference's minimum-image loop
+      wrap = g.ny < 6 || g.nz < 6 || cy <= 1 || cy >= g.ny - 2 || cz <= 1 || cz >= g.nz - 2;
+    }
+    double f[3];
+    usher_energy<ST, G>(A, pt, S, c, ox, oy, oz, nc, wrap, k1, gl, gbase, gmask, E, f);
+    if (gl == 0) {
+      mypath[np * 3 + 0] = c[0];
+      mypath[np * 3 + 1] = c[1];
+      mypath[np * 3 + 2] = c[2];
+    }
+    np++;
+    for (int d = 0; d < 3; d++) {  // conservative fp32 bounding box of the evaluated points
+      blo[d] = fminf(blo[d], __double2float_rd(c[d]));
+      bhi[d] = fmaxf(bhi[d], __double2float_ru(c[d]));
+    }
+    bool done = false;
+    if (E < fd.etarget + EPSILON_FIX) done = true;
+    else {
+      const double fabs_ = sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+      if (fabs_ < EPSILON_FIX) {  // the reference `continue`s without progress: report it
+        if (gl == 0) A.sc->usher_error = OBMD_ERR_USHER;
+        done = true;
+      } else {
+        double ds;
+        if (E > fd.uovlp) ds = fd.dsovlp - pow(4 * fd.eps / E, 1.0 / 12.0);
+        else ds = fmin((E - fd.etarget) / fabs_, fd.ds0);
+        c[0] += f[0] / fabs_ * ds;
+        c[1] += f[1] / fabs_ * ds;
+        c[2] += f[2] / fabs_ * ds;
+        if (!block_inside(reg, c[0], c[1], c[2])) done = true;  // check_mol_region (:1700-1712)
+        else {
+          i += 1;
+          if (i >= u.natt) done = true;
+        }
+      }
+    }
+    if (!done) continue;
+
+    bool ok = (E < fd.etarget + EPSILON_FIX);
+    // check_mol_proc / check_proc (:1645-1696) on the owning rank: half-open box in x,y; the top z
+    // face belongs to the last processor
+    if (ok) {
+      const bool in = c[0] >= fd.boxlo[0] && c[0] < fd.boxhi[0] && c[1] >= fd.boxlo[1] && c[1] < fd.boxhi[1] &&
+          c[2] >= fd.boxlo[2];
+      if (!in) ok = false;
+    }
+    if (ok && !block_inside(reg, c[0], c[1], c[2])) ok = false;  // :1107-1108
+    if (gl == 0) {
+      obmd_trial r;
+      for (int d = 0; d < 3; d++) {
+        r.start[d] = start[d];
+        r.end[d] = c[d];
+      }
+      r.energy = E;
+      r.iter = i;
+      r.accepted = ok ? 1 : 0;
+      r.side = side;
+      r.tag = 0;
+      A.cur[t] = r;
+      A.npts[t] = np;
+      for (int d = 0; d < 3; d++) {
+        A.bbox[(size_t) t * 6 + d] = blo[d];
+        A.bbox[(size_t) t * 6 + 3 + d] = bhi[d];
+      }
+    }
+    active = false;
+  }
+}
+
+#ifndef USH_G
+#define USH_G 32
+#endif
+#ifndef USH_MINB
+#define USH_MINB 6
+#endif
+
+template <bool ST, int G>
+__global__ void __launch_bounds__(USH_T, USH_MINB) k_usher_eval(const __grid_constant__ UsherArgs A, const __grid_constant__ PairTab pt, int nl)
+{
+  extern __shared__ __align__(16) unsigned char usm[];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nl > 0) A.sc->nrounds_work++;
+  usher_trials<ST, G>(A, pt, reinterpret_cast<UGroup *>(usm), nullptr, nl, &A.sc->trial_cursor, 0, 0);
+}
+
+// ---- maxattempt > 1 ------------------------------------------------------------------------------
+// (:912-1172): insertion slot k draws attempts from the RNG stream until one is accepted or
+// maxattempt have failed, then slot k+1 continues where it stopped.  Given the accept flag of every
+// possible attempt, the attempts actually made are a prefix of the stream: a slot boundary sits
+// behind every accepted attempt and behind every maxattempt-th consecutive failure.
+// nused = index of the slots-th boundary + 1.  One CTA of nt <= 1024 threads, chunked scans.
+__device__ void usher_resolve(const obmd_trial *cur, int ntr, int slots, int M, StepScalars *sc, int *s_last,
+                              int *s_cnt)
+{
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int per = (ntr + nt - 1) / nt, b = tid * per, e = min(b + per, ntr);
+  int last = -1;
+  for (int a = b; a < e; a++)
+    if (__ldcg(&cur[a].accepted)) last = a;
+  s_last[tid] = last;
+  __syncthreads();
+  if (tid == 0) {  // exclusive running maximum over the chunks
+    int run = -1;
+    for (int k = 0; k < nt; k++) {
+      const int v = s_last[k];
+      s_last[k] = run;
+      run = max(run, v);
+    }
+  }
+  __syncthreads();
+  int la = s_last[tid], nb = 0;
+  for (int a = b; a < e; a++) {
+    const bool acc = __ldcg(&cur[a].accepted) != 0;
+    nb += (acc || ((a - la) % M == 0)) ? 1 : 0;
+    if (acc) la = a;
+  }
+  s_cnt[tid] = nb;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int k = 0; k < nt; k++) {
+      const int v = s_cnt[k];
+      s_cnt[k] = run;
+      run += v;
+    }
+    if (run < slots) sc->nused = ntr;  // cannot happen for ntr == slots * M; keep the state sane
+  }
+  __syncthreads();
+  int c0 = s_cnt[tid];
+  if (c0 < slots && c0 + nb >= slots) {
+    la = s_last[tid];
+    for (int a = b; a < e; a++) {
+      const bool acc = __ldcg(&cur[a].accepted) != 0;
+      if (acc || ((a - la) % M == 0)) {
+        if (++c0 == slots) {
+          sc->nused = a + 1;
+          break;
+        }
+      }
+      if (acc) la = a;
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) k_usher_resolve(const obmd_trial *cur, int ntr, int slots, int M,
+                                                        StepScalars *sc)
+{
+  __shared__ int s_last[1024], s_cnt[1024];
+  usher_resolve(cur, ntr, slots, M, sc, s_last, s_cnt);
+}
+
+// ---- diff: which trials changed the set of accepted atoms -----------------------------------------
+// The accepted atom of trial t, if any, is spec entry spec_of_trial[t].  A trial whose latest
+// evaluation disagrees with it (accepted flag or position; maxattempt > 1: only attempts the serial
+// loop really makes, t < nused, can insert) retires the old entry, publishes a new one in the
+// per-cell list of its cell and leaves a change record for the dirty test.  Entry order in a cell
+// list is irrelevant: contributions are ordered by local index when they are summed.
+__device__ __forceinline__ void usher_diff_one(const UsherArgs &A, int t, int par)
+{
+  const obmd_trial *b = A.cur + t;
+  const int newacc = __ldcg(&b->accepted) && (!A.limit || t < *(volatile int *) &A.sc->nused);
+  const int eold = __ldcg(A.spec_of_trial + t);
+  double o[3] = {0, 0, 0}, n[3];
+  for (int d = 0; d < 3; d++) n[d] = __ldcg(&b->end[d]);
+  bool ch = (eold >= 0) != (newacc != 0);
+  if (eold >= 0) {
+    for (int d = 0; d < 3; d++) o[d] = __ldcg(A.spec_pos + 3 * (size_t) eold + d);
+    if (newacc && (o[0] != n[0] || o[1] != n[1] || o[2] != n[2])) ch = true;
+  }
+  if (!ch) return;
+  ChgRec r;
+  for (int d = 0; d < 3; d++) {
+    r.o[d] = o[d];
+    r.n[d] = n[d];
+  }
+  r.q = t;
+  r.flags = (eold >= 0 ? 1 : 0) | (newacc ? 2 : 0);
+  A.chg[atomicAdd(&A.sc->nchg2[par], 1)] = r;
+  if (eold >= 0) A.spec_trial[eold] = 0x7fffffff;
+  int enew = -1;
+  if (newacc) {
+    enew = atomicAdd(&A.sc->nspec, 1);
+    if (enew >= A.spec_cap) {
+      A.sc->usher_error = OBMD_ERR_CAPACITY + 1000;
+      enew = -1;
+    } else {
+      const Grid &g = A.g;
+      const int lc = min(max(cell_cx(g, n[0]), 0), g.nx - 1);
+      const int cc = (lc * g.ny + cell_cy(g, n[1])) * g.nz + cell_cz(g, n[2]);
+      for (int d = 0; d < 3; d++) A.spec_pos[3 * (size_t) enew + d] = n[d];
+      A.spec_trial[enew] = t;
+      A.spec_cell[enew] = cc;
+      __threadfence();  // the entry is complete before it becomes reachable
+      A.spec_next[enew] = atomicExch(&A.spec_head[cc], enew);
+    }
+  }
+  A.spec_of_trial[t] = enew;
+}
+
+__global__ void k_usher_diff(const __grid_constant__ UsherArgs A)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < A.ntr) usher_diff_one(A, t, 0);
+}
+
+// ---- dirty test -----------------------------------------------------------------------------------
+// all points involved lie inside the box, so one periodic shift suffices
+__device__ __forceinline__ bool near_pt(const double *a, double bx, double by, double bz, const Grid &g,
+                                        double rsqmax)
+{
+  double dx = a[0] - bx, dy = a[1] - by, dz = a[2] - bz;
+  if (dy > g.half[1]) dy -= g.prd[1];
+  else if (dy < -g.half[1]) dy += g.prd[1];
+  if (dz > g.half[2]) dz -= g.prd[2];
+  else if (dz < -g.half[2]) dz += g.prd[2];
+  return dx * dx + dy * dy + dz * dz <= rsqmax;
+}
+
+// is coordinate v (or a periodic image) within rc of the interval [lo, hi]?
+__device__ __forceinline__ bool axis_near(double v, double lo, double hi, double rc, double L, bool periodic)
+{
+  lo -= rc;
+  hi += rc;
+  if (v >= lo && v <= hi) return true;
+  if (!periodic) return false;
+  return (v + L >= lo && v + L <= hi) || (v - L >= lo && v - L <= hi);
+}
+
+__device__ __forceinline__ bool near_bbox(const double *a, const float *bb, const Grid &g, double rc)
+{
+  return axis_near(a[0], bb[0], bb[3], rc, 0.0, false) && axis_near(a[1], bb[1], bb[4], rc, g.prd[1], true) &&
+      axis_near(a[2], bb[2], bb[5], rc, g.prd[2], true);
+}
+
+// A trial must be re-run when an earlier trial whose state changed has its old or new atom within
+// the cutoff of any point the trial evaluated (a superset test with a small margin).
+// kfirst[t] = index of the first such point: the re-run resumes there.  One warp per trial.
+__device__ __forceinline__ void usher_dirty_one(const UsherArgs &A, int t, int par, int lane)
+{
+  const Grid &g = A.g;
+  const double *mp = A.path + (size_t) t * (A.u.natt + 1) * 3;
+  float bb[6];
+  for (int d = 0; d < 6; d++) bb[d] = __ldcg(A.bbox + (size_t) t * 6 + d);
+  const int np = __ldcg(A.npts + t), nchg = A.sc->nchg2[par];
+  int kf = np;  // first affected point found so far
+  // lanes prefilter 32 change records at a time against the trial's bounding box; every record that
+  // passes is then tested against all evaluated points by the whole warp (points are read coalesced)
+  for (int q0 = 0; q0 < nchg; q0 += 32) {
+    const int qi = q0 + lane;
+    ChgRec r;
+    r.flags = 0;
+    r.q = 1 << 30;
+    for (int d = 0; d < 3; d++) r.o[d] = r.n[d] = 0.0;
+    if (qi < nchg) {
+      const ChgRec *src = A.chg + qi;
+      for (int d = 0; d < 3; d++) {
+        r.o[d] = __ldcg(&src->o[d]);
+        r.n[d] = __ldcg(&src->n[d]);
+      }
+      r.q = __ldcg(&src->q);
+      r.flags = __ldcg(&src->flags);
+    }
+    const bool oldacc = r.q < t && (r.flags & 1) && near_bbox(r.o, bb, g, A.rc);
+    const bool newacc = r.q < t && (r.flags & 2) && near_bbox(r.n, bb, g, A.rc);
+    unsigned m = __ballot_sync(0xffffffffu, oldacc || newacc);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1u;
+      double o[3], n[3];
+      for (int d = 0; d < 3; d++) {
+        o[d] = __shfl_sync(0xffffffffu, r.o[d], src);
+        n[d] = __shfl_sync(0xffffffffu, r.n[d], src);
+      }
+      const bool oa = __shfl_sync(0xffffffffu, (int) oldacc, src) != 0;
+      const bool na = __shfl_sync(0xffffffffu, (int) newacc, src) != 0;
+      for (int k0 = 0; k0 < kf; k0 += 32) {  // kf stays warp-uniform: it is only set from ballots
+        const int k = k0 + lane;
+        bool hit = false;
+        if (k < kf) {
+          const double bx = __ldcg(mp + 3 * k), by = __ldcg(mp + 3 * k + 1), bz = __ldcg(mp + 3 * k + 2);
+          hit = (oa && near_pt(o, bx, by, bz, g, A.rsqmax)) || (na && near_pt(n, bx, by, bz, g, A.rsqmax));
+        }
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (hm) {
+          kf = k0 + __ffs(hm) - 1;
+          break;
+        }
+      }
+    }
+  }
+  if (kf < np && lane == 0) {
+    A.kfirst[t] = kf;
+    A.list[atomicAdd(&A.sc->ndirty2[par], 1)] = t;
+  }
+}
+
+__global__ void k_usher_dirty(const __grid_constant__ UsherArgs A)
+{
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= A.ntr || A.sc->nchg2[0] == 0) return;
+  usher_dirty_one(A, t, 0, threadIdx.x & 31);
+}
+
+// ---- re-run rounds, all in one launch ---------------------------------------------------------------
+// One thread-block cluster.  Round r >= 1: re-run the trials the dirty test of round r-1 listed (one
+// warp per trial: the rounds are a handful of dependent 40-iteration chains, latency is what
+// counts), then resolve / diff / dirty as after round 0, until a round changes nothing.  Finally the
+// accepted trials are compacted in order into acc_list (they become local indices nbase, nbase+1, ...
+// and tags maxtag+1, ...) and the per-cell lists are cleared for the next call.
+template <bool ST>
+__global__ void __cluster_dims__(FIX_CL, 1, 1) __launch_bounds__(FIX_T, 1) k_usher_fix(const __grid_constant__ UsherArgs A, const __grid_constant__ PairTab pt)
+{
+  extern __shared__ __align__(16) unsigned char usm[];
+  __shared__ int s_a[FIX_T], s_b[FIX_T];
+  __shared__ int s_base;
+  cg::cluster_group cl = cg::this_cluster();
+  const int rank = (int) cl.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nwarp = FIX_CL * (FIX_T / 32), gw = rank * (FIX_T / 32) + (tid >> 5);
+  const int gtid = rank * FIX_T + tid, gthreads = FIX_CL * FIX_T;
+  StepScalars *sc = A.sc;
+  volatile int *ndirty2 = sc->ndirty2, *nchg2 = sc->nchg2;
+  for (int round = 1;; round++) {
+    const int par = round & 1, pprev = par ^ 1;
+    const int nd = ndirty2[pprev];
+    if (nd == 0) break;
+    if (round > A.ntr + 2) {  // cannot happen: trial t settles after at most t + 1 rounds
+      if (gtid == 0) sc->usher_error = OBMD_ERR_STATE;
+      break;
+    }
+    usher_trials<ST, 32>(A, pt, reinterpret_cast<UGroup *>(usm), A.list, nd, nullptr, gw, nwarp);
+    if (gtid == 0) sc->nrounds_work++;
+    __threadfence();
+    cl.sync();
+    if (A.limit) {
+      if (rank == 0) usher_resolve(A.cur, A.ntr, A.u.slots, A.u.maxatt, sc, s_a, s_b);
+      __threadfence();
+      cl.sync();
+      for (int t = gtid; t < A.ntr; t += gthreads) usher_diff_one(A, t, par);
+    } else {
+      for (int k = gtid; k < nd; k += gthreads) usher_diff_one(A, __ldcg(A.list + k), par);
+    }
+    if (gtid == 0) {  // the counters of the previous round have been consumed by everybody
+      ndirty2[pprev] = 0;
+      nchg2[pprev] = 0;
+      sc->nused_prev = sc->nused;
+    }
+    __threadfence();
+    cl.sync();
+    if (nchg2[par] > 0)
+      for (int t = gw; t < A.ntr; t += nwarp) usher_dirty_one(A, t, par, lane);
+    __threadfence();
+    cl.sync();
+  }
+  // ordered compaction of the accepted trials (CTA 0): every thread owns a contiguous run of trials,
+  // a block scan of the counts gives its offset
+  if (rank == 0) {
+    const int nlim = A.limit ? *(volatile int *) &sc->nused : A.ntr;
+    const int per = (nlim + FIX_T - 1) / FIX_T, tb = tid * per, te = min(tb + per, nlim);
+    int cnt = 0;
+    for (int t = tb; t < te; t++) cnt += (__ldcg(A.spec_of_trial + t) >= 0) ? 1 : 0;
+    s_a[tid] = cnt;
+    __syncthreads();
+    if (tid < 32) {  // exclusive scan of FIX_T counts by one warp, a contiguous run per lane
+      constexpr int RUN = FIX_T / 32;
+      int s = 0;
+      for (int k = 0; k < RUN; k++) s += s_a[tid * RUN + k];
+      int inc = s;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (tid >= d) inc += v;
+      }
+      int run = inc - s;
+      for (int k = 0; k < RUN; k++) {
+        const int v = s_a[tid * RUN + k];
+        s_b[tid * RUN + k] = run;
+        run += v;
+      }
+      if (tid == 31) s_base = inc;
+    }
+    __syncthreads();
+    int off = s_b[tid];
+    for (int t = tb; t < te; t++)
+      if (__ldcg(A.spec_of_trial + t) >= 0) A.acc_list[off++] = t;
+    if (tid == 0) sc->naccept = s_base;
+  }
+  // leave the per-cell lists empty
+  const int nspec = min(*(volatile int *) &sc->nspec, A.spec_cap);
+  for (int e = gtid; e < nspec; e += gthreads) A.spec_head[__ldcg(A.spec_cell + e)] = -1;
+}
+
+// create_atom + tag/mask/image/v assignment (:1121-1150, atom_vec.cpp:1592-1612), appended after
+// every other extra atom; the new atoms are then threaded into the per-cell lists the pair kernel
+// walks (fix_link_extras).
+__global__ void k_usher_commit(Planes p, Extras ex, int tag0, FixDev fd, obmd_trial *__restrict__ cur,
+                               const int *__restrict__ acc_list, int nacc, double *fx, double *fy, double *fz)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nacc) {
+    obmd_trial &r = cur[acc_list[k]];
+    int s = ex.base + ex.narr + ex.nghost + ex.nins + k;  // ex.nins: atoms of an earlier pass
+    p.x[s] = r.end[0];
+    p.y[s] = r.end[1];
+    p.z[s] = r.end[2];
+    p.vx[s] = p.vy[s] = p.vz[s] = 0.0;
+    p.type[s] = fd.ntype;
+    p.tag[s] = tag0 + k + 1;
+    p.image[s] = IMG0;
+    p.lidx[s] = s;  // appended: local index == slot (serial runs: nlocal-after-deletion + k)
+    fx[s] = fy[s] = fz[s] = 0.0;
+    r.tag = tag0 + k + 1;
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+
+// Device buffers of the USHER trials.  Regrowing them costs a dozen cudaFree/cudaMalloc pairs (each
+// an implicit device synchronisation) in the middle of a step, so they start at 16 Ki trials and
+// double; the pinned host copy of the trial records is only made when a caller asks for them.
+static int ensure_trials(obmd_ctx *c, int ntr, int natt)
+{
+  if (ntr <= c->tr_cap && natt <= c->tr_natt) return OBMD_OK;
+  int cap = c->tr_cap;
+  if (ntr > cap) {
+    cap = cap < 16384 ? 16384 : cap;
+    while (cap < ntr) cap *= 2;
+  }
+  int na = natt > c->tr_natt ? natt : c->tr_natt;
+  cudaFree(c->tr_d); cudaFree(c->tr_path); cudaFree(c->tr_npts); cudaFree(c->tr_list);
+  cudaFree(c->tr_kfirst); cudaFree(c->acc_list); cudaFree(c->tr_bbox); cudaFree(c->tr_chg);
+  cudaFree(c->spec_next); cudaFree(c->spec_cell); cudaFree(c->spec_trial); cudaFree(c->spec_of_trial);
+  cudaFree(c->spec_pos);
+  CK(cudaMalloc(&c->tr_bbox, sizeof(float) * 6 * cap));
+  CK(cudaMalloc(&c->tr_d, sizeof(obmd_trial) * cap));
+  CK(cudaMalloc(&c->tr_path, sizeof(double) * 3 * (size_t) cap * (na + 1)));
+  CK(cudaMalloc(&c->tr_npts, sizeof(int) * cap));
+  CK(cudaMalloc(&c->tr_list, sizeof(int) * cap));
+  CK(cudaMalloc(&c->tr_kfirst, sizeof(int) * cap));
+  CK(cudaMalloc(&c->tr_chg, sizeof(ChgRec) * cap));
+  CK(cudaMalloc(&c->acc_list, sizeof(int) * cap));
+  // accepted-atom entries are append-only within a call: one per change of a trial's accepted state
+  CK(cudaMalloc(&c->spec_next, sizeof(int) * 2 * cap));
+  CK(cudaMalloc(&c->spec_cell, sizeof(int) * 2 * cap));
+  CK(cudaMalloc(&c->spec_trial, sizeof(int) * 2 * cap));
+  CK(cudaMalloc(&c->spec_pos, sizeof(double) * 3 * 2 * (size_t) cap));
+  CK(cudaMalloc(&c->spec_of_trial, sizeof(int) * cap));
+  c->tr_cap = cap;
+  c->tr_natt = na;
+  return OBMD_OK;
+}
+
+int usher_trials_to_host(obmd_ctx *c, obmd_trial *dst, int ncopy)
+{
+  if (ncopy <= 0) return OBMD_OK;
+  if (ncopy > c->tr_h_cap) {
+    if (c->tr_h) cudaFreeHost(c->tr_h);
+    c->tr_h = nullptr;
+    c->tr_h_cap = 0;
+    int cap = ncopy < 4096 ? 4096 : 2 * ncopy;
+    CK(cudaMallocHost(&c->tr_h, sizeof(obmd_trial) * cap));
+    c->tr_h_cap = cap;
+  }
+  CK(cudaMemcpyAsync(c->tr_h, c->tr_d, sizeof(obmd_trial) * ncopy, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  memcpy(dst, c->tr_h, sizeof(obmd_trial) * ncopy);
+  return OBMD_OK;
+}
+
+template <bool ST, int G>
+static int launch_eval(obmd_ctx *c, const UsherArgs &A, int ntr)
+{
+  const size_t smem = sizeof(UGroup) * (USH_T / 32) * (32 / G);
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    CK(cudaFuncSetAttribute(k_usher_eval<ST, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    attr_done = true;
+  }
+  const int groups_per_cta = (USH_T / 32) * (32 / G);
+  int grid = cdiv(ntr, groups_per_cta);
+  const int full = c->ush_ctas_per_sm * NSM;
+  if (grid > full) grid = full;
+  LAUNCH((k_usher_eval<ST, G>), grid, USH_T, smem, A, c->pt, ntr);
+  return OBMD_OK;
+}
+
+template <bool ST>
+static int launch_fix(obmd_ctx *c, const UsherArgs &A)
+{
+  const size_t smem = sizeof(UGroup) * (FIX_T / 32);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CK(cudaFuncSetAttribute(k_usher_fix<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    attr_done = true;
+  }
+  LAUNCH(k_usher_fix<ST>, FIX_CL, FIX_T, smem, A, c->pt);
+  return OBMD_OK;
+}
+
+// One pass of try_inserting for ntr_loc trials on this rank (maxattempt == 1: both sides together;
+// maxattempt > 1: one side).  Enqueues round 0, the first diff / dirty test and the fix-up kernel,
+// then reads the outcome back (the only host round trip of the pass).
+int usher_pass(obmd_ctx *c, const UsherCfg &u, int ntr_loc, int limit, int *nacc_out, int *nused_out,
+               int *rounds_out)
+{
+  int rc;
+  if ((rc = ensure_trials(c, ntr_loc, c->fa.nattempt))) return rc;
+  UsherArgs A;
+  memset(&A, 0, sizeof(A));
+  A.p = c->cur;
+  A.g = c->grid;
+  A.fd = c->fd;
+  A.u = u;
+  A.ex = extras_of(c);
+  A.cell_start = c->cell_start;
+  A.extra_head = c->extra_head;
+  A.extra_next = c->extra_next;
+  A.spec_head = c->spec_head;
+  A.spec_next = c->spec_next;
+  A.spec_cell = c->spec_cell;
+  A.spec_trial = c->spec_trial;
+  A.spec_of_trial = c->spec_of_trial;
+  A.spec_pos = c->spec_pos;
+  A.spec_cap = 2 * c->tr_cap;
+  A.cur = c->tr_d;
+  A.path = c->tr_path;
+  A.npts = c->tr_npts;
+  A.bbox = c->tr_bbox;
+  A.kfirst = c->tr_kfirst;
+  A.list = c->tr_list;
+  A.chg = c->tr_chg;
+  A.acc_list = c->acc_list;
+  A.sc = c->sc_d;
+  A.ntr = ntr_loc;
+  A.limit = limit;
+  // the bounding boxes are fp32 (rounded outwards); 1e-3 covers the prefilter's own rounding
+  A.rc = c->pt.cutmax * (1.0 + 1e-9) + 1e-3;
+  A.rsqmax = c->pt.cutmax * c->pt.cutmax * (1.0 + 1e-9);
+  // nchg2, ndirty2, naccept, nrounds_work, trial_cursor, nused, nused_prev, nspec
+  CK(cudaMemsetAsync(&c->sc_d->nchg2[0], 0, 10 * sizeof(int), c->stream));
+  CK(cudaMemsetAsync(c->spec_of_trial, 0xff, sizeof(int) * ntr_loc, c->stream));
+  const bool st = (c->ntypes == 1);
+  {
+    ScopedTimer t5(c, "usher_eval0");
+    const int G = c->ush_group;
+    if (st) {
+      if (G == 8) rc = launch_eval<true, 8>(c, A, ntr_loc);
+      else if (G == 16) rc = launch_eval<true, 16>(c, A, ntr_loc);
+      else rc = launch_eval<true, 32>(c, A, ntr_loc);
+    } else {
+      if (G == 8) rc = launch_eval<false, 8>(c, A, ntr_loc);
+      else if (G == 16) rc = launch_eval<false, 16>(c, A, ntr_loc);
+      else rc = launch_eval<false, 32>(c, A, ntr_loc);
+    }
+    if (rc) return rc;
+  }
+  // Round 0 fills the machine; obmd_run hooks in here to start the pair kernel on the side stream
+  // right behind it (OBMD_B200_PAIR_FIRST=0).
+  if (c->round0_hook) {
+    int (*hook)(obmd_ctx *) = c->round0_hook;
+    c->round0_hook = nullptr;
+    if ((rc = hook(c))) return rc;
+  }
+  {
+    ScopedTimer t6(c, "usher_fix");
+    if (limit) LAUNCH(k_usher_resolve, 1, 1024, 0, c->tr_d, ntr_loc, u.slots, u.maxatt, c->sc_d);
+    LAUNCH(k_usher_diff, cdiv(ntr_loc, 256), 256, 0, A);
+    LAUNCH(k_usher_dirty, cdiv(ntr_loc, 4), 128, 0, A);
+    if (st) rc = launch_fix<true>(c, A);
+    else rc = launch_fix<false>(c, A);
+    if (rc) return rc;
+  }
+  if ((rc = read_scalars(c))) return rc;
+  const int err = c->sc_h->usher_error;
+  NEED(err != OBMD_ERR_USHER, OBMD_ERR_USHER,
+       "fix obmd: USHER force vanished with E above target (the reference would not terminate)");
+  NEED(err != OBMD_ERR_CAPACITY, OBMD_ERR_CAPACITY,
+       "fix obmd: more than %d neighbours near the cutoff of a USHER point (or %d atoms in its stencil)",
+       USH_CAP, USH_CAND);
+  NEED(err != OBMD_ERR_CAPACITY + 1000, OBMD_ERR_CAPACITY, "fix obmd: too many accepted-state changes in one call");
+  NEED(err != OBMD_ERR_STATE, OBMD_ERR_STATE, "fix obmd: USHER commit did not converge");
+  *nacc_out = c->sc_h->naccept;
+  *nused_out = limit ? c->sc_h->nused : ntr_loc;
+  *rounds_out = c->sc_h->nrounds_work;
+  return OBMD_OK;
+}
+
+int usher_commit(obmd_ctx *c, int tag0, int nacc)
+{
+  LAUNCH(k_usher_commit, cdiv(nacc, 128), 128, 0, c->cur, extras_of(c), tag0, c->fd, c->tr_d, c->acc_list, nacc,
+         c->fx, c->fy, c->fz);
+  return OBMD_OK;
+}
