@@ -237,7 +237,7 @@ def ours(args):
     sampler.stop_flag = True; sampler.join()
     fam = {}
     for name in ("nve", "bin", "sort", "comm", "pre_exchange", "usher", "usher_round0", "usher_rerun",
-                 "usher_commit", "usher_allreduce", "usher_eval0", "usher_evalN", "host_wait_scalars", "host_step", "host_cells", "host_comm", "host_pre_exchange", "host_usher",
+                 "usher_commit", "usher_allreduce", "usher_eval0", "usher_evalN", "usher_fix", "host_wait_scalars", "host_step", "host_cells", "host_comm", "host_pre_exchange", "host_usher",
                  "host_allreduce", "host_post", "host_final_sync", "pbc", "pair", "post_force"):
         t, nl = sim.timing_get(name)
         fam[name] = {"ms_per_step": t / args.steps, "launches_per_step": nl / args.steps}

@@ -82,8 +82,9 @@ extern "C" int obmd_create(obmd_ctx **out, int device)
   if (const char *e5 = getenv("OBMD_B200_PT")) c->row_threads = atoi(e5);
   if (const char *e10 = getenv("OBMD_B200_USH_G")) {
     const int gsz = atoi(e10);
-    if (gsz == 8 || gsz == 16 || gsz == 32) c->ush_group = gsz;
+    if (gsz == 16 || gsz == 32) c->ush_group = gsz;
   }
+  if (const char *e12 = getenv("OBMD_B200_FIX_CL")) c->fix_cluster = atoi(e12) == 1 ? 1 : 8;
   if (const char *e11 = getenv("OBMD_B200_USH_CTAS")) {
     const int v = atoi(e11);
     if (v >= 1 && v <= 16) c->ush_ctas_per_sm = v;
@@ -112,7 +113,6 @@ extern "C" void obmd_destroy(obmd_ctx *c)
   cudaFree(c->cid); cudaFree(c->rank); cudaFree(c->perm);
   cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->scan_tmp);
   cudaFree(c->extra_head); cudaFree(c->extra_next); cudaFree(c->extra_cell);
-  cudaFree(c->spec_head); cudaFree(c->spec_next); cudaFree(c->spec_cell);
   cudaFree(c->stage_d); cudaFree(c->stage_i);
   cudaFree(c->sc_d); cudaFreeHost(c->sc_h);
   cudaFree(c->red_d); cudaFreeHost(c->red_h);
@@ -120,7 +120,7 @@ extern "C" void obmd_destroy(obmd_ctx *c)
   cudaFree(c->del_key); cudaFree(c->del_val); cudaFree(c->tail_key); cudaFree(c->tail_val); cudaFree(c->del_src); cudaFree(c->del_mv);
   cudaFree(c->tr_d); cudaFree(c->tr_path); cudaFree(c->tr_npts);
   cudaFree(c->tr_list); cudaFree(c->tr_kfirst); cudaFree(c->tr_chg); cudaFree(c->acc_list); cudaFree(c->tr_bbox);
-  cudaFree(c->spec_trial); cudaFree(c->spec_of_trial); cudaFree(c->spec_pos);
+  cudaFree(c->spec_trial); cudaFree(c->spec_of_trial); cudaFree(c->spec_pos); cudaFree(c->tr_pairs);
   if (c->tr_h) cudaFreeHost(c->tr_h);
   cudaFree(c->partials);
   cudaFree(c->redo_flag); cudaFree(c->redo_list); cudaFree(c->redo_count);
@@ -272,20 +272,18 @@ int setup_grid(obmd_ctx *c)
   g.own_b = c->gx1 - 1 - g.cxoff;
   g.ny = nn[1];
   g.nz = nn[2];
+  for (int d = 0; d < 3; d++) g.w[d] = g.prd[d] / nn[d];
   NEED((double) g.nx * nn[1] * nn[2] < 2.0e9, OBMD_ERR_CAPACITY, "obmd_pair_init: too many cells");
   g.ncell = g.nx * nn[1] * nn[2];
   if (g.ncell + 6 > c->cell_cap) {
     cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->scan_tmp); cudaFree(c->extra_head);
-    cudaFree(c->spec_head);
     c->cell_cap = g.ncell + 6;
-    CK(cudaMalloc(&c->spec_head, sizeof(int) * c->cell_cap));
     CK(cudaMalloc(&c->cell_count, sizeof(int) * c->cell_cap));
     CK(cudaMalloc(&c->cell_start, sizeof(int) * c->cell_cap));
     CK(cudaMalloc(&c->scan_tmp, sizeof(int) * (c->cell_cap / 4096 + 2)));
     CK(cudaMalloc(&c->extra_head, sizeof(int) * c->cell_cap));
   }
   LAUNCH(k_fill_int, cdiv(c->cell_cap, 256), 256, 0, c->extra_head, c->cell_cap, -1);
-  LAUNCH(k_fill_int, cdiv(c->cell_cap, 256), 256, 0, c->spec_head, c->cell_cap, -1);
   CK(cudaStreamSynchronize(c->stream));
   c->nextra = c->narr = c->nghost = c->nins = 0;
   c->cells_valid = false;

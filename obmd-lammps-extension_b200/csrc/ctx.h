@@ -35,6 +35,7 @@ struct Grid {
   int gnx, cxoff;         // global column count; global index of local column 0
   int own_a, own_b;       // owned local columns (inclusive); the others hold ghosts only
   double lo[3], hi[3], prd[3], inv[3], half[3];
+  double w[3];            // cell widths prd / n
 };
 
 // Atoms appended after the cell-sorted range [0, base): arrivals from neighbour slabs (mine),
@@ -78,7 +79,10 @@ struct StepScalars {
   int trial_cursor;         // next entry of the round's trial list to hand to a warp
   int nused, nused_prev;    // maxattempt > 1: attempts of the RNG stream the serial loop consumes (a prefix)
   int nspec;                // accepted-atom entries published so far in this call (usher.cu)
+  int npairs;               // (trial, change record) pairs queued by the dirty test of a re-run round
   int rng_seed;             // RanPark state after the deletion draws
+  int redo_overflow;        // k_mark_redo found more atoms near the insertions than its list holds (sticky,
+                            // outside the range pre_exchange zeroes)
   double vnewl[3], vnewr[3];
   double gsum[4];           // G_left, G_right, Gperp_left, Gperp_right
   double kin[5];
@@ -187,14 +191,16 @@ struct obmd_ctx {
   int *tr_npts = nullptr;
   float *tr_bbox = nullptr;         // [tr_cap][6] bounding box of the evaluated points (rounded outwards)
   int *tr_list = nullptr;           // trials to re-run this round
+  int *tr_pairs = nullptr;          // [8 * tr_cap] int2 queue of the dirty test
   int *tr_kfirst = nullptr;         // first evaluation point of a listed trial that must be redone
   struct ChgRec *tr_chg = nullptr;  // compact records of the trials whose state changed this round
   int *acc_list = nullptr;          // accepted trial ids in order (final)
-  // atoms accepted so far in this call: append-only entries threaded into per-cell lists
-  int *spec_head = nullptr, *spec_next = nullptr, *spec_cell = nullptr, *spec_trial = nullptr;
+  // atoms accepted so far in this call: append-only entries (usher.cu)
+  int *spec_trial = nullptr;
   int *spec_of_trial = nullptr;     // [tr_cap] entry of trial t's accepted atom, -1 if none
   double *spec_pos = nullptr;
   int ush_group = 32;               // lanes per trial in round 0 (OBMD_B200_USH_G: 8, 16, 32)
+  int fix_cluster = 8;              // CTAs in the cluster of the USHER fix-up kernel (OBMD_B200_FIX_CL: 1 or 8)
   int ush_ctas_per_sm = 6;          // persistent grid of round 0 (OBMD_B200_USH_CTAS)
   double *partials = nullptr;       // block partial sums for deterministic reductions
   int partial_cap = 0;

@@ -524,11 +524,14 @@ __global__ void k_mark_redo(Extras ex, Grid g, const int *__restrict__ cell_star
 }
 
 __global__ void k_clear_redo(int *__restrict__ flag, const int *__restrict__ list, const int *__restrict__ count,
-                             int cap)
+                             int cap, StepScalars *sc)
 {
   int q = blockIdx.x * blockDim.x + threadIdx.x;
   int n = min(*count, cap);
   if (q < n) flag[list[q]] = 0;
+  // more atoms around the insertions than the list holds (24 per cell): the surplus atoms would keep their
+  // flag and miss the new atoms' force terms; reported at the next read of the step scalars
+  if (q == 0 && *count > cap) sc->redo_overflow = 1;
 }
 
 int fix_redo_pair_near_insertions(obmd_ctx *c, long long step)
@@ -552,7 +555,7 @@ int fix_redo_pair_near_insertions(obmd_ctx *c, long long step)
          c->extra_head, c->extra_next, c->redo_flag, c->redo_list, c->redo_count, cap);
   int rc = pair_add_insertions(c, step, c->redo_list, c->redo_count, cap);
   if (rc) return rc;
-  LAUNCH(k_clear_redo, cdiv(cap, 256), 256, 0, c->redo_flag, c->redo_list, c->redo_count, cap);
+  LAUNCH(k_clear_redo, cdiv(cap, 256), 256, 0, c->redo_flag, c->redo_list, c->redo_count, cap, c->sc_d);
   return OBMD_OK;
 }
 
@@ -677,6 +680,8 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
       if ((rc = read_scalars(c))) return rc;
       const StepScalars &s = *c->sc_h;
       NEED(s.usher_error == 0, OBMD_ERR_STATE, "fix obmd: deletion bookkeeping invariant violated");
+      NEED(s.redo_overflow == 0, OBMD_ERR_CAPACITY,
+           "fix obmd: more than 24 atoms per cell around the insertions of the previous step (pair update list)");
       cntL = s.cnt_left; cntR = s.cnt_right; maxtag = s.maxtag;
       for (int d = 0; d < 3; d++) { vnewl[d] = s.vnewl[d]; vnewr[d] = s.vnewr[d]; }
     } else {
@@ -716,12 +721,14 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
   if (!serial) {
     const Grid &g = c->grid;
     const double slab_lo = g.lo[0] + c->gx0 / g.inv[0], slab_hi = g.lo[0] + c->gx1 / g.inv[0];
-    NEED(!doL || c->fd.region[4].hi[0] <= slab_hi, OBMD_ERR_ARG,
-         "slab run: region5 (x <= %g) must lie inside the first rank's slab (x < %g)", c->fd.region[4].hi[0],
-         slab_hi);
-    NEED(!doR || c->fd.region[5].lo[0] >= slab_lo, OBMD_ERR_ARG,
-         "slab run: region6 (x >= %g) must lie inside the last rank's slab (x >= %g)", c->fd.region[5].lo[0],
-         slab_lo);
+    // an atom inserted within the cutoff of the inner slab face would act on the neighbour's atoms only
+    // through a halo that was exchanged before it existed: keep the insertion regions one cutoff away
+    NEED(!doL || c->fd.region[4].hi[0] <= slab_hi - c->pt.cutmax, OBMD_ERR_ARG,
+         "slab run: region5 (x <= %g) must end at least one cutoff before the first rank's slab face (x = %g)",
+         c->fd.region[4].hi[0], slab_hi);
+    NEED(!doR || c->fd.region[5].lo[0] >= slab_lo + c->pt.cutmax, OBMD_ERR_ARG,
+         "slab run: region6 (x >= %g) must start at least one cutoff behind the last rank's slab face (x = %g)",
+         c->fd.region[5].lo[0], slab_lo);
   }
   const int ntr_loc = (doL ? ntrL : 0) + (doR ? ntrR : 0);
   const int tg0 = doL ? 0 : ntrL;

@@ -216,9 +216,8 @@ __global__ void __launch_bounds__(PR_TMAX, 1)
 
   // ---- cell populations of the window (sorted range + appended atoms), then their scan ---------
   const bool have_extras = (ex.narr + ex.nghost + ex.nins) > 0;
-  const unsigned nw_inv = 65536u / (unsigned) nw + 1u;  // q / nw == (q * nw_inv) >> 16 for q < 65536 / nw
   for (int q = tid; q < ncw; q += T) {
-    const int r = (int) (((unsigned) q * nw_inv) >> 16), w = q - r * nw;  // threads walk z: coalesced reads
+    const int r = q / nw, w = q - r * nw;  // threads walk z: coalesced reads (ncw <= 1152: a few trips)
     int cnt = 0, gb = 0;
     if (H.row_base[r] >= 0) {
       int zu = z0 - 1 + w;

@@ -22,6 +22,9 @@
 // index and summed left to right by one lane per quantity.
 #include <cooperative_groups.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "ctx.h"
 
 namespace cg = cooperative_groups;
@@ -32,8 +35,10 @@ namespace cg = cooperative_groups;
 #define USH_CAND 144  // atoms in the 27 stencil cells of a point (mean 81 at rho = 3)
 #define USH_CAP 48    // fp32-screened neighbours of a point (mean 13 at rho = 3)
 #define USH_T 128     // threads per CTA of the round-0 kernel
-#define FIX_CL 8      // CTAs in the cluster of the fix-up kernel
 #define FIX_T 512     // threads per CTA there (one warp per re-run trial: 128 trials at a time)
+#ifndef USHER_DEBUG
+#define USHER_DEBUG 0  // 1: OBMD_B200_DEBUG_FIX=1 prints phase times of the fix-up kernel (costs registers)
+#endif
 #define KEY_DROP 0x7fffff00  // keys of screened candidates that fail the exact cutoff test (+ slot)
 
 // per lane group: the stencil of the cell the point is in, and the scratch of one energy evaluation
@@ -42,7 +47,6 @@ struct __align__(16) UGroup {
   double e[USH_CAP], fx[USH_CAP], fy[USH_CAP], fz[USH_CAP];
   int key[USH_CAP];              // LAMMPS local index of the contributing atom
   unsigned short hq[USH_CAP];    // candidate index of each screened neighbour
-  unsigned char inv[USH_CAP];    // inv[rank by key] = position in the arrays above
 };
 
 struct UsherArgs {
@@ -52,8 +56,10 @@ struct UsherArgs {
   UsherCfg u;
   Extras ex;
   const int *cell_start, *extra_head, *extra_next;
-  // atoms accepted so far in this call ("spec" entries, append-only; a dead entry has trial INT_MAX)
-  int *spec_head, *spec_next, *spec_cell, *spec_trial, *spec_of_trial;
+  // atoms accepted so far in this call ("spec" entries, append-only; a dead entry has trial INT_MAX).
+  // There are few of them (one per accepted trial), so a gather filters the whole array against
+  // its 27-cell window instead of walking per-cell lists.
+  int *spec_trial, *spec_of_trial;
   double *spec_pos;
   int spec_cap;
   obmd_trial *cur;
@@ -61,11 +67,24 @@ struct UsherArgs {
   int *npts;
   float *bbox;
   int *kfirst, *list;
+  int2 *pairs;        // (trial, change record) pairs that passed the bounding-box test
+  int pair_cap;
   ChgRec *chg;
   int *acc_list;
   StepScalars *sc;
   int ntr, limit;
   double rc, rsqmax;  // dirty test: cutoff with a small margin
+  float wf[3], pf[3], ipf[3];  // fp32 screen: cell widths, periods, inverse periods
+  float cut32;        // widened squared cutoff of the fp32 screen
+  int debug;          // OBMD_B200_DEBUG_FIX: print the phase times of the fix-up kernel
+};
+
+// the accepted-atom entries of this call, cached in shared memory by the fix-up kernel at the start of
+// every re-run round (entries beyond the cache are read from global memory)
+struct SpecSm {
+  const double *x, *y, *z;
+  const int *tr;
+  int n_sm, n_all;
 };
 
 __device__ __forceinline__ int ranpark_pow(long long n)
@@ -110,47 +129,67 @@ __device__ __forceinline__ void usher_single(double a0, double cut, double rsq, 
 }
 
 // ---- stencil gather -------------------------------------------------------------------------------
-// The lanes of a group own the 27 cells around (cx, cy, cz): cell ranges of the sorted atoms, the
-// atoms appended after the sort (slab runs, earlier passes) and the atoms accepted earlier in this
-// call by trials < t.  A group scan turns the counts into a flat candidate list (slot codes first,
-// then one balanced pass loads the coordinates and stores the fp32 screening copy).
+// The lanes of a group own the 27 cells around (cx, cy, cz).  Each lane reads its cells' ranges (sorted
+// atoms plus the atoms appended after the sort: slab runs, earlier passes), a group scan gives it
+// its place in the candidate list, and it stores the fp32 screening copy of its own atoms directly:
+// coordinates relative to the corner of the centre cell, shifted to the periodic image next to it
+// (the lane knows whether its cell was reached across a periodic face).  Atoms in a face cell may
+// still carry coordinates Domain::pbc has not wrapped yet; only those cells pay for a generic fix.
+// Atoms accepted earlier in this call by trials < t are filtered against the 27-cell window.
+struct LaneCell {  // per lane, fixed for the kernel: offsets of the cells it owns
+  int ox[2], oy[2], oz[2];
+};
+
 template <int G>
-__device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroup &S, int cx, int cy, int cz, int t,
-                                            double ox, double oy, double oz, int gl, unsigned gmask,
-                                            bool have_extras, bool have_spec)
+__device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroup &S, const LaneCell &lc, int cx, int cy,
+                                            int cz, int t, double ox, double oy, double oz, int gl, int gbase,
+                                            unsigned gmask, bool have_extras, const SpecSm *sp)
 {
   constexpr int NCL = (27 + G - 1) / G;
+  static_assert(NCL <= 2, "lane groups of at least 16 lanes");
+  constexpr unsigned GM = (G == 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
   const Grid &g = A.g;
-  int jb[NCL], cnt[NCL], cc[NCL], oyz[NCL];
+  if (G == 32 && gl < 25) {
+    // the next gather of this trial is at most one cell away: pull the cell_start rows of the 5 x 5
+    // columns around this cell into L1 now, so that its first dependent round trip is short
+    const int a = (gl * 13) >> 6;  // gl / 5 for gl < 25
+    const int bx = cx + a - 2;
+    int by = cy + (gl - 5 * a) - 2;
+    by = by < 0 ? by + g.ny : (by >= g.ny ? by - g.ny : by);
+    if (bx >= 0 && bx < g.nx && by >= 0 && by < g.ny) {
+      const int *row = A.cell_start + (bx * g.ny + by) * g.nz;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(row + max(cz - 2, 0)));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(row + min(cz + 3, g.nz)));
+    }
+  }
+  int jb[NCL], cnt[NCL], hd[NCL];
+  double oyl[NCL], ozl[NCL];
+  bool face[NCL];
   int tot = 0;
 #pragma unroll
   for (int s = 0; s < NCL; s++) {
-    const int n = gl + s * G;
-    cc[s] = -1;
     jb[s] = 0;
     cnt[s] = 0;
-    oyz[s] = 0;
-    if (n < 27) {
-      const int a = (n * 11) >> 5;  // n / 3 for n < 32
-      const int oz_ = n - 3 * a - 1;
-      const int b = (a * 11) >> 5;  // n / 9
-      const int oy_ = a - 3 * b - 1, ox_ = b - 1;
-      const int bx = cx + ox_;
-      if (bx >= 0 && bx < g.nx) {
-        int by = cy + oy_, bz = cz + oz_;  // offsets are +-1: wrap without a division
-        by = by < 0 ? by + g.ny : (by >= g.ny ? by - g.ny : by);
-        bz = bz < 0 ? bz + g.nz : (bz >= g.nz ? bz - g.nz : bz);
-        const int c2 = (bx * g.ny + by) * g.nz + bz;
-        cc[s] = c2;
-        jb[s] = __ldg(A.cell_start + c2);
-        cnt[s] = __ldg(A.cell_start + c2 + 1) - jb[s];
-        oyz[s] = (oy_ + 1) | ((oz_ + 1) << 2);
-        tot += cnt[s];
-        if (have_extras)
-          for (int e = __ldg(A.extra_head + c2); e >= 0; e = __ldg(A.extra_next + e)) tot++;
-        if (have_spec)
-          for (int e = __ldcg(A.spec_head + c2); e >= 0; e = __ldcg(A.spec_next + e))
-            tot += (__ldcg(A.spec_trial + e) < t) ? 1 : 0;
+    hd[s] = -1;
+    oyl[s] = oy;
+    ozl[s] = oz;
+    face[s] = false;
+    const int bx = cx + lc.ox[s];
+    if (gl + s * G < 27 && bx >= 0 && bx < g.nx) {
+      int by = cy + lc.oy[s], bz = cz + lc.oz[s];  // offsets are +-1: wrap without a division
+      // a cell reached across the low face holds atoms one period above their image next to the centre
+      if (by < 0) { by += g.ny; oyl[s] = oy + g.prd[1]; }
+      else if (by >= g.ny) { by -= g.ny; oyl[s] = oy - g.prd[1]; }
+      if (bz < 0) { bz += g.nz; ozl[s] = oz + g.prd[2]; }
+      else if (bz >= g.nz) { bz -= g.nz; ozl[s] = oz - g.prd[2]; }
+      face[s] = by == 0 || by == g.ny - 1 || bz == 0 || bz == g.nz - 1;
+      const int c2 = (bx * g.ny + by) * g.nz + bz;
+      jb[s] = __ldg(A.cell_start + c2);
+      cnt[s] = __ldg(A.cell_start + c2 + 1) - jb[s];
+      tot += cnt[s];
+      if (have_extras) {
+        hd[s] = __ldg(A.extra_head + c2);
+        for (int e = hd[s]; e >= 0; e = __ldg(A.extra_next + e)) tot++;
       }
     }
   }
@@ -160,69 +199,112 @@ __device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroup &S, int c
     const int v = __shfl_up_sync(gmask, inc, d, G);
     if (gl >= d) inc += v;
   }
-  const int ncand = __shfl_sync(gmask, inc, G - 1, G);
+  int ncand = __shfl_sync(gmask, inc, G - 1, G);
   if (ncand > USH_CAND) {
     if (gl == 0) A.sc->usher_error = OBMD_ERR_CAPACITY;
     return 0;
   }
   int off = inc - tot;  // exclusive
-  int2 *codes = reinterpret_cast<int2 *>(S.scr);  // candidate q: {slot code, (oy+1) | (oz+1) << 2} in .z/.w
 #pragma unroll
   for (int s = 0; s < NCL; s++) {
-    if (cc[s] < 0) continue;
-    for (int k = 0; k < cnt[s]; k++) codes[2 * (off++) + 1] = make_int2(jb[s] + k, oyz[s]);
-    if (have_extras)
-      for (int e = __ldg(A.extra_head + cc[s]); e >= 0; e = __ldg(A.extra_next + e))
-        codes[2 * (off++) + 1] = make_int2(A.ex.base + e, oyz[s]);
-    if (have_spec)
-      for (int e = __ldcg(A.spec_head + cc[s]); e >= 0; e = __ldcg(A.spec_next + e))
-        if (__ldcg(A.spec_trial + e) < t) codes[2 * (off++) + 1] = make_int2(-(e + 1), oyz[s]);
-  }
-  __syncwarp(gmask);
-  const float wy = (float) (g.prd[1] / g.ny), wz = (float) (g.prd[2] / g.nz);
-  const float py = (float) g.prd[1], pz = (float) g.prd[2];
-  const float ipy = 1.0f / py, ipz = 1.0f / pz;
-  for (int q = gl; q < ncand; q += G) {
-    const int2 cd = codes[2 * q + 1];
-    double xj, yj, zj;
-    if (cd.x >= 0) {
-      xj = __ldg(A.p.x + cd.x);
-      yj = __ldg(A.p.y + cd.x);
-      zj = __ldg(A.p.z + cd.x);
-    } else {  // accepted earlier in this call
-      const double *sp = A.spec_pos + 3 * (size_t) (-cd.x - 1);
-      xj = __ldcg(sp);
-      yj = __ldcg(sp + 1);
-      zj = __ldcg(sp + 2);
+    const float ty = ((float) lc.oy[s] + 0.5f) * A.wf[1], tz = ((float) lc.oz[s] + 0.5f) * A.wf[2];
+    // the cell's sorted atoms, four at a time with all twelve coordinate loads in flight at once (a
+    // cell holds ~3 atoms: one round trip in almost every case), then its list of appended atoms
+    for (int k0 = 0; k0 < cnt[s]; k0 += 4) {
+      double xj[4], yj[4], zj[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int j = jb[s] + min(k0 + q, cnt[s] - 1);
+        xj[q] = __ldg(A.p.x + j);
+        yj[q] = __ldg(A.p.y + j);
+        zj[q] = __ldg(A.p.z + j);
+      }
+      // the exact evaluation will want the local index of the few candidates inside the cutoff
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(A.p.lidx + jb[s] + k0));
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if (k0 + q >= cnt[s]) break;
+        const float rx = (float) (xj[q] - ox);
+        float ry = (float) (yj[q] - oyl[s]), rz = (float) (zj[q] - ozl[s]);
+        if (face[s]) {  // coordinates Domain::pbc has not wrapped yet
+          ry -= A.pf[1] * rintf((ry - ty) * A.ipf[1]);
+          rz -= A.pf[2] * rintf((rz - tz) * A.ipf[2]);
+        }
+        S.scr[off++] = make_uint4(__float_as_uint(rx), __float_as_uint(ry), __float_as_uint(rz),
+                                  (unsigned) (jb[s] + k0 + q));
+      }
     }
-    const float rx = (float) (xj - ox);
-    float ry = (float) (yj - oy), rz = (float) (zj - oz);
-    // periodic image next to the centre cell (also covers coordinates Domain::pbc has not wrapped
-    // yet): the candidate's cell is at offset o, its centre at (o + 0.5) cell widths
-    const float ty = ((float) (cd.y & 3) - 0.5f) * wy, tz = ((float) (cd.y >> 2) - 0.5f) * wz;
-    ry -= py * rintf((ry - ty) * ipy);
-    rz -= pz * rintf((rz - tz) * ipz);
-    S.scr[q] = make_uint4(__float_as_uint(rx), __float_as_uint(ry), __float_as_uint(rz), (unsigned) cd.x);
+    for (int e = hd[s]; e >= 0; e = __ldg(A.extra_next + e)) {
+      const int j = A.ex.base + e;
+      const double xj = __ldg(A.p.x + j), yj = __ldg(A.p.y + j), zj = __ldg(A.p.z + j);
+      const float rx = (float) (xj - ox);
+      float ry = (float) (yj - oyl[s]), rz = (float) (zj - ozl[s]);
+      if (face[s]) {
+        ry -= A.pf[1] * rintf((ry - ty) * A.ipf[1]);
+        rz -= A.pf[2] * rintf((rz - tz) * A.ipf[2]);
+      }
+      S.scr[off++] = make_uint4(__float_as_uint(rx), __float_as_uint(ry), __float_as_uint(rz), (unsigned) j);
+    }
+  }
+  if (sp) {
+    // atoms accepted earlier in this call by trials < t: the entries whose position falls into the
+    // 27-cell window (a superset of those within the cutoff of any point of the centre cell) are
+    // appended, already in screening form
+    const float lox = -1.001f * A.wf[0], hix = 2.001f * A.wf[0], loy = -1.001f * A.wf[1], hiy = 2.001f * A.wf[1];
+    const float loz = -1.001f * A.wf[2], hiz = 2.001f * A.wf[2];
+    for (int e0 = 0; e0 < sp->n_all; e0 += G) {
+      const int e = e0 + gl;
+      bool in = false;
+      float rx = 0.f, ry = 0.f, rz = 0.f;
+      if (e < sp->n_all) {
+        const bool sm = e < sp->n_sm;
+        const int tr = sm ? sp->tr[e] : __ldcg(A.spec_trial + e);
+        if (tr < t) {  // a retired entry has trial INT_MAX
+          const double xs = sm ? sp->x[e] : __ldcg(A.spec_pos + 3 * (size_t) e);
+          const double ys = sm ? sp->y[e] : __ldcg(A.spec_pos + 3 * (size_t) e + 1);
+          const double zs = sm ? sp->z[e] : __ldcg(A.spec_pos + 3 * (size_t) e + 2);
+          rx = (float) (xs - ox);
+          ry = (float) (ys - oy);
+          rz = (float) (zs - oz);
+          ry -= A.pf[1] * rintf((ry - 0.5f * A.wf[1]) * A.ipf[1]);
+          rz -= A.pf[2] * rintf((rz - 0.5f * A.wf[2]) * A.ipf[2]);
+          in = rx > lox && rx < hix && ry > loy && ry < hiy && rz > loz && rz < hiz;
+        }
+      }
+      const unsigned m = (G == 32) ? __ballot_sync(gmask, in) : ((__ballot_sync(gmask, in) >> gbase) & GM);
+      if (in) {
+        const int pos = ncand + __popc(m & ((1u << gl) - 1u));
+        if (pos < USH_CAND)
+          S.scr[pos] = make_uint4(__float_as_uint(rx), __float_as_uint(ry), __float_as_uint(rz), (unsigned) (-(e + 1)));
+      }
+      ncand += __popc(m);
+    }
+    if (ncand > USH_CAND) {
+      if (gl == 0) A.sc->usher_error = OBMD_ERR_CAPACITY;
+      ncand = 0;
+    }
   }
   __syncwarp(gmask);
   return ncand;
 }
 
 // ---- one energy evaluation (:1774-1810) -------------------------------------------------------------
-// Returns E and f in every lane of the group.
+// Returns E in every lane of the group and f[d] in lane d + 1 (lane 0: E) as `mine`.
 template <bool ST, int G>
 __device__ __forceinline__ void usher_energy(const UsherArgs &A, const PairTab &pt, UGroup &S, const double c[3],
                                              double ox, double oy, double oz, int nc, bool wrap,
                                              const double k1[3], int gl, int gbase, unsigned gmask,
-                                             double &E, double f[3])
+                                             double &E, double f[3], long long *pc)
 {
   constexpr unsigned GM = (G == 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+  constexpr int NS = (USH_CAP + G - 1) / G;
+  long long c0 = pc ? clock64() : 0;
   const Grid &g = A.g;
   const int it = A.fd.ntype;
   // fp32 screen: a superset of the exact test (coordinates relative to the cell corner are below three
   // cell widths, so the absolute error of rsq is ~1e-6; the margin is 1e-3)
   const float px = (float) (c[0] - ox), py = (float) (c[1] - oy), pz = (float) (c[2] - oz);
-  const float cut32 = (float) pt.cutmax * (float) pt.cutmax * 1.001f;
+  const unsigned lt = (1u << gl) - 1u;
   int nh = 0;
   for (int q0 = 0; q0 < nc; q0 += G) {
     const int q = q0 + gl;
@@ -230,11 +312,11 @@ __device__ __forceinline__ void usher_energy(const UsherArgs &A, const PairTab &
     if (q < nc) {
       const uint4 s = S.scr[q];
       const float dx = px - __uint_as_float(s.x), dy = py - __uint_as_float(s.y), dz = pz - __uint_as_float(s.z);
-      hit = dx * dx + dy * dy + dz * dz < cut32;
+      hit = dx * dx + dy * dy + dz * dz < A.cut32;
     }
-    const unsigned m = (__ballot_sync(gmask, hit) >> gbase) & GM;
+    const unsigned m = (G == 32) ? __ballot_sync(gmask, hit) : ((__ballot_sync(gmask, hit) >> gbase) & GM);
     if (hit) {
-      const int s2 = nh + __popc(m & ((1u << gl) - 1u));
+      const int s2 = nh + __popc(m & lt);
       if (s2 < USH_CAP) S.hq[s2] = (unsigned short) q;
     }
     nh += __popc(m);
@@ -244,82 +326,107 @@ __device__ __forceinline__ void usher_energy(const UsherArgs &A, const PairTab &
     nh = USH_CAP;
   }
   __syncwarp(gmask);
+  if (pc) { long long c1 = clock64(); pc[2] += c1 - c0; c0 = c1; }
   // exact evaluation of the screened candidates: separation with the reference's minimum_image loop
   // (domain.cpp:980-1008, y and z periodic; skipped when the stencil touches no periodic face, where
-  // it cannot change anything), exact cutoff test, PairDPD::single
-  for (int k = gl; k < nh; k += G) {
-    const int code = (int) S.scr[S.hq[k]].w;
-    double xj, yj, zj;
-    int key, tj = it;
-    if (code >= 0) {
-      xj = __ldg(A.p.x + code);
-      yj = __ldg(A.p.y + code);
-      zj = __ldg(A.p.z + code);
-      key = __ldg(A.p.lidx + code);
-      if (!ST) tj = __ldg(A.p.type + code);
-    } else {  // created earlier in this call: local index nbase + (rank among the accepted trials);
-              // the trial index orders the created atoms the same way
-      const int e = -code - 1;
-      const double *sp = A.spec_pos + 3 * (size_t) e;
-      xj = __ldcg(sp);
-      yj = __ldcg(sp + 1);
-      zj = __ldcg(sp + 2);
-      key = A.u.nbase + __ldcg(A.spec_trial + e);
-    }
-    double delx = c[0] - xj, dely = c[1] - yj, delz = c[2] - zj;
-    if (wrap) {
-      while (fabs(dely) > g.half[1]) {
-        if (dely < 0.0) dely += g.prd[1];
-        else dely -= g.prd[1];
+  // it cannot change anything), exact cutoff test, PairDPD::single.  Results stay in registers until
+  // every key is known.
+  double ev[NS], xv[NS], yv[NS], zv[NS];
+  int kv[NS];
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    const int k = gl + s * G;
+    kv[s] = 0;
+    ev[s] = xv[s] = yv[s] = zv[s] = 0.0;
+    if (k < nh) {
+      const int code = (int) S.scr[S.hq[k]].w;
+      double xj, yj, zj;
+      int key, tj = it;
+      if (code >= 0) {
+        xj = __ldg(A.p.x + code);
+        yj = __ldg(A.p.y + code);
+        zj = __ldg(A.p.z + code);
+        key = __ldg(A.p.lidx + code);
+        if (!ST) tj = __ldg(A.p.type + code);
+      } else {  // created earlier in this call: local index nbase + (rank among the accepted trials);
+                // the trial index orders the created atoms the same way
+        const int e = -code - 1;
+        const double *sp = A.spec_pos + 3 * (size_t) e;
+        xj = __ldcg(sp);
+        yj = __ldcg(sp + 1);
+        zj = __ldcg(sp + 2);
+        key = A.u.nbase + __ldcg(A.spec_trial + e);
       }
-      while (fabs(delz) > g.half[2]) {
-        if (delz < 0.0) delz += g.prd[2];
-        else delz -= g.prd[2];
+      double delx = c[0] - xj, dely = c[1] - yj, delz = c[2] - zj;
+      if (wrap) {
+        while (fabs(dely) > g.half[1]) {
+          if (dely < 0.0) dely += g.prd[1];
+          else dely -= g.prd[1];
+        }
+        while (fabs(delz) > g.half[2]) {
+          if (delz < 0.0) delz += g.prd[2];
+          else delz -= g.prd[2];
+        }
       }
+      const double rsq = delx * delx + dely * dely + delz * delz;
+      if (rsq < (ST ? k1[2] : pt.cutsq[it][tj])) {
+        xv[s] = delx;
+        yv[s] = dely;
+        zv[s] = delz;
+        if (ST) usher_single(k1[0], k1[1], rsq, ev[s], xv[s], yv[s], zv[s]);
+        else usher_single(pt.a0[it][tj], pt.cut[it][tj], rsq, ev[s], xv[s], yv[s], zv[s]);
+      } else
+        key = KEY_DROP + k;  // outside the exact cutoff: contributes +0.0 behind every real term
+      kv[s] = key;
+      S.key[k] = key;
     }
-    const double rsq = delx * delx + dely * dely + delz * delz;
-    double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
-    if (rsq < (ST ? k1[2] : pt.cutsq[it][tj])) {
-      fx = delx;
-      fy = dely;
-      fz = delz;
-      if (ST) usher_single(k1[0], k1[1], rsq, e, fx, fy, fz);
-      else usher_single(pt.a0[it][tj], pt.cut[it][tj], rsq, e, fx, fy, fz);
-    } else
-      key = KEY_DROP + k;  // outside the exact cutoff: contributes +0.0 behind every real term
-    S.key[k] = key;
-    S.e[k] = e;
-    S.fx[k] = fx;
-    S.fy[k] = fy;
-    S.fz[k] = fz;
+  }
+  const int nh4 = (nh + 3) & ~3;
+  if (gl < nh4 - nh) S.key[nh + gl] = 0x7fffffff;  // pad: the rank loop reads four keys per trip
+  __syncwarp(gmask);
+  if (pc) { long long c1 = clock64(); pc[3] += c1 - c0; c0 = c1; }
+  // every contribution goes to its rank by local index (keys are distinct), then left-to-right sums
+  // in ascending local index, one lane per quantity -- the reference's loop order (:1790-1807)
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    const int k = gl + s * G;
+    if (k < nh) {
+      const int key = kv[s];
+      int r = 0;
+      for (int k2 = 0; k2 < nh4; k2 += 4) {
+        const int4 kk = *reinterpret_cast<const int4 *>(&S.key[k2]);
+        r += (kk.x < key) + (kk.y < key) + (kk.z < key) + (kk.w < key);
+      }
+      S.e[r] = ev[s];
+      S.fx[r] = xv[s];
+      S.fy[r] = yv[s];
+      S.fz[r] = zv[s];
+    }
+  }
+  if (gl < nh4 - nh) {  // adding the +0.0 padding is exact
+    S.e[nh + gl] = 0.0;
+    S.fx[nh + gl] = 0.0;
+    S.fy[nh + gl] = 0.0;
+    S.fz[nh + gl] = 0.0;
   }
   __syncwarp(gmask);
-  // rank by local index (keys are distinct), then left-to-right sums in ascending local index, one
-  // lane per quantity -- the reference's loop order (:1790-1807)
-  for (int k = gl; k < nh; k += G) {
-    const int key = S.key[k];
-    int r = 0;
-    for (int k2 = 0; k2 < nh; k2++) r += (S.key[k2] < key) ? 1 : 0;
-    S.inv[r] = (unsigned char) k;
-  }
-  __syncwarp(gmask);
+  if (pc) { long long c1 = clock64(); pc[4] += c1 - c0; c0 = c1; }
   double acc = 0.0;
   if (gl < 4) {
     const double *arr = gl == 0 ? S.e : (gl == 1 ? S.fx : (gl == 2 ? S.fy : S.fz));
-    int r = 0;
-    for (; r + 4 <= nh; r += 4) {
-      const double a0 = arr[S.inv[r]], a1 = arr[S.inv[r + 1]], a2 = arr[S.inv[r + 2]], a3 = arr[S.inv[r + 3]];
-      acc += a0;
-      acc += a1;
-      acc += a2;
-      acc += a3;
+    for (int r = 0; r < nh4; r += 4) {
+      const double2 a01 = *reinterpret_cast<const double2 *>(arr + r), a23 = *reinterpret_cast<const double2 *>(arr + r + 2);
+      acc += a01.x;
+      acc += a01.y;
+      acc += a23.x;
+      acc += a23.y;
     }
-    for (; r < nh; r++) acc += arr[S.inv[r]];
   }
   E = __shfl_sync(gmask, acc, 0, G);
   f[0] = __shfl_sync(gmask, acc, 1, G);
   f[1] = __shfl_sync(gmask, acc, 2, G);
   f[2] = __shfl_sync(gmask, acc, 3, G);
+  if (pc) { long long c1 = clock64(); pc[5] += c1 - c0; pc[7] += nh; }
 }
 
 // ---- trials ------------------------------------------------------------------------------------
@@ -328,7 +435,8 @@ __device__ __forceinline__ void usher_energy(const UsherArgs &A, const PairTab &
 // re-run from their first affected evaluation point (static assignment: group first, first + stride ...).
 template <bool ST, int G>
 __device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &pt, UGroup *groups,
-                                             const int *list, int nl, int *cursor, int first, int stride)
+                                             const int *list, int nl, int *cursor, int first, int stride,
+                                             const SpecSm *sp)
 {
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1), gbase = lane & ~(G - 1);
@@ -340,8 +448,14 @@ __device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &
   const UsherCfg &u = A.u;
   const double k1[3] = {pt.a0[fd.ntype][fd.ntype], pt.cut[fd.ntype][fd.ntype], pt.cutsq[fd.ntype][fd.ntype]};
   const bool have_extras = (A.ex.narr + A.ex.nghost + A.ex.nins) > 0;
-  const bool have_spec = list != nullptr;  // nothing has been accepted yet in round 0
-  const double wx = g.prd[0] / g.gnx, wy = g.prd[1] / g.ny, wz = g.prd[2] / g.nz;
+  LaneCell lc;
+  for (int s = 0; s < 2; s++) {
+    const int n = min(gl + s * G, 26);
+    const int a = (n * 11) >> 5, b = (((n * 11) >> 5) * 11) >> 5;  // n / 3, n / 9 for n < 32
+    lc.oz[s] = n - 3 * a - 1;
+    lc.oy[s] = a - 3 * b - 1;
+    lc.ox[s] = b - 1;
+  }
 
   bool active = false, more = true;
   int t = 0, side = 0, i = 0, np = 0, nc = 0, gx = 0, gy = 0, gz = 0, nextli = first;
@@ -349,6 +463,10 @@ __device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &
   double c[3] = {0, 0, 0}, start[3] = {0, 0, 0}, E = 0.0, ox = 0.0, oy = 0.0, oz = 0.0;
   float blo[3] = {0, 0, 0}, bhi[3] = {0, 0, 0};
   double *mypath = A.path;
+  unsigned long long tdbg0 = 0;
+  int idbg0 = 0, ngath = 0;
+  const bool dbgp = USHER_DEBUG && A.debug && list;
+  long long pcl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (;;) {
     if (!active && more) {
       int li;
@@ -392,6 +510,12 @@ __device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &
         gx = -(1 << 30);
         E = 0.0;
         active = true;
+        if (USHER_DEBUG && A.debug && list) {
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg0));
+          idbg0 = i;
+          ngath = 0;
+          for (int q = 0; q < 8; q++) pcl[q] = 0;
+        }
       } else
         more = false;
     }
@@ -399,6 +523,7 @@ __device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &
     if (!active) continue;
 
     const obmd_block &reg = fd.region[4 + side];
+    long long cA = dbgp ? clock64() : 0;
     // the point is inside the insertion region, hence inside the box: the cell index is at most one
     // period off (y == yhi exactly), so the wrap needs no division
     const int cx = cell_cx(g, c[0]);
@@ -407,21 +532,25 @@ __device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &
     else if (cy >= g.ny) cy -= g.ny;
     if (cz < 0 || cz >= 2 * g.nz) cz = cell_wrap(cz, g.nz);
     else if (cz >= g.nz) cz -= g.nz;
+    if (dbgp) { long long c1 = clock64(); pcl[0] += c1 - cA; cA = c1; }
     if (cx != gx || cy != gy || cz != gz) {
-      ox = g.lo[0] + (cx + g.cxoff) * wx;
-      oy = g.lo[1] + cy * wy;
-      oz = g.lo[2] + cz * wz;
-      nc = usher_gather<G>(A, S, cx, cy, cz, t, ox, oy, oz, gl, gmask, have_extras, have_spec);
+      ox = g.lo[0] + (cx + g.cxoff) * g.w[0];
+      oy = g.lo[1] + cy * g.w[1];
+      oz = g.lo[2] + cz * g.w[2];
+      nc = usher_gather<G>(A, S, lc, cx, cy, cz, t, ox, oy, oz, gl, gbase, gmask, have_extras, sp);
       gx = cx;
       gy = cy;
       gz = cz;
+      ngath++;
       // pre_exchange runs before Domain::pbc: an atom that has just left through a periodic face still
       // carries its unwrapped coordinate and sits in a face cell, so stencils reaching the face layer
       // (points in the two outermost layers) need the reference's minimum-image loop
       wrap = g.ny < 6 || g.nz < 6 || cy <= 1 || cy >= g.ny - 2 || cz <= 1 || cz >= g.nz - 2;
     }
+    if (dbgp) { long long c1 = clock64(); pcl[1] += c1 - cA; cA = c1; }
     double f[3];
-    usher_energy<ST, G>(A, pt, S, c, ox, oy, oz, nc, wrap, k1, gl, gbase, gmask, E, f);
+    usher_energy<ST, G>(A, pt, S, c, ox, oy, oz, nc, wrap, k1, gl, gbase, gmask, E, f, dbgp ? pcl : nullptr);
+    if (dbgp) cA = clock64();
     if (gl == 0) {
       mypath[np * 3 + 0] = c[0];
       mypath[np * 3 + 1] = c[1];
@@ -440,12 +569,15 @@ __device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &
         if (gl == 0) A.sc->usher_error = OBMD_ERR_USHER;
         done = true;
       } else {
+        // the four quotients by |f| (:1586-1600), one lane each: the division sequence is issued once
+        const double num = gl == 0 ? E - fd.etarget : (gl == 1 ? f[0] : (gl == 2 ? f[1] : f[2]));
+        const double quo = num / fabs_;
         double ds;
         if (E > fd.uovlp) ds = fd.dsovlp - pow(4 * fd.eps / E, 1.0 / 12.0);
-        else ds = fmin((E - fd.etarget) / fabs_, fd.ds0);
-        c[0] += f[0] / fabs_ * ds;
-        c[1] += f[1] / fabs_ * ds;
-        c[2] += f[2] / fabs_ * ds;
+        else ds = fmin(__shfl_sync(gmask, quo, 0, G), fd.ds0);
+        c[0] += __shfl_sync(gmask, quo, 1, G) * ds;
+        c[1] += __shfl_sync(gmask, quo, 2, G) * ds;
+        c[2] += __shfl_sync(gmask, quo, 3, G) * ds;
         if (!block_inside(reg, c[0], c[1], c[2])) done = true;  // check_mol_region (:1700-1712)
         else {
           i += 1;
@@ -453,6 +585,7 @@ __device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &
         }
       }
     }
+    if (dbgp) { long long c1 = clock64(); pcl[6] += c1 - cA; }
     if (!done) continue;
 
     bool ok = (E < fd.etarget + EPSILON_FIX);
@@ -483,22 +616,21 @@ __device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &
       }
     }
     active = false;
+    if (USHER_DEBUG && A.debug && list && gl == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      printf("  trial %d: evals %d gathers %d nc %d ns %llu | cyc cell %lld gather %lld screen %lld exact %lld rank %lld sum %lld step %lld nh %lld\n",
+             t, np - idbg0, ngath, nc, t1 - tdbg0, pcl[0], pcl[1], pcl[2], pcl[3], pcl[4], pcl[5], pcl[6], pcl[7]);
+    }
   }
 }
 
-#ifndef USH_G
-#define USH_G 32
-#endif
-#ifndef USH_MINB
-#define USH_MINB 6
-#endif
-
-template <bool ST, int G>
-__global__ void __launch_bounds__(USH_T, USH_MINB) k_usher_eval(const __grid_constant__ UsherArgs A, const __grid_constant__ PairTab pt, int nl)
+template <bool ST, int G, int MINB>
+__global__ void __launch_bounds__(USH_T, MINB) k_usher_eval(const __grid_constant__ UsherArgs A, const __grid_constant__ PairTab pt, int nl)
 {
   extern __shared__ __align__(16) unsigned char usm[];
   if (blockIdx.x == 0 && threadIdx.x == 0 && nl > 0) A.sc->nrounds_work++;
-  usher_trials<ST, G>(A, pt, reinterpret_cast<UGroup *>(usm), nullptr, nl, &A.sc->trial_cursor, 0, 0);
+  usher_trials<ST, G>(A, pt, reinterpret_cast<UGroup *>(usm), nullptr, nl, &A.sc->trial_cursor, 0, 0, nullptr);
 }
 
 // ---- maxattempt > 1 ------------------------------------------------------------------------------
@@ -572,8 +704,8 @@ __global__ void __launch_bounds__(1024) k_usher_resolve(const obmd_trial *cur, i
 // The accepted atom of trial t, if any, is spec entry spec_of_trial[t].  A trial whose latest
 // evaluation disagrees with it (accepted flag or position; maxattempt > 1: only attempts the serial
 // loop really makes, t < nused, can insert) retires the old entry, publishes a new one in the
-// per-cell list of its cell and leaves a change record for the dirty test.  Entry order in a cell
-// list is irrelevant: contributions are ordered by local index when they are summed.
+// entry array and leaves a change record for the dirty test.  Entry order is irrelevant:
+// contributions are ordered by local index when they are summed.
 __device__ __forceinline__ void usher_diff_one(const UsherArgs &A, int t, int par)
 {
   const obmd_trial *b = A.cur + t;
@@ -603,14 +735,8 @@ __device__ __forceinline__ void usher_diff_one(const UsherArgs &A, int t, int pa
       A.sc->usher_error = OBMD_ERR_CAPACITY + 1000;
       enew = -1;
     } else {
-      const Grid &g = A.g;
-      const int lc = min(max(cell_cx(g, n[0]), 0), g.nx - 1);
-      const int cc = (lc * g.ny + cell_cy(g, n[1])) * g.nz + cell_cz(g, n[2]);
       for (int d = 0; d < 3; d++) A.spec_pos[3 * (size_t) enew + d] = n[d];
       A.spec_trial[enew] = t;
-      A.spec_cell[enew] = cc;
-      __threadfence();  // the entry is complete before it becomes reachable
-      A.spec_next[enew] = atomicExch(&A.spec_head[cc], enew);
     }
   }
   A.spec_of_trial[t] = enew;
@@ -654,6 +780,7 @@ __device__ __forceinline__ bool near_bbox(const double *a, const float *bb, cons
 // A trial must be re-run when an earlier trial whose state changed has its old or new atom within
 // the cutoff of any point the trial evaluated (a superset test with a small margin).
 // kfirst[t] = index of the first such point: the re-run resumes there.  One warp per trial.
+template <bool CACHED>  // CACHED: the inputs were written by an earlier kernel (L1 may hold them)
 __device__ __forceinline__ void usher_dirty_one(const UsherArgs &A, int t, int par, int lane)
 {
   const Grid &g = A.g;
@@ -672,12 +799,15 @@ __device__ __forceinline__ void usher_dirty_one(const UsherArgs &A, int t, int p
     for (int d = 0; d < 3; d++) r.o[d] = r.n[d] = 0.0;
     if (qi < nchg) {
       const ChgRec *src = A.chg + qi;
-      for (int d = 0; d < 3; d++) {
-        r.o[d] = __ldcg(&src->o[d]);
-        r.n[d] = __ldcg(&src->n[d]);
+      if (CACHED) r = *src;
+      else {
+        for (int d = 0; d < 3; d++) {
+          r.o[d] = __ldcg(&src->o[d]);
+          r.n[d] = __ldcg(&src->n[d]);
+        }
+        r.q = __ldcg(&src->q);
+        r.flags = __ldcg(&src->flags);
       }
-      r.q = __ldcg(&src->q);
-      r.flags = __ldcg(&src->flags);
     }
     const bool oldacc = r.q < t && (r.flags & 1) && near_bbox(r.o, bb, g, A.rc);
     const bool newacc = r.q < t && (r.flags & 2) && near_bbox(r.n, bb, g, A.rc);
@@ -717,40 +847,138 @@ __global__ void k_usher_dirty(const __grid_constant__ UsherArgs A)
 {
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= A.ntr || A.sc->nchg2[0] == 0) return;
-  usher_dirty_one(A, t, 0, threadIdx.x & 31);
+  usher_dirty_one<true>(A, t, 0, threadIdx.x & 31);
 }
 
 // ---- re-run rounds, all in one launch ---------------------------------------------------------------
+#define SPEC_SM 2048  // accepted-atom entries cached in shared memory (more are read from global memory)
+
+// Dirty test of a re-run round, in three sweeps separated by cluster barriers.  The change records
+// are few (one per re-run trial at most), so they are staged in shared memory once per CTA.
+//  1. every THREAD takes a trial: one round trip for its bounding box, then the records at shared-memory
+//     speed; a (trial, record) pair that passes the box test goes to a queue;
+//  2. one warp per queued pair tests all evaluated points of the trial at once and lowers kfirst[t];
+//  3. the trials with kfirst[t] < npts[t] form the list of the next round.
+__device__ void usher_dirty_sweep1(const UsherArgs &A, int nchg, ChgRec *srec, int gtid, int gthreads)
+{
+  const Grid &g = A.g;
+  for (int k = threadIdx.x; k < nchg * (int) (sizeof(ChgRec) / 4); k += blockDim.x)
+    reinterpret_cast<int *>(srec)[k] = __ldcg(reinterpret_cast<const int *>(A.chg) + k);
+  __syncthreads();
+  for (int t = gtid; t < A.ntr; t += gthreads) {
+    float bb[6];
+    for (int d = 0; d < 6; d++) bb[d] = __ldcg(A.bbox + (size_t) t * 6 + d);
+    A.kfirst[t] = 0x7fffffff;
+    for (int q = 0; q < nchg; q++) {
+      const ChgRec &r = srec[q];
+      if (r.q >= t) continue;
+      const bool oa = (r.flags & 1) && near_bbox(r.o, bb, g, A.rc);
+      const bool na = (r.flags & 2) && near_bbox(r.n, bb, g, A.rc);
+      if (!(oa || na)) continue;
+      const int k = atomicAdd(&A.sc->npairs, 1);
+      if (k < A.pair_cap) A.pairs[k] = make_int2(t, q);
+      else A.sc->usher_error = OBMD_ERR_CAPACITY + 1000;
+    }
+  }
+}
+
+__device__ void usher_dirty_sweep2(const UsherArgs &A, int gw, int nwarp, int lane)
+{
+  const Grid &g = A.g;
+  const int npairs = min(*(volatile int *) &A.sc->npairs, A.pair_cap);
+  for (int k = gw; k < npairs; k += nwarp) {
+    const int2 pr = __ldcg(A.pairs + k);
+    const int t = pr.x;
+    const ChgRec *src = A.chg + pr.y;
+    double o[3], n[3];
+    for (int d = 0; d < 3; d++) {
+      o[d] = __ldcg(&src->o[d]);
+      n[d] = __ldcg(&src->n[d]);
+    }
+    const int flags = __ldcg(&src->flags);
+    const int np = __ldcg(A.npts + t);
+    const double *mp = A.path + (size_t) t * (A.u.natt + 1) * 3;
+    for (int k0 = 0; k0 < np; k0 += 32) {
+      const int kk = k0 + lane;
+      bool hit = false;
+      if (kk < np) {
+        const double bx = __ldcg(mp + 3 * kk), by = __ldcg(mp + 3 * kk + 1), bz = __ldcg(mp + 3 * kk + 2);
+        hit = ((flags & 1) && near_pt(o, bx, by, bz, g, A.rsqmax)) || ((flags & 2) && near_pt(n, bx, by, bz, g, A.rsqmax));
+      }
+      const unsigned hm = __ballot_sync(0xffffffffu, hit);
+      if (hm) {
+        if (lane == 0) atomicMin(&A.kfirst[t], k0 + __ffs(hm) - 1);
+        break;
+      }
+    }
+  }
+}
+
+__device__ void usher_dirty_sweep3(const UsherArgs &A, int par, int gtid, int gthreads)
+{
+  for (int t = gtid; t < A.ntr; t += gthreads)
+    if (__ldcg(A.kfirst + t) < __ldcg(A.npts + t)) A.list[atomicAdd(&A.sc->ndirty2[par], 1)] = t;
+}
+
 // One thread-block cluster.  Round r >= 1: re-run the trials the dirty test of round r-1 listed (one
 // warp per trial: the rounds are a handful of dependent 40-iteration chains, latency is what
 // counts), then resolve / diff / dirty as after round 0, until a round changes nothing.  Finally the
 // accepted trials are compacted in order into acc_list (they become local indices nbase, nbase+1, ...
-// and tags maxtag+1, ...) and the per-cell lists are cleared for the next call.
-template <bool ST>
-__global__ void __cluster_dims__(FIX_CL, 1, 1) __launch_bounds__(FIX_T, 1) k_usher_fix(const __grid_constant__ UsherArgs A, const __grid_constant__ PairTab pt)
+// and tags maxtag+1, ...).
+template <bool ST, int FIX_CL>
+__global__ void __launch_bounds__(FIX_T, 1)
+    k_usher_fix(const __grid_constant__ UsherArgs A, const __grid_constant__ PairTab pt)
 {
   extern __shared__ __align__(16) unsigned char usm[];
   __shared__ int s_a[FIX_T], s_b[FIX_T];
   __shared__ int s_base;
   cg::cluster_group cl = cg::this_cluster();
   const int rank = (int) cl.block_rank();
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int nwarp = FIX_CL * (FIX_T / 32), gw = rank * (FIX_T / 32) + (tid >> 5);
   const int gtid = rank * FIX_T + tid, gthreads = FIX_CL * FIX_T;
   StepScalars *sc = A.sc;
   volatile int *ndirty2 = sc->ndirty2, *nchg2 = sc->nchg2;
+  UGroup *groups = reinterpret_cast<UGroup *>(usm);
+  constexpr size_t GROUP_BYTES = sizeof(UGroup) * (FIX_T / 32);
+  double *ssx = reinterpret_cast<double *>(usm + GROUP_BYTES), *ssy = ssx + SPEC_SM, *ssz = ssy + SPEC_SM;
+  int *sstr = reinterpret_cast<int *>(ssz + SPEC_SM);
+  unsigned long long tdbg[5] = {0, 0, 0, 0, 0};
+  auto now = []() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+  };
   for (int round = 1;; round++) {
     const int par = round & 1, pprev = par ^ 1;
     const int nd = ndirty2[pprev];
     if (nd == 0) break;
+    if (USHER_DEBUG && A.debug) tdbg[0] = now();
     if (round > A.ntr + 2) {  // cannot happen: trial t settles after at most t + 1 rounds
       if (gtid == 0) sc->usher_error = OBMD_ERR_STATE;
       break;
     }
-    usher_trials<ST, 32>(A, pt, reinterpret_cast<UGroup *>(usm), A.list, nd, nullptr, gw, nwarp);
+    // the atoms accepted so far, into shared memory
+    SpecSm sp;
+    sp.n_all = min(*(volatile int *) &sc->nspec, A.spec_cap);
+    sp.n_sm = min(sp.n_all, SPEC_SM);
+    sp.x = ssx;
+    sp.y = ssy;
+    sp.z = ssz;
+    sp.tr = sstr;
+    for (int e = tid; e < sp.n_sm; e += FIX_T) {
+      ssx[e] = __ldcg(A.spec_pos + 3 * (size_t) e);
+      ssy[e] = __ldcg(A.spec_pos + 3 * (size_t) e + 1);
+      ssz[e] = __ldcg(A.spec_pos + 3 * (size_t) e + 2);
+      sstr[e] = __ldcg(A.spec_trial + e);
+    }
+    __syncthreads();
+    if (USHER_DEBUG && A.debug) tdbg[1] = now();
+    usher_trials<ST, 32>(A, pt, groups, A.list, nd, nullptr, gw, nwarp, &sp);
     if (gtid == 0) sc->nrounds_work++;
     __threadfence();
     cl.sync();
+    if (USHER_DEBUG && A.debug) tdbg[2] = now();
     if (A.limit) {
       if (rank == 0) usher_resolve(A.cur, A.ntr, A.u.slots, A.u.maxatt, sc, s_a, s_b);
       __threadfence();
@@ -762,14 +990,31 @@ __global__ void __cluster_dims__(FIX_CL, 1, 1) __launch_bounds__(FIX_T, 1) k_ush
     if (gtid == 0) {  // the counters of the previous round have been consumed by everybody
       ndirty2[pprev] = 0;
       nchg2[pprev] = 0;
-      sc->nused_prev = sc->nused;
     }
     __threadfence();
     cl.sync();
-    if (nchg2[par] > 0)
-      for (int t = gw; t < A.ntr; t += nwarp) usher_dirty_one(A, t, par, lane);
+    if (USHER_DEBUG && A.debug) tdbg[3] = now();
+    const int nchg = nchg2[par];
+    if (nchg > 0) {
+      if ((size_t) nchg * sizeof(ChgRec) <= GROUP_BYTES) {
+        usher_dirty_sweep1(A, nchg, reinterpret_cast<ChgRec *>(usm), gtid, gthreads);
+        __threadfence();
+        cl.sync();
+        usher_dirty_sweep2(A, gw, nwarp, tid & 31);
+        __threadfence();
+        cl.sync();
+        usher_dirty_sweep3(A, par, gtid, gthreads);
+        if (gtid == 0) sc->npairs = 0;
+      } else
+        for (int t = gw; t < A.ntr; t += nwarp) usher_dirty_one<false>(A, t, par, tid & 31);
+    }
     __threadfence();
     cl.sync();
+    if (USHER_DEBUG && A.debug && gtid == 0) {
+      tdbg[4] = now();
+      printf("fix round %d: nd %d nchg %d nspec %d | load %llu eval %llu diff %llu dirty %llu ns\n", round, nd, nchg,
+             sp.n_all, tdbg[1] - tdbg[0], tdbg[2] - tdbg[1], tdbg[3] - tdbg[2], tdbg[4] - tdbg[3]);
+    }
   }
   // ordered compaction of the accepted trials (CTA 0): every thread owns a contiguous run of trials,
   // a block scan of the counts gives its offset
@@ -804,9 +1049,6 @@ __global__ void __cluster_dims__(FIX_CL, 1, 1) __launch_bounds__(FIX_T, 1) k_ush
       if (__ldcg(A.spec_of_trial + t) >= 0) A.acc_list[off++] = t;
     if (tid == 0) sc->naccept = s_base;
   }
-  // leave the per-cell lists empty
-  const int nspec = min(*(volatile int *) &sc->nspec, A.spec_cap);
-  for (int e = gtid; e < nspec; e += gthreads) A.spec_head[__ldcg(A.spec_cell + e)] = -1;
 }
 
 // create_atom + tag/mask/image/v assignment (:1121-1150, atom_vec.cpp:1592-1612), appended after
@@ -848,8 +1090,8 @@ static int ensure_trials(obmd_ctx *c, int ntr, int natt)
   int na = natt > c->tr_natt ? natt : c->tr_natt;
   cudaFree(c->tr_d); cudaFree(c->tr_path); cudaFree(c->tr_npts); cudaFree(c->tr_list);
   cudaFree(c->tr_kfirst); cudaFree(c->acc_list); cudaFree(c->tr_bbox); cudaFree(c->tr_chg);
-  cudaFree(c->spec_next); cudaFree(c->spec_cell); cudaFree(c->spec_trial); cudaFree(c->spec_of_trial);
-  cudaFree(c->spec_pos);
+  cudaFree(c->spec_trial); cudaFree(c->spec_of_trial); cudaFree(c->spec_pos); cudaFree(c->tr_pairs);
+  CK(cudaMalloc(&c->tr_pairs, sizeof(int) * 2 * 8 * (size_t) cap));
   CK(cudaMalloc(&c->tr_bbox, sizeof(float) * 6 * cap));
   CK(cudaMalloc(&c->tr_d, sizeof(obmd_trial) * cap));
   CK(cudaMalloc(&c->tr_path, sizeof(double) * 3 * (size_t) cap * (na + 1)));
@@ -859,8 +1101,6 @@ static int ensure_trials(obmd_ctx *c, int ntr, int natt)
   CK(cudaMalloc(&c->tr_chg, sizeof(ChgRec) * cap));
   CK(cudaMalloc(&c->acc_list, sizeof(int) * cap));
   // accepted-atom entries are append-only within a call: one per change of a trial's accepted state
-  CK(cudaMalloc(&c->spec_next, sizeof(int) * 2 * cap));
-  CK(cudaMalloc(&c->spec_cell, sizeof(int) * 2 * cap));
   CK(cudaMalloc(&c->spec_trial, sizeof(int) * 2 * cap));
   CK(cudaMalloc(&c->spec_pos, sizeof(double) * 3 * 2 * (size_t) cap));
   CK(cudaMalloc(&c->spec_of_trial, sizeof(int) * cap));
@@ -886,33 +1126,47 @@ int usher_trials_to_host(obmd_ctx *c, obmd_trial *dst, int ncopy)
   return OBMD_OK;
 }
 
-template <bool ST, int G>
+template <bool ST, int G, int MINB>
 static int launch_eval(obmd_ctx *c, const UsherArgs &A, int ntr)
 {
   const size_t smem = sizeof(UGroup) * (USH_T / 32) * (32 / G);
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
-    CK(cudaFuncSetAttribute(k_usher_eval<ST, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    CK(cudaFuncSetAttribute((k_usher_eval<ST, G, MINB>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     attr_done = true;
   }
   const int groups_per_cta = (USH_T / 32) * (32 / G);
   int grid = cdiv(ntr, groups_per_cta);
-  const int full = c->ush_ctas_per_sm * NSM;
+  const int full = MINB * NSM;
   if (grid > full) grid = full;
-  LAUNCH((k_usher_eval<ST, G>), grid, USH_T, smem, A, c->pt, ntr);
+  LAUNCH((k_usher_eval<ST, G, MINB>), grid, USH_T, smem, A, c->pt, ntr);
   return OBMD_OK;
 }
 
-template <bool ST>
+template <bool ST, int CL>
 static int launch_fix(obmd_ctx *c, const UsherArgs &A)
 {
-  const size_t smem = sizeof(UGroup) * (FIX_T / 32);
+  const size_t smem = sizeof(UGroup) * (FIX_T / 32) + SPEC_SM * (3 * sizeof(double) + sizeof(int));
   static bool attr_done = false;
   if (!attr_done) {
-    CK(cudaFuncSetAttribute(k_usher_fix<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    CK(cudaFuncSetAttribute((k_usher_fix<ST, CL>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     attr_done = true;
   }
-  LAUNCH(k_usher_fix<ST>, FIX_CL, FIX_T, smem, A, c->pt);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(CL, 1, 1);
+  cfg.blockDim = dim3(FIX_T, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, (k_usher_fix<ST, CL>), A, c->pt));
+  c->launches++;
   return OBMD_OK;
 }
 
@@ -934,9 +1188,6 @@ int usher_pass(obmd_ctx *c, const UsherCfg &u, int ntr_loc, int limit, int *nacc
   A.cell_start = c->cell_start;
   A.extra_head = c->extra_head;
   A.extra_next = c->extra_next;
-  A.spec_head = c->spec_head;
-  A.spec_next = c->spec_next;
-  A.spec_cell = c->spec_cell;
   A.spec_trial = c->spec_trial;
   A.spec_of_trial = c->spec_of_trial;
   A.spec_pos = c->spec_pos;
@@ -947,6 +1198,8 @@ int usher_pass(obmd_ctx *c, const UsherCfg &u, int ntr_loc, int limit, int *nacc
   A.bbox = c->tr_bbox;
   A.kfirst = c->tr_kfirst;
   A.list = c->tr_list;
+  A.pairs = reinterpret_cast<int2 *>(c->tr_pairs);
+  A.pair_cap = 8 * c->tr_cap;
   A.chg = c->tr_chg;
   A.acc_list = c->acc_list;
   A.sc = c->sc_d;
@@ -955,21 +1208,33 @@ int usher_pass(obmd_ctx *c, const UsherCfg &u, int ntr_loc, int limit, int *nacc
   // the bounding boxes are fp32 (rounded outwards); 1e-3 covers the prefilter's own rounding
   A.rc = c->pt.cutmax * (1.0 + 1e-9) + 1e-3;
   A.rsqmax = c->pt.cutmax * c->pt.cutmax * (1.0 + 1e-9);
-  // nchg2, ndirty2, naccept, nrounds_work, trial_cursor, nused, nused_prev, nspec
-  CK(cudaMemsetAsync(&c->sc_d->nchg2[0], 0, 10 * sizeof(int), c->stream));
+  for (int d = 0; d < 3; d++) {
+    A.wf[d] = (float) c->grid.w[d];
+    A.pf[d] = (float) c->grid.prd[d];
+    A.ipf[d] = 1.0f / A.pf[d];
+  }
+  A.cut32 = (float) c->pt.cutmax * (float) c->pt.cutmax * 1.001f;
+  A.debug = getenv("OBMD_B200_DEBUG_FIX") ? 1 : 0;
+  // nchg2, ndirty2, naccept, nrounds_work, trial_cursor, nused, nused_prev, nspec, npairs
+  CK(cudaMemsetAsync(&c->sc_d->nchg2[0], 0, 11 * sizeof(int), c->stream));
   CK(cudaMemsetAsync(c->spec_of_trial, 0xff, sizeof(int) * ntr_loc, c->stream));
   const bool st = (c->ntypes == 1);
   {
     ScopedTimer t5(c, "usher_eval0");
+    // one warp per trial; 8 resident CTAs per SM (64 registers) when there are more trials than the
+    // 6-CTA build (80 registers) can hold at once; OBMD_B200_USH_G=16 packs two trials per warp
     const int G = c->ush_group;
+    const bool dense = c->ush_ctas_per_sm >= 8;
     if (st) {
-      if (G == 8) rc = launch_eval<true, 8>(c, A, ntr_loc);
-      else if (G == 16) rc = launch_eval<true, 16>(c, A, ntr_loc);
-      else rc = launch_eval<true, 32>(c, A, ntr_loc);
+      if (G == 16) rc = launch_eval<true, 16, 6>(c, A, ntr_loc);
+      else if (dense) rc = launch_eval<true, 32, 8>(c, A, ntr_loc);
+      else if (c->ush_ctas_per_sm == 5) rc = launch_eval<true, 32, 5>(c, A, ntr_loc);
+      else rc = launch_eval<true, 32, 6>(c, A, ntr_loc);
     } else {
-      if (G == 8) rc = launch_eval<false, 8>(c, A, ntr_loc);
-      else if (G == 16) rc = launch_eval<false, 16>(c, A, ntr_loc);
-      else rc = launch_eval<false, 32>(c, A, ntr_loc);
+      if (G == 16) rc = launch_eval<false, 16, 6>(c, A, ntr_loc);
+      else if (dense) rc = launch_eval<false, 32, 8>(c, A, ntr_loc);
+      else if (c->ush_ctas_per_sm == 5) rc = launch_eval<false, 32, 5>(c, A, ntr_loc);
+      else rc = launch_eval<false, 32, 6>(c, A, ntr_loc);
     }
     if (rc) return rc;
   }
@@ -985,8 +1250,9 @@ int usher_pass(obmd_ctx *c, const UsherCfg &u, int ntr_loc, int limit, int *nacc
     if (limit) LAUNCH(k_usher_resolve, 1, 1024, 0, c->tr_d, ntr_loc, u.slots, u.maxatt, c->sc_d);
     LAUNCH(k_usher_diff, cdiv(ntr_loc, 256), 256, 0, A);
     LAUNCH(k_usher_dirty, cdiv(ntr_loc, 4), 128, 0, A);
-    if (st) rc = launch_fix<true>(c, A);
-    else rc = launch_fix<false>(c, A);
+    // one cluster of 8 CTAs (OBMD_B200_FIX_CL=1: a single CTA)
+    if (c->fix_cluster == 1) rc = st ? launch_fix<true, 1>(c, A) : launch_fix<false, 1>(c, A);
+    else rc = st ? launch_fix<true, 8>(c, A) : launch_fix<false, 8>(c, A);
     if (rc) return rc;
   }
   if ((rc = read_scalars(c))) return rc;

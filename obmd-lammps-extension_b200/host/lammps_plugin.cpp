@@ -161,6 +161,11 @@ class PairDPDB200 : public Pair {
   {
     if (force->newton_pair == 0 && comm->me == 0)
       error->warning(FLERR, "Pair dpd needs newton pair on for momentum conservation");
+    // The device mirrors atoms by LAMMPS local index and refreshes only x and v while nlocal is
+    // unchanged: a spatial re-sort (Atom::sort, atom.cpp:2288-2378) would silently permute type and
+    // tag under it.  The reference decks all run with sorting off; refuse anything else.
+    if (atom->sortfreq > 0)
+      error->all(FLERR, "pair_style dpd (obmd_b200 plugin) requires 'atom_modify sort 0 0'");
     push_domain(lmp, sh);
     OBMD_CK(lmp, sh, obmd_pair_settings(sh.ctx, temperature, cut_global, seed));
     for (int i = 1; i <= atom->ntypes; i++)

@@ -229,6 +229,87 @@ def make_b8(wd):
     print("b8: deletions", ndel, "insertions", int(ver[:, 0].sum()), "atoms", len(r1))
 
 
+
+def make_b9(wd, n0):
+    """B9: the B1 USHER deck with uovlp = 150 instead of 1e4, so that the overlap branch of usher()
+    (fix_obmd_merged.cpp:1566-1580: ds = dsovlp - pow(4 eps / E, 1/12)) is taken by the many trial
+    points whose energy exceeds 150 (the mean energy of a random point in this fluid is ~132)."""
+    deck = (head() + fix(alpha=1.0, nbuf=2000).replace("usher 1 31.03 1.0 0.02 10000 1.5 1.0 40",
+                                                       "usher 1 31.03 1.0 0.02 150 1.5 1.0 40") +
+            "dump d all custom 10 dump.b9 id x y z\ndump_modify d format float %.17g\n"
+            "thermo 1\nthermo_style custom step atoms\nrun 10\n")
+    assert "0.02 150 1.5" in deck
+    lines = run_deck("b9", deck, wd)
+    frames = read_dump(os.path.join(wd, "dump.b9"))
+    step, rows = frames[-1]
+    assert step == 10
+    ver = parse_usher(lines)
+    np.savez_compressed(os.path.join(HERE, "b9_usher_overlap.npz"),
+                        verdicts=ver, final_tag=rows[:, 0].astype(np.int32),
+                        inserted_x=rows[n0:, 1:4].copy(), nsteps=10)
+    print("b9: trials", len(ver), "accepted", int(ver[:, 0].sum()), "final atoms", len(rows))
+
+
+def read_chunk_file(path, ncol):
+    """fix ave/chunk text output -> list of (step, array[nchunk, ncol])."""
+    out = []
+    with open(path) as fh:
+        lines = [ln for ln in fh if not ln.startswith("#")]
+    i = 0
+    while i < len(lines):
+        w = lines[i].split()
+        step, nch = int(w[0]), int(w[1])
+        rows = np.array([ln.split() for ln in lines[i + 1:i + 1 + nch]], dtype=np.float64)
+        out.append((step, rows[:, :ncol].copy()))
+        i += 1 + nch
+    return out
+
+
+def make_r1_long(wd, equil=2000, sample=2000, block=200, nbins=48):
+    """Steady-exchange regime R1 of the shipped deck: `equil` steps from v = 0, a snapshot
+    of x and v (the start state bench.py tiles for BOTH arms), then `sample` more steps with the 1-D
+    profiles along x that the statistical parity test compares (compute chunk/atom + fix ave/chunk:
+    number density, <vx>, kinetic temperature, per-atom stress xx), one row per block of `block`
+    steps so the test can form block-averaged error bars."""
+    deck = (head().replace("atom_modify     sort 0 0\n", "atom_modify     sort 0 0\n") + "fix 1 all nve\n" +
+            fix(alpha=1.0, nbuf=1895) +
+            "thermo 100\nthermo_style custom step atoms temp press\n"
+            "thermo_modify format float %%.15g lost ignore\n"
+            "run %d\n"
+            "write_dump all custom dump.snap id x y z vx vy vz modify format float %%.17g\n"
+            "compute cc all chunk/atom bin/1d x lower %.17g units box\n"
+            "compute st all stress/atom NULL\n"
+            "fix av all ave/chunk 1 %d %d cc density/number vx temp c_st[1] c_st[2] c_st[3] norm all file prof.txt\n"
+            "run %d\n" % (equil, BOX[0][1] / nbins, block, block, sample))
+    lines = run_deck("r1long", deck, wd)
+    (_, rows), = read_dump(os.path.join(wd, "dump.snap"))
+    order = np.argsort(rows[:, 0], kind="stable")
+    rows = rows[order]
+    np.savez_compressed(os.path.join(HERE, "equil_r1.npz"), tag=rows[:, 0].astype(np.int32),
+                        x=rows[:, 1:4].copy(), v=rows[:, 4:7].copy(), box=np.array(BOX), steps=equil)
+    # columns of fix ave/chunk: chunk coord ncount density/number vx temp c_st[1..3]
+    prof = read_chunk_file(os.path.join(wd, "prof.txt"), 9)
+    th = []
+    on = False
+    for ln in lines:
+        w = ln.split()
+        if w[:2] == ["Step", "Atoms"]:
+            on = True; continue
+        if on:
+            if len(w) == 4 and w[0].isdigit():
+                th.append([float(t) for t in w])
+            elif w and w[0] == "Loop":
+                on = False
+    ver = parse_usher(lines)
+    ndel = sum(1 for ln in lines if ln.startswith("Deleting"))
+    np.savez_compressed(os.path.join(HERE, "r1_profiles.npz"), blocks=np.array([r for _, r in prof]),
+                        block_steps=np.array([s for s, _ in prof]), thermo=np.array(th), nbins=nbins,
+                        equil=equil, sample=sample, block=block, ndel=ndel, ntrials=len(ver),
+                        nacc=int(ver[:, 0].sum()))
+    print("r1_long: snapshot atoms", len(rows), "blocks", len(prof), "trials", len(ver),
+          "accepted", int(ver[:, 0].sum()), "deleted", ndel)
+
+
 def main():
     if not os.path.exists(LMP):
         sys.exit("oracle/_ref/lmp_serial missing: run `bash oracle/build_ref.sh` first")
@@ -242,6 +323,12 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "b8":   # only the two-mass ballistic fixture
         make_b8(wd)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "b9":   # only the overlap-branch USHER fixture
+        make_b9(wd, 12637)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "r1long":   # only the long R1 run (snapshot + profiles), ~20 min
+        make_r1_long(wd)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "b7":   # only the two-type USHER fixture
         make_b7(wd, 12637)
@@ -273,6 +360,7 @@ def main():
     make_b6(wd, n0)
     make_b7(wd, n0)
     make_b8(wd)
+    make_b9(wd, n0)
 
     # ---- B2/B5: normal force distribution, static atoms, pair force zeroed ----
     deck = (head(a0=0.0, gamma=0.0) + fix(dpxx=10.0, freq=5.0) +

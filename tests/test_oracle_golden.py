@@ -88,6 +88,37 @@ def test_b1_usher_stream_bit_exact(shipped):
         assert np.array_equal(a.view("x")[len(tag):], g["inserted_x"])  # bit-exact
 
 
+def test_b9_usher_overlap_branch_bit_exact(shipped):
+    """uovlp = 150: the overlap branch of usher() (fix_obmd_merged.cpp:1566-1580, ds = dsovlp -
+    pow(4 eps / E, 1/12)) is taken by a large share of the trials; verdicts, accepted positions and
+    tags of 10 steps of the unmodified reference binary."""
+    tag, x, box = shipped
+    L = O.lib()
+    g = load("b9_usher_overlap.npz")
+    ush = (1, 31.03, 1.0, 0.02, 150.0, 1.5, 1.0, 40)
+    for use_cells in (0, 1):
+        p = O.make_fix(box[:, 0], box[:, 1], alpha=1.0, nbuf=2000.0, use_cells=use_cells, usher=ush)
+        a = O.OracleAtoms(x, tag=tag)
+        trials = (O.Trial * 4096)()
+        ver = []
+        nover = 0
+        for _ in range(int(g["nsteps"])):
+            L.orc_fix_pre_exchange(C.byref(p), C.byref(a.c), trials, 4096)
+            for k in range(p.last_ntrials):
+                t = trials[k]
+                ver.append((t.accepted, sig6(t.energy), t.iter if t.accepted else -1))
+                nover += t.energy > 150.0
+        ref = g["verdicts"]
+        assert len(ver) == len(ref)
+        got = np.array(ver, dtype=np.float64)
+        assert np.array_equal(got[:, 0], ref[:, 0])
+        assert np.array_equal(got[:, 2], ref[:, 2])
+        assert np.allclose(got[:, 1], ref[:, 1], rtol=2e-6, atol=0)
+        assert np.array_equal(a.view("tag"), g["final_tag"])
+        assert np.array_equal(a.view("x")[len(tag):], g["inserted_x"])  # bit-exact
+        assert nover > 5      # trials that END above uovlp; many more pass through the branch on the way
+
+
 def test_b6_usher_maxattempt3_slot_bookkeeping(shipped):
     """maxattempt 3 (fix_obmd_merged.cpp:912-1172): verdicts WITH the attempt number inside each
     insertion slot, accepted positions and tags, 6 steps of the unmodified reference binary."""
