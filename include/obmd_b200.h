@@ -165,6 +165,15 @@ int obmd_run(obmd_ctx *ctx, long long first_step, int nsteps);
 int obmd_reduce_kinetic(obmd_ctx *ctx, double out[5]);
 /* 1-D profiles along x in nbins bins over the box: count[nbins], vx sums [nbins] */
 int obmd_profile_x(obmd_ctx *ctx, int nbins, double *count, double *mvx);
+/* The profiles `compute chunk/atom bin/1d x` + `fix ave/chunk ... density/number vx temp c_stress[1]`
+ * accumulate (compute_chunk_atom.cpp, fix_ave_chunk.cpp, compute_stress_atom.cpp): per bin the atom
+ * count, sum m vx, sum m v^2 and the sum of the per-atom stress xx = -(m vx^2 + W_xx,i), where W_xx,i
+ * is the atom's share of the pair virial as Pair::ev_tally assigns it (pair.cpp:1068-1230).  mv2 and
+ * sxx may be NULL; sxx needs obmd_pair_compute(..., vflag != 0) on the current positions first. */
+int obmd_profile_x2(obmd_ctx *ctx, int nbins, double *count, double *mvx, double *mv2, double *sxx);
+/* Diagnostic for the statistical parity tests: out[k] = the N(0,1) variate PairDPD uses for the pair
+ * (tag0 + k, tag0 + k + 1) at timestep ntimestep (stands in for RanMars::gaussian, random_mars.cpp:103). */
+int obmd_pair_gaussian_sample(obmd_ctx *ctx, int n, int tag0, long long ntimestep, double *out);
 
 /* ---- multi-GPU: x-slab decomposition over NCCL (replaces CommBrick::exchange/borders, ------
  *      comm_brick.cpp:652-978, and the fix's MPI_Allreduce/Scan calls) ------------ */

@@ -97,6 +97,8 @@ SIGNATURES = {
     "obmd_run": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int]),
     "obmd_reduce_kinetic": (C.c_int, [C.c_void_p, _dp]),
     "obmd_profile_x": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
+    "obmd_profile_x2": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]),
+    "obmd_pair_gaussian_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, _dp]),
     "obmd_comm_unique_id": (C.c_int, [C.c_char_p]),
     "obmd_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     "obmd_comm_finalize": (C.c_int, [C.c_void_p]),
@@ -451,6 +453,18 @@ class ObmdB200:
         cnt = np.zeros(nbins); mvx = np.zeros(nbins)
         self._ck(self.L.obmd_profile_x(self.h, nbins, _dptr(cnt), _dptr(mvx)))
         return cnt, mvx
+
+    def profile_x2(self, nbins, stress=True):
+        """count, sum m vx, sum m v^2 [, sum of per-atom stress xx] per x-bin (obmd_profile_x2)."""
+        cnt = np.zeros(nbins); mvx = np.zeros(nbins); mv2 = np.zeros(nbins); sxx = np.zeros(nbins)
+        self._ck(self.L.obmd_profile_x2(self.h, nbins, _dptr(cnt), _dptr(mvx), _dptr(mv2),
+                                        _dptr(sxx) if stress else None))
+        return cnt, mvx, mv2, sxx
+
+    def gaussian_sample(self, n, tag0=1, step=1):
+        out = np.zeros(n)
+        self._ck(self.L.obmd_pair_gaussian_sample(self.h, n, tag0, step, _dptr(out)))
+        return out
 
     # ---- timing ----------------------------------------------------------------------
     def timing(self, on=True): self._ck(self.L.obmd_timing_enable(self.h, int(on)))

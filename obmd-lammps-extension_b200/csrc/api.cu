@@ -123,6 +123,7 @@ extern "C" void obmd_destroy(obmd_ctx *c)
   cudaFree(c->spec_trial); cudaFree(c->spec_of_trial); cudaFree(c->spec_pos); cudaFree(c->tr_pairs);
   if (c->tr_h) cudaFreeHost(c->tr_h);
   cudaFree(c->partials);
+  cudaFree(c->vatom);
   cudaFree(c->redo_flag); cudaFree(c->redo_list); cudaFree(c->redo_count);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   for (auto &p : c->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
@@ -734,7 +735,20 @@ extern "C" int obmd_reduce_kinetic(obmd_ctx *c, double out[5])
 extern "C" int obmd_profile_x(obmd_ctx *c, int nbins, double *count, double *mvx)
 {
   NEED(c && count && mvx, OBMD_ERR_ARG, "NULL argument");
-  return fix_profile_x(c, nbins, count, mvx);
+  return fix_profile_x(c, nbins, count, mvx, nullptr, nullptr);
+}
+
+extern "C" int obmd_profile_x2(obmd_ctx *c, int nbins, double *count, double *mvx, double *mv2, double *sxx)
+{
+  NEED(c && count && mvx, OBMD_ERR_ARG, "NULL argument");
+  return fix_profile_x(c, nbins, count, mvx, mv2, sxx);
+}
+
+extern "C" int obmd_pair_gaussian_sample(obmd_ctx *c, int n, int tag0, long long ntimestep, double *out)
+{
+  NEED(c && out && n > 0 && tag0 > 0, OBMD_ERR_ARG, "obmd_pair_gaussian_sample: bad argument");
+  NEED(c->have_pair, OBMD_ERR_STATE, "obmd_pair_gaussian_sample: call obmd_pair_settings first");
+  return pair_gaussian_sample(c, n, tag0, ntimestep, out);
 }
 
 // ---- timing ------------------------------------------------------------------------------

@@ -204,5 +204,6 @@ int cells_build(obmd_ctx *c)
   c->nextra = c->narr = c->nghost = c->nins = 0;
   c->cells_valid = true;
   c->forces_valid = false;
+  c->vatom_valid = false;
   return OBMD_OK;
 }

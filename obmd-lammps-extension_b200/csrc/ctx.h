@@ -203,6 +203,9 @@ struct obmd_ctx {
   int fix_cluster = 8;              // CTAs in the cluster of the USHER fix-up kernel (OBMD_B200_FIX_CL: 1 or 8)
   int ush_ctas_per_sm = 6;          // persistent grid of round 0 (OBMD_B200_USH_CTAS)
   double *partials = nullptr;       // block partial sums for deterministic reductions
+  double *vatom = nullptr;          // per-atom virial xx of the latest tally call (stress profile)
+  int vatom_cap = 0;
+  bool vatom_valid = false;
   int partial_cap = 0;
   // last pre_exchange report
   obmd_pre_exchange_report rep;
@@ -307,7 +310,8 @@ int fix_pre_begin(obmd_ctx *c);
 int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials);
 int fix_post_force(obmd_ctx *c);
 int fix_reduce_kinetic(obmd_ctx *c, double out[5]);
-int fix_profile_x(obmd_ctx *c, int nbins, double *count, double *mvx);
+int fix_profile_x(obmd_ctx *c, int nbins, double *count, double *mvx, double *mv2, double *sxx);
+int pair_gaussian_sample(obmd_ctx *c, int n, int tag0, long long step, double *out);
 int fix_clear_extras(obmd_ctx *c);
 int read_scalars(obmd_ctx *c);  // copies *sc_d to *sc_h and synchronises the stream
 int comm_exchange(obmd_ctx *c);  // comm.cu: migrate + halo + ghost lists

@@ -1131,27 +1131,37 @@ int fix_reduce_kinetic(obmd_ctx *c, double out[5])
   return OBMD_OK;
 }
 
+// 1-D profiles along x (what `compute chunk/atom bin/1d x` + `fix ave/chunk` accumulate): per bin the
+// atom count, sum m vx, sum m v^2 and sum of the per-atom stress xx = -(m vx^2 + W_xx)
+// (compute_stress_atom.cpp: kinetic + virial contribution, pressure*volume units).
 __global__ void k_profile_x(Planes p, int n, PairTab pt, double lo, double inv, int nbins,
-                            double *__restrict__ count, double *__restrict__ mvx)
+                            const double *__restrict__ vatom, double *__restrict__ out)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int b = (int) floor((p.x[i] - lo) * inv);
   b = min(max(b, 0), nbins - 1);
-  atomicAdd(&count[b], 1.0);
-  atomicAdd(&mvx[b], pt.mass[p.type[i]] * p.vx[i]);
+  const double m = pt.mass[p.type[i]], vx = p.vx[i], vy = p.vy[i], vz = p.vz[i];
+  atomicAdd(&out[b], 1.0);
+  atomicAdd(&out[nbins + b], m * vx);
+  atomicAdd(&out[2 * nbins + b], m * (vx * vx + vy * vy + vz * vz));
+  if (vatom) atomicAdd(&out[3 * nbins + b], -(m * vx * vx + vatom[i]));
 }
 
-int fix_profile_x(obmd_ctx *c, int nbins, double *count, double *mvx)
+int fix_profile_x(obmd_ctx *c, int nbins, double *count, double *mvx, double *mv2, double *sxx)
 {
   NEED(nbins > 0 && nbins <= 65536, OBMD_ERR_ARG, "obmd_profile_x: bad nbins");
+  NEED(!sxx || (c->vatom && c->vatom_valid), OBMD_ERR_STATE,
+       "obmd_profile_x2: the stress profile needs obmd_pair_compute(..., vflag = 1) on the current positions");
   double *d = nullptr;
-  CK(cudaMalloc(&d, sizeof(double) * 2 * nbins));
-  CK(cudaMemsetAsync(d, 0, sizeof(double) * 2 * nbins, c->stream));
+  CK(cudaMalloc(&d, sizeof(double) * 4 * nbins));
+  CK(cudaMemsetAsync(d, 0, sizeof(double) * 4 * nbins, c->stream));
   LAUNCH(k_profile_x, cdiv(c->n, 256), 256, 0, c->cur, c->n, c->pt, c->boxlo[0],
-         nbins / (c->boxhi[0] - c->boxlo[0]), nbins, d, d + nbins);
+         nbins / (c->boxhi[0] - c->boxlo[0]), nbins, sxx ? c->vatom : nullptr, d);
   CK(cudaMemcpyAsync(count, d, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(mvx, d + nbins, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
+  if (mv2) CK(cudaMemcpyAsync(mv2, d + 2 * nbins, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
+  if (sxx) CK(cudaMemcpyAsync(sxx, d + 3 * nbins, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   cudaFree(d);
   return OBMD_OK;

@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(PAIR_T)
     k_pair_dpd(Planes p, ColRange cr, Extras ex, Grid g, PairTab pt,
                const int *__restrict__ cell_start, const int *__restrict__ extra_head,
                const int *__restrict__ extra_next, double *__restrict__ fx, double *__restrict__ fy,
-               double *__restrict__ fz, unsigned step, int random_on, double *__restrict__ partials)
+               double *__restrict__ fz, unsigned step, int random_on, double *__restrict__ partials,
+               double *__restrict__ vatom)
 {
   __shared__ int hits[PAIR_HCAP * PAIR_T];
   const int i = colrange_slot(cr, blockIdx.x * PAIR_T + threadIdx.x, g, cell_start, ex);
@@ -281,6 +282,8 @@ __global__ void __launch_bounds__(PAIR_T)
     fx[i] = acc.fx;
     fy[i] = acc.fy;
     fz[i] = acc.fz;
+    // per-atom virial xx (what `compute stress/atom` gets from ev_tally: half of every pair term)
+    if (TALLY && vatom) vatom[i] = acc.v0;
   }
   if (TALLY) {
     // deterministic block reduction of (e, v[6]) -> partials[block][7]
@@ -442,6 +445,24 @@ __global__ void k_pair_tally_final(const double *__restrict__ partials, int nblo
   }
 }
 
+// diagnostic: the counter-based N(0,1) variate of pairs (tag0 + k, tag0 + k + 1) at one timestep
+__global__ void k_gaussian_sample(int n, int tag0, unsigned step, unsigned seed, double *__restrict__ out)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = dpd_gaussian(tag0 + k, tag0 + k + 1, step, seed);
+}
+
+int pair_gaussian_sample(obmd_ctx *c, int n, int tag0, long long step, double *out)
+{
+  double *d = nullptr;
+  CK(cudaMalloc(&d, sizeof(double) * n));
+  LAUNCH(k_gaussian_sample, cdiv(n, 256), 256, 0, n, tag0, (unsigned) step, (unsigned) c->pair_seed, d);
+  CK(cudaMemcpyAsync(out, d, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d);
+  return OBMD_OK;
+}
+
 ColRange all_columns(const obmd_ctx *c)
 {
   ColRange cr;
@@ -567,6 +588,12 @@ static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &
   const int nmax = cr.n == 0 ? c->nextra : colrange_bound(c, cr);
   if (nmax <= 0) return OBMD_OK;
   const int nb = cdiv(nmax, PAIR_T);
+  if (tally && c->vatom_cap < c->cap) {  // per-atom virial xx for the stress profile (obmd_profile_x2)
+    cudaFree(c->vatom);
+    c->vatom = nullptr;
+    CK(cudaMalloc(&c->vatom, sizeof(double) * c->cap));
+    c->vatom_cap = c->cap;
+  }
   if (tally && nb * 7 > c->partial_cap) {
     if (c->partials) cudaFree(c->partials);
     c->partial_cap = nb * 7 + 1024;
@@ -574,7 +601,7 @@ static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &
   }
 #define PAIR_ARGS                                                                             \
   c->cur, cr, extras_of(c), c->grid, c->pt, c->cell_start, c->extra_head, c->extra_next,          \
-      c->fx, c->fy, c->fz, (unsigned) step, random_on, c->partials
+      c->fx, c->fy, c->fz, (unsigned) step, random_on, c->partials, (tally ? c->vatom : nullptr)
   if (prewrap) {  // side-stream launch of obmd_run: coordinates may not be wrapped yet
     if (single) LAUNCH_ON(st, (k_pair_dpd<true, false, true>), nb, PAIR_T, 0, PAIR_ARGS);
     else LAUNCH_ON(st, (k_pair_dpd<false, false, true>), nb, PAIR_T, 0, PAIR_ARGS);
@@ -602,5 +629,6 @@ int pair_compute(obmd_ctx *c, long long step, int eflag, int vflag)
   int rc = pair_launch(c, step, eflag || vflag, all_columns(c), c->stream);
   if (rc) return rc;
   c->forces_valid = true;
+  c->vatom_valid = (eflag || vflag);
   return OBMD_OK;
 }

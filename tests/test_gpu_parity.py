@@ -656,3 +656,209 @@ def test_b8_ballistic_two_masses(shipped):
     assert np.allclose(out["v"], g["v20"], rtol=0, atol=1e-10)
     assert cc.mixed_rel_err(out["f"], g["f20"]) < FTOL
     sim.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: the production (row-tiled, no-tally) pair kernel against the reference fixtures
+# ---------------------------------------------------------------------------------------------
+
+def test_pair_row_kernel_T0_vs_reference_fixtures(shipped):
+    """obmd_pair_compute WITHOUT energy/virial tallies runs k_pair_row (pair_row.cuh), the kernel
+    obmd_run uses.  Its forces against the forces of the unmodified reference binary: one type
+    (p0_pair_T0.npz) and two types with per-pair a0, gamma, cutoff (p1_pair_two_types_T0.npz)."""
+    import obmd_b200 as ob
+    tag, x, box = shipped
+    g = cc.load("p0_pair_T0.npz")
+    sim = cc.device_sim(box, temperature=0.0, fix=False)
+    sim.upload(x, g["v"], np.ones(len(x), np.int32), tag)
+    sim.build_cells(); sim.pbc(); sim.pair_compute(0)          # eflag = vflag = 0: the row kernel
+    f = sim.download(("f",))["f"]
+    sim.close()
+    assert cc.mixed_rel_err(f, g["f"]) < FTOL
+    g = cc.load("p1_pair_two_types_T0.npz")
+    sim = ob.ObmdB200(0)
+    sim.set_box(box[:, 0], box[:, 1]); sim.set_masses([1.0, 2.0]); sim.set_timestep(0.001464)
+    sim.pair_style_dpd(0.0, 1.0, 2616)
+    for (i, j), (a0, gamma, rc) in {(1, 1): (209.6, 4.5, 1.0), (1, 2): (150.0, 3.0, 0.9),
+                                    (2, 2): (100.0, 6.0, 0.8)}.items():
+        sim.pair_coeff(i, j, a0, gamma, rc)
+    sim.pair_init(1.0)
+    sim.upload(x, g["v"], g["type"], tag)
+    sim.build_cells(); sim.pbc(); sim.pair_compute(0)
+    f = sim.download(("f",))["f"]
+    sim.close()
+    assert cc.mixed_rel_err(f, g["f"]) < FTOL
+
+
+def test_pair_gaussian_moments_and_tails(shipped):
+    """The counter-based N(0,1) variate that stands in for RanMars::gaussian (random_mars.cpp:103):
+    mean, variance, skewness, kurtosis and tail mass over 1e7 pair keys, symmetric in the pair, and
+    independent between timesteps.  Tolerances are 5 standard errors of each estimator for n = 1e7."""
+    tag, x, box = shipped
+    sim = cc.device_sim(box, fix=False)
+    n = 10_000_000
+    z = sim.gaussian_sample(n, tag0=1, step=1234)
+    z2 = sim.gaussian_sample(n, tag0=1, step=1235)
+    sim.close()
+    se = 1.0 / np.sqrt(n)
+    assert abs(z.mean()) < 5 * se
+    assert abs(z.var() - 1.0) < 5 * np.sqrt(2.0) * se
+    assert abs(np.mean(z ** 3)) < 5 * np.sqrt(15.0) * se
+    assert abs(np.mean(z ** 4) - 3.0) < 5 * np.sqrt(96.0) * se
+    from math import erfc, sqrt
+    for k in (1.0, 2.0, 3.0, 4.0):
+        pk = erfc(k / sqrt(2.0))                       # P(|z| > k)
+        got = float(np.mean(np.abs(z) > k))
+        assert abs(got - pk) < 5 * np.sqrt(pk / n) + 1e-9, (k, got, pk)
+    assert np.abs(z).max() < 6.7                       # fp32 Box-Muller: u1 >= 2^-32 caps |z| at 6.66
+    assert abs(np.mean(z * z2)) < 5 * se               # successive timesteps are uncorrelated
+    assert abs(np.mean(z[:-1] * z[1:])) < 5 * se       # neighbouring keys are uncorrelated
+
+
+def test_pre_exchange_1M_atoms_bit_exact_vs_oracle():
+    """One pre_exchange at BASELINE config 2 size (1 010 960 atoms, thousands of trials, hundreds of
+    deletions) against orc_fix_pre_exchange(use_cells = 1): every trial record, the deletion order,
+    tags, positions and the RanPark state bit for bit."""
+    tag, x, box = cc.tiled((4, 5, 4), jitter=0.02, seed=5)
+    rng = np.random.default_rng(11)
+    v = rng.normal(0.0, 1.0, x.shape)
+    # push ~400 atoms through the open faces so deletion and insertion share the call
+    idx = rng.choice(len(x), 400, replace=False)
+    x[idx[:200], 0] = -rng.uniform(1e-6, 0.3, 200)
+    x[idx[200:], 0] = box[0, 1] + rng.uniform(1e-6, 0.3, 200)
+    B = 0.15 * box[0, 1]
+    inside = (x[:, 0] >= 0) & (x[:, 0] <= box[0, 1])
+    cnt = int(np.sum(inside & (x[:, 0] <= B)))
+    kw = dict(alpha=1.0, nbuf=float(cnt + 4000), tau=0.005)     # ~1170 trials per side
+    sim = cc.device_sim(box, **kw)
+    sim.upload(x, v, np.ones(len(x), np.int32), tag, capacity=len(x) + 20000)
+    sim.build_cells()
+    rep, tr = sim.pre_exchange(maxtrials=8192)
+    p, a = cc.oracle_sim(box, x, v=v, tag=tag, use_cells=1, **kw)
+    trials = (O.Trial * 8192)()
+    O.lib().orc_fix_pre_exchange(C.byref(p), C.byref(a.c), trials, 8192)
+    assert rep.ndel == p.last_ndel == 400
+    assert rep.ntrials == p.last_ntrials and rep.ntrials > 2000
+    assert rep.naccept == p.last_naccept and rep.naccept > 0
+    bad = [k for k in range(rep.ntrials) if tuple(tr[k].end) != tuple(trials[k].end) or
+           tr[k].energy != trials[k].energy or tr[k].iter != trials[k].iter or
+           (tr[k].accepted, tr[k].tag) != (trials[k].accepted, trials[k].tag)]
+    assert not bad, bad[:10]
+    out = sim.download(("x", "tag"))
+    assert np.array_equal(out["tag"], a.view("tag")) and np.array_equal(out["x"], a.view("x"))
+    assert sim.fix_state().rng_seed == p.rng_seed
+    assert tuple(rep.vnewl) == tuple(p.vnewl) and tuple(rep.vnewr) == tuple(p.vnewr)
+    sim.close()
+
+
+def test_deletion_more_than_1024_atoms_vs_oracle(shipped):
+    """More deletions in one call than k_delete_fixup keeps in shared memory (1024): the global-memory
+    path (bitonic sort, serial sums) must give the same order, momentum sums and RanPark state."""
+    tag, x, box = shipped
+    x = x.copy()
+    rng = np.random.default_rng(23)
+    out = rng.choice(len(x), 2600, replace=False)
+    x[out[:1300], 0] = -rng.uniform(1e-6, 0.5, 1300)
+    x[out[1300:], 0] = box[0, 1] + rng.uniform(1e-6, 0.5, 1300)
+    v = rng.normal(0, 1, x.shape)
+    kw = dict(alpha=0.1, nbuf=100.0)   # no insertion
+    sim = cc.device_sim(box, **kw)
+    sim.upload(x, v, np.ones(len(x), np.int32), tag)
+    sim.build_cells()
+    rep, _ = sim.pre_exchange()
+    p, a = cc.oracle_sim(box, x, v=v, tag=tag, **kw)
+    O.lib().orc_fix_pre_exchange(C.byref(p), C.byref(a.c), None, 0)
+    assert rep.ndel == p.last_ndel == 2600 and rep.nlocal == a.n
+    assert tuple(rep.vnewl) == tuple(p.vnewl) and tuple(rep.vnewr) == tuple(p.vnewr)
+    o = sim.download(("x", "v", "tag"))
+    assert np.array_equal(o["tag"], a.view("tag"))
+    assert np.array_equal(o["x"], a.view("x")) and np.array_equal(o["v"], a.view("v"))
+    assert sim.fix_state().rng_seed == p.rng_seed
+    sim.close()
+
+
+def test_capacity_limits_are_reported_not_silent(shipped):
+    """Fixed capacities must fail loudly (OBMD_ERR_CAPACITY through obmd_last_error), never corrupt:
+    (i) more atoms in the 27-cell stencil of a USHER point than the evaluation holds (144);
+    (ii) more than LINK_MAX (6000) insertions in one call."""
+    import obmd_b200 as ob
+    tag, x, box = shipped
+    # (i) a dense clump of 400 atoms inside one cell of the left insertion region
+    rng = np.random.default_rng(3)
+    clump = np.array([2.5, 5.5, 5.5]) + rng.uniform(-0.45, 0.45, (400, 3))
+    xs = np.concatenate([x, clump])
+    ts = np.concatenate([tag, np.arange(tag.max() + 1, tag.max() + 401, dtype=np.int32)])
+    regions = ob.default_regions(box[:, 0], box[:, 1], 0.15 * box[0, 1], 0.0)
+    regions = list(regions)
+    regions[4] = (np.array([2.0, 5.0, 5.0]), np.array([3.0, 6.0, 6.0]))      # region5: around the clump
+    kw = dict(alpha=1.0, nbuf=4000.0, regions=regions)
+    sim = cc.device_sim(box, **kw)
+    sim.upload(xs, np.zeros_like(xs), np.ones(len(xs), np.int32), ts, capacity=2 * len(xs))
+    sim.build_cells()
+    with pytest.raises(ob.ObmdError) as ei:
+        sim.pre_exchange(maxtrials=16)
+    assert ei.value.code == -4 and "stencil" in ei.value.msg
+    sim.close()
+    # (ii) zero pair force: every trial is accepted at once; ask for > 6000 insertions in one call
+    kw = dict(alpha=1.0, nbuf=1895.0 + 3300.0, tau=0.001464, a0=0.0, gamma=0.0)   # ninsert ~ 3300 per side
+    sim = cc.device_sim(box, **kw)
+    sim.upload(x, np.zeros_like(x), np.ones(len(x), np.int32), tag, capacity=3 * len(x))
+    sim.build_cells()
+    with pytest.raises(ob.ObmdError) as ei:
+        sim.pre_exchange()
+    assert ei.value.code == -4
+    sim.close()
+
+
+def test_profiles_vs_reference_r1_run(shipped):
+    """Statistical parity of the observables north_star names: number density, <vx>,
+    kinetic temperature and stress xx profiles along the open axis in steady exchange (R1).  Protocol
+    as tests/golden/make_golden.py make_r1_long ran the unmodified reference binary: 2000 steps from
+    v = 0, then 10 blocks of 200 steps, 48 bins (fix ave/chunk).  The pair RNG differs by design, so
+    the comparison is per bin |mean_gpu - mean_ref| <= 5 * sqrt(se_gpu^2 + se_ref^2), with the
+    standard errors taken from the block means of each run, plus the run totals."""
+    tag, x, box = shipped
+    g = cc.load("r1_profiles.npz")
+    ref = g["blocks"]                      # [block, bin, (chunk coord ncount dens vx temp sxx syy szz)]
+    nb, nbins = ref.shape[0], int(g["nbins"])
+    kw = dict(alpha=1.0, nbuf=1895.0)
+    sim = cc.device_sim(box, **kw)
+    sim.upload(x, np.zeros_like(x), np.ones(len(x), np.int32), tag, capacity=2 * len(x))
+    sim.setup(0)
+    step = 1
+    sim.run(step, int(g["equil"])); step += int(g["equil"])
+    blk = int(g["block"])
+    vol = (box[0, 1] / nbins) * box[1, 1] * box[2, 1]
+    mine = np.zeros((nb, nbins, 4))
+    for b in range(nb):
+        acc = np.zeros((4, nbins))
+        for s in range(blk):
+            sim.run(step, 1)
+            # same positions and step key: the same pair forces again, plus the per-atom virial; the
+            # buffer forces post_force added must be restored for the next half-kick
+            sim.pair_compute(step, vflag=1)
+            sim.post_force()
+            acc += np.array(sim.profile_x2(nbins))
+            step += 1
+        cnt, mvx, mv2, sxx = acc
+        mine[b, :, 0] = cnt / blk / vol                # density/number
+        mine[b, :, 1] = mvx / cnt                      # <vx> (mass 1)
+        mine[b, :, 2] = mv2 / (3.0 * cnt)              # temp: dof = 3 per atom in the chunk
+        mine[b, :, 3] = sxx / cnt                      # per-atom stress xx
+    st1 = sim.fix_state()
+    sim.close()
+    cols = {0: 3, 1: 4, 2: 5, 3: 6}
+    names = ["density", "vx", "temp", "sxx"]
+    worst = {}
+    for k, c in cols.items():
+        mr, sr = ref[:, :, c].mean(0), ref[:, :, c].std(0, ddof=1) / np.sqrt(nb)
+        mg, sg = mine[:, :, k].mean(0), mine[:, :, k].std(0, ddof=1) / np.sqrt(nb)
+        zscore = np.abs(mg - mr) / np.sqrt(sr ** 2 + sg ** 2)
+        worst[names[k]] = (float(zscore.max()), int(zscore.argmax()), float(mg[zscore.argmax()]), float(mr[zscore.argmax()]))
+    # 48 bins x 4 observables: a 5-sigma criterion per bin keeps the family-wise false-alarm rate ~1e-4
+    assert all(w[0] < 5.0 for w in worst.values()), worst
+    # run totals over all 4000 steps (the fixture counts the reference's verdict lines from step 1):
+    # deletions, accepted insertions and USHER trials within 3 %
+    assert abs(st1.ndeleted - int(g["ndel"])) < 0.03 * int(g["ndel"]), (st1.ndeleted, int(g["ndel"]))
+    assert abs(st1.ninserted - int(g["nacc"])) < 0.03 * int(g["nacc"]), (st1.ninserted, int(g["nacc"]))
+    assert abs(st1.ntrials - int(g["ntrials"])) < 0.03 * int(g["ntrials"]), (st1.ntrials, int(g["ntrials"]))
