@@ -187,6 +187,17 @@ int obmd_comm_init(obmd_ctx *ctx, int rank, int nranks, const char *id128);
 int obmd_comm_finalize(obmd_ctx *ctx);
 /* x-range [lo, hi) of the columns this rank owns (what the host uses to split the atoms). */
 int obmd_comm_slab(const obmd_ctx *ctx, double *lo, double *hi);
+/* Comm::exchange + Comm::borders (comm_brick.cpp:652-978) for callers that drive the per-step hooks
+ * themselves in a slab run: after obmd_build_cells, before obmd_pre_exchange (obmd_run does it itself).
+ * No-op on one rank. */
+int obmd_exchange(obmd_ctx *ctx);
+/* Order in which USHER sums the contributions to a trial point's energy and force (energy(),
+ * fix_obmd_merged.cpp:1790-1807).  0 (default, one rank): ascending LAMMPS local index -- the
+ * reference's loop order, bit-identical to the serial reference.  1: ascending atom tag -- independent
+ * of the decomposition; slab runs always use it, so a slab run on any number of ranks reproduces a
+ * one-rank run with by_tag = 1 bit for bit as long as both see the same atoms (the reference's own
+ * multi-rank sums differ from its serial ones in the same way: per-rank partial sums + MPI_Allreduce). */
+int obmd_set_usher_order(obmd_ctx *ctx, int by_tag);
 
 /* ---- timing / introspection ----------------------------------------------------- */
 /* Accumulated CUDA-event milliseconds and launch counts per kernel family since the last

@@ -97,6 +97,8 @@ SIGNATURES = {
     "obmd_run": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int]),
     "obmd_reduce_kinetic": (C.c_int, [C.c_void_p, _dp]),
     "obmd_profile_x": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
+    "obmd_exchange": (C.c_int, [C.c_void_p]),
+    "obmd_set_usher_order": (C.c_int, [C.c_void_p, C.c_int]),
     "obmd_profile_x2": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]),
     "obmd_pair_gaussian_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, _dp]),
     "obmd_comm_unique_id": (C.c_int, [C.c_char_p]),
@@ -440,6 +442,9 @@ class ObmdB200:
         lo = C.c_double(); hi = C.c_double()
         self._ck(self.L.obmd_comm_slab(self.h, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
+
+    def exchange(self): self._ck(self.L.obmd_exchange(self.h))
+    def set_usher_order(self, by_tag): self._ck(self.L.obmd_set_usher_order(self.h, int(by_tag)))
 
     def run(self, first_step, nsteps):
         self._ck(self.L.obmd_run(self.h, first_step, nsteps))

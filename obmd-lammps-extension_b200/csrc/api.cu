@@ -265,6 +265,30 @@ int setup_grid(obmd_ctx *c)
   const int per = nn[0] / P, rem = nn[0] % P;
   c->gx0 = r * per + (r < rem ? r : rem);
   c->gx1 = c->gx0 + per + (r < rem ? 1 : 0);
+  // The edge ranks run the USHER trials of their side, so the insertion regions (region5 / region6)
+  // plus one cutoff must fit inside the first / last slab.  When an even split is too narrow for that
+  // (BASELINE config 5: 16 M atoms on 8 GPUs, buffer 0.15 Lx > Lx / 8) the two edge slabs are widened
+  // to hold them and the interior ranks share the rest evenly -- SURVEY 8(e) "non-uniform slabs".
+  if (P > 2 && c->have_fix) {
+    const double w = (c->boxhi[0] - c->boxlo[0]) / nn[0];
+    const int needL = (int) ceil((c->fd.region[4].hi[0] + pt.cutmax - c->boxlo[0]) / w) + 1;
+    const int needR = (int) ceil((c->boxhi[0] - c->fd.region[5].lo[0] + pt.cutmax) / w) + 1;
+    const int edge = needL > needR ? needL : needR;
+    if (edge > per) {
+      const int inner = nn[0] - 2 * edge;
+      NEED(inner >= 2 * (P - 2), OBMD_ERR_ARG,
+           "slab run: the insertion regions leave fewer than 2 cell columns per interior rank (%d columns, %d ranks)",
+           nn[0], P);
+      const int iper = inner / (P - 2), irem = inner % (P - 2);
+      if (r == 0) { c->gx0 = 0; c->gx1 = edge; }
+      else if (r == P - 1) { c->gx0 = nn[0] - edge; c->gx1 = nn[0]; }
+      else {
+        const int k = r - 1;
+        c->gx0 = edge + k * iper + (k < irem ? k : irem);
+        c->gx1 = c->gx0 + iper + (k < irem ? 1 : 0);
+      }
+    }
+  }
   g.gnx = nn[0];
   g.cxoff = c->gx0 > 0 ? c->gx0 - 1 : 0;
   const int hi = c->gx1 < nn[0] ? c->gx1 + 1 : nn[0];
@@ -358,6 +382,8 @@ extern "C" int obmd_fix_create(obmd_ctx *c, const obmd_fix_args *a)
   fd.eps = a->eps;
   fd.nattempt = a->nattempt;
   c->have_fix = true;
+  // the slab partition depends on the insertion regions (setup_grid): redo it if atoms are not resident yet
+  if (c->nranks > 2 && c->pair_ready && c->n == 0) return setup_grid(c);
   return OBMD_OK;
 }
 
@@ -369,6 +395,24 @@ extern "C" int obmd_fix_set_flux(obmd_ctx *c, double pxx, double pxy, double pxz
   c->fa.pxx = pxx; c->fa.pxy = pxy; c->fa.pxz = pxz; c->fa.dpxx = dpxx; c->fa.freq = freq;
   c->fa.alpha = alpha; c->fa.tau = tau; c->fa.nbuf = nbuf;
   return OBMD_OK;
+}
+
+extern "C" int obmd_set_usher_order(obmd_ctx *c, int by_tag)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  c->usher_by_tag = by_tag != 0;
+  return OBMD_OK;
+}
+
+// Comm::exchange + Comm::borders for callers that drive the hooks themselves (obmd_run does this itself)
+extern "C" int obmd_exchange(obmd_ctx *c)
+{
+  NEED(c, OBMD_ERR_ARG, "NULL context");
+  if (c->nranks == 1) return OBMD_OK;
+  NEED(c->have_fix && c->cells_valid, OBMD_ERR_STATE, "obmd_exchange: call obmd_build_cells first");
+  int rc = fix_pre_begin(c);
+  if (rc) return rc;
+  return comm_exchange(c);
 }
 
 extern "C" int obmd_fix_get_state(const obmd_ctx *c, obmd_fix_state *out)
@@ -531,7 +575,7 @@ extern "C" int obmd_download(obmd_ctx *c, int *n_out, double *x, double *v, doub
   return OBMD_OK;
 }
 
-extern "C" int obmd_nlocal(const obmd_ctx *c) { return c ? c->n : 0; }
+extern "C" int obmd_nlocal(const obmd_ctx *c) { return c ? c->n - c->nghost : 0; }  // owned atoms
 
 // ---- hooks -------------------------------------------------------------------------------
 
@@ -550,6 +594,10 @@ extern "C" int obmd_nve_final(obmd_ctx *c)
 extern "C" int obmd_build_cells(obmd_ctx *c)
 {
   NEED(c, OBMD_ERR_ARG, "NULL context");
+  if (c->nghost > 0) {  // a hook-driven slab step leaves the ghosts of the previous exchange behind
+    int rc = fix_compact_extras(c);
+    if (rc) return rc;
+  }
   fix_clear_extras(c);
   return cells_build(c);
 }

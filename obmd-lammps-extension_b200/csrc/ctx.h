@@ -200,6 +200,7 @@ struct obmd_ctx {
   int *spec_of_trial = nullptr;     // [tr_cap] entry of trial t's accepted atom, -1 if none
   double *spec_pos = nullptr;
   int ush_group = 32;               // lanes per trial in round 0 (OBMD_B200_USH_G: 8, 16, 32)
+  bool usher_by_tag = false;        // serial runs: sum USHER contributions in tag order (obmd_set_usher_order)
   int fix_cluster = 8;              // CTAs in the cluster of the USHER fix-up kernel (OBMD_B200_FIX_CL: 1 or 8)
   int ush_ctas_per_sm = 6;          // persistent grid of round 0 (OBMD_B200_USH_CTAS)
   double *partials = nullptr;       // block partial sums for deterministic reductions
@@ -327,7 +328,7 @@ struct UsherCfg {
   int slots, maxatt;  // maxattempt > 1 (one side per pass): insertions wanted, attempts allowed for each
 };
 
-int usher_pass(obmd_ctx *c, const UsherCfg &u, int ntr_loc, int limit, int *nacc_out, int *nused_out,
+int usher_pass(obmd_ctx *c, const UsherCfg &u, int ntr_loc, int limit, int maxtag, int *nacc_out, int *nused_out,
                int *rounds_out);
 int usher_commit(obmd_ctx *c, int tag0, int nacc);
 int usher_trials_to_host(obmd_ctx *c, obmd_trial *dst, int ncopy);

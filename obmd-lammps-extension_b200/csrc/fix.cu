@@ -744,9 +744,6 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
     HostTimer hu(c, "host_usher");
     const int M = fa.maxattempt;
     NEED(M >= 1, OBMD_ERR_ARG, "fix obmd: maxattempt must be >= 1");
-    NEED(M == 1 || serial, OBMD_ERR_ARG,
-         "fix obmd: maxattempt > 1 in slab runs is not implemented (the right side's position in the RanPark "
-         "stream depends on the left rank's outcomes)");
     // maxattempt == 1: trial t of either side sits at a fixed place of the RanPark stream, both sides
     // go through the commit rounds together.  maxattempt > 1: the attempts a side consumes depend on
     // its outcomes (k_usher_resolve), so the left side is finished and committed first and the right
@@ -781,7 +778,9 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
         // round 0, the first diff / dirty test and the fix-up kernel that runs every re-run round are
         // enqueued back to back; the outcome is read back once (usher.cu)
         int rounds_p = 0;
-        if ((rc = usher_pass(c, u, ntr_loc, limit, &nacc_p, &nused_p, &rounds_p))) return rc;
+        int nused_loc = 0;
+        if ((rc = usher_pass(c, u, ntr_loc, limit, maxtag, &nacc_p, &nused_loc, &rounds_p))) return rc;
+        if (limit) nused_p = nused_loc;  // maxattempt == 1: every trial of the pass (on any rank) is made
         rounds += rounds_p;
       }
 
@@ -800,6 +799,22 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
           naccR = (int) c->red_h[1];
         }
       }
+      int nacc_before = nacc;  // atoms created by earlier passes, on any rank (tags continue behind them)
+      if (npass == 2 && !serial) {
+        // maxattempt > 1 in a slab run: only the rank owning the side ran the pass; how many attempts it
+        // consumed (where the other side starts in the replicated RanPark stream) and how many atoms it
+        // created (natoms, the next tag) go to everybody
+        ScopedTimer t3(c, "usher_allreduce");
+        double h[2] = {ntr_loc > 0 ? (double) nused_p : 0.0, ntr_loc > 0 ? (double) nacc_p : 0.0};
+        CK(cudaMemcpyAsync(c->red_d, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+        if ((rc = comm_allreduce(c, c->red_d, 2, 0))) return rc;
+        CK(cudaMemcpyAsync(c->red_h, c->red_d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        nused_p = (int) c->red_h[0];
+        if (ip == 0) naccL = (int) c->red_h[1];
+        else naccR = (int) c->red_h[1];
+        nacc_before = (ip == 0) ? 0 : naccL;
+      }
       // every attempt made consumes exactly three draws (ATOM mode, uniform distribution, block region)
       c->fs.rng_seed = ranpark_skip(c->fs.rng_seed, 3LL * nused_p);
       nused_total += nused_p;
@@ -808,12 +823,12 @@ int fix_pre_exchange(obmd_ctx *c, obmd_trial *trials, int maxtrials)
         // after its pair kernel has finished (obmd_run sets commit_wait)
         ScopedTimer t4(c, "usher_commit");
         if (c->commit_wait) CK(cudaStreamWaitEvent(c->stream, c->commit_wait, 0));
-        const int tag0 = maxtag + nacc + ((npass == 1 && doR && !doL) ? naccL : 0);
+        const int tag0 = maxtag + nacc_before + ((npass == 1 && doR && !doL) ? naccL : 0);
         if ((rc = usher_commit(c, tag0, nacc_p))) return rc;
         if ((rc = fix_link_extras(c, c->narr + c->nghost + c->nins, nacc_p, false))) return rc;
       }
       if (trials && maxtrials > ncopied && ntr_loc > 0) {
-        const int nloc_used = limit ? nused_p : ntr_loc;
+        const int nloc_used = limit ? (nused_p < ntr_loc ? nused_p : ntr_loc) : ntr_loc;
         const int ncopy = nloc_used < maxtrials - ncopied ? nloc_used : maxtrials - ncopied;
         if ((rc = usher_trials_to_host(c, trials + ncopied, ncopy))) return rc;
         ncopied += ncopy;

@@ -56,6 +56,8 @@ struct UsherArgs {
   UsherCfg u;
   Extras ex;
   const int *cell_start, *extra_head, *extra_next;
+  const int *keys;    // summation-order key of every stored atom: LAMMPS local index, or the tag (see usher_pass)
+  int spec_key0;      // key of the atom trial 0 of the call would create (later trials: + global trial index)
   // atoms accepted so far in this call ("spec" entries, append-only; a dead entry has trial INT_MAX).
   // There are few of them (one per accepted trial), so a gather filters the whole array against
   // its 27-cell window instead of walking per-cell lists.
@@ -220,7 +222,7 @@ __device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroup &S, const
         zj[q] = __ldg(A.p.z + j);
       }
       // the exact evaluation will want the local index of the few candidates inside the cutoff
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(A.p.lidx + jb[s] + k0));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(A.keys + jb[s] + k0));
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         if (k0 + q >= cnt[s]) break;
@@ -346,7 +348,7 @@ __device__ __forceinline__ void usher_energy(const UsherArgs &A, const PairTab &
         xj = __ldg(A.p.x + code);
         yj = __ldg(A.p.y + code);
         zj = __ldg(A.p.z + code);
-        key = __ldg(A.p.lidx + code);
+        key = __ldg(A.keys + code);
         if (!ST) tj = __ldg(A.p.type + code);
       } else {  // created earlier in this call: local index nbase + (rank among the accepted trials);
                 // the trial index orders the created atoms the same way
@@ -355,7 +357,7 @@ __device__ __forceinline__ void usher_energy(const UsherArgs &A, const PairTab &
         xj = __ldcg(sp);
         yj = __ldcg(sp + 1);
         zj = __ldcg(sp + 2);
-        key = A.u.nbase + __ldcg(A.spec_trial + e);
+        key = A.spec_key0 + __ldcg(A.spec_trial + e);
       }
       double delx = c[0] - xj, dely = c[1] - yj, delz = c[2] - zj;
       if (wrap) {
@@ -1173,7 +1175,7 @@ static int launch_fix(obmd_ctx *c, const UsherArgs &A)
 // One pass of try_inserting for ntr_loc trials on this rank (maxattempt == 1: both sides together;
 // maxattempt > 1: one side).  Enqueues round 0, the first diff / dirty test and the fix-up kernel,
 // then reads the outcome back (the only host round trip of the pass).
-int usher_pass(obmd_ctx *c, const UsherCfg &u, int ntr_loc, int limit, int *nacc_out, int *nused_out,
+int usher_pass(obmd_ctx *c, const UsherCfg &u, int ntr_loc, int limit, int maxtag, int *nacc_out, int *nused_out,
                int *rounds_out)
 {
   int rc;
@@ -1185,6 +1187,14 @@ int usher_pass(obmd_ctx *c, const UsherCfg &u, int ntr_loc, int limit, int *nacc
   A.fd = c->fd;
   A.u = u;
   A.ex = extras_of(c);
+  // Order of the USHER energy sums.  Serial runs: ascending LAMMPS local index, the reference's loop
+  // order (fix_obmd_merged.cpp:1790-1807).  Slab runs (and serial runs with obmd_set_usher_order(1)):
+  // ascending tag, which does not depend on the decomposition -- any number of ranks then produces
+  // bit-identical trial outcomes, equal to the serial tag-ordered run.  Atoms created earlier in the
+  // call come after every existing atom in both orders, among themselves in trial order.
+  const bool by_tag = c->nranks > 1 || c->usher_by_tag;
+  A.keys = by_tag ? c->cur.tag : c->cur.lidx;
+  A.spec_key0 = by_tag ? maxtag + 1 + u.tg0 : u.nbase;
   A.cell_start = c->cell_start;
   A.extra_head = c->extra_head;
   A.extra_next = c->extra_next;

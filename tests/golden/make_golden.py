@@ -285,8 +285,10 @@ def make_r1_long(wd, equil=2000, sample=2000, block=200, nbins=48):
     (_, rows), = read_dump(os.path.join(wd, "dump.snap"))
     order = np.argsort(rows[:, 0], kind="stable")
     rows = rows[order]
-    np.savez_compressed(os.path.join(HERE, "equil_r1.npz"), tag=rows[:, 0].astype(np.int32),
-                        x=rows[:, 1:4].copy(), v=rows[:, 4:7].copy(), box=np.array(BOX), steps=equil)
+    for dst in (HERE, os.path.join(ROOT, "obmd-lammps-extension_b200", "data")):   # the second copy feeds bench.py
+        os.makedirs(dst, exist_ok=True)
+        np.savez_compressed(os.path.join(dst, "equil_r1.npz"), tag=rows[:, 0].astype(np.int32),
+                            x=rows[:, 1:4].copy(), v=rows[:, 4:7].copy(), box=np.array(BOX), steps=equil)
     # columns of fix ave/chunk: chunk coord ncount density/number vx temp c_st[1..3]
     prof = read_chunk_file(os.path.join(wd, "prof.txt"), 9)
     th = []

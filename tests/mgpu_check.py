@@ -51,6 +51,50 @@ def main():
     B = 0.15 * 33.59462486002239          # fixed physical buffer: fits inside the edge slabs
     ok = True
 
+    # ---- 0. USHER on static atoms: the slab run must reproduce the one-GPU run with the same
+    # (tag-ordered) summation bit for bit -- trial stream, verdicts, accepted positions, tags, RanPark
+    # state -- for maxattempt 1 and 2 (hook-driven: build_cells, exchange, pre_exchange)
+    for maxatt in (1, 2):
+        kw = dict(alpha=1.0, nbuf=float(int(0.15 * 12637) + 150), buffer_size=B, maxattempt=maxatt)
+        sim, mine = make_slab_sim(box, x, np.zeros_like(x), tag, rank, world, **kw)
+        ref = None
+        if rank == 0:
+            ref = cc.device_sim(box, device=0, **kw)
+            ref.set_usher_order(1)
+            ref.upload(x, np.zeros_like(x), np.ones(len(x), np.int32), tag, capacity=2 * len(x))
+        for call in range(3):
+            sim.build_cells(); sim.exchange()
+            rep, tr = sim.pre_exchange(maxtrials=4096)
+            recs = [(t.start[:], t.end[:], t.energy, t.iter, t.accepted, t.side, t.tag) for t in tr]
+            recs = [r for r in recs if r[0] != [0.0, 0.0, 0.0]]   # the report counts every rank's trials; a rank fills in its own
+            allr = [None] * world
+            dist.all_gather_object(allr, recs)
+            seeds = [None] * world
+            dist.all_gather_object(seeds, (sim.fix_state().rng_seed, rep.naccept, rep.ntrials))
+            if rank == 0:
+                ref.build_cells()
+                rrep, rtr = ref.pre_exchange(maxtrials=4096)
+                want = [(t.start[:], t.end[:], t.energy, t.iter, t.accepted, t.side, t.tag) for t in rtr]
+                gotr = [r for part in allr for r in part]      # rank 0: left side, last rank: right side
+                same = gotr == want
+                st_ok = all(s == (ref.fix_state().rng_seed, rrep.naccept, rrep.ntrials) for s in seeds)
+                print("usher static maxattempt %d call %d: trials %d accepted %d identical %s state %s"
+                      % (maxatt, call, len(want), rrep.naccept, same, st_ok))
+                if not (same and st_ok):
+                    print("   slab states", seeds, "serial", (ref.fix_state().rng_seed, rrep.naccept, rrep.ntrials),
+                          "n slab", [len(p) for p in allr], "first diff",
+                          next(((k, a, b) for k, (a, b) in enumerate(zip(gotr, want)) if a != b), None))
+                ok &= same and st_ok and len(want) > 50
+        got, tags = gather_by_tag(sim, ("x", "tag"))
+        if rank == 0:
+            r = ref.download(("x", "tag"))
+            o = np.argsort(r["tag"])
+            same = np.array_equal(np.sort(tags), r["tag"][o]) and np.array_equal(got["x"], r["x"][o])
+            print("usher static maxattempt %d: final atoms %d identical %s" % (maxatt, len(tags), same))
+            ok &= same
+            ref.close()
+        sim.close()
+
     # ---- 1. setup forces, T = 0 -------------------------------------------------------
     kw = dict(temperature=0.0, alpha=0.7, nbuf=float(int(0.7 * 0.15 * 12637 * 2)), buffer_size=B)
     sim, mine = make_slab_sim(box, x, v, tag, rank, world, **kw)
