@@ -7,11 +7,14 @@
 A "step" is one MD timestep of the whole hot path (FixNVE halves, cell build, fix obmd
 pre_exchange incl. batched USHER, PairDPD, fix obmd post_force) over every atom.
 
-Start state (both arms): the shipped configuration after 2000 steps of the UNMODIFIED reference in
-the steady-exchange regime R1 (obmd-lammps-extension_b200/data/equil_r1.npz, written by
-tests/golden/make_golden.py r1long: positions AND velocities, T ~ 1.1), tiled by integer
-translations.  So the timed region starts at the steady trial / insertion / deletion rates instead
-of climbing towards them from v = 0.
+Start state of the named workloads: the shipped configuration (uniform DPD fluid, rho = 3) tiled by
+integer translations, Maxwell-Boltzmann velocities at T = 1, then --equil (default 2000) untimed
+steps of the full open-boundary step so that the density / velocity profiles at the open faces and
+the trial / insertion / deletion rates are the steady ones before the timed region starts.
+`like_for_like` is the one workload BOTH arms can run from the SAME state: the shipped system after
+2000 steps of the UNMODIFIED reference in regime R1 (obmd-lammps-extension_b200/data/equil_r1.npz,
+written by tests/golden/make_golden.py r1long: positions AND velocities), tiled across the periodic
+cross-section only -- an exact steady state, which the reference arm is timed on as well.
 
 N = 1: BASELINE config 2, "OBMD-DPD fluid at equilibrium, 1M particles" = 4x5x4 tiles, regime R1
 (alpha 1.0, nbuf = int(0.15 N)).  Secondary objects in the same line: `r0` (the shipped parameters,
@@ -51,17 +54,27 @@ N0_TILE = 12637              # atoms of the shipped data file: nbuf is defined f
 TILINGS = {"1m": (4, 5, 4), "4m": (5, 8, 8), "16m": (20, 8, 8)}
 
 
-def snapshot():
-    d = np.load(os.path.join(ROOT, "obmd-lammps-extension_b200", "data", "equil_r1.npz"))
-    return d["x"].copy(), d["v"].copy(), d["box"].copy()
+DATA = os.path.join(ROOT, "obmd-lammps-extension_b200", "data")
 
 
-def tiled(reps):
-    x, v, box = snapshot()
+def tiled(reps, snapshot=False):
+    """snapshot=False: the shipped configuration (examples/OBMD_DPD/dpd_8map_obmd.data) tiled reps times,
+    Maxwell-Boltzmann velocities at T = 1 (seeded).  snapshot=True: the reference's own R1 steady state
+    (positions + velocities); only meaningful with reps[0] == 1 (the open faces are part of it)."""
+    if snapshot:
+        d = np.load(os.path.join(DATA, "equil_r1.npz"))
+        x, v, box = d["x"].copy(), d["v"].copy(), d["box"].copy()
+    else:
+        d = np.load(os.path.join(DATA, "dpd_8map_obmd.npz"))
+        x, v, box = d["x"].copy(), None, d["box"].copy()
     L = box[:, 1] - box[:, 0]
     shifts = [np.array([i, j, k]) * L for i in range(reps[0]) for j in range(reps[1]) for k in range(reps[2])]
     X = np.concatenate([x + s for s in shifts])
-    V = np.concatenate([v] * len(shifts))
+    if v is None:
+        V = np.random.default_rng(4928459).normal(0.0, 1.0, X.shape)
+        V -= V.mean(0)
+    else:
+        V = np.concatenate([v] * len(shifts))
     B = np.array([[0.0, L[0] * reps[0]], [0.0, L[1] * reps[1]], [0.0, L[2] * reps[2]]])
     return X, V, B
 
@@ -148,8 +161,10 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------ our arm
 
-def regime_kw(regime, ntiles):
-    n_nominal = N0_TILE * ntiles
+def regime_kw(regime, ntiles, buffer_frac=1.0):
+    """alpha and nbuf of the regime; nbuf = the nominal buffer population 0.15 N (README.UserGuide.md:190-233),
+    scaled when the buffer is shorter than 0.15 Lx (weak scaling keeps the N = 1 physical length)."""
+    n_nominal = N0_TILE * ntiles * buffer_frac
     if regime == "R1":
         return dict(alpha=1.0, nbuf=float(int(0.15 * n_nominal)))
     return dict(alpha=0.7, nbuf=float(int(0.7 * 0.15 * n_nominal)))
@@ -172,15 +187,15 @@ def fix_args(ob, box, buffer_size, alpha, nbuf):
     return a
 
 
-def build_sim(reps, device, regime, rank=0, world=1, buffer_size=None):
+def build_sim(reps, device, regime, rank=0, world=1, buffer_size=None, snapshot=False):
     """Context for this rank: pair_style dpd 1.0 1.0 2616, pair_coeff * * 209.6 4.5 1.0, dt 0.001464.
     world > 1: x-slab decomposition (obmd_comm_init), every rank uploads only the atoms inside its
     slab; the NCCL unique id travels through torch.distributed."""
     import obmd_b200 as ob
-    x, v, box = tiled(reps)
+    x, v, box = tiled(reps, snapshot)
     ntiles = reps[0] * reps[1] * reps[2]
-    kw = regime_kw(regime, ntiles)
     B = buffer_size if buffer_size is not None else 0.15 * box[0, 1]
+    kw = regime_kw(regime, ntiles, B / (0.15 * box[0, 1]))
     sim = ob.ObmdB200(device)
     sim.set_box(box[:, 0], box[:, 1])
     sim.set_masses([1.0])
@@ -259,11 +274,11 @@ def reduce_over_ranks(ms, atom_steps, world):
     return tmax[0].item(), tsum[1].item()
 
 
-def secondary(reps, local, regime, rank, world, steps, warmup, equil, scaling, buffer_size=None):
+def secondary(reps, local, regime, rank, world, steps, warmup, equil, scaling, buffer_size=None, snapshot=False):
     """One more workload measured the same way (no e2e, no roofline): a compact object for the line."""
     import torch
     import torch.distributed as dist
-    sim, info = build_sim(reps, local, regime, rank=rank, world=world, buffer_size=buffer_size)
+    sim, info = build_sim(reps, local, regime, rank=rank, world=world, buffer_size=buffer_size, snapshot=snapshot)
     stream = torch.cuda.ExternalStream(sim.L.obmd_stream(sim.h), device=local)
 
     def barrier():
@@ -410,22 +425,30 @@ def ours(args):
     sec_steps = max(5, min(args.steps, args.secondary_steps))
     if not args.no_secondary:
         if world == 1:
-            extra["r0"] = secondary(reps, local, "R0", rank, world, sec_steps, args.warmup, min(args.equil, 100),
+            extra["r0"] = secondary(reps, local, "R0", rank, world, sec_steps, args.warmup, min(args.equil, 300),
                                     scaling, buffer_size)
             if rank == 0:
                 extra["r0"]["note"] = ("regime R0: the parameters exactly as shipped (alpha 0.7); the buffers only "
                                        "drain, no USHER -- the step is cell build + PairDPD + force distribution + deletion")
             extra["strong_16m"] = secondary(TILINGS["16m"], local, "R1", rank, world, sec_steps, args.warmup,
-                                            min(args.equil, 60), "strong")
+                                            min(args.equil, 300), "strong")
             extra["strong_16m"]["note"] = ("BASELINE config 5 on ONE GPU: the N = 1 point of the strong-scaling series "
                                            "`bench.py --gpus N` reports as its primary value for N > 1")
+            lreps = tuple(args.like_reps)
+            extra["like_for_like"] = secondary(lreps, local, "R1", rank, world, args.steps, args.warmup, 0, "n/a",
+                                               None, snapshot=True)
+            extra["like_for_like"]["note"] = ("the workload `bench.py --impl reference` times: the reference's own R1 "
+                                              "steady state (positions + velocities after 2000 of its steps) tiled "
+                                              "%dx%dx%d across the periodic cross-section; same deck, same start state, "
+                                              "no equilibration on either side.  Far too small to fill a B200: it is "
+                                              "here so that one ratio is between identical configurations" % lreps)
         elif workload != "1m":
             r1 = tuple(args.reps)
             extra["weak_1m_per_gpu"] = secondary((r1[0] * world, r1[1], r1[2]), local, "R1", rank, world, sec_steps,
-                                                 args.warmup, min(args.equil, 100), "weak", 0.15 * TILE_LX * r1[0])
+                                                 args.warmup, min(args.equil, 300), "weak", 0.15 * TILE_LX * r1[0])
         else:
             extra["strong_16m"] = secondary(TILINGS["16m"], local, "R1", rank, world, sec_steps, args.warmup,
-                                            min(args.equil, 60), "strong")
+                                            min(args.equil, 300), "strong")
 
     if rank == 0:
         hbm, how = peaks()
@@ -446,7 +469,8 @@ def ours(args):
                        "parallelism": ("x-slab decomposition over %d GPUs: NCCL send/recv halo + migration, "
                                        "packed allreduces" % world) if world > 1 else "single GPU",
                        "l2": "per-step working set (%.0f MB per GPU) exceeds the 126 MB L2" % (n0 * 168 / 1e6),
-                       "start_state": "reference R1 run, 2000 steps (positions + velocities), tiled",
+                       "start_state": "shipped configuration tiled, Maxwell-Boltzmann velocities T = 1, then "
+                                      "equil_steps untimed steps of the full step",
                        "equil_steps": args.equil},
             "gpu_launches": int(r["launches"]),
             # host wall time of the individual steps on rank 0 (diagnostics: the GPU hosts are noisy
@@ -503,14 +527,14 @@ def ours(args):
         if world == 1 and args.lammps_steps > 0:
             line["e2e_lammps_plugin"] = lammps_plugin_e2e(tuple(args.reps), args.lammps_steps)
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_budget)
+            line["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_budget, steps=10, reps=tuple(args.like_reps))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def workload_name(reps, natoms, regime, kw):
-    return ("OBMD-DPD fluid, reference R1 snapshot of the shipped configuration tiled %dx%dx%d = %d atoms, "
+    return ("OBMD-DPD fluid, shipped configuration tiled %dx%dx%d = %d atoms, "
             "regime %s (alpha %.1f, nbuf %d, buffer %.2f), T=1, dt=0.001464, rc=1, usher 31.03"
             % (tuple(reps) + (natoms, regime, kw["alpha"], int(kw["nbuf"]), kw["buffer"])))
 
@@ -572,11 +596,11 @@ def ref_binary():
     return p if os.path.exists(p) else None
 
 
-def run_reference(reps, nsteps, regime="R1", plugin=None):
-    """Run the unmodified reference (oracle/_ref/lmp_serial, 1 core, MPI stubs) on the tiled snapshot
-    (positions and velocities: the same start state as our arm); returns (atom_steps, loop_seconds,
-    usher_trials)."""
-    x, v, box = tiled(reps)
+def run_reference(reps, nsteps, regime="R1", plugin=None, snapshot=True):
+    """Run the unmodified reference (oracle/_ref/lmp_serial, 1 core, MPI stubs) on a tiled start state
+    with velocities (snapshot=True: its own R1 steady state, as `like_for_like` in our arm); returns
+    (atom_steps, loop_seconds, usher_trials)."""
+    x, v, box = tiled(reps, snapshot)
     n = len(x)
     wd = tempfile.mkdtemp(prefix="obmd_ref_")
     data = os.path.join(wd, "tiled.data")
@@ -619,7 +643,7 @@ def lammps_plugin_e2e(reps, nsteps):
     plug = os.path.join(ROOT, "obmd-lammps-extension_b200", "libobmd_b200_lammps.so")
     if ref_binary() is None or not os.path.exists(plug):
         return {"value": None, "unit": UNIT, "note": "reference binary or plugin not built"}
-    a, loop, _ = run_reference(reps, nsteps, plugin=plug)
+    a, loop, _ = run_reference(reps, nsteps, plugin=plug, snapshot=False)
     return {"value": a / loop, "unit": UNIT, "steps": nsteps,
             "note": "oracle/_ref/lmp_serial + plugin, LAMMPS loop time %.3f s; host FixNVE prints debug "
                     "lines every step (SURVEY Q8)" % loop}
@@ -635,8 +659,8 @@ def ref_cost_per_step(reps):
 
 
 def pick_sample(total_steps, budget_s):
-    """Largest tiling, same length along the open axis as the 1 M workload, whose run fits the budget."""
-    for reps in ((4, 5, 4), (4, 3, 3), (4, 2, 2), (4, 1, 2), (4, 1, 1), (2, 1, 1), (1, 1, 1)):
+    """Largest tiling of the reference's R1 snapshot across the periodic cross-section whose run fits the budget."""
+    for reps in ((1, 5, 4), (1, 3, 3), (1, 2, 3), (1, 2, 2), (1, 1, 2), (1, 1, 1)):
         n = 12008 * reps[0] * reps[1] * reps[2]
         if ref_cost_per_step(reps) * total_steps + 6e-6 * n <= budget_s:
             return reps
@@ -646,14 +670,15 @@ def pick_sample(total_steps, budget_s):
 def sample_text(reps, steps, loop, ntrials):
     n = 12008 * reps[0] * reps[1] * reps[2]
     full = ref_cost_per_step((4, 5, 4))
-    return ("%d steps of the SAME deck and start state (reference R1 snapshot, positions + velocities) tiled "
-            "%dx%dx%d (%d atoms, same length along the open axis, %d/20 of the cross-section), unmodified "
-            "reference (LAMMPS 7Feb2024 + src/OBMD, g++ -O3, MPI stubs, 1 core; no MPI in the image), LAMMPS "
-            "loop time %.2f s, %d USHER trials.  The reference's USHER energy is a brute-force scan of all "
-            "owned atoms per iteration, so its atom-steps/s FALLS with the tiling: the 4x5x4 workload itself "
-            "would take ~%.0f s per step (cost model in bench.py), i.e. ~%.1f k atom-steps/s"
-            % (steps, reps[0], reps[1], reps[2], n, reps[1] * reps[2], loop, ntrials, full,
-               12008 * 80 / full / 1e3))
+    return ("%d steps of the same deck from the reference's own R1 steady state (positions + velocities after "
+            "2000 of its steps) tiled %dx%dx%d across the periodic cross-section (%d atoms: %d/20 of the "
+            "cross-section and 1/4 of the length of the 1 M workload), unmodified reference (LAMMPS 7Feb2024 + "
+            "src/OBMD, g++ -O3, MPI stubs, 1 core; no MPI in the image), LAMMPS loop time %.2f s, %d USHER "
+            "trials; our arm times the identical workload as `like_for_like`.  The reference's USHER energy is "
+            "a brute-force scan of all owned atoms per iteration, so its atom-steps/s FALLS with the tiling: "
+            "the 4x5x4 workload itself would take ~%.0f s per step (cost model in bench.py), i.e. ~%.1f k "
+            "atom-steps/s" % (steps, reps[0], reps[1], reps[2], n, reps[1] * reps[2], loop, ntrials, full,
+                              12008 * 80 / full / 1e3))
 
 
 def cpu_baseline(budget_s=25.0, steps=4, reps=None):
@@ -662,7 +687,7 @@ def cpu_baseline(budget_s=25.0, steps=4, reps=None):
                 "sample": "oracle/_ref/lmp_serial missing (run oracle/build_ref.sh)"}
     reps = reps or pick_sample(steps, budget_s)
     a, loop, ntr = run_reference(reps, steps)
-    return {"value": a / loop, "unit": UNIT, "cores": 1, "kind": "reference",
+    return {"tiling": list(reps), "value": a / loop, "unit": UNIT, "cores": 1, "kind": "reference",
             "sample": sample_text(reps, steps, loop, ntr)}
 
 
@@ -671,7 +696,7 @@ def reference_arm(args):
     if rank != 0:
         return
     total = args.steps + args.warmup
-    reps = pick_sample(total, args.ref_budget)
+    reps = tuple(args.like_reps) if args.like_reps else pick_sample(total, args.ref_budget)
     if ref_binary() is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/lmp_serial not built"}))
         return
@@ -696,7 +721,6 @@ def reference_arm(args):
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_name(wreps, 12008 * nt, args.regime, kw),
-                       "start_state": "reference R1 run, 2000 steps (positions + velocities), tiled",
                        "sample": sample_text(reps, args.steps, loop, ntr)},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference",
                              "sample": sample_text(reps, args.steps, loop, ntr)},
@@ -717,8 +741,10 @@ def main():
     ap.add_argument("--regime", default="R1", choices=["R0", "R1"])
     ap.add_argument("--lammps-steps", type=int, default=5,
                     help="also time the reference LAMMPS binary + plugin (drop-in e2e) for this many steps")
-    ap.add_argument("--equil", type=int, default=200,
-                    help="untimed steps after tiling the equilibrated snapshot (decorrelates the tiles)")
+    ap.add_argument("--equil", type=int, default=2000,
+                    help="untimed steps of the full step before the timed region (reach steady exchange)")
+    ap.add_argument("--like-reps", type=int, nargs=3, default=[1, 1, 2],
+                    help="tiling of the reference's R1 snapshot that BOTH arms time (like_for_like / --impl reference)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--secondary-steps", type=int, default=50)
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (r0, strong_16m / weak)")

@@ -84,7 +84,10 @@ extern "C" int obmd_create(obmd_ctx **out, int device)
     const int gsz = atoi(e10);
     if (gsz == 16 || gsz == 32) c->ush_group = gsz;
   }
-  if (const char *e12 = getenv("OBMD_B200_FIX_CL")) c->fix_cluster = atoi(e12) == 1 ? 1 : 8;
+  if (const char *e12 = getenv("OBMD_B200_FIX_CL")) {
+    const int v = atoi(e12);
+    c->fix_cluster = (v == 1 || v == 16) ? v : 8;
+  }
   if (const char *e11 = getenv("OBMD_B200_USH_CTAS")) {
     const int v = atoi(e11);
     if (v >= 1 && v <= 16) c->ush_ctas_per_sm = v;

@@ -201,7 +201,7 @@ struct obmd_ctx {
   double *spec_pos = nullptr;
   int ush_group = 32;               // lanes per trial in round 0 (OBMD_B200_USH_G: 8, 16, 32)
   bool usher_by_tag = false;        // serial runs: sum USHER contributions in tag order (obmd_set_usher_order)
-  int fix_cluster = 8;              // CTAs in the cluster of the USHER fix-up kernel (OBMD_B200_FIX_CL: 1 or 8)
+  int fix_cluster = 16;             // CTAs in the cluster of the USHER fix-up kernel (OBMD_B200_FIX_CL: 1, 8 or 16)
   int ush_ctas_per_sm = 6;          // persistent grid of round 0 (OBMD_B200_USH_CTAS)
   double *partials = nullptr;       // block partial sums for deterministic reductions
   double *vatom = nullptr;          // per-atom virial xx of the latest tally call (stress profile)

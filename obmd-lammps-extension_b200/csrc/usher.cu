@@ -1160,6 +1160,13 @@ static int launch_fix(obmd_ctx *c, const UsherArgs &A)
   cfg.blockDim = dim3(FIX_T, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = c->stream;
+  if (CL > 8) {  // more than 8 CTAs per cluster is a non-portable size: opt in once
+    static bool np_done = false;
+    if (!np_done) {
+      CK(cudaFuncSetAttribute((k_usher_fix<ST, CL>), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      np_done = true;
+    }
+  }
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CL;
@@ -1262,6 +1269,7 @@ int usher_pass(obmd_ctx *c, const UsherCfg &u, int ntr_loc, int limit, int maxta
     LAUNCH(k_usher_dirty, cdiv(ntr_loc, 4), 128, 0, A);
     // one cluster of 8 CTAs (OBMD_B200_FIX_CL=1: a single CTA)
     if (c->fix_cluster == 1) rc = st ? launch_fix<true, 1>(c, A) : launch_fix<false, 1>(c, A);
+    else if (c->fix_cluster == 16) rc = st ? launch_fix<true, 16>(c, A) : launch_fix<false, 16>(c, A);
     else rc = st ? launch_fix<true, 8>(c, A) : launch_fix<false, 8>(c, A);
     if (rc) return rc;
   }
