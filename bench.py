@@ -587,7 +587,7 @@ fix 1 all nve
 fix 2 all obmd 1 1 6111 188.0 0 0 0 0 {alpha} 0.005 {nbuf} region1 leftB region2 rightB region3 leftshear region4 rightshear region5 leftB region6 rightB buffersize {B:.17g} gfac 0.25 stepparallel 0 stepperp 1 maxattempt 1 usher 1 31.03 1.0 0.02 10000 1.5 1.0 40 charged 0
 thermo_style custom step atoms
 thermo {nsteps}
-run {nsteps}
+{run_cmd} {nsteps}
 """
 
 
@@ -596,7 +596,7 @@ def ref_binary():
     return p if os.path.exists(p) else None
 
 
-def run_reference(reps, nsteps, regime="R1", plugin=None, snapshot=True):
+def run_reference(reps, nsteps, regime="R1", plugin=None, snapshot=True, run_cmd="run"):
     """Run the unmodified reference (oracle/_ref/lmp_serial, 1 core, MPI stubs) on a tiled start state
     with velocities (snapshot=True: its own R1 steady state, as `like_for_like` in our arm); returns
     (atom_steps, loop_seconds, usher_trials)."""
@@ -615,7 +615,7 @@ def run_reference(reps, nsteps, regime="R1", plugin=None, snapshot=True):
     kw = regime_kw(regime, reps[0] * reps[1] * reps[2])
     deck = ("plugin load %s\n" % plugin if plugin else "") + DECK.format(
         data=data, xlB=B, xrB=box[0, 1] - B, xhi=box[0, 1], yhi=box[1, 1], zhi=box[2, 1],
-        alpha=kw["alpha"], nbuf=int(kw["nbuf"]), B=B, nsteps=nsteps)
+        alpha=kw["alpha"], nbuf=int(kw["nbuf"]), B=B, nsteps=nsteps, run_cmd=run_cmd)
     inp = os.path.join(wd, "in.ref")
     open(inp, "w").write(deck)
     out = os.path.join(wd, "out.ref")
@@ -639,14 +639,15 @@ def run_reference(reps, nsteps, regime="R1", plugin=None, snapshot=True):
 
 def lammps_plugin_e2e(reps, nsteps):
     """The real drop-in: the unmodified reference LAMMPS binary with `plugin load
-    libobmd_b200_lammps.so` (fix obmd + pair_style dpd on the GPU, FixNVE/pbc/comm on the host)."""
+    libobmd_b200_lammps.so` and `run_obmd N` (stage B: fix nve + fix obmd + pair_style dpd device-resident,
+    atoms back on the host only on output steps and at the end)."""
     plug = os.path.join(ROOT, "obmd-lammps-extension_b200", "libobmd_b200_lammps.so")
     if ref_binary() is None or not os.path.exists(plug):
         return {"value": None, "unit": UNIT, "note": "reference binary or plugin not built"}
-    a, loop, _ = run_reference(reps, nsteps, plugin=plug, snapshot=False)
+    a, loop, _ = run_reference(reps, nsteps, plugin=plug, snapshot=False, run_cmd="run_obmd")
     return {"value": a / loop, "unit": UNIT, "steps": nsteps,
-            "note": "oracle/_ref/lmp_serial + plugin, LAMMPS loop time %.3f s; host FixNVE prints debug "
-                    "lines every step (SURVEY Q8)" % loop}
+            "note": "oracle/_ref/lmp_serial + plugin, `run_obmd` (device-resident), LAMMPS loop time %.3f s, "
+                    "from the tiled shipped configuration with thermal velocities (no equilibration)" % loop}
 
 
 def ref_cost_per_step(reps):
@@ -739,7 +740,7 @@ def main():
                     help="default: 1m at --gpus 1 (BASELINE config 2), 16m at --gpus N > 1 (config 5, strong "
                          "scaling); 1m at N > 1 is weak scaling, one tiling per GPU")
     ap.add_argument("--regime", default="R1", choices=["R0", "R1"])
-    ap.add_argument("--lammps-steps", type=int, default=5,
+    ap.add_argument("--lammps-steps", type=int, default=100,
                     help="also time the reference LAMMPS binary + plugin (drop-in e2e) for this many steps")
     ap.add_argument("--equil", type=int, default=2000,
                     help="untimed steps of the full step before the timed region (reach steady exchange)")

@@ -1,9 +1,12 @@
 // LAMMPS style shim: registers `fix obmd` and `pair_style dpd` from a plugin and forwards them to
 // libobmd_b200.so through the C ABI (include/obmd_b200.h).  Input-script syntax, hook points and
 // coefficients are the reference's (OBMD/fix_obmd_merged.{h,cpp}, DPD-BASIC/pair_dpd.{h,cpp}); this
-// file only marshals arguments and LAMMPS-owned host pointers.  It is "stage A" of the residency
-// ladder (DESIGN.md / INTEGRATION.md): LAMMPS keeps FixNVE, Domain::pbc and Comm on the host, so
-// every step uploads x,v (48 B/atom) and downloads f (24 B/atom).
+// file only marshals arguments and LAMMPS-owned host pointers.  Two routes (DESIGN.md / INTEGRATION.md):
+//   stage A  `run N`: LAMMPS' own Verlet drives the hooks; FixNVE, Domain::pbc and Comm stay on the host,
+//            so every step uploads x,v (48 B/atom) and downloads f (24 B/atom);
+//   stage B  `run_obmd N`: a command style registered by the same plugin runs the whole timestep
+//            device-resident (obmd_run, the hook sequence of Verlet::run, verlet.cpp:229-363) and
+//            brings the atoms back to the host only on thermo / dump steps and at the end.
 //
 // Build (needs the LAMMPS headers, i.e. only where the reference tree is mounted):
 //   make -C obmd-lammps-extension_b200/host plugin LAMMPS_SRC=/root/reference/code/src
@@ -13,15 +16,21 @@
 #include "atom.h"
 #include "atom_vec.h"
 #include "comm.h"
+#include "command.h"
 #include "domain.h"
 #include "error.h"
+#include "finish.h"
 #include "fix.h"
 #include "force.h"
 #include "group.h"
+#include "integrate.h"
 #include "lammpsplugin.h"
 #include "memory.h"
+#include "modify.h"
+#include "output.h"
 #include "pair.h"
 #include "region.h"
+#include "timer.h"
 #include "update.h"
 #include "version.h"
 
@@ -296,6 +305,10 @@ class FixObmdB200 : public Fix {
       OBMD_CK(lmp, sh, obmd_fix_create(sh.ctx, &fa));
       created = true;
     }
+    if (have_pending_state) {
+      OBMD_CK(lmp, sh, obmd_fix_set_state(sh.ctx, &pending_state));
+      have_pending_state = false;
+    }
   }
 
   void setup(int vflag) override  // :542-545
@@ -343,6 +356,34 @@ class FixObmdB200 : public Fix {
     }
     next_reneighbor += fa.nfreq;  // :632
   }
+
+  // restart_global = 1 (:74): the reference sets the flag but saves nothing, so RanPark state and
+  // simulation_time are lost across a restart file.  Here the fix state goes in and out.
+  void write_restart(FILE *fp) override
+  {
+    obmd_fix_state st;
+    if (obmd_fix_get_state(sh.ctx, &st) != OBMD_OK) return;
+    if (comm->me == 0) {
+      int size = (int) sizeof(st);
+      fwrite(&size, sizeof(int), 1, fp);
+      fwrite(&st, 1, sizeof(st), fp);
+    }
+  }
+  void restart(char *buf) override
+  {
+    memcpy(&pending_state, buf, sizeof(pending_state));
+    have_pending_state = true;  // applied in init(), once the device fix exists
+  }
+
+  bool has_variables() const
+  {
+    for (int k = 0; k < 8; k++)
+      if (!varname[k].empty()) return true;
+    return false;
+  }
+  void refresh_for_step() { refresh_variables(); }
+  void after_device_run(bigint ntimestep) { next_reneighbor = ntimestep + fa.nfreq; }
+  int group_bit() const { return groupbit; }
 
   void post_force(int) override  // :1229-1240
   {
@@ -451,9 +492,137 @@ class FixObmdB200 : public Fix {
   Shared &sh;
   obmd_fix_args fa;
   bool created = false;
+  obmd_fix_state pending_state;
+  bool have_pending_state = false;
   std::string idregion[6];
   std::string varname[8];
   std::vector<double> fbuf;
+};
+
+// ------------------------------------------------------------------------------------------
+// run_obmd N : N timesteps device-resident (stage B).  Same set-up as `run` (Run::command, run.cpp:37-260:
+// lmp->init(), Integrate::setup -> step-0 forces, fix setup, thermo header), then obmd_run in chunks that
+// end on the output steps (Output::next); the atoms come back to the host only there and at the end.
+// Needs: pair_style dpd and fix obmd from this plugin, fix nve on group all (its two half-kicks run on the
+// device: fix_nve.cpp:134-145,236-244), atom_modify sort 0 0, one MPI rank.
+// ------------------------------------------------------------------------------------------
+class RunObmd : public Command {
+ public:
+  RunObmd(LAMMPS *lmp) : Command(lmp) {}
+  void command(int narg, char **arg) override
+  {
+    if (narg != 1) error->all(FLERR, "Illegal run_obmd command (usage: run_obmd N)");
+    if (domain->box_exist == 0) error->all(FLERR, "run_obmd command before simulation box is defined");
+    const bigint nsteps = utils::bnumeric(FLERR, arg[0], false, lmp);
+    if (nsteps < 0 || nsteps > MAXSMALLINT) error->all(FLERR, "Invalid run_obmd command N value: {}", nsteps);
+    FixObmdB200 *fobmd = nullptr;
+    for (auto &f : modify->get_fix_list())
+      if (!fobmd) fobmd = dynamic_cast<FixObmdB200 *>(f);
+    if (!fobmd) error->all(FLERR, "run_obmd requires fix obmd from the obmd_b200 plugin");
+    if (!dynamic_cast<PairDPDB200 *>(force->pair))
+      error->all(FLERR, "run_obmd requires pair_style dpd from the obmd_b200 plugin");
+    if (modify->get_fix_by_style("^nve$").empty())
+      error->all(FLERR, "run_obmd integrates with FixNVE on the device: define `fix ID all nve`");
+    if (modify->get_fix_list().size() != 2)
+      error->all(FLERR, "run_obmd supports exactly two fixes: nve and obmd (others run on the host: use run)");
+    Shared &sh = acquire(lmp);
+    sh.users--;  // borrowed: the pair style and the fix own the context
+
+    update->whichflag = 1;
+    timer->init_timeout();
+    update->nsteps = (int) nsteps;
+    update->firststep = update->ntimestep;
+    update->laststep = update->ntimestep + nsteps;
+    update->beginstep = update->firststep;
+    update->endstep = update->laststep;
+    lmp->init();
+    update->integrate->setup(1);  // host path once: exchange, step-0 forces, fix setup, thermo header
+
+    // everything to the device, forces included (Integrate::setup left the complete forces on the host)
+    Atom *a = atom;
+    OBMD_CK(lmp, sh, obmd_set_timestep(sh.ctx, update->dt));
+    OBMD_CK(lmp, sh, obmd_upload(sh.ctx, a->nlocal, &a->x[0][0], &a->v[0][0], &a->f[0][0], a->type, a->tag,
+                                 a->image, a->nmax));
+    sh.resident = a->nlocal;
+    {  // atoms->natoms follows the fix's counters from here on
+      obmd_fix_state st0;
+      obmd_fix_get_state(sh.ctx, &st0);
+      seen_ins = st0.ninserted;
+      seen_del = st0.ndeleted;
+    }
+
+    timer->init();
+    timer->barrier_start();
+    const bool per_step = fobmd->has_variables();  // v_ arguments are evaluated on the host every step
+    while (update->ntimestep < update->laststep) {
+      bigint next = update->laststep;
+      if (output->next > update->ntimestep && output->next < next) next = output->next;
+      if (per_step) {
+        next = update->ntimestep + 1;
+        update->ntimestep = next;  // variables see the step being taken, as in Verlet::run
+        fobmd->refresh_for_step();
+        update->ntimestep = next - 1;
+      }
+      const int n = (int) (next - update->ntimestep);
+      OBMD_CK(lmp, sh, obmd_run(sh.ctx, (long long) update->ntimestep + 1, n));
+      update->ntimestep = next;
+      if (next == output->next || next == update->laststep) {
+        const bool out = (next == output->next);
+        to_host(sh, fobmd, out);
+        if (out) {
+          timer->stamp();
+          output->write(next);
+          timer->stamp(Timer::OUTPUT);
+        }
+      }
+    }
+    timer->barrier_stop();
+    fobmd->after_device_run(update->ntimestep);
+    update->integrate->cleanup();
+    Finish finish(lmp);
+    finish.end(1);
+    update->whichflag = 0;
+    update->firststep = update->laststep = 0;
+    update->beginstep = update->endstep = 0;
+  }
+
+ private:
+  // the device state in LAMMPS' arrays, local order (what AtomVec::copy / create_atom would have left,
+  // :827-841, :1121-1150); on output steps also the pair tallies thermo may ask for
+  void to_host(Shared &sh, FixObmdB200 *fobmd, bool tallies)
+  {
+    Atom *a = atom;
+    if (tallies) {
+      // energy / virial of this step's configuration (same step key: the same random forces), then the
+      // buffer forces post_force had added
+      OBMD_CK(lmp, sh, obmd_pair_compute(sh.ctx, (long long) update->ntimestep, 1, 1));
+      OBMD_CK(lmp, sh, obmd_post_force(sh.ctx));
+      double e, v[6];
+      OBMD_CK(lmp, sh, obmd_pair_tallies(sh.ctx, &e, v));
+      force->pair->eng_vdwl = e;
+      force->pair->eng_coul = 0.0;
+      for (int k = 0; k < 6; k++) force->pair->virial[k] = v[k];
+      update->eflag_global = update->vflag_global = update->ntimestep;
+    }
+    const int n = obmd_nlocal(sh.ctx);
+    while (n > a->nmax) a->avec->grow(0);
+    int nn = 0;
+    OBMD_CK(lmp, sh, obmd_download(sh.ctx, &nn, &a->x[0][0], &a->v[0][0], &a->f[0][0], a->type, a->tag, a->image));
+    for (int i = 0; i < nn; i++) a->mask[i] = 1 | fobmd->group_bit();
+    obmd_fix_state st;
+    obmd_fix_get_state(sh.ctx, &st);
+    a->natoms += (bigint) (st.ninserted - seen_ins) - (bigint) (st.ndeleted - seen_del);
+    seen_ins = st.ninserted;
+    seen_del = st.ndeleted;
+    a->nlocal = nn;
+    a->nghost = 0;
+    if (a->map_style != Atom::MAP_NONE) {
+      a->map_init();
+      a->map_set();
+    }
+    sh.resident = nn;
+  }
+  long long seen_ins = 0, seen_del = 0;
 };
 
 }    // namespace
@@ -468,6 +637,7 @@ double FixObmdB200::input_variable_equal(int iv)
 }
 
 static Pair *pair_creator(LAMMPS *lmp) { return new PairDPDB200(lmp); }
+static Command *run_creator(LAMMPS *lmp) { return new RunObmd(lmp); }
 static Fix *fix_creator(LAMMPS *lmp, int argc, char **argv) { return new FixObmdB200(lmp, argc, argv); }
 
 extern "C" void lammpsplugin_init(void *lmp, void *handle, void *regfunc)
@@ -488,5 +658,11 @@ extern "C" void lammpsplugin_init(void *lmp, void *handle, void *regfunc)
   plugin.name = "obmd";  // overrides the built-in fix obmd (PLUGIN/plugin.cpp:228-233)
   plugin.info = "fix obmd on B200 (libobmd_b200)";
   plugin.creator.v2 = (lammpsplugin_factory2 *) &fix_creator;
+  (*register_plugin)(&plugin, lmp);
+
+  plugin.style = "command";
+  plugin.name = "run_obmd";  // device-resident `run` (stage B): see RunObmd above
+  plugin.info = "run N timesteps of fix nve + fix obmd + pair dpd resident on B200 (libobmd_b200)";
+  plugin.creator.v1 = (lammpsplugin_factory1 *) &run_creator;
   (*register_plugin)(&plugin, lmp);
 }

@@ -135,3 +135,65 @@ def test_plugin_ballistic_bookkeeping(tmp_path):
     assert np.allclose(r1[:, 1:4], g["x20"], rtol=0, atol=1e-11)
     assert np.allclose(r1[:, 4:7], g["v20"], rtol=0, atol=1e-10)
     assert cc.mixed_rel_err(r1[:, 7:10], g["f20"]) < 1e-9
+
+
+def test_plugin_run_obmd_device_resident_ballistic(tmp_path):
+    """Stage B: `run_obmd 20` (command style of the same plugin) runs the b3 deck device-resident
+    (obmd_run) and brings the atoms back only for the dump at step 20: identical tags, x, v, f vs the
+    fixture the unmodified reference produced with its own `run 20`."""
+    need()
+    tag, x, box = cc.shipped()
+    B = 0.15 * box[0, 1]
+    body = ("velocity all create 25.0 4928459 loop geom\nfix 1 all nve\n" +
+            FIX.format(alpha=1.0, tau=0.05, nbuf=2000, B=B) +
+            "dump d all custom 20 dump.b3 id x y z vx vy vz fx fy fz\n"
+            "dump_modify d format float %.17g\nthermo 10\nthermo_style custom step atoms temp pe press\n"
+            "run_obmd 20\n")
+    out, *_ = run(tmp_path, body, a0=0.0, gamma=0.0, dt=0.01)
+    g = cc.load("b3_ballistic.npz")
+    (s0, r0), (s1, r1) = read_dump(str(tmp_path / "dump.b3"))
+    assert (s0, s1) == (0, 20)
+    assert np.array_equal(r1[:, 0].astype(np.int32), g["tag20"])
+    assert np.allclose(r1[:, 1:4], g["x20"], rtol=0, atol=1e-11)
+    assert np.allclose(r1[:, 4:7], g["v20"], rtol=0, atol=1e-10)
+    assert cc.mixed_rel_err(r1[:, 7:10], g["f20"]) < 1e-9
+    assert "Loop time of" in out
+    # thermo rows at steps 0, 10, 20 with the atom count the fix keeps (natoms)
+    rows = [ln.split() for ln in out.split("\n") if len(ln.split()) == 5 and ln.split()[0] in ("0", "10", "20")]
+    assert [r[0] for r in rows] == ["0", "10", "20"] and int(rows[-1][1]) == len(r1)
+
+
+def test_plugin_run_obmd_steady_exchange_and_restart(tmp_path):
+    """Stage B on the real deck (T = 1, USHER active), then write_restart / read_restart: the fix state
+    (RanPark seed, simulation time, counters: obmd_fix_get/set_state) survives, so a run continued from
+    the restart file inserts with the same RanPark stream as the uninterrupted run."""
+    need()
+    tag, x, box = cc.shipped()
+    B = 0.15 * box[0, 1]
+    fix = FIX.format(alpha=1.0, tau=0.005, nbuf=1895, B=B)
+    body = ("fix 1 all nve\n" + fix + "thermo 50\nthermo_style custom step atoms temp\n"
+            "run_obmd 100\nwrite_restart obmd.restart\n"
+            "dump d all custom 50 dump.a id x y z\ndump_modify d format float %.17g\nrun_obmd 50\n")
+    out, *_ = run(tmp_path, body)
+    (_, ra), = [f for f in read_dump(str(tmp_path / "dump.a")) if f[0] == 150]
+    # continue from the restart file in a fresh LAMMPS
+    deck = ("plugin load %s\nread_restart obmd.restart\ncomm_modify vel yes\natom_modify sort 0 0\n"
+            "region leftB block %.17g %.17g %.17g %.17g %.17g %.17g\n"
+            "region rightB block %.17g %.17g %.17g %.17g %.17g %.17g\n"
+            "region leftshear block 0.0 0.0 0.0 0.0 0.0 0.0\nregion rightshear block 0.0 0.0 0.0 0.0 0.0 0.0\n"
+            "pair_style dpd 1.0 1.0 2616\npair_coeff * * 209.6 4.5 1.0\nneighbor 0.4 bin\ntimestep 0.001464\n"
+            % (PLUGIN, box[0, 0], box[0, 0] + B, box[1, 0], box[1, 1], box[2, 0], box[2, 1],
+               box[0, 1] - B, box[0, 1], box[1, 0], box[1, 1], box[2, 0], box[2, 1]) +
+            "fix 1 all nve\n" + fix +
+            "dump d all custom 50 dump.b id x y z\ndump_modify d format float %.17g\nrun_obmd 50\n")
+    inp = str(tmp_path / "in.restart")
+    open(inp, "w").write(deck)
+    r = subprocess.run([LMP, "-in", inp, "-log", "none"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    (_, rb), = [f for f in read_dump(str(tmp_path / "dump.b")) if f[0] == 150]
+    # same atoms with the same tags (insertions drew the same RanPark stream); positions agree to the
+    # accuracy the restart file's arithmetic allows (forces are recomputed at setup)
+    assert np.array_equal(np.sort(ra[:, 0]), np.sort(rb[:, 0]))
+    oa, ob_ = np.argsort(ra[:, 0]), np.argsort(rb[:, 0])
+    assert np.abs(ra[oa, 1:4] - rb[ob_, 1:4]).max() < 1e-6
+    assert len(ra) != len(tag)      # the run did insert / delete
