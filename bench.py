@@ -740,7 +740,7 @@ def main():
                     help="default: 1m at --gpus 1 (BASELINE config 2), 16m at --gpus N > 1 (config 5, strong "
                          "scaling); 1m at N > 1 is weak scaling, one tiling per GPU")
     ap.add_argument("--regime", default="R1", choices=["R0", "R1"])
-    ap.add_argument("--lammps-steps", type=int, default=100,
+    ap.add_argument("--lammps-steps", type=int, default=500,
                     help="also time the reference LAMMPS binary + plugin (drop-in e2e) for this many steps")
     ap.add_argument("--equil", type=int, default=2000,
                     help="untimed steps of the full step before the timed region (reach steady exchange)")

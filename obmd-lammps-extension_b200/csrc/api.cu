@@ -740,7 +740,10 @@ extern "C" int obmd_run(obmd_ctx *c, long long first_step, int nsteps)
       // while the host reads the counts back and prepares the USHER launches (no difference on a quiet
       // host, the difference between 1.3 and 1.7 ms/step on a noisy one).  OBMD_B200_PAIR_FIRST=0
       // launches it right behind USHER round 0 instead.
-      const bool pair_first = c->pair_first != 0;
+      // Small systems in steady exchange: USHER round 0 is the longer branch and runs faster with the
+      // machine to itself, the pair kernel then overlaps the re-run rounds (a handful of CTAs).  Large
+      // systems: the pair kernel is the longer branch and starts first.  OBMD_B200_PAIR_FIRST overrides.
+      const bool pair_first = c->pair_first < 0 ? (c->n > 3000000) : (c->pair_first != 0);
       if (pair_first) {
         if ((rc = pair_on_side_stream(c))) return rc;
         c->round0_hook = nullptr;

@@ -111,7 +111,7 @@ struct obmd_ctx {
   int *redo_flag = nullptr, *redo_list = nullptr, *redo_count = nullptr;  // pair recompute near insertions
   int redo_cap = 0, redo_list_cap = 0;
   bool overlap = true;
-  int pair_first = 1;  // side-stream pair kernel before pre_exchange (1) or right behind USHER round 0 (0)
+  int pair_first = -1;  // side-stream pair kernel before pre_exchange (1), right behind USHER round 0 (0), by size (-1)
   bool tile_kernel = true;   // OBMD_B200_TILE=0: PairDPD through the per-atom list kernel instead of pair_row.cuh
   int row_rows = 0, row_zc = 0, row_threads = 0;  // tuning overrides (OBMD_B200_ROWS, _ZC, _PT); 0 = automatic
   size_t row_smem_set = 0;

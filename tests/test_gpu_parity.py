@@ -107,12 +107,12 @@ def test_b1_usher_stream_bit_exact(shipped):
     sim.close()
 
 
-@pytest.mark.xfail(reason="device pow() differs from glibc's in the last bit on ~0.1 % of the arguments", strict=False)
 def test_b9_usher_overlap_branch_bit_exact(shipped):
     """uovlp = 150: trials whose energy exceeds it step by ds = dsovlp - pow(4 eps / E, 1/12)
-    (fix_obmd_merged.cpp:1566-1580).  The device evaluates pow() itself, so this pins that its result
-    equals glibc's on every value the deck produces: trial records bit-exact vs the oracle, verdicts,
-    tags and accepted positions bit-exact vs 10 steps of the unmodified reference binary."""
+    (fix_obmd_merged.cpp:1566-1580).  CUDA's pow differs from GNU libm's in the last bit for ~0.1 % of
+    the arguments (2 of 530 trials of this deck took another path), so the device restates libm's
+    algorithm (usher.cu glibc_pow): trial records bit-exact vs the oracle, verdicts, tags and accepted
+    positions bit-exact vs 10 steps of the unmodified reference binary."""
     tag, x, box = shipped
     g = cc.load("b9_usher_overlap.npz")
     kw = dict(alpha=1.0, nbuf=2000.0, usher=(1, 31.03, 1.0, 0.02, 150.0, 1.5, 1.0, 40))
