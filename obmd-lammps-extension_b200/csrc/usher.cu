@@ -42,13 +42,24 @@ namespace cg = cooperative_groups;
 #endif
 #define KEY_DROP 0x7fffff00  // keys of screened candidates that fail the exact cutoff test (+ slot)
 
-// per lane group: the stencil of the cell the point is in, and the scratch of one energy evaluation
-struct __align__(16) UGroup {
+// per lane group: the stencil of the cell the point is in, and the scratch of one energy evaluation.
+// FAT (re-run rounds, where latency is everything and shared memory is plentiful): the exact
+// coordinates and summation keys of the candidates are kept too, so an evaluation never leaves the SM.
+template <bool FAT>
+struct UGroupFat {};
+template <>
+struct UGroupFat<true> {
+  double cx[USH_CAND], cy[USH_CAND], cz[USH_CAND];
+  int ckey[USH_CAND];
+};
+template <bool FAT>
+struct __align__(16) UGroupT : UGroupFat<FAT> {
   uint4 scr[USH_CAND];  // x, y, z (fp32 bits, relative to the cell corner), w = slot (>= 0) or -(entry + 1)
   double e[USH_CAP], fx[USH_CAP], fy[USH_CAP], fz[USH_CAP];
   int key[USH_CAP];              // LAMMPS local index of the contributing atom
   unsigned short hq[USH_CAP];    // candidate index of each screened neighbour
 };
+typedef UGroupT<false> UGroup;
 
 struct UsherArgs {
   Planes p;
@@ -84,9 +95,12 @@ struct UsherArgs {
 
 // the accepted-atom entries of this call, cached in shared memory by the fix-up kernel at the start of
 // every re-run round (entries beyond the cache are read from global memory)
+// The cached entries hang off per-cell chains (head[cell & hmask] -> next[e]; an entry remembers its cell),
+// so a gather finds the accepted atoms of its 27 cells with one shared-memory load per cell.
 struct SpecSm {
   const double *x, *y, *z;
-  const int *tr;
+  const int *tr, *cell, *next, *head;
+  int hmask;
   int n_sm, n_all;
 };
 
@@ -210,15 +224,18 @@ struct LaneCell {  // per lane, fixed for the kernel: offsets of the cells it ow
   int ox[2], oy[2], oz[2];
 };
 
-template <int G>
-__device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroup &S, const LaneCell &lc, int cx, int cy,
+template <int G, bool FAT>
+__device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroupT<FAT> &S, const LaneCell &lc, int cx, int cy,
                                             int cz, int t, double ox, double oy, double oz, int gl, int gbase,
-                                            unsigned gmask, bool have_extras, const SpecSm *sp)
+                                            unsigned gmask, bool have_extras, const SpecSm *sp,
+                                            long long *pc = nullptr)
 {
   constexpr int NCL = (27 + G - 1) / G;
+  long long gc0 = pc ? clock64() : 0;
   static_assert(NCL <= 2, "lane groups of at least 16 lanes");
   constexpr unsigned GM = (G == 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
   const Grid &g = A.g;
+  int pf_a = 0, pf_b = 0;  // re-run rounds: slots of the five z-cells around cz in this lane's column
   if (G == 32 && gl < 25) {
     // the next gather of this trial is at most one cell away: pull the cell_start rows of the 5 x 5
     // columns around this cell into L1 now, so that its first dependent round trip is short
@@ -228,11 +245,20 @@ __device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroup &S, const
     by = by < 0 ? by + g.ny : (by >= g.ny ? by - g.ny : by);
     if (bx >= 0 && bx < g.nx && by >= 0 && by < g.ny) {
       const int *row = A.cell_start + (bx * g.ny + by) * g.nz;
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(row + max(cz - 2, 0)));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(row + min(cz + 3, g.nz)));
+      const int z0 = max(cz - 2, 0), z1 = min(cz + 3, g.nz);
+      if (sp) {
+        // A re-run round is a handful of dependent chains and every gather is two or three dependent
+        // trips to L2 / HBM.  Read the slot range of the column's five cells now (used at the end of
+        // this gather) and prefetch those atoms: the next gather then finds everything in L1.
+        pf_a = __ldg(row + z0);
+        pf_b = __ldg(row + z1);
+      } else {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(row + z0));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(row + z1));
+      }
     }
   }
-  int jb[NCL], cnt[NCL], hd[NCL];
+  int jb[NCL], cnt[NCL], hd[NCL], c2s[NCL];
   double oyl[NCL], ozl[NCL];
   bool face[NCL];
   int tot = 0;
@@ -241,6 +267,7 @@ __device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroup &S, const
     jb[s] = 0;
     cnt[s] = 0;
     hd[s] = -1;
+    c2s[s] = -1;
     oyl[s] = oy;
     ozl[s] = oz;
     face[s] = false;
@@ -261,6 +288,11 @@ __device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroup &S, const
         hd[s] = __ldg(A.extra_head + c2);
         for (int e = hd[s]; e >= 0; e = __ldg(A.extra_next + e)) tot++;
       }
+      if (sp) {  // atoms accepted earlier in this call by trials < t (a retired entry has trial INT_MAX)
+        c2s[s] = c2;
+        for (int e = sp->head[c2 & sp->hmask]; e >= 0; e = sp->next[e])
+          if (sp->cell[e] == c2 && sp->tr[e] < t) tot++;
+      }
     }
   }
   int inc = tot;
@@ -275,6 +307,7 @@ __device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroup &S, const
     return 0;
   }
   int off = inc - tot;  // exclusive
+  if (pc) { long long c1 = clock64(); pc[8] += c1 - gc0; gc0 = c1; }
 #pragma unroll
   for (int s = 0; s < NCL; s++) {
     const float ty = ((float) lc.oy[s] + 0.5f) * A.wf[1], tz = ((float) lc.oz[s] + 0.5f) * A.wf[2];
@@ -282,15 +315,17 @@ __device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroup &S, const
     // cell holds ~3 atoms: one round trip in almost every case), then its list of appended atoms
     for (int k0 = 0; k0 < cnt[s]; k0 += 4) {
       double xj[4], yj[4], zj[4];
+      int kj[4];
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         const int j = jb[s] + min(k0 + q, cnt[s] - 1);
         xj[q] = __ldg(A.p.x + j);
         yj[q] = __ldg(A.p.y + j);
         zj[q] = __ldg(A.p.z + j);
+        if (FAT) kj[q] = __ldg(A.keys + j);
       }
       // the exact evaluation will want the local index of the few candidates inside the cutoff
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(A.keys + jb[s] + k0));
+      if (!FAT) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.keys + jb[s] + k0));
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         if (k0 + q >= cnt[s]) break;
@@ -300,8 +335,15 @@ __device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroup &S, const
           ry -= A.pf[1] * rintf((ry - ty) * A.ipf[1]);
           rz -= A.pf[2] * rintf((rz - tz) * A.ipf[2]);
         }
-        S.scr[off++] = make_uint4(__float_as_uint(rx), __float_as_uint(ry), __float_as_uint(rz),
-                                  (unsigned) (jb[s] + k0 + q));
+        S.scr[off] = make_uint4(__float_as_uint(rx), __float_as_uint(ry), __float_as_uint(rz),
+                                (unsigned) (jb[s] + k0 + q));
+        if constexpr (FAT) {
+          S.cx[off] = xj[q];
+          S.cy[off] = yj[q];
+          S.cz[off] = zj[q];
+          S.ckey[off] = kj[q];
+        }
+        off++;
       }
     }
     for (int e = hd[s]; e >= 0; e = __ldg(A.extra_next + e)) {
@@ -313,26 +355,70 @@ __device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroup &S, const
         ry -= A.pf[1] * rintf((ry - ty) * A.ipf[1]);
         rz -= A.pf[2] * rintf((rz - tz) * A.ipf[2]);
       }
-      S.scr[off++] = make_uint4(__float_as_uint(rx), __float_as_uint(ry), __float_as_uint(rz), (unsigned) j);
+      S.scr[off] = make_uint4(__float_as_uint(rx), __float_as_uint(ry), __float_as_uint(rz), (unsigned) j);
+      if constexpr (FAT) {
+        S.cx[off] = xj;
+        S.cy[off] = yj;
+        S.cz[off] = zj;
+        S.ckey[off] = __ldg(A.keys + j);
+      }
+      off++;
+    }
+    if (sp && c2s[s] >= 0) {
+      for (int e = sp->head[c2s[s] & sp->hmask]; e >= 0; e = sp->next[e]) {
+        const int tr = sp->tr[e];
+        if (sp->cell[e] != c2s[s] || tr >= t) continue;
+        const double xj = sp->x[e], yj = sp->y[e], zj = sp->z[e];
+        const float rx = (float) (xj - ox);
+        float ry = (float) (yj - oyl[s]), rz = (float) (zj - ozl[s]);
+        if (face[s]) {  // an end point exactly on the upper periodic face is binned into layer 0
+          ry -= A.pf[1] * rintf((ry - ty) * A.ipf[1]);
+          rz -= A.pf[2] * rintf((rz - tz) * A.ipf[2]);
+        }
+        S.scr[off] = make_uint4(__float_as_uint(rx), __float_as_uint(ry), __float_as_uint(rz), (unsigned) (-(e + 1)));
+        if constexpr (FAT) {
+          S.cx[off] = xj;
+          S.cy[off] = yj;
+          S.cz[off] = zj;
+          S.ckey[off] = A.spec_key0 + tr;
+        }
+        off++;
+      }
     }
   }
-  if (sp) {
-    // atoms accepted earlier in this call by trials < t: the entries whose position falls into the
-    // 27-cell window (a superset of those within the cutoff of any point of the centre cell) are
-    // appended, already in screening form
+  if (pc) { long long c1 = clock64(); pc[9] += c1 - gc0; gc0 = c1; }
+  if (sp && pf_b > pf_a) {
+    // one 128-byte line holds 16 coordinates / 32 keys: a column's five cells (~15 atoms) are one or
+    // two lines per plane
+    const char *px = reinterpret_cast<const char *>(A.p.x), *py = reinterpret_cast<const char *>(A.p.y);
+    const char *pz = reinterpret_cast<const char *>(A.p.z), *pk = reinterpret_cast<const char *>(A.keys);
+    const size_t d0 = ((size_t) pf_a * 8) & ~(size_t) 127, d1 = (size_t) pf_b * 8;
+    for (size_t o = d0; o < d1; o += 128) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(px + o));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(py + o));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pz + o));
+    }
+    for (size_t o = ((size_t) pf_a * 4) & ~(size_t) 127; o < (size_t) pf_b * 4; o += 128)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pk + o));
+  }
+  if (sp && sp->n_all > sp->n_sm) {
+    // accepted atoms beyond the shared-memory cache (thousands of insertions in one call): the entries
+    // whose position falls into the 27-cell window (a superset of those within the cutoff of any point
+    // of the centre cell) are appended, already in screening form
     const float lox = -1.001f * A.wf[0], hix = 2.001f * A.wf[0], loy = -1.001f * A.wf[1], hiy = 2.001f * A.wf[1];
     const float loz = -1.001f * A.wf[2], hiz = 2.001f * A.wf[2];
-    for (int e0 = 0; e0 < sp->n_all; e0 += G) {
+    for (int e0 = sp->n_sm; e0 < sp->n_all; e0 += G) {
       const int e = e0 + gl;
       bool in = false;
       float rx = 0.f, ry = 0.f, rz = 0.f;
+      double xs = 0.0, ys = 0.0, zs = 0.0;
+      int tr = 0x7fffffff;
       if (e < sp->n_all) {
-        const bool sm = e < sp->n_sm;
-        const int tr = sm ? sp->tr[e] : __ldcg(A.spec_trial + e);
+        tr = __ldcg(A.spec_trial + e);
         if (tr < t) {  // a retired entry has trial INT_MAX
-          const double xs = sm ? sp->x[e] : __ldcg(A.spec_pos + 3 * (size_t) e);
-          const double ys = sm ? sp->y[e] : __ldcg(A.spec_pos + 3 * (size_t) e + 1);
-          const double zs = sm ? sp->z[e] : __ldcg(A.spec_pos + 3 * (size_t) e + 2);
+          xs = __ldcg(A.spec_pos + 3 * (size_t) e);
+          ys = __ldcg(A.spec_pos + 3 * (size_t) e + 1);
+          zs = __ldcg(A.spec_pos + 3 * (size_t) e + 2);
           rx = (float) (xs - ox);
           ry = (float) (ys - oy);
           rz = (float) (zs - oz);
@@ -344,8 +430,15 @@ __device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroup &S, const
       const unsigned m = (G == 32) ? __ballot_sync(gmask, in) : ((__ballot_sync(gmask, in) >> gbase) & GM);
       if (in) {
         const int pos = ncand + __popc(m & ((1u << gl) - 1u));
-        if (pos < USH_CAND)
+        if (pos < USH_CAND) {
           S.scr[pos] = make_uint4(__float_as_uint(rx), __float_as_uint(ry), __float_as_uint(rz), (unsigned) (-(e + 1)));
+          if constexpr (FAT) {
+            S.cx[pos] = xs;
+            S.cy[pos] = ys;
+            S.cz[pos] = zs;
+            S.ckey[pos] = A.spec_key0 + tr;
+          }
+        }
       }
       ncand += __popc(m);
     }
@@ -355,13 +448,14 @@ __device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroup &S, const
     }
   }
   __syncwarp(gmask);
+  if (pc) { long long c1 = clock64(); pc[10] += c1 - gc0; }
   return ncand;
 }
 
 // ---- one energy evaluation (:1774-1810) -------------------------------------------------------------
 // Returns E in every lane of the group and f[d] in lane d + 1 (lane 0: E) as `mine`.
-template <bool ST, int G>
-__device__ __forceinline__ void usher_energy(const UsherArgs &A, const PairTab &pt, UGroup &S, const double c[3],
+template <bool ST, int G, bool FAT>
+__device__ __forceinline__ void usher_energy(const UsherArgs &A, const PairTab &pt, UGroupT<FAT> &S, const double c[3],
                                              double ox, double oy, double oz, int nc, bool wrap,
                                              const double k1[3], int gl, int gbase, unsigned gmask,
                                              double &E, double f[3], long long *pc)
@@ -409,10 +503,17 @@ __device__ __forceinline__ void usher_energy(const UsherArgs &A, const PairTab &
     kv[s] = 0;
     ev[s] = xv[s] = yv[s] = zv[s] = 0.0;
     if (k < nh) {
-      const int code = (int) S.scr[S.hq[k]].w;
+      const int hq = S.hq[k];
+      const int code = (int) S.scr[hq].w;
       double xj, yj, zj;
       int key, tj = it;
-      if (code >= 0) {
+      if constexpr (FAT) {
+        xj = S.cx[hq];
+        yj = S.cy[hq];
+        zj = S.cz[hq];
+        key = S.ckey[hq];
+        if (!ST && code >= 0) tj = __ldg(A.p.type + code);
+      } else if (code >= 0) {
         xj = __ldg(A.p.x + code);
         yj = __ldg(A.p.y + code);
         zj = __ldg(A.p.z + code);
@@ -503,8 +604,8 @@ __device__ __forceinline__ void usher_energy(const UsherArgs &A, const PairTab &
 // Every group of G lanes runs whole trials.  `list` == nullptr: trial li is li (round 0, handed out
 // from a device counter because trial lengths differ widely); otherwise the trials of `list` are
 // re-run from their first affected evaluation point (static assignment: group first, first + stride ...).
-template <bool ST, int G>
-__device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &pt, UGroup *groups,
+template <bool ST, int G, bool FAT>
+__device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &pt, UGroupT<FAT> *groups,
                                              const int *list, int nl, int *cursor, int first, int stride,
                                              const SpecSm *sp)
 {
@@ -512,7 +613,7 @@ __device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &
   const int gl = lane & (G - 1), gbase = lane & ~(G - 1);
   constexpr unsigned GM = (G == 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
   const unsigned gmask = GM << gbase;
-  UGroup &S = groups[(threadIdx.x >> 5) * (32 / G) + (lane / G)];
+  UGroupT<FAT> &S = groups[(threadIdx.x >> 5) * (32 / G) + (lane / G)];
   const Grid &g = A.g;
   const FixDev &fd = A.fd;
   const UsherCfg &u = A.u;
@@ -536,7 +637,7 @@ __device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &
   unsigned long long tdbg0 = 0;
   int idbg0 = 0, ngath = 0;
   const bool dbgp = USHER_DEBUG && A.debug && list;
-  long long pcl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long pcl[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (;;) {
     if (!active && more) {
       int li;
@@ -584,7 +685,7 @@ __device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg0));
           idbg0 = i;
           ngath = 0;
-          for (int q = 0; q < 8; q++) pcl[q] = 0;
+          for (int q = 0; q < 12; q++) pcl[q] = 0;
         }
       } else
         more = false;
@@ -607,7 +708,8 @@ __device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &
       ox = g.lo[0] + (cx + g.cxoff) * g.w[0];
       oy = g.lo[1] + cy * g.w[1];
       oz = g.lo[2] + cz * g.w[2];
-      nc = usher_gather<G>(A, S, lc, cx, cy, cz, t, ox, oy, oz, gl, gbase, gmask, have_extras, sp);
+      nc = usher_gather<G, FAT>(A, S, lc, cx, cy, cz, t, ox, oy, oz, gl, gbase, gmask, have_extras, sp,
+                           dbgp ? pcl : nullptr);
       gx = cx;
       gy = cy;
       gz = cz;
@@ -619,7 +721,7 @@ __device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &
     }
     if (dbgp) { long long c1 = clock64(); pcl[1] += c1 - cA; cA = c1; }
     double f[3];
-    usher_energy<ST, G>(A, pt, S, c, ox, oy, oz, nc, wrap, k1, gl, gbase, gmask, E, f, dbgp ? pcl : nullptr);
+    usher_energy<ST, G, FAT>(A, pt, S, c, ox, oy, oz, nc, wrap, k1, gl, gbase, gmask, E, f, dbgp ? pcl : nullptr);
     if (dbgp) cA = clock64();
     if (gl == 0) {
       mypath[np * 3 + 0] = c[0];
@@ -689,8 +791,8 @@ __device__ __forceinline__ void usher_trials(const UsherArgs &A, const PairTab &
     if (USHER_DEBUG && A.debug && list && gl == 0) {
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      printf("  trial %d: evals %d gathers %d nc %d ns %llu | cyc cell %lld gather %lld screen %lld exact %lld rank %lld sum %lld step %lld nh %lld\n",
-             t, np - idbg0, ngath, nc, t1 - tdbg0, pcl[0], pcl[1], pcl[2], pcl[3], pcl[4], pcl[5], pcl[6], pcl[7]);
+      printf("  trial %d: evals %d gathers %d nc %d ns %llu | cyc cell %lld gather %lld (cells %lld atoms %lld spec %lld) screen %lld exact %lld rank %lld sum %lld step %lld nh %lld\n",
+             t, np - idbg0, ngath, nc, t1 - tdbg0, pcl[0], pcl[1], pcl[8], pcl[9], pcl[10], pcl[2], pcl[3], pcl[4], pcl[5], pcl[6], pcl[7]);
     }
   }
 }
@@ -700,7 +802,7 @@ __global__ void __launch_bounds__(USH_T, MINB) k_usher_eval(const __grid_constan
 {
   extern __shared__ __align__(16) unsigned char usm[];
   if (blockIdx.x == 0 && threadIdx.x == 0 && nl > 0) A.sc->nrounds_work++;
-  usher_trials<ST, G>(A, pt, reinterpret_cast<UGroup *>(usm), nullptr, nl, &A.sc->trial_cursor, 0, 0, nullptr);
+  usher_trials<ST, G, false>(A, pt, reinterpret_cast<UGroup *>(usm), nullptr, nl, &A.sc->trial_cursor, 0, 0, nullptr);
 }
 
 // ---- maxattempt > 1 ------------------------------------------------------------------------------
@@ -921,7 +1023,9 @@ __global__ void k_usher_dirty(const __grid_constant__ UsherArgs A)
 }
 
 // ---- re-run rounds, all in one launch ---------------------------------------------------------------
-#define SPEC_SM 2048  // accepted-atom entries cached in shared memory (more are read from global memory)
+#define SPEC_SM 1024  // accepted-atom entries cached in shared memory (more are read from global memory)
+#define SPEC_H 2048   // heads of their per-cell chains (cell index modulo SPEC_H)
+typedef UGroupT<true> UGroupFix;
 
 // Dirty test of a re-run round, in three sweeps separated by cluster barriers.  The change records
 // are few (one per re-run trial at most), so they are staged in shared memory once per CTA.
@@ -1009,10 +1113,11 @@ __global__ void __launch_bounds__(FIX_T, 1)
   const int gtid = rank * FIX_T + tid, gthreads = FIX_CL * FIX_T;
   StepScalars *sc = A.sc;
   volatile int *ndirty2 = sc->ndirty2, *nchg2 = sc->nchg2;
-  UGroup *groups = reinterpret_cast<UGroup *>(usm);
-  constexpr size_t GROUP_BYTES = sizeof(UGroup) * (FIX_T / 32);
+  UGroupFix *groups = reinterpret_cast<UGroupFix *>(usm);
+  constexpr size_t GROUP_BYTES = sizeof(UGroupFix) * (FIX_T / 32);
   double *ssx = reinterpret_cast<double *>(usm + GROUP_BYTES), *ssy = ssx + SPEC_SM, *ssz = ssy + SPEC_SM;
-  int *sstr = reinterpret_cast<int *>(ssz + SPEC_SM);
+  int *sstr = reinterpret_cast<int *>(ssz + SPEC_SM), *scell = sstr + SPEC_SM, *snext = scell + SPEC_SM;
+  int *shead = snext + SPEC_SM;
   unsigned long long tdbg[5] = {0, 0, 0, 0, 0};
   auto now = []() {
     unsigned long long v;
@@ -1036,15 +1141,31 @@ __global__ void __launch_bounds__(FIX_T, 1)
     sp.y = ssy;
     sp.z = ssz;
     sp.tr = sstr;
+    sp.cell = scell;
+    sp.next = snext;
+    sp.head = shead;
+    sp.hmask = SPEC_H - 1;
+    for (int h = tid; h < SPEC_H; h += FIX_T) shead[h] = -1;
+    __syncthreads();
     for (int e = tid; e < sp.n_sm; e += FIX_T) {
-      ssx[e] = __ldcg(A.spec_pos + 3 * (size_t) e);
-      ssy[e] = __ldcg(A.spec_pos + 3 * (size_t) e + 1);
-      ssz[e] = __ldcg(A.spec_pos + 3 * (size_t) e + 2);
-      sstr[e] = __ldcg(A.spec_trial + e);
+      const double xs = __ldcg(A.spec_pos + 3 * (size_t) e), ys = __ldcg(A.spec_pos + 3 * (size_t) e + 1);
+      const double zs = __ldcg(A.spec_pos + 3 * (size_t) e + 2);
+      const int tr = __ldcg(A.spec_trial + e);
+      ssx[e] = xs;
+      ssy[e] = ys;
+      ssz[e] = zs;
+      sstr[e] = tr;
+      if (tr != 0x7fffffff) {  // live: thread it into the chain of its cell (the cell a trial's gather computes)
+        const int c2 = (cell_cx(A.g, xs) * A.g.ny + cell_cy(A.g, ys)) * A.g.nz + cell_cz(A.g, zs);
+        scell[e] = c2;
+        snext[e] = atomicExch(&shead[c2 & (SPEC_H - 1)], e);
+      }
     }
     __syncthreads();
     if (USHER_DEBUG && A.debug) tdbg[1] = now();
-    usher_trials<ST, 32>(A, pt, groups, A.list, nd, nullptr, gw, nwarp, &sp);
+    // listed trial li runs on CTA li % FIX_CL: a round of a few dozen trials is spread over all SMs of
+    // the cluster (each chain then has a scheduler and most of an L1 to itself)
+    usher_trials<ST, 32, true>(A, pt, groups, A.list, nd, nullptr, (tid >> 5) * FIX_CL + rank, nwarp, &sp);
     if (gtid == 0) sc->nrounds_work++;
     __threadfence();
     cl.sync();
@@ -1216,7 +1337,8 @@ static int launch_eval(obmd_ctx *c, const UsherArgs &A, int ntr)
 template <bool ST, int CL>
 static int launch_fix(obmd_ctx *c, const UsherArgs &A)
 {
-  const size_t smem = sizeof(UGroup) * (FIX_T / 32) + SPEC_SM * (3 * sizeof(double) + sizeof(int));
+  const size_t smem = sizeof(UGroupFix) * (FIX_T / 32) + SPEC_SM * (3 * sizeof(double) + 3 * sizeof(int)) +
+      SPEC_H * sizeof(int);
   static bool attr_done = false;
   if (!attr_done) {
     CK(cudaFuncSetAttribute((k_usher_fix<ST, CL>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -1299,7 +1421,11 @@ int usher_pass(obmd_ctx *c, const UsherCfg &u, int ntr_loc, int limit, int maxta
     A.ipf[d] = 1.0f / A.pf[d];
   }
   A.cut32 = (float) c->pt.cutmax * (float) c->pt.cutmax * 1.001f;
-  A.debug = getenv("OBMD_B200_DEBUG_FIX") ? 1 : 0;
+  {  // OBMD_B200_DEBUG_FIX=N (builds with -DUSHER_DEBUG=1): phase times of the fix-up kernel from call N on
+    static long long ncall = 0;
+    const char *e = getenv("OBMD_B200_DEBUG_FIX");
+    A.debug = (e && ++ncall >= atoll(e)) ? 1 : 0;
+  }
   // nchg2, ndirty2, naccept, nrounds_work, trial_cursor, nused, nused_prev, nspec, npairs
   CK(cudaMemsetAsync(&c->sc_d->nchg2[0], 0, 11 * sizeof(int), c->stream));
   CK(cudaMemsetAsync(c->spec_of_trial, 0xff, sizeof(int) * ntr_loc, c->stream));
