@@ -391,7 +391,8 @@ def ours(args):
     sim.build_cells()
     if world > 1:
         sim.exchange()
-    sim.pre_exchange()
+    # no pre_exchange here: inside obmd_run the pair kernel is launched on the freshly sorted atoms,
+    # before USHER appends this step's insertions (those get their forces from k_pair_add_new)
     sim.timing(True); sim.timing_reset()
     n_alone = 5
     for k in range(n_alone):
