@@ -74,9 +74,10 @@ extern "C" int obmd_create(obmd_ctx **out, int device)
   memset(&c->alt, 0, sizeof(Planes));
   for (int t = 0; t <= MAXT; t++) c->mass[t] = 0.0;
   if (const char *e2 = getenv("OBMD_B200_OVERLAP")) c->overlap = atoi(e2) != 0;
-  if (const char *e3 = getenv("OBMD_B200_TILE")) c->tile_kernel = atoi(e3) != 0;
+  if (const char *e3 = getenv("OBMD_B200_TILE")) c->tile_kernel = atoi(e3);
   if (const char *e4 = getenv("OBMD_B200_ZC")) c->row_zc = atoi(e4);
   if (const char *e6 = getenv("OBMD_B200_ROWS")) c->row_rows = atoi(e6);
+  if (const char *e7 = getenv("OBMD_B200_COLS")) c->row_cols = atoi(e7);
   if (const char *e9 = getenv("OBMD_B200_PAIR_FIRST")) c->pair_first = atoi(e9);
   if (const char *e8 = getenv("OBMD_B200_CAPSCALE")) c->row_capscale = atof(e8);
   if (const char *e5 = getenv("OBMD_B200_PT")) c->row_threads = atoi(e5);
@@ -112,7 +113,7 @@ extern "C" void obmd_destroy(obmd_ctx *c)
   cudaStreamSynchronize(c->stream2);
   free_planes(c->cur);
   free_planes(c->alt);
-  cudaFree(c->fx); cudaFree(c->fy); cudaFree(c->fz);
+  cudaFree(c->fx); cudaFree(c->fy); cudaFree(c->fz); cudaFree(c->rec); cudaFree(c->aux);
   cudaFree(c->cid); cudaFree(c->rank); cudaFree(c->perm);
   cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->scan_tmp);
   cudaFree(c->extra_head); cudaFree(c->extra_next); cudaFree(c->extra_cell);
@@ -314,7 +315,7 @@ int setup_grid(obmd_ctx *c)
   LAUNCH(k_fill_int, cdiv(c->cell_cap, 256), 256, 0, c->extra_head, c->cell_cap, -1);
   CK(cudaStreamSynchronize(c->stream));
   c->nextra = c->narr = c->nghost = c->nins = 0;
-  c->cells_valid = false;
+  c->cells_valid = c->rec_valid = false;
   return OBMD_OK;
 }
 
@@ -463,6 +464,7 @@ int obmd_ensure_capacity(obmd_ctx *c, int cap)
     CK(regrow(p.type, o, nn, c->stream)); CK(regrow(p.image, o, nn, c->stream));
   }
   CK(regrow(c->fx, o, nn, c->stream)); CK(regrow(c->fy, o, nn, c->stream)); CK(regrow(c->fz, o, nn, c->stream));
+  CK(regrow(c->rec, o, nn, c->stream)); CK(regrow(c->aux, o, nn, c->stream));
   CK(regrow(c->cid, o, nn, c->stream)); CK(regrow(c->rank, o, nn, c->stream));
   CK(regrow(c->perm, o, nn, c->stream));
   CK(regrow(c->extra_next, o, nn, c->stream)); CK(regrow(c->extra_cell, o, nn, c->stream));
@@ -510,7 +512,7 @@ extern "C" int obmd_upload(obmd_ctx *c, int n, const double *x, const double *v,
   c->n = n;
   c->nsorted = c->nparked = c->nextra = c->narr = c->nghost = c->nins = 0;
   c->pre_begun = false;
-  c->cells_valid = false;
+  c->cells_valid = c->rec_valid = false;
   c->forces_valid = (f != nullptr);
   return OBMD_OK;
 }
@@ -534,7 +536,7 @@ extern "C" int obmd_upload_xv(obmd_ctx *c, int n, const double *x, const double 
   CK(cudaMemcpyAsync(sv, v, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
   LAUNCH(k_unpack_xv, cdiv(n, 256), 256, 0, c->cur, sx, sv, n);
   CK(cudaStreamSynchronize(c->stream));
-  c->cells_valid = false;
+  c->cells_valid = c->rec_valid = false;
   return OBMD_OK;
 }
 

@@ -135,21 +135,31 @@ __global__ void k_cell_order(const int *__restrict__ cell_start, int *__restrict
   }
 }
 
-__global__ void k_gather(Planes src, Planes dst, const int *__restrict__ perm, int n, int renumber)
+// Permutes the planes into cell order and writes the records the pair kernel stages by bulk copy
+// (pair_brick.cuh): four 16-byte stores per thread, contiguous per warp.
+__global__ void k_gather(Planes src, Planes dst, AtomRec *__restrict__ rec, int4 *__restrict__ aux,
+                         const int *__restrict__ perm, int n, int renumber)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int j = perm[i];
-  dst.x[i] = src.x[j];
-  dst.y[i] = src.y[j];
-  dst.z[i] = src.z[j];
-  dst.vx[i] = src.vx[j];
-  dst.vy[i] = src.vy[j];
-  dst.vz[i] = src.vz[j];
-  dst.tag[i] = src.tag[j];
+  const double x = src.x[j], y = src.y[j], z = src.z[j], vx = src.vx[j], vy = src.vy[j], vz = src.vz[j];
+  const int tag = src.tag[j], type = src.type[j];
+  dst.x[i] = x;
+  dst.y[i] = y;
+  dst.z[i] = z;
+  dst.vx[i] = vx;
+  dst.vy[i] = vy;
+  dst.vz[i] = vz;
+  dst.tag[i] = tag;
   dst.lidx[i] = renumber ? i : src.lidx[j];  // slab mode: local order = storage order
-  dst.type[i] = src.type[j];
+  dst.type[i] = type;
   dst.image[i] = src.image[j];
+  double2 *r = reinterpret_cast<double2 *>(rec + i);
+  r[0] = make_double2(x, y);
+  r[1] = make_double2(z, vx);
+  r[2] = make_double2(vy, vz);
+  aux[i] = make_int4(tag, type, 0, 0);
 }
 
 int cells_build(obmd_ctx *c)
@@ -172,7 +182,7 @@ int cells_build(obmd_ctx *c)
     ScopedTimer t(c, "sort");
     LAUNCH(k_perm, cdiv(n, 256), 256, 0, c->cid, c->rank, c->cell_start, c->perm, n);
     LAUNCH(k_cell_order, cdiv(g.ncell, 128), 128, 0, c->cell_start, c->perm, g.ncell);
-    LAUNCH(k_gather, cdiv(n, 256), 256, 0, c->cur, c->alt, c->perm, n, c->nranks > 1 ? 1 : 0);
+    LAUNCH(k_gather, cdiv(n, 256), 256, 0, c->cur, c->alt, c->rec, c->aux, c->perm, n, c->nranks > 1 ? 1 : 0);
     Planes t2 = c->cur;
     c->cur = c->alt;
     c->alt = t2;
@@ -203,6 +213,7 @@ int cells_build(obmd_ctx *c)
   NEED(c->nranks > 1 || (c->nmigL == 0 && c->nmigR == 0), OBMD_ERR_STATE, "cell build: stray migrants");
   c->nextra = c->narr = c->nghost = c->nins = 0;
   c->cells_valid = true;
+  c->rec_valid = true;
   c->forces_valid = false;
   c->vatom_valid = false;
   return OBMD_OK;

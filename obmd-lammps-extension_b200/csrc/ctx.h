@@ -28,6 +28,13 @@ struct Planes {
   int *tag, *lidx, *type, *image;
 };
 
+// One cell-sorted atom as the pair kernel stages it (pair_brick.cuh): a 48-byte record of positions
+// and velocities plus a 16-byte record {tag, type, 0, 0}.  The copy engine's granule is 16 bytes, so any
+// run of either is a legal bulk copy.  Written by the sort's gather next to the planes.
+struct __align__(16) AtomRec {
+  double x, y, z, vx, vy, vz;
+};
+
 // Cell grid: cell size >= max cutoff; linear index (cx*ny + cy)*nz + cz, x slowest, z fastest,
 // so each open-boundary buffer is one contiguous slot range and a z-row of a stencil is contiguous.
 struct Grid {
@@ -112,8 +119,8 @@ struct obmd_ctx {
   int redo_cap = 0, redo_list_cap = 0;
   bool overlap = true;
   int pair_first = -1;  // side-stream pair kernel before pre_exchange (1), right behind USHER round 0 (0), by size (-1)
-  bool tile_kernel = true;   // OBMD_B200_TILE=0: PairDPD through the per-atom list kernel instead of pair_row.cuh
-  int row_rows = 0, row_zc = 0, row_threads = 0;  // tuning overrides (OBMD_B200_ROWS, _ZC, _PT); 0 = automatic
+  int tile_kernel = 2;       // OBMD_B200_TILE: 2 bulk-staged bricks (pair_brick.cuh), 1 thread-staged row tiles (pair_row.cuh), 0 per-atom list kernel
+  int row_rows = 0, row_zc = 0, row_threads = 0, row_cols = 0;  // tuning overrides (OBMD_B200_ROWS, _ZC, _PT, _COLS); 0 = automatic
   size_t row_smem_set = 0;
   double row_capscale = 1.0;  // OBMD_B200_CAPSCALE (tests): < 1 forces tiles onto the overflow path
   char err[1024] = {0};
@@ -166,6 +173,9 @@ struct obmd_ctx {
   bool cells_valid = false;
   bool forces_valid = false;
   Planes cur, alt;
+  AtomRec *rec = nullptr;      // records of the sorted atoms [0, nsorted), as of the latest cell build
+  int4 *aux = nullptr;         // {tag, type, 0, 0} of the same atoms
+  bool rec_valid = false;      // nothing has changed x, v, tag or type of a sorted atom since (Domain::pbc may have run)
   double *fx = nullptr, *fy = nullptr, *fz = nullptr;
   int *cid = nullptr, *rank = nullptr, *perm = nullptr;
   int *cell_count = nullptr, *cell_start = nullptr, *scan_tmp = nullptr;

@@ -104,7 +104,7 @@ int fix_nve_initial(obmd_ctx *c)
   ScopedTimer t(c, "nve");
   LAUNCH(k_nve_initial, cdiv(c->n, 256), 256, 0, c->cur, c->fx, c->fy, c->fz, c->n, c->dt,
          0.5 * c->dt, c->pt);
-  c->cells_valid = false;
+  c->cells_valid = c->rec_valid = false;
   return OBMD_OK;
 }
 
@@ -113,6 +113,7 @@ int fix_nve_final(obmd_ctx *c)
   NEED(c->n > 0 && c->dt > 0.0, OBMD_ERR_STATE, "obmd_nve_final: atoms and timestep must be set");
   ScopedTimer t(c, "nve");
   LAUNCH(k_nve_final, cdiv(c->n, 256), 256, 0, c->cur, c->fx, c->fy, c->fz, c->n, 0.5 * c->dt, c->pt);
+  c->rec_valid = false;  // velocities changed
   return OBMD_OK;
 }
 
@@ -597,7 +598,7 @@ int fix_compact_extras(obmd_ctx *c)
   c->n = c->nsorted + c->narr + c->nins;
   c->nsorted = c->n;  // no longer cell-sorted as a whole, but contiguous; the next sort rebuilds
   c->narr = c->nghost = c->nins = c->nextra = 0;
-  c->cells_valid = false;
+  c->cells_valid = c->rec_valid = false;
   return OBMD_OK;
 }
 

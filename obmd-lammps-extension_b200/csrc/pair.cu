@@ -307,6 +307,7 @@ __global__ void __launch_bounds__(PAIR_T)
 }
 
 #include "pair_row.cuh"
+#include "pair_brick.cuh"
 
 // ---- forces after USHER insertions, without recomputing anybody from scratch -----------------
 // obmd_run computes PairDPD on the side stream while USHER is still searching, i.e. without the
@@ -541,30 +542,124 @@ static int pair_row_plan(obmd_ctx *c, bool single, RowPlan &best)
   return OBMD_OK;
 }
 
-static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &cr, cudaStream_t st,
-                       bool prewrap = false)
+// Brick shape of the bulk-staged kernel (pair_brick.cuh) for this box and density: columns C and rows R
+// per brick (1, 2, 4), z-cells per brick zc, threads T, landing capacity; ranked by a small cost model
+// fitted to tools/pair_bench.py sweeps.  OBMD_B200_COLS / _ROWS / _ZC / _PT override.
+struct BrickPlan {
+  int C, R, nchunk, zc, T, capL;
+  size_t smem;
+};
+
+static int pair_brick_plan(obmd_ctx *c, bool single, BrickPlan &best)
+{
+  const Grid &g = c->grid;
+  const double rho = (double) c->nsorted / ((double) (g.own_b - g.own_a + 1) * g.ny * g.nz);
+  const int ncols = g.own_b - g.own_a + 1;
+  double best_score = -1.0;
+  for (int C = 1; C <= 4; C *= 2) {
+    if (c->row_cols > 0 && C != c->row_cols) continue;
+    if (C > 1 && C > ncols) continue;
+    for (int R = 1; R <= 4; R *= 2) {
+      if (c->row_rows > 0 && R != c->row_rows) continue;
+      if (R > 1 && R > g.ny) continue;
+      const int NROW = (C + 2) * (R + 2);
+      for (int nchunk = 1; nchunk <= g.nz; nchunk++) {
+        const int zc = cdiv(g.nz, nchunk);
+        if (zc > PB_MAXZC) continue;
+        if (c->row_zc > 0 && zc != cdiv(g.nz, cdiv(g.nz, c->row_zc))) continue;
+        const double atoms = C * R * zc * rho;
+        int T = 32 * cdiv((long long) (atoms * 1.03 + 2.0), 32);
+        if (c->row_threads > 0) T = c->row_threads / 32 * 32;
+        if (T < 64) T = 64;
+        if (T > PB_TMAX) T = PB_TMAX;  // several passes over the brick's atoms
+        const int nw = zc + 2;
+        // landing capacity: the mean plus the larger of 5 % + 16 and 2.5 sigma of a Poisson count (a dense
+        // DPD fluid fluctuates far less); a brick that still overflows takes the global-memory path
+        const double nmean = NROW * nw * rho;
+        const double slack = fmax(0.05 * nmean + 16.0, 2.5 * sqrt(nmean));
+        const int capL = ((int) ((nmean + slack) * c->row_capscale) + 7) / 8 * 8;
+        if (capL > 60000) continue;  // landing indices are 16-bit
+        const size_t smem = pair_brick_smem_bytes(C, R, capL, nw, T, single);
+        if (smem > 200 * 1024) continue;
+        int ctas = (int) ((227 * 1024) / (smem + 1024));
+        if (ctas > 2048 / T) ctas = 2048 / T;
+        if (ctas > 32) ctas = 32;
+        const double warps = ctas * (T / 32.0);
+        const double passes = ceil(atoms / T);
+        const double lane_eff = atoms / (passes * T);
+        const double redundancy = (double) NROW * nw / (C * R * zc);
+        const double score = lane_eff * (atoms / (atoms + 40.0)) * (warps < 24.0 ? warps / 24.0 : 1.0) /
+            (1.0 + 0.10 * redundancy);
+        if (score > best_score) {
+          best_score = score;
+          best = {C, R, nchunk, zc, T, capL, smem};
+        }
+      }
+    }
+  }
+  NEED(best_score > 0.0, OBMD_ERR_CAPACITY, "pair_brick: no brick shape fits (nz %d, density %.2f)", g.nz, rho);
+  return OBMD_OK;
+}
+
+static int colrange_columns(const ColRange &cr)
+{
+  int n = 0;
+  for (int k = 0; k < cr.n; k++) n += cr.b[k] - cr.a[k] + 1;
+  return n;
+}
+
+template <int C, int R, bool S>
+static int pair_launch_brick_t(obmd_ctx *c, long long step, const ColRange &cr, cudaStream_t st, const BrickPlan &pl)
+{
+  static size_t smem_set = 0;  // per instantiation
+  if (pl.smem > smem_set) {
+    CK(cudaFuncSetAttribute(k_pair_brick<C, R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl.smem));
+    smem_set = pl.smem;
+  }
+  int ncoltiles = 0;
+  for (int k = 0; k < cr.n; k++) ncoltiles += (cr.b[k] - cr.a[k] + C) / C;
+  const int ntiles = ncoltiles * cdiv(c->grid.ny, R) * pl.nchunk;
+  const int random_on = c->temperature > 0.0 ? 1 : 0;
+  LAUNCH_ON(st, (k_pair_brick<C, R, S>), ntiles, pl.T, pl.smem, c->rec, c->aux, c->cur, cr, c->grid, c->pt,
+            c->cell_start, c->fx, c->fy, c->fz, (unsigned) step, random_on, pl.nchunk, pl.zc, pl.capL);
+  CK(cudaGetLastError());
+  return OBMD_OK;
+}
+
+static int pair_launch_brick(obmd_ctx *c, long long step, const ColRange &cr, cudaStream_t st)
+{
+  const bool single = (c->ntypes == 1);
+  BrickPlan pl;
+  int rc = pair_brick_plan(c, single, pl);
+  if (rc) return rc;
+#define BRICK_CASE(NC_, NR_)                                                       \
+  if (pl.C == NC_ && pl.R == NR_)                                                  \
+    return single ? pair_launch_brick_t<NC_, NR_, true>(c, step, cr, st, pl)       \
+                  : pair_launch_brick_t<NC_, NR_, false>(c, step, cr, st, pl)
+  BRICK_CASE(1, 1); BRICK_CASE(1, 2); BRICK_CASE(1, 4);
+  BRICK_CASE(2, 1); BRICK_CASE(2, 2); BRICK_CASE(2, 4);
+  BRICK_CASE(4, 1); BRICK_CASE(4, 2); BRICK_CASE(4, 4);
+#undef BRICK_CASE
+  return obmd_fail(c, OBMD_ERR_STATE, "pair_brick: no kernel for the planned shape");
+}
+
+static int pair_launch_row(obmd_ctx *c, long long step, const ColRange &cr, cudaStream_t st, bool prewrap)
 {
   const bool single = (c->ntypes == 1);
   const int random_on = c->temperature > 0.0 ? 1 : 0;
-  c->pt.dtinvsqrt = 1.0 / sqrt(c->dt);
   const Grid &g = c->grid;
-  if (!tally && c->tile_kernel && cr.n > 0 && c->nsorted > 0) {
-    // cell-sorted atoms of the column set: row-tiled kernel (pair_row.cuh), one CTA per
-    // (column, row strip, z-chunk); the atoms appended after the sort go through the list kernel below
-    int ncols = 0;
-    for (int k = 0; k < cr.n; k++) ncols += cr.b[k] - cr.a[k] + 1;
-    RowPlan pl;
-    int rc = pair_row_plan(c, single, pl);
-    if (rc) return rc;
-    if (pl.smem > c->row_smem_set) {
+  RowPlan pl;
+  int rc = pair_row_plan(c, single, pl);
+  if (rc) return rc;
+  if (pl.smem > c->row_smem_set) {
 #define ROW_ATTR(R, S, P) \
   CK(cudaFuncSetAttribute(k_pair_row<R, S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl.smem))
-      ROW_ATTR(1, true, true); ROW_ATTR(1, true, false); ROW_ATTR(1, false, true); ROW_ATTR(1, false, false);
-      ROW_ATTR(2, true, true); ROW_ATTR(2, true, false); ROW_ATTR(2, false, true); ROW_ATTR(2, false, false);
-      ROW_ATTR(4, true, true); ROW_ATTR(4, true, false); ROW_ATTR(4, false, true); ROW_ATTR(4, false, false);
-      c->row_smem_set = pl.smem;
-    }
-    const int ntiles = ncols * cdiv(g.ny, pl.R) * pl.nchunk;
+    ROW_ATTR(1, true, true); ROW_ATTR(1, true, false); ROW_ATTR(1, false, true); ROW_ATTR(1, false, false);
+    ROW_ATTR(2, true, true); ROW_ATTR(2, true, false); ROW_ATTR(2, false, true); ROW_ATTR(2, false, false);
+    ROW_ATTR(4, true, true); ROW_ATTR(4, true, false); ROW_ATTR(4, false, true); ROW_ATTR(4, false, false);
+    c->row_smem_set = pl.smem;
+  }
+  const int ntiles = colrange_columns(cr) * cdiv(g.ny, pl.R) * pl.nchunk;
 #define ROW_ARGS                                                                                       \
   c->cur, cr, extras_of(c), c->grid, c->pt, c->cell_start, c->extra_head, c->extra_next, c->fx, c->fy, \
       c->fz, (unsigned) step, random_on, pl.nchunk, pl.zc, pl.cap
@@ -575,10 +670,50 @@ static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &
     else if (prewrap) LAUNCH_ON(st, (k_pair_row<R, false, true>), ntiles, pl.T, pl.smem, ROW_ARGS);      \
     else LAUNCH_ON(st, (k_pair_row<R, false, false>), ntiles, pl.T, pl.smem, ROW_ARGS);                  \
   } while (0)
-    if (pl.R == 1) ROW_LAUNCH(1);
-    else if (pl.R == 2) ROW_LAUNCH(2);
-    else ROW_LAUNCH(4);
-    CK(cudaGetLastError());
+  if (pl.R == 1) ROW_LAUNCH(1);
+  else if (pl.R == 2) ROW_LAUNCH(2);
+  else ROW_LAUNCH(4);
+  CK(cudaGetLastError());
+  return OBMD_OK;
+}
+
+static int pair_launch(obmd_ctx *c, long long step, bool tally, const ColRange &cr, cudaStream_t st,
+                       bool prewrap = false)
+{
+  const bool single = (c->ntypes == 1);
+  const int random_on = c->temperature > 0.0 ? 1 : 0;
+  c->pt.dtinvsqrt = 1.0 / sqrt(c->dt);
+  const Grid &g = c->grid;
+  if (!tally && c->tile_kernel && cr.n > 0 && c->nsorted > 0) {
+    // cell-sorted atoms of the column set: the brick kernel (pair_brick.cuh, staged by the copy engine from
+    // the records the sort wrote) for the columns whose stencil holds no appended atoms, the thread-staged
+    // row kernel (pair_row.cuh) for the others (the two columns next to each slab face; every column when
+    // insertions are pending or the records are stale).  The atoms appended after the sort go through
+    // the list kernel below.
+    int ca = 0, cb = -1;  // columns the brick kernel may take
+    if (c->tile_kernel >= 2 && c->nins == 0 && c->rec_valid) {
+      if (c->narr + c->nghost == 0) { ca = 0; cb = g.nx - 1; }
+      else { ca = g.own_a + 2; cb = g.own_b - 2; }
+    }
+    ColRange in, out[2];
+    memset(&in, 0, sizeof(in));
+    memset(out, 0, sizeof(out));
+    int nout = 0;
+    for (int k = 0; k < cr.n; k++) {
+      const int a = cr.a[k], b = cr.b[k];
+      const int ia = a > ca ? a : ca, ib = b < cb ? b : cb;
+      if (ia <= ib) {
+        in.a[in.n] = ia; in.b[in.n] = ib; in.n++;
+        if (a < ia) { ColRange &o = out[nout / 2]; o.a[o.n] = a; o.b[o.n] = ia - 1; o.n++; nout++; }
+        if (ib < b) { ColRange &o = out[nout / 2]; o.a[o.n] = ib + 1; o.b[o.n] = b; o.n++; nout++; }
+      } else {
+        ColRange &o = out[nout / 2]; o.a[o.n] = a; o.b[o.n] = b; o.n++; nout++;
+      }
+    }
+    int rc = OBMD_OK;
+    if (in.n > 0 && (rc = pair_launch_brick(c, step, in, st))) return rc;
+    for (int k = 0; k < 2; k++)
+      if (out[k].n > 0 && (rc = pair_launch_row(c, step, out[k], st, prewrap))) return rc;
     if (!cr.extras || c->narr + c->nins == 0) return OBMD_OK;
     ColRange xr;
     memset(&xr, 0, sizeof(xr));

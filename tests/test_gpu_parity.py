@@ -393,7 +393,7 @@ def test_row_tiled_pair_kernel_matches_list_kernel(shipped, monkeypatch):
         assert len(x) == n_expected
         v = np.random.default_rng(9).normal(0, 1, x.shape)
         res = []
-        for tile in ("0", "1"):
+        for tile in ("0", "1", "2"):
             monkeypatch.setenv("OBMD_B200_TILE", tile)
             monkeypatch.setenv("OBMD_B200_ZC", zc)
             monkeypatch.setenv("OBMD_B200_ROWS", rows)
@@ -405,10 +405,12 @@ def test_row_tiled_pair_kernel_matches_list_kernel(shipped, monkeypatch):
         scale = np.abs(res[0]).max()
         assert scale > 1.0
         assert np.abs(res[0] - res[1]).max() <= 1e-12 * scale
+        # the brick kernel (pair_brick.cuh, the default): same pairs, its own summation order and rsqrt
+        assert np.abs(res[0] - res[2]).max() <= 1e-12 * scale
     # a tile whose window does not fit the shared-memory capacity takes the global-memory path:
     # shrink the capacity so that every tile (0.5) or only the densest ones (0.99) overflow
-    for capscale in ("0.5", "0.99"):
-        monkeypatch.setenv("OBMD_B200_TILE", "1")
+    for capscale, tile in (("0.5", "1"), ("0.99", "1"), ("0.5", "2"), ("0.99", "2")):
+        monkeypatch.setenv("OBMD_B200_TILE", tile)
         monkeypatch.setenv("OBMD_B200_ZC", "0"); monkeypatch.setenv("OBMD_B200_ROWS", "0")
         monkeypatch.setenv("OBMD_B200_CAPSCALE", capscale)
         tag, x, box = cc.tiled((1, 2, 5))
@@ -420,6 +422,7 @@ def test_row_tiled_pair_kernel_matches_list_kernel(shipped, monkeypatch):
         sim.close()
         assert np.abs(f - res[1]).max() <= 1e-12 * np.abs(res[1]).max()
     monkeypatch.delenv("OBMD_B200_CAPSCALE")
+    monkeypatch.delenv("OBMD_B200_TILE")
 
 
 def test_pair_two_types_row_and_list_kernels_vs_oracle(shipped, monkeypatch):
@@ -436,7 +439,7 @@ def test_pair_two_types_row_and_list_kernels_vs_oracle(shipped, monkeypatch):
     coeff = {(1, 1): (209.6, 4.5, 1.0), (1, 2): (150.0, 3.0, 0.9), (2, 2): (100.0, 6.0, 0.8)}
     res = {}
     for temperature in (0.0, 1.0):
-        for tile in ("0", "1"):
+        for tile in ("0", "1", "2"):
             monkeypatch.setenv("OBMD_B200_TILE", tile)
             sim = ob.ObmdB200(0)
             sim.set_box(box[:, 0], box[:, 1]); sim.set_masses([1.0, 2.0]); sim.set_timestep(0.001464)
@@ -456,10 +459,11 @@ def test_pair_two_types_row_and_list_kernels_vs_oracle(shipped, monkeypatch):
     O.lib().orc_pair_compute(C.byref(p), C.byref(a.c), 0, 5, None, None)
     fr = a.view("f")
     assert np.abs(fr).max() > 1.0
-    for tile in ("0", "1"):
+    for tile in ("0", "1", "2"):
         assert cc.mixed_rel_err(res[(0.0, tile)], fr) < FTOL
     scale = np.abs(res[(1.0, "0")]).max()
     assert np.abs(res[(1.0, "0")] - res[(1.0, "1")]).max() <= 1e-12 * scale
+    assert np.abs(res[(1.0, "0")] - res[(1.0, "2")]).max() <= 1e-12 * scale
     assert np.abs(res[(1.0, "1")] - res[(0.0, "1")]).max() > 1.0   # the random term is on
 
 
