@@ -120,9 +120,13 @@ __global__ void k_perm(const int *__restrict__ cid, const int *__restrict__ rank
 }
 
 // One thread per cell: its entries are few (rho * rc^3 ~ 3), insertion sort in place.
-__global__ void k_cell_order(const int *__restrict__ cell_start, int *__restrict__ perm, int ncell)
+// Thread c < nx also reports the population of cell column c (the density profile along the open axis is
+// not flat: the pair kernel sizes its shared-memory window for the fullest column).
+__global__ void k_cell_order(const int *__restrict__ cell_start, int *__restrict__ perm, int ncell, int nx, int nyz,
+                             StepScalars *sc)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < nx) atomicMax(&sc->colmax, cell_start[(c + 1) * nyz] - cell_start[c * nyz]);
   if (c >= ncell) return;
   int b = cell_start[c], e = cell_start[c + 1];
   for (int a = b + 1; a < e; a++) {
@@ -171,7 +175,7 @@ int cells_build(obmd_ctx *c)
   {
     ScopedTimer t(c, "bin");
     CK(cudaMemsetAsync(c->cell_count, 0, sizeof(int) * (m + 1), c->stream));
-    CK(cudaMemsetAsync(&c->sc_d->nonfinite, 0, sizeof(int), c->stream));
+    CK(cudaMemsetAsync(&c->sc_d->nonfinite, 0, 2 * sizeof(int), c->stream));  // nonfinite, colmax
     LAUNCH(k_bin, cdiv(n, 256), 256, 0, c->cur, n, g, c->cid, c->rank, c->cell_count, c->sc_d);
     int nb = cdiv(m, SCAN_T * SCAN_E);
     LAUNCH(k_scan_block, nb, SCAN_T, 0, c->cell_count, c->cell_start, c->scan_tmp, m);
@@ -181,7 +185,7 @@ int cells_build(obmd_ctx *c)
   {
     ScopedTimer t(c, "sort");
     LAUNCH(k_perm, cdiv(n, 256), 256, 0, c->cid, c->rank, c->cell_start, c->perm, n);
-    LAUNCH(k_cell_order, cdiv(g.ncell, 128), 128, 0, c->cell_start, c->perm, g.ncell);
+    LAUNCH(k_cell_order, cdiv(g.ncell, 128), 128, 0, c->cell_start, c->perm, g.ncell, g.nx, g.ny * g.nz, c->sc_d);
     LAUNCH(k_gather, cdiv(n, 256), 256, 0, c->cur, c->alt, c->rec, c->aux, c->perm, n, c->nranks > 1 ? 1 : 0);
     Planes t2 = c->cur;
     c->cur = c->alt;
@@ -199,12 +203,13 @@ int cells_build(obmd_ctx *c)
     CK(cudaMemcpyAsync(seg + 7, &c->cell_start[(g.own_b + 1) * nyz], sizeof(int), cudaMemcpyDeviceToHost,
                        c->stream));
   }
-  CK(cudaMemcpyAsync(&c->sc_h->nonfinite, &c->sc_d->nonfinite, sizeof(int), cudaMemcpyDeviceToHost,
-                     c->stream));
+  CK(cudaMemcpyAsync(&c->sc_h->nonfinite, &c->sc_d->nonfinite, 2 * sizeof(int), cudaMemcpyDeviceToHost,
+                     c->stream));  // nonfinite, colmax
   CK(cudaStreamSynchronize(c->stream));
   for (int k = 0; k < 4; k++) c->col_ab[k] = (c->nranks > 1) ? seg[4 + k] : 0;
   NEED(!c->sc_h->nonfinite, OBMD_ERR_NONFINITE, "Non-numeric atom coords - simulation unstable");
   c->nsorted = seg[0];
+  c->colmax = c->sc_h->colmax;
   c->nparked = seg[1] - seg[0];
   c->seg_migL = seg[1];
   c->seg_migR = seg[2];

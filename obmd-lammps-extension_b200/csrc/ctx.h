@@ -77,6 +77,7 @@ struct StepScalars {
   int maxtag;
   int ntail;                // survivors with lidx >= nprime found by the scan
   int nonfinite;            // non-numeric coordinate seen while binning
+  int colmax;               // atoms in the fullest cell column (cells.cu; sizes the pair kernel's shared-memory window)
   int usher_error;          // see OBMD_ERR_USHER / capacity
   // USHER commit rounds run without host round trips: counters are double-buffered by round parity
   int nchg2[2];             // trials whose state changed in round r (index r & 1)
@@ -158,6 +159,7 @@ struct obmd_ctx {
   int nparked = 0;  // [nsorted, nsorted+nparked) atoms outside the box in x (before pre_exchange)
   int nextra = 0;   // atoms appended after the sort: [nsorted, nsorted+nextra) = arrivals|ghosts|inserted
   int narr = 0, nghost = 0, nins = 0;
+  int colmax = 0;   // atoms in the fullest cell column at the latest cell build
   int nmigL = 0, nmigR = 0, seg_migL = 0, seg_migR = 0;  // migrant segments after the sort
   int ndel_local = 0;
   int col_ab[4] = {0, 0, 0, 0};  // slot ranges of the first / last owned column (halo source)

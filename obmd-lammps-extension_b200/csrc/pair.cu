@@ -555,6 +555,10 @@ static int pair_brick_plan(obmd_ctx *c, bool single, BrickPlan &best)
   const Grid &g = c->grid;
   const double rho = (double) c->nsorted / ((double) (g.own_b - g.own_a + 1) * g.ny * g.nz);
   const int ncols = g.own_b - g.own_a + 1;
+  // the density profile along the open axis is not flat (buffers vs region of interest): the landing
+  // capacity follows the fullest cell column
+  const double rho_col = (double) c->colmax / ((double) g.ny * g.nz);
+  const double rho_max = rho_col > rho ? rho_col : rho;
   double best_score = -1.0;
   for (int C = 1; C <= 4; C *= 2) {
     if (c->row_cols > 0 && C != c->row_cols) continue;
@@ -575,7 +579,7 @@ static int pair_brick_plan(obmd_ctx *c, bool single, BrickPlan &best)
         const int nw = zc + 2;
         // landing capacity: the mean plus the larger of 5 % + 16 and 2.5 sigma of a Poisson count (a dense
         // DPD fluid fluctuates far less); a brick that still overflows takes the global-memory path
-        const double nmean = NROW * nw * rho;
+        const double nmean = NROW * nw * rho_max;
         const double slack = fmax(0.05 * nmean + 16.0, 2.5 * sqrt(nmean));
         const int capL = ((int) ((nmean + slack) * c->row_capscale) + 7) / 8 * 8;
         if (capL > 60000) continue;  // landing indices are 16-bit

@@ -173,9 +173,9 @@ def test_plugin_run_obmd_steady_exchange_and_restart(tmp_path):
     fix = FIX.format(alpha=1.0, tau=0.005, nbuf=1895, B=B)
     body = ("fix 1 all nve\n" + fix + "thermo 50\nthermo_style custom step atoms temp\n"
             "run_obmd 100\nwrite_restart obmd.restart\n"
-            "dump d all custom 50 dump.a id x y z\ndump_modify d format float %.17g\nrun_obmd 50\n")
+            "dump d all custom 10 dump.a id x y z\ndump_modify d format float %.17g\nrun_obmd 10\n")
     out, *_ = run(tmp_path, body)
-    (_, ra), = [f for f in read_dump(str(tmp_path / "dump.a")) if f[0] == 150]
+    (_, ra), = [f for f in read_dump(str(tmp_path / "dump.a")) if f[0] == 110]
     # continue from the restart file in a fresh LAMMPS
     deck = ("plugin load %s\nread_restart obmd.restart\ncomm_modify vel yes\natom_modify sort 0 0\n"
             "region leftB block %.17g %.17g %.17g %.17g %.17g %.17g\n"
@@ -185,15 +185,17 @@ def test_plugin_run_obmd_steady_exchange_and_restart(tmp_path):
             % (PLUGIN, box[0, 0], box[0, 0] + B, box[1, 0], box[1, 1], box[2, 0], box[2, 1],
                box[0, 1] - B, box[0, 1], box[1, 0], box[1, 1], box[2, 0], box[2, 1]) +
             "fix 1 all nve\n" + fix +
-            "dump d all custom 50 dump.b id x y z\ndump_modify d format float %.17g\nrun_obmd 50\n")
+            "dump d all custom 10 dump.b id x y z\ndump_modify d format float %.17g\nrun_obmd 10\n")
     inp = str(tmp_path / "in.restart")
     open(inp, "w").write(deck)
     r = subprocess.run([LMP, "-in", inp, "-log", "none"], cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-    (_, rb), = [f for f in read_dump(str(tmp_path / "dump.b")) if f[0] == 150]
-    # same atoms with the same tags (insertions drew the same RanPark stream); positions agree to the
-    # accuracy the restart file's arithmetic allows (forces are recomputed at setup)
+    (_, rb), = [f for f in read_dump(str(tmp_path / "dump.b")) if f[0] == 110]
+    # same atoms with the same tags (~70 insertions drew the same RanPark stream); positions agree to the
+    # accuracy the restart allows: forces are recomputed at setup in another atom order, and the dense
+    # fluid amplifies that rounding difference by ~10 orders of magnitude in 50 steps (which is why the
+    # comparison is made 10 steps after the restart, not 50: by then a USHER verdict may flip)
     assert np.array_equal(np.sort(ra[:, 0]), np.sort(rb[:, 0]))
     oa, ob_ = np.argsort(ra[:, 0]), np.argsort(rb[:, 0])
-    assert np.abs(ra[oa, 1:4] - rb[ob_, 1:4]).max() < 1e-6
+    assert np.abs(ra[oa, 1:4] - rb[ob_, 1:4]).max() < 1e-9
     assert len(ra) != len(tag)      # the run did insert / delete
