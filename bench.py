@@ -54,6 +54,9 @@ N0_TILE = 12637              # atoms of the shipped data file: nbuf is defined f
 TILINGS = {"1m": (4, 5, 4), "4m": (5, 8, 8), "16m": (20, 8, 8)}
 
 
+SHEAR_NOTE = ("BASELINE config 3: 4 M particles under a prescribed oscillatory tangential momentum flux, pxy(t) = "
+              "0.5 sin(2 pi 0.1 t) set through obmd_fix_set_flux before every step (what the plugin does for v_ "
+              "arguments), shear regions a quarter of the buffer long; 1 and 2 GPUs")
 DATA = os.path.join(ROOT, "obmd-lammps-extension_b200", "data")
 
 
@@ -170,7 +173,7 @@ def regime_kw(regime, ntiles, buffer_frac=1.0):
     return dict(alpha=0.7, nbuf=float(int(0.7 * 0.15 * n_nominal)))
 
 
-def fix_args(ob, box, buffer_size, alpha, nbuf):
+def fix_args(ob, box, buffer_size, alpha, nbuf, shear_size=0.0):
     """`fix obmd 1 1 6111 188.0 0 0 0 0 alpha 0.005 nbuf ... usher 1 31.03 1.0 0.02 10000 1.5 1.0 40`
     (README.UserGuide.md:190-233) with regions built from the exact box bounds."""
     a = ob.FixArgs()
@@ -180,14 +183,14 @@ def fix_args(ob, box, buffer_size, alpha, nbuf):
     a.buffer_size, a.g_fac = buffer_size, 0.25
     a.step_parallel, a.step_perp, a.maxattempt = 0, 1, 1
     (a.usherflag, a.etarget, a.ds0, a.dtheta0, a.uovlp, a.dsovlp, a.eps, a.nattempt) = USHER
-    for k, (lo, hi) in enumerate(ob.default_regions(box[:, 0], box[:, 1], buffer_size, 0.0)):
+    for k, (lo, hi) in enumerate(ob.default_regions(box[:, 0], box[:, 1], buffer_size, shear_size)):
         for d in range(3):
             a.region[k].lo[d] = lo[d]
             a.region[k].hi[d] = hi[d]
     return a
 
 
-def build_sim(reps, device, regime, rank=0, world=1, buffer_size=None, snapshot=False):
+def build_sim(reps, device, regime, rank=0, world=1, buffer_size=None, snapshot=False, shear=False):
     """Context for this rank: pair_style dpd 1.0 1.0 2616, pair_coeff * * 209.6 4.5 1.0, dt 0.001464.
     world > 1: x-slab decomposition (obmd_comm_init), every rank uploads only the atoms inside its
     slab; the NCCL unique id travels through torch.distributed."""
@@ -203,7 +206,7 @@ def build_sim(reps, device, regime, rank=0, world=1, buffer_size=None, snapshot=
     sim.pair_style_dpd(1.0, 1.0, 2616)
     sim.pair_coeff("*", "*", 209.6, 4.5, 1.0)
     sim.pair_init(1.0)
-    sim.fix_obmd(fix_args(ob, box, B, kw["alpha"], kw["nbuf"]))
+    sim.fix_obmd(fix_args(ob, box, B, kw["alpha"], kw["nbuf"], 0.25 * B if shear else 0.0))
     n = len(x)
     tag = np.arange(1, n + 1, dtype=np.int32)
     if world > 1:
@@ -225,12 +228,20 @@ FAMILIES = ("nve", "bin", "sort", "comm", "pre_exchange", "usher", "usher_eval0"
             "host_comm", "host_pre_exchange", "host_usher", "host_post", "host_final_sync")
 
 
-def timed_run(sim, stream, barrier, steps, warmup, equil, sampler=None):
+def timed_run(sim, stream, barrier, steps, warmup, equil, sampler=None, per_step=None):
+    """per_step(step): host work before every step (the plugin evaluates v_ variables of `fix obmd` there
+    and calls obmd_fix_set_flux; fix_obmd_merged.cpp:563-572)."""
     import torch
     step = 1
     if equil > 0:
-        sim.run(step, equil); step += equil
+        if per_step is None:
+            sim.run(step, equil); step += equil
+        else:
+            for _ in range(equil):
+                per_step(step); sim.run(step, 1); step += 1
     for _ in range(warmup):
+        if per_step:
+            per_step(step)
         sim.run(step, 1); step += 1
     sim.timing(True); sim.timing_reset()
     st0 = sim.fix_state()
@@ -243,6 +254,8 @@ def timed_run(sim, stream, barrier, steps, warmup, equil, sampler=None):
     e0.record(stream)
     for _ in range(steps):
         tw = time.perf_counter()
+        if per_step:
+            per_step(step)
         sim.run(step, 1); step += 1
         wall.append(time.perf_counter() - tw)   # obmd_run returns after a stream synchronize
         atom_steps += sim.nlocal
@@ -274,18 +287,27 @@ def reduce_over_ranks(ms, atom_steps, world):
     return tmax[0].item(), tsum[1].item()
 
 
-def secondary(reps, local, regime, rank, world, steps, warmup, equil, scaling, buffer_size=None, snapshot=False):
-    """One more workload measured the same way (no e2e, no roofline): a compact object for the line."""
+def secondary(reps, local, regime, rank, world, steps, warmup, equil, scaling, buffer_size=None, snapshot=False,
+              shear=False):
+    """One more workload measured the same way (no e2e, no roofline): a compact object for the line.
+    shear: BASELINE config 3 -- shear regions of a quarter of the buffer length and a tangential momentum
+    flux pxy(t) = 0.5 sin(2 pi 0.1 t) prescribed through obmd_fix_set_flux before every step."""
     import torch
     import torch.distributed as dist
-    sim, info = build_sim(reps, local, regime, rank=rank, world=world, buffer_size=buffer_size, snapshot=snapshot)
+    sim, info = build_sim(reps, local, regime, rank=rank, world=world, buffer_size=buffer_size, snapshot=snapshot,
+                          shear=shear)
+    per_step = None
+    if shear:
+        def per_step(step):
+            pxy = 0.5 * np.sin(2.0 * np.pi * 0.1 * step * 0.001464)
+            sim.set_flux(188.0, pxy, 0.0, 0.0, 0.0, info["alpha"], 0.005, info["nbuf"])
     stream = torch.cuda.ExternalStream(sim.L.obmd_stream(sim.h), device=local)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    r = timed_run(sim, stream, barrier, steps, warmup, equil)
+    r = timed_run(sim, stream, barrier, steps, warmup, equil, per_step=per_step)
     ms, atom_steps = reduce_over_ranks(r["ms"], r["atom_steps"], world)
     out = {"value": atom_steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "n_gpus": world,
            "scaling": scaling, "steps": steps, "equil_steps": equil,
@@ -431,10 +453,18 @@ def ours(args):
             if rank == 0:
                 extra["r0"]["note"] = ("regime R0: the parameters exactly as shipped (alpha 0.7); the buffers only "
                                        "drain, no USHER -- the step is cell build + PairDPD + force distribution + deletion")
+            extra["r1_equil300"] = secondary(reps, local, "R1", rank, world, max(sec_steps, 100), args.warmup, 300,
+                                             scaling, buffer_size)
+            extra["r1_equil300"]["note"] = ("the primary workload under the round-1 protocol (300 equilibration steps "
+                                            "instead of 2000: the USHER trial count is still climbing, ~4.5 k per step "
+                                            "instead of ~13 k), kept so that round-over-round numbers are comparable")
             extra["strong_16m"] = secondary(TILINGS["16m"], local, "R1", rank, world, sec_steps, args.warmup,
                                             min(args.equil, 300), "strong")
             extra["strong_16m"]["note"] = ("BASELINE config 5 on ONE GPU: the N = 1 point of the strong-scaling series "
                                            "`bench.py --gpus N` reports as its primary value for N > 1")
+            extra["shear_4m"] = secondary(TILINGS["4m"], local, "R1", rank, world, sec_steps, args.warmup,
+                                          min(args.equil, 300), "strong", shear=True)
+            extra["shear_4m"]["note"] = SHEAR_NOTE
             lreps = tuple(args.like_reps)
             extra["like_for_like"] = secondary(lreps, local, "R1", rank, world, args.steps, args.warmup, 0, "n/a",
                                                None, snapshot=True)
@@ -444,6 +474,10 @@ def ours(args):
                                               "no equilibration on either side.  Far too small to fill a B200: it is "
                                               "here so that one ratio is between identical configurations" % lreps)
         elif workload != "1m":
+            if world == 2:
+                extra["shear_4m"] = secondary(TILINGS["4m"], local, "R1", rank, world, sec_steps, args.warmup,
+                                              min(args.equil, 300), "strong", shear=True)
+                extra["shear_4m"]["note"] = SHEAR_NOTE
             r1 = tuple(args.reps)
             extra["weak_1m_per_gpu"] = secondary((r1[0] * world, r1[1], r1[2]), local, "R1", rank, world, sec_steps,
                                                  args.warmup, min(args.equil, 300), "weak", 0.15 * TILE_LX * r1[0])
@@ -479,7 +513,7 @@ def ours(args):
             "ms_per_step_median": round(1e3 * float(np.median(r["wall"])), 5),
             "ms_per_step_p90": round(1e3 * float(np.percentile(r["wall"], 90)), 5),
             "kernel_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in fam.items()},
-            "roofline": {"kernel": "k_pair_row", "bound": "hbm", "achieved": achieved, "peak": hbm,
+            "roofline": {"kernel": "k_pair_brick", "bound": "hbm", "achieved": achieved, "peak": hbm,
                          "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic, "peak_source": how,
                          "algorithmic_bytes_per_atom": PAIR_BYTES_PER_ATOM,
                          "launch_ms": round(pair_alone_ms, 5), "in_step_ms": round(pair_ms, 5),
