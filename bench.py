@@ -46,7 +46,7 @@ METRIC = "OBMD-DPD atom-steps/sec"
 UNIT = "atom-steps/s"
 PAIR_BYTES_PER_ATOM = 80.0   # x,v,tag,type in + f out
 NVE_BYTES_PER_ATOM = 192.0   # initial 72 r + 48 w, final 48 r + 24 w
-CELLS_BYTES_PER_ATOM = 172.0  # bin 24 + 8, perm 12, gather 64 r + 64 w
+CELLS_BYTES_PER_ATOM = 236.0  # bin 24 + 8, perm 12, gather 64 r + 64 w + 64 w of records
 POST_BYTES_PER_BUFFER_ATOM = 100.0
 USHER = (1, 31.03, 1.0, 0.02, 1e4, 1.5, 1.0, 40)
 TILE_LX = 33.59462486002239
@@ -532,7 +532,7 @@ def ours(args):
         for name, key, kernels, byts, units in (
                 ("nve", "nve", "k_nve_initial + k_nve_final", NVE_BYTES_PER_ATOM, nat),
                 ("cell build", None, "k_bin, k_scan_*, k_perm, k_cell_order, k_gather", CELLS_BYTES_PER_ATOM, nat),
-                ("post_force", "post_force", "k_weight_sums, k_weight_final, k_apply_forces",
+                ("post_force", "post_force", "k_weight_sums, k_apply_forces",
                  POST_BYTES_PER_BUFFER_ATOM, nbuf_atoms)):
             t = fam[key]["ms_per_step"] if key else fam["bin"]["ms_per_step"] + fam["sort"]["ms_per_step"]
             if t > 0:

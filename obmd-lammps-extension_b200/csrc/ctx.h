@@ -89,6 +89,7 @@ struct StepScalars {
   int nspec;                // accepted-atom entries published so far in this call (usher.cu)
   int npairs;               // (trial, change record) pairs queued by the dirty test of a re-run round
   int rng_seed;             // RanPark state after the deletion draws
+  int wsum_done;            // blocks of k_weight_sums that have published their partials (reset by the last one)
   int redo_overflow;        // k_mark_redo found more atoms near the insertions than its list holds (sticky,
                             // outside the range pre_exchange zeroes)
   double vnewl[3], vnewr[3];

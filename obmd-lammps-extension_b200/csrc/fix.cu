@@ -4,7 +4,7 @@
 // reference is an x86-64 build without FMA.
 //
 //   pre_exchange (:550-633)      -> k_scan_ids, k_count_regions, k_delete_fixup; batched USHER in usher.cu
-//   post_force   (:1229-1240)    -> k_weight_sums, k_apply_forces
+//   post_force   (:1229-1240)    -> k_weight_sums (last block adds the partials), k_apply_forces
 //   FixNVE       (fix_nve.cpp)   -> k_nve_initial, k_nve_final
 //   Domain::pbc  (domain.cpp)    -> k_pbc
 #include <chrono>
@@ -935,7 +935,8 @@ __device__ __forceinline__ double g_par_global_term(const FixDev &fd, double mas
 // one partial per block: the final value does not depend on scheduling.
 __global__ void __launch_bounds__(FB_THREADS)
     k_weight_sums(Planes p, Extras ex, Grid g, FixDev fd, PairTab pt, ForceCfg fc,
-                  const int *__restrict__ cell_start, double *__restrict__ partials)
+                  const int *__restrict__ cell_start, double *__restrict__ partials, double *__restrict__ gsum,
+                  int *__restrict__ done)
 {
   double s[4] = {0, 0, 0, 0};
   const int nyz = g.ny * g.nz;
@@ -961,6 +962,7 @@ __global__ void __launch_bounds__(FB_THREADS)
     }
   }
   __shared__ double sh[4][FB_THREADS / 32];
+  __shared__ int s_last;
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
   for (int r = 0; r < 4; r++) {
@@ -973,6 +975,30 @@ __global__ void __launch_bounds__(FB_THREADS)
     double v = 0.0;
     for (int ww = 0; ww < FB_THREADS / 32; ww++) v += sh[threadIdx.x][ww];
     partials[blockIdx.x * 4 + threadIdx.x] = v;
+  }
+  // The block that finishes last adds the per-block partials in a fixed order (chunks of 16 blocks, then
+  // the chunks): G does not depend on which block that is, and no second launch is needed.
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(done, 1) == (int) gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  __shared__ double ch[4][64];
+  const int nb = (int) gridDim.x, nch = (nb + 15) / 16;  // FB_BLOCKS <= 1024
+  if (threadIdx.x < 4 * 64) {
+    const int r = threadIdx.x & 3, q = threadIdx.x >> 2;
+    double v = 0.0;
+    if (q < nch)
+      for (int b = q * 16; b < min(q * 16 + 16, nb); b++) v += __ldcg(partials + b * 4 + r);
+    ch[r][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = 0.0;
+    for (int q = 0; q < nch; q++) v += ch[threadIdx.x][q];
+    gsum[threadIdx.x] = v;
+    if (threadIdx.x == 0) *done = 0;
   }
 }
 
@@ -1025,21 +1051,6 @@ __global__ void __launch_bounds__(FB_THREADS)
   }
 }
 
-// fixed-order sum of the per-CTA partials -> gsum[4] (deterministic, no atomics)
-// Fixed-order sum of the per-CTA partials (b = 0, 1, ...): staged through shared memory with one
-// coalesced sweep so the four sequential add chains do not wait on global memory.
-__global__ void __launch_bounds__(256) k_weight_final(const double *__restrict__ partials, double *__restrict__ gsum)
-{
-  __shared__ double sh[FB_BLOCKS * 4];
-  for (int k = threadIdx.x; k < FB_BLOCKS * 4; k += blockDim.x) sh[k] = partials[k];
-  __syncthreads();
-  if (threadIdx.x < 4) {
-    double v = 0.0;
-    for (int b = 0; b < FB_BLOCKS; b++) v += sh[b * 4 + threadIdx.x];
-    gsum[threadIdx.x] = v;
-  }
-}
-
 static void region_cols(const obmd_ctx *c, int r, int margin, int &a, int &e);
 static int merge_intervals(int *lo, int *hi, int n);
 
@@ -1080,8 +1091,7 @@ int fix_post_force(obmd_ctx *c)
   }
   const Extras ex = extras_of(c);
   LAUNCH(k_weight_sums, FB_BLOCKS, FB_THREADS, 0, c->cur, ex, c->grid, c->fd, c->pt, fc, c->cell_start,
-         c->partials);
-  LAUNCH(k_weight_final, 1, 256, 0, c->partials, c->red_d);
+         c->partials, c->red_d, &c->sc_d->wsum_done);
   if (c->nranks > 1) {  // a buffer may span slabs: G is a global sum (fix_obmd_merged.cpp:1305,1378)
     int rc = comm_allreduce(c, c->red_d, 4, 0);
     if (rc) return rc;
