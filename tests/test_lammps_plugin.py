@@ -199,3 +199,59 @@ def test_plugin_run_obmd_steady_exchange_and_restart(tmp_path):
     oa, ob_ = np.argsort(ra[:, 0]), np.argsort(rb[:, 0])
     assert np.abs(ra[oa, 1:4] - rb[ob_, 1:4]).max() < 1e-9
     assert len(ra) != len(tag)      # the run did insert / delete
+
+
+def run_expecting_error(tmp_path, body, head=HEAD, **kw):
+    tag, x, box = cc.shipped()
+    data = str(tmp_path / "shipped.data")
+    write_data(data, tag, x, box)
+    B = 0.15 * box[0, 1]
+    d = dict(plugin=PLUGIN, data=data, T=1.0, a0=209.6, gamma=4.5, dt=0.001464, xlo=box[0, 0], xhi=box[0, 1],
+             ylo=box[1, 0], yhi=box[1, 1], zlo=box[2, 0], zhi=box[2, 1], xlB=box[0, 0] + B, xrB=box[0, 1] - B)
+    d.update(kw)
+    inp = str(tmp_path / "in.deck")
+    open(inp, "w").write(head.format(**d) + body)
+    out = subprocess.run([LMP, "-in", inp, "-log", "none"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert out.returncode != 0, "LAMMPS accepted the deck:\n" + out.stdout[-2000:]
+    return out.stdout + out.stderr, B
+
+
+def test_plugin_argument_errors(tmp_path):
+    """The C++ argument parser that ships (host/lammps_plugin.cpp: FixObmdB200 constructor / options,
+    PairDPDB200::settings / coeff), driven through the reference binary: malformed commands stop LAMMPS
+    with the reference's own messages (fix_obmd_merged.cpp:104-135, :1990-2130; pair_dpd.cpp:195-251)."""
+    need()
+    B = 0.15 * cc.shipped()[2][0, 1]
+    good = FIX.format(alpha=0.7, tau=0.005, nbuf=1327, B=B)
+    cases = [
+        ("fix 2 all obmd 1 1 6111 188.0 0 0 0 0 0.7 0.005\n", "Illegal fix obmd command (check # of arguments)"),
+        (good.replace(" 6111 ", " 0 "), "Illegal fix obmd command"),
+        (good.replace("obmd 1 1", "obmd 7 1"), "Invalid atom type in fix obmd command"),
+        (good.replace("region1 leftB", "region1 nosuch"), "for fix obmd does not exist"),
+        (good.replace("gfac 0.25", "gfac 1.5"), "Parameter gfac should be between 0.0 and 1.0"),
+        (good.replace("buffersize %.17g" % B, "buffersize -1.0"), "Parameter buffersize should be larger than 0.0"),
+        (good.replace("usher 1 31.03", "usher 0 31.03"), "You must pick either usher or near"),
+        (good.replace("stepparallel 0", "stepparallel 1"), "only the smooth transition distribution function"),
+        (good.replace("charged 0", "bogus 0"), "Illegal fix obmd command"),
+        (good.replace("region1 leftB ", ""), "Must specify a region in fix obmd"),
+        (good.replace("region5 leftB ", ""), "Region ID for fix obmd does not exist"),
+    ]
+    for k, (fixline, msg) in enumerate(cases):
+        sub = tmp_path / ("case%d" % k)
+        sub.mkdir()
+        out, _ = run_expecting_error(sub, "fix 1 all nve\n" + fixline + "run 0\n")
+        assert msg in out, (fixline, out[-1500:])
+    # pair_style / pair_coeff (pair_dpd.cpp:195-251)
+    bad_style = HEAD.replace("pair_style      dpd {T} 1.0 2616", "pair_style      dpd {T} 1.0")
+    out, _ = run_expecting_error(tmp_path, "run 0\n", head=bad_style)
+    assert "Illegal pair_style command" in out
+    bad_seed = HEAD.replace("pair_style      dpd {T} 1.0 2616", "pair_style      dpd {T} 1.0 0")
+    out, _ = run_expecting_error(tmp_path, "run 0\n", head=bad_seed)
+    assert "Illegal pair_style command" in out
+    bad_coeff = HEAD.replace("pair_coeff      * * {a0} {gamma} 1.0", "pair_coeff      * * {a0}")
+    out, _ = run_expecting_error(tmp_path, "run 0\n", head=bad_coeff)
+    assert "Incorrect args for pair coefficients" in out
+    # the working deck still needs `atom_modify sort 0 0` (the device keeps the LAMMPS local order)
+    no_sort = HEAD.replace("atom_modify     sort 0 0\n", "")
+    out, _ = run_expecting_error(tmp_path, "fix 1 all nve\n" + good + "run 0\n", head=no_sort)
+    assert "requires 'atom_modify sort 0 0'" in out
