@@ -481,6 +481,14 @@ def ours(args):
             r1 = tuple(args.reps)
             extra["weak_1m_per_gpu"] = secondary((r1[0] * world, r1[1], r1[2]), local, "R1", rank, world, sec_steps,
                                                  args.warmup, min(args.equil, 300), "weak", 0.15 * TILE_LX * r1[0])
+            # the N = 1 point of this strong-scaling series, measured in the same run on rank 0's GPU (the
+            # other ranks wait): the driver's own N = 1 run times BASELINE config 2 (1 M atoms), not this workload
+            if rank == 0:
+                extra["n1_same_workload"] = secondary(reps, local, args.regime, 0, 1, sec_steps, args.warmup,
+                                                      args.equil, "strong")
+                extra["n1_same_workload"]["note"] = ("the primary workload of this line on ONE GPU (rank 0's), same "
+                                                     "equilibration: the denominator of the strong-scaling efficiency")
+            dist.barrier()
         else:
             extra["strong_16m"] = secondary(TILINGS["16m"], local, "R1", rank, world, sec_steps, args.warmup,
                                             min(args.equil, 300), "strong")

@@ -1,3 +1,2 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-B="python bench.py --steps 5 --warmup 3 --equil 2000 --no-secondary --no-cpu --e2e-steps 0 --lammps-steps 0"
-ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 56000 -c 300 --csv --log-file gpurun_out/r2_launches_steady.csv $B > gpurun_out/r2_ncu_launch.log 2>&1; echo "ncu launches rc=$?"; tail -2 gpurun_out/r2_ncu_launch.log | cut -c1-200
+python -m pytest tests/test_lammps_plugin.py -x -q -k argument_errors 2>&1 | tail -3
+OBMD_B200_DEBUG_FIX=2090 python bench.py --steps 100 --warmup 5 --equil 2000 --no-secondary --no-cpu --e2e-steps 0 --lammps-steps 0 2>&1 | grep -E "fix round|  trial" | head -400 > gpurun_out/r2_fix_debug.txt; wc -l gpurun_out/r2_fix_debug.txt
