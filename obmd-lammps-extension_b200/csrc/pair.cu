@@ -10,13 +10,17 @@
 // for the (i,j) and (j,i) evaluations so Newton's third law holds exactly (DESIGN.md "RNG").
 //
 // Kernels in this translation unit:
-//   * k_pair_row (pair_row.cuh): the production path for the cell-sorted atoms -- row tiles staged in
-//     shared memory, fp32 screen, fp64 evaluation;
+//   * k_pair_brick (pair_brick.cuh): the production path for the cell-sorted atoms -- bricks of
+//     C x R x zc cells whose window the copy engine stages (cp.async.bulk + mbarrier) from the 48 + 16-byte
+//     atom records the sort wrote, fp32 screen, fp64 evaluation;
+//   * k_pair_row (pair_row.cuh): the thread-staged row tile of round 1; it folds the per-cell lists of
+//     appended atoms (slab arrivals, ghosts, insertions) into its window, so it takes the columns whose
+//     stencil holds such atoms, and everything when the records are stale;
 //   * k_pair_dpd: per-atom kernel that walks global memory (L1/L2) with a minimum-image test: a
 //     distance screen over the 9 stencil rows (the 3 z-cells of a row are one contiguous slot range
 //     because z is the fastest cell index) that pushes the slots inside the cutoff to a per-thread
 //     list, then a dense evaluation of the list.  Used for energy/virial tallies, for the few atoms
-//     appended after the sort, as the overflow path of k_pair_row, and under OBMD_B200_TILE=0;
+//     appended after the sort, as the overflow path of the tiled kernels, and under OBMD_B200_TILE=0;
 //   * k_pair_new_atoms / k_pair_add_new: the incremental update after USHER insertions.
 //
 // Roofline: algorithmic traffic is 80 B/atom (x,v,tag,type in, f out); neighbour reads are served by

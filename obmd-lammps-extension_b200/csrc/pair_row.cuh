@@ -1,4 +1,7 @@
-// Row-tiled PairDPD kernel (included by pair.cu): the production path for the cell-sorted atoms.
+// Row-tiled PairDPD kernel (included by pair.cu): the thread-staged tile of round 1.  Since round 2 the
+// brick kernel (pair_brick.cuh) is the production path; this one takes the columns whose stencil holds
+// atoms appended after the sort (it folds their per-cell lists into the window) and everything when the
+// sort's atom records are stale.
 //
 // A tile is the atoms of R (1, 2 or 4) y-adjacent cell rows of one column over a run of z-cells: R
 // contiguous slot ranges, because z is the fastest cell index.  Its stencil is the 3 x (R+2) rows
