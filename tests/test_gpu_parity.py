@@ -425,6 +425,53 @@ def test_row_tiled_pair_kernel_matches_list_kernel(shipped, monkeypatch):
     monkeypatch.delenv("OBMD_B200_TILE")
 
 
+def test_brick_pair_kernel_shapes_and_stale_records(shipped, monkeypatch):
+    """The brick kernel (csrc/pair_brick.cuh: C x R x zc cells per CTA, window staged by cp.async.bulk from the
+    atom records the sort writes) against the per-atom list kernel for every brick shape the planner can
+    pick, on the shipped box (nx = 33, ny = nz = 11: partial bricks in every direction, windows that wrap
+    through both periodic faces, z-chunks of 3, 4 and 11 cells) and with the random term on; then with
+    STALE records (velocities changed after the sort, no new cell build): the pair step must notice and
+    read the planes (row kernel), not the records."""
+    tag, x, box = shipped
+    v = np.random.default_rng(21).normal(0, 1, x.shape)
+    monkeypatch.setenv("OBMD_B200_TILE", "0")
+    sim = cc.device_sim(box, fix=False)
+    sim.upload(x, v, np.ones(len(x), np.int32), tag)
+    sim.build_cells(); sim.pbc(); sim.pair_compute(9)
+    ref = sim.download(("f",))["f"]
+    sim.close()
+    scale = np.abs(ref).max()
+    monkeypatch.setenv("OBMD_B200_TILE", "2")
+    for cols in ("1", "2", "4"):
+        for rows in ("1", "2", "4"):
+            for zc in ("3", "4", "11"):
+                monkeypatch.setenv("OBMD_B200_COLS", cols)
+                monkeypatch.setenv("OBMD_B200_ROWS", rows)
+                monkeypatch.setenv("OBMD_B200_ZC", zc)
+                sim = cc.device_sim(box, fix=False)
+                sim.upload(x, v, np.ones(len(x), np.int32), tag)
+                sim.build_cells(); sim.pbc(); sim.pair_compute(9)
+                f = sim.download(("f",))["f"]
+                sim.close()
+                assert np.abs(f - ref).max() <= 1e-12 * scale, (cols, rows, zc)
+    for k in ("OBMD_B200_COLS", "OBMD_B200_ROWS", "OBMD_B200_ZC"):
+        monkeypatch.delenv(k)
+    # stale records: nve_final changes the velocities after the sort; forces must follow the planes
+    res = []
+    for tile in ("0", "2"):
+        monkeypatch.setenv("OBMD_B200_TILE", tile)
+        sim = cc.device_sim(box, fix=False)
+        sim.upload(x, v, np.ones(len(x), np.int32), tag)
+        sim.build_cells(); sim.pbc(); sim.pair_compute(9)
+        sim.nve_final()                      # v += dt/2 f/m: the drag term of the next evaluation changes
+        sim.pair_compute(9)
+        res.append(sim.download(("f",))["f"])
+        sim.close()
+    assert np.abs(res[0] - ref).max() > 1e-6 * scale          # the velocities did change the forces
+    assert np.abs(res[0] - res[1]).max() <= 1e-12 * scale
+    monkeypatch.delenv("OBMD_B200_TILE")
+
+
 def test_pair_two_types_row_and_list_kernels_vs_oracle(shipped, monkeypatch):
     """Two atom types with different a0, gamma and cutoffs per type pair (pair_coeff i j a0 gamma rc):
     the row-tiled kernel screens with the largest cutoff and applies the exact per-pair test in
