@@ -1,13 +1,12 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-B="python bench.py --steps 100 --warmup 5 --equil 2000 --no-cpu --e2e-steps 0 --lammps-steps 0 --secondary-steps 30"
-for cfg in "OBMD_B200_X=1" "OBMD_B200_USH_PLANES=1"; do
-echo "== $cfg"; env $cfg $B 2>&1 | python -c "
-import sys, json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d = json.loads(l); k = d['kernel_ms_per_step']
-        print(d['ms_per_step'], {a: k[a] for a in ('usher','usher_eval0','usher_fix','pair','sort','host_step')}, d['usher']['trials_per_step'])
-        for s in ('r1_equil300','strong_16m','shear_4m','like_for_like'):
-            print(s, d[s]['ms_per_step'], d[s]['trials_per_step'], d[s]['kernel_ms_per_step'].get('usher_eval0'))
-"
-done
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_bench_final.json').read().strip().splitlines()[-1])
+print('value', d['value'], 'ms', d['ms_per_step'], 'launches', d['gpu_launches'], 'frac', d['roofline']['frac'], d['roofline']['launch_ms'])
+print(d['rooflines'])
+print('e2e', d['e2e']['value'], 'plugin', d['e2e_lammps_plugin']['value'], 'cpu', d['cpu_baseline']['value'])
+for k in ('r0','r1_equil300','strong_16m','shear_4m','like_for_like'):
+    print(k, round(d[k]['ms_per_step'],4), round(d[k]['value']/1e6,1), d[k]['trials_per_step'])
+PY
