@@ -199,6 +199,21 @@ int obmd_exchange(obmd_ctx *ctx);
  * multi-rank sums differ from its serial ones in the same way: per-rank partial sums + MPI_Allreduce). */
 int obmd_set_usher_order(obmd_ctx *ctx, int by_tag);
 
+/* ---- bonded forces (BASELINE config 4, the bonded path only) ----------------------- */
+/* bond_style harmonic + bond_coeff t K r0 (MOLECULE/bond_harmonic.cpp:126-149): k and r0 are 1-based,
+ * nbondtypes + 1 entries each (entry 0 unused), nbondtypes <= OBMD_MAXTYPES. */
+int obmd_bond_style_harmonic(obmd_ctx *ctx, int nbondtypes, const double *k, const double *r0);
+/* The bond topology by atom tags, one entry per bond (Atom::bond_type / bond_atom as read_data leaves
+ * them with newton_bond on; NTopoBondAll::build, ntopo_bond_all.cpp:36-77, turns them into the bond list
+ * every step through Atom::map and Domain::closest_image).  The topology is static: molecule-aware
+ * deletion / insertion (fix_obmd_merged.cpp:709-821, :993-1027, :1132-1168) is not implemented, and
+ * obmd_bond_compute reports an error when a bonded atom has been deleted. */
+int obmd_upload_bonds(obmd_ctx *ctx, int nbonds, const int *type, const int *tag1, const int *tag2);
+/* BondHarmonic::compute (MOLECULE/bond_harmonic.cpp:48-103): adds the bond forces to the device forces
+ * (call after obmd_pair_compute, which overwrites them).  eflag != 0 also reduces the bond energy. */
+int obmd_bond_compute(obmd_ctx *ctx, int eflag);
+int obmd_bond_energy(obmd_ctx *ctx, double *ebond);
+
 /* ---- timing / introspection ----------------------------------------------------- */
 /* Accumulated CUDA-event milliseconds and launch counts per kernel family since the last
  * reset.  names: "bin", "sort", "pair", "post_force", "nve", "pre_exchange", "usher", "pbc". */

@@ -100,6 +100,10 @@ SIGNATURES = {
     "obmd_exchange": (C.c_int, [C.c_void_p]),
     "obmd_set_usher_order": (C.c_int, [C.c_void_p, C.c_int]),
     "obmd_profile_x2": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]),
+    "obmd_bond_style_harmonic": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
+    "obmd_upload_bonds": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip, _ip]),
+    "obmd_bond_compute": (C.c_int, [C.c_void_p, C.c_int]),
+    "obmd_bond_energy": (C.c_int, [C.c_void_p, _dp]),
     "obmd_pair_gaussian_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, _dp]),
     "obmd_comm_unique_id": (C.c_int, [C.c_char_p]),
     "obmd_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
@@ -385,6 +389,27 @@ class ObmdB200:
         return self.L.obmd_nlocal(self.h)
 
     # ---- hooks -----------------------------------------------------------------------
+    # ---- bonded path (bond_style harmonic; static topology) -----------------------------
+    def bond_style_harmonic(self, k, r0):
+        """k, r0: per bond type, 1-based lists WITHOUT the unused entry 0 (bond_coeff t K r0)."""
+        kk = np.ascontiguousarray([0.0] + list(k), np.float64)
+        rr = np.ascontiguousarray([0.0] + list(r0), np.float64)
+        self._ck(self.L.obmd_bond_style_harmonic(self.h, len(kk) - 1, _dptr(kk), _dptr(rr)))
+
+    def upload_bonds(self, btype, tag1, tag2):
+        t = np.ascontiguousarray(btype, np.int32); a = np.ascontiguousarray(tag1, np.int32)
+        b = np.ascontiguousarray(tag2, np.int32)
+        self._ck(self.L.obmd_upload_bonds(self.h, len(t), _iptr(t), _iptr(a), _iptr(b)))
+
+    def bond_compute(self, eflag=0):
+        self._ck(self.L.obmd_bond_compute(self.h, eflag))
+
+    def bond_energy(self):
+        e = C.c_double(0.0)
+        self._ck(self.L.obmd_bond_energy(self.h, C.byref(e)))
+        return e.value
+
+    def zero_forces(self): self._ck(self.L.obmd_zero_forces(self.h))
     def nve_initial(self): self._ck(self.L.obmd_nve_initial(self.h))
     def nve_final(self): self._ck(self.L.obmd_nve_final(self.h))
     def build_cells(self): self._ck(self.L.obmd_build_cells(self.h))

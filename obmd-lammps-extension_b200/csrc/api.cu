@@ -114,6 +114,7 @@ extern "C" void obmd_destroy(obmd_ctx *c)
   free_planes(c->cur);
   free_planes(c->alt);
   cudaFree(c->fx); cudaFree(c->fy); cudaFree(c->fz); cudaFree(c->rec); cudaFree(c->aux);
+  bond_free(c);
   cudaFree(c->cid); cudaFree(c->rank); cudaFree(c->perm);
   cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->scan_tmp);
   cudaFree(c->extra_head); cudaFree(c->extra_next); cudaFree(c->extra_cell);

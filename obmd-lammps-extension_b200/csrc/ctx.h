@@ -221,6 +221,12 @@ struct obmd_ctx {
   int vatom_cap = 0;
   bool vatom_valid = false;
   int partial_cap = 0;
+  // bonded path (bond.cu): harmonic coefficients, topology in CSR form indexed by atom tag, tag -> slot map
+  int nbondtypes = 0;
+  double bond_k[MAXT + 1], bond_r0[MAXT + 1];
+  int nbonds = 0, bond_maxtag = 0;
+  int *bond_off = nullptr, *bond_partner = nullptr, *bond_ptype = nullptr, *tag_map = nullptr;
+  double *bond_e = nullptr;         // [1] bond energy of the latest obmd_bond_compute(eflag = 1)
   // last pre_exchange report
   obmd_pre_exchange_report rep;
 };
@@ -327,6 +333,7 @@ int fix_reduce_kinetic(obmd_ctx *c, double out[5]);
 int fix_profile_x(obmd_ctx *c, int nbins, double *count, double *mvx, double *mv2, double *sxx);
 int pair_gaussian_sample(obmd_ctx *c, int n, int tag0, long long step, double *out);
 int fix_clear_extras(obmd_ctx *c);
+void bond_free(obmd_ctx *c);  // bond.cu
 int read_scalars(obmd_ctx *c);  // copies *sc_d to *sc_h and synchronises the stream
 int comm_exchange(obmd_ctx *c);  // comm.cu: migrate + halo + ghost lists
 int comm_allreduce(obmd_ctx *c, double *dev, int nsum, int nmax);  // first nsum: sum, next nmax: max

@@ -810,3 +810,44 @@ void orc_step(orc_fix *p, orc_atoms *a, int rng_mode, unsigned step, orc_trial *
   orc_fix_post_force(p, a);
   orc_nve_final(p, a);
 }
+
+/* ---- bonded forces ------------------------------------------------------------------------------ */
+
+/* MOLECULE/bond_harmonic.cpp:48-103.  The reference walks neighbor->bondlist, which NTopoBondAll::build
+   (ntopo_bond_all.cpp:36-77) fills in local-index order with the partner's closest image; with
+   newton_bond on every bond is stored once, on the atom the data file lists first. */
+double orc_bond_harmonic(const orc_fix *p, orc_atoms *a, int nbonds, const int *btype, const int *tag1,
+                         const int *tag2, const double *k, const double *r0)
+{
+  int maxtag = 0;
+  for (int i = 0; i < a->nlocal; i++)
+    if (a->tag[i] > maxtag) maxtag = a->tag[i];
+  int *map = (int *) malloc(sizeof(int) * (size_t) (maxtag + 1));
+  for (int t = 0; t <= maxtag; t++) map[t] = -1;
+  for (int i = 0; i < a->nlocal; i++) map[a->tag[i]] = i;
+  const double prd[3] = {0.0, p->boxhi[1] - p->boxlo[1], p->boxhi[2] - p->boxlo[2]};
+  double etot = 0.0;
+  for (int n = 0; n < nbonds; n++) {
+    if (tag1[n] > maxtag || tag2[n] > maxtag) continue;
+    const int i1 = map[tag1[n]], i2 = map[tag2[n]];
+    if (i1 < 0 || i2 < 0) continue;
+    double del[3];
+    for (int d = 0; d < 3; d++) del[d] = a->x[3 * i1 + d] - a->x[3 * i2 + d];
+    for (int d = 1; d < 3; d++) { /* Domain::closest_image (domain.cpp:1148-1172) */
+      if (del[d] > 0.5 * prd[d]) del[d] -= prd[d];
+      else if (del[d] < -0.5 * prd[d]) del[d] += prd[d];
+    }
+    const double rsq = del[0] * del[0] + del[1] * del[1] + del[2] * del[2];
+    const double r = sqrt(rsq);
+    const double dr = r - r0[btype[n]];
+    const double rk = k[btype[n]] * dr;
+    const double fbond = (r > 0.0) ? -2.0 * rk / r : 0.0;
+    etot += rk * dr;
+    for (int d = 0; d < 3; d++) {
+      a->f[3 * i1 + d] += del[d] * fbond;
+      a->f[3 * i2 + d] -= del[d] * fbond;
+    }
+  }
+  free(map);
+  return etot;
+}

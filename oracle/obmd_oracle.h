@@ -119,6 +119,13 @@ double orc_g_par_local(const orc_fix *p, double mass, double xv); /* :1312-1340 
 double orc_usher(const orc_fix *p, const orc_atoms *a, const orc_block *reg, double *coord, int *iter);
 double orc_energy(const orc_fix *p, const orc_atoms *a, int itype, const double *coord, double *fusher); /* :1774-1810 */
 
+/* ---- bonded forces (BASELINE config 4, SURVEY 8f N3: the bonded path only) ---- */
+/* BondHarmonic::compute (MOLECULE/bond_harmonic.cpp:48-103) over a bond list given by atom tags
+   (NTopoBondAll::build, ntopo_bond_all.cpp:36-77: atom->map + Domain::closest_image, here the minimum
+   image in y and z).  k, r0: 1-based per bond type.  Adds to a->f, returns the bond energy. */
+double orc_bond_harmonic(const orc_fix *p, orc_atoms *a, int nbonds, const int *btype, const int *tag1,
+                         const int *tag2, const double *k, const double *r0);
+
 /* ---- integrator / geometry ---- */
 void orc_nve_initial(const orc_fix *p, orc_atoms *a);  /* fix_nve.cpp:80-145 */
 void orc_nve_final(const orc_fix *p, orc_atoms *a);    /* fix_nve.cpp:185-244 */

@@ -250,6 +250,73 @@ def make_b9(wd, n0):
     print("b9: trials", len(ver), "accepted", int(ver[:, 0].sum()), "final atoms", len(rows))
 
 
+def make_m0(wd):
+    """M0: the bonded path of BASELINE config 4 in miniature.  The shipped atoms, rewritten
+    in atom_style bond: nearest neighbours closer than 0.9 are paired into dimers (bond type 1), and every
+    third dimer is linked to the next free atom within 1.1 (bond type 2) -- ~4000 bonds, some of them across
+    the periodic y / z faces.  `bond_style harmonic` (MOLECULE/bond_harmonic.cpp:48-103), `special_bonds lj
+    1 1 1` (no pair exclusions), T = 0.  Two runs of the reference binary: bonds only (`pair_style zero`)
+    and bonds + DPD; forces, ebond."""
+    from scipy.spatial import cKDTree
+    rows = [ln.split() for ln in open(DATA).read().split("Atoms")[1].strip().split("\n") if len(ln.split()) == 5]
+    tag = np.array([int(r[0]) for r in rows]); x = np.array([[float(v) for v in r[2:5]] for r in rows])
+    (xlo, xhi), (ylo, yhi), (zlo, zhi) = BOX
+    L = np.array([1.0e6, yhi - ylo, zhi - zlo])          # x is not periodic
+    xw = x.copy(); xw[:, 1:] = np.mod(xw[:, 1:], L[1:])
+    tree = cKDTree(xw, boxsize=L)
+    free = np.ones(len(x), bool)
+    bonds = []
+    pairs = sorted(tree.query_pairs(0.9))
+    ndim = 0
+    for i, j in pairs:
+        if free[i] and free[j]:
+            free[i] = free[j] = False
+            bonds.append((1, tag[i], tag[j]))
+            ndim += 1
+            if ndim % 3 == 0:
+                for k in tree.query_ball_point(xw[j], 1.1):
+                    if free[k]:
+                        free[k] = False
+                        bonds.append((2, tag[j], tag[k]))
+                        break
+    bonds = np.array(bonds, dtype=np.int32)
+    mol = np.zeros(len(x), np.int32)
+    data = os.path.join(wd, "m0.data")
+    with open(data, "w") as fh:
+        fh.write("bonded DPD beads\n\n%d atoms\n1 atom types\n%d bonds\n2 bond types\n\n" % (len(x), len(bonds)))
+        for (lo, hi), n in zip(BOX, "xyz"):
+            fh.write("%.17g %.17g %slo %shi\n" % (lo, hi, n, n))
+        fh.write("\nMasses\n\n1 1\n\nAtoms # bond\n\n")
+        for t, m, r in zip(tag, mol, x):
+            fh.write("%d %d 1 %.17g %.17g %.17g\n" % (t, m, r[0], r[1], r[2]))
+        fh.write("\nBonds\n\n")
+        for k, (bt, a, b) in enumerate(bonds):
+            fh.write("%d %d %d %d\n" % (k + 1, bt, a, b))
+    out = {}
+    for name, pair in (("bond", "pair_style zero 1.0\npair_coeff * *\n"),
+                       ("both", "pair_style dpd 0.0 1.0 2616\npair_coeff * * 209.6 4.5 1.0\n")):
+        deck = ("units lj\nboundary f p p\natom_style bond\natom_modify sort 0 0\ncomm_modify vel yes\n"
+                "newton on\nread_data %s\n%sbond_style harmonic\nbond_coeff 1 100.0 0.5\nbond_coeff 2 50.0 0.8\n"
+                "special_bonds lj 1.0 1.0 1.0\nneighbor 0.4 bin\nneigh_modify delay 0 every 1\ntimestep 0.001464\n"
+                "velocity all create 1.0 4928459 loop geom\n"
+                "dump d all custom 1 dump.m0 id vx vy vz fx fy fz\ndump_modify d format float %%.17g\n"
+                "thermo_style custom step pe ebond\nthermo_modify format float %%.15g norm no\nrun 0\n" % (data, pair))
+        lines = run_deck("m0" + name, deck, wd)
+        (_, r), = read_dump(os.path.join(wd, "dump.m0"))
+        th = None
+        for k, ln in enumerate(lines):
+            if ln.split()[:2] == ["Step", "PotEng"]:
+                th = np.array(lines[k + 1].split(), dtype=np.float64)
+        assert np.array_equal(r[:, 0].astype(np.int64), tag)
+        out[name] = (r, th)
+    np.savez_compressed(os.path.join(HERE, "m0_bond_harmonic.npz"), bonds=bonds, v=out["both"][0][:, 1:4].copy(),
+                        f_bond=out["bond"][0][:, 4:7].copy(), f_both=out["both"][0][:, 4:7].copy(),
+                        ebond=out["bond"][1][2], thermo_both=out["both"][1], k=np.array([0.0, 100.0, 50.0]),
+                        r0=np.array([0.0, 0.5, 0.8]))
+    print("m0: bonds", len(bonds), "type-2", int((bonds[:, 0] == 2).sum()), "ebond", out["bond"][1][2],
+          "|f_bond|max", np.abs(out["bond"][0][:, 4:7]).max())
+
+
 def read_chunk_file(path, ncol):
     """fix ave/chunk text output -> list of (step, array[nchunk, ncol])."""
     out = []
@@ -317,6 +384,9 @@ def main():
         sys.exit("oracle/_ref/lmp_serial missing: run `bash oracle/build_ref.sh` first")
     wd = tempfile.mkdtemp(prefix="obmd_golden_")
     print("working in", wd)
+    if len(sys.argv) > 1 and sys.argv[1] == "m0":   # only the bonded-path fixture
+        make_m0(wd)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "b6":   # only the maxattempt fixture (the others are unchanged)
         make_b6(wd, 12637)
         return

@@ -913,3 +913,57 @@ def test_profiles_vs_reference_r1_run(shipped):
     assert abs(st1.ndeleted - int(g["ndel"])) < 0.03 * int(g["ndel"]), (st1.ndeleted, int(g["ndel"]))
     assert abs(st1.ninserted - int(g["nacc"])) < 0.03 * int(g["nacc"]), (st1.ninserted, int(g["nacc"]))
     assert abs(st1.ntrials - int(g["ntrials"])) < 0.03 * int(g["ntrials"]), (st1.ntrials, int(g["ntrials"]))
+
+
+def test_bond_harmonic_vs_reference_and_oracle(shipped):
+    """Bonded path (BASELINE config 4, bonded forces only; csrc/bond.cu): obmd_bond_compute against the
+    reference binary's BondHarmonic (MOLECULE/bond_harmonic.cpp:48-103) on 6803 bonds of two types, some
+    across the periodic faces: bond-only forces and energy, bonds + T = 0 DPD forces, before and after the
+    cell sort has permuted the atoms (the topology is indexed by tag), and after 5 device steps against the
+    oracle stepping the same system."""
+    tag, x, box = shipped
+    g = cc.load("m0_bond_harmonic.npz")
+    b = g["bonds"]
+    DT = 1.0e-5                                                   # nobody leaves through an open face in 5 steps
+    sim = cc.device_sim(box, temperature=0.0, fix=False, dt=DT)
+    sim.bond_style_harmonic(g["k"][1:], g["r0"][1:])
+    sim.upload(x, g["v"], np.ones(len(x), np.int32), tag)
+    sim.upload_bonds(b[:, 0], b[:, 1], b[:, 2])
+    sim.zero_forces(); sim.bond_compute(1)                       # before any cell build
+    f0 = sim.download(("f",))["f"]
+    scale = np.abs(g["f_bond"]).max()
+    assert np.abs(f0 - g["f_bond"]).max() <= 1e-9 * scale
+    assert abs(sim.bond_energy() - float(g["ebond"])) <= 1e-10 * abs(float(g["ebond"]))
+    sim.build_cells(); sim.pbc()
+    sim.zero_forces(); sim.bond_compute(1)                       # storage order is now the cell order
+    f1 = sim.download(("f",))["f"]
+    assert np.abs(f1 - g["f_bond"]).max() <= 1e-9 * scale
+    assert abs(sim.bond_energy() - float(g["ebond"])) <= 1e-10 * abs(float(g["ebond"]))
+    sim.pair_compute(0); sim.bond_compute(0)                     # pair forces overwrite, bonds add
+    f2 = sim.download(("f",))["f"]
+    assert np.abs(f2 - g["f_both"]).max() <= 1e-9 * np.abs(g["f_both"]).max()
+    assert abs(f2.sum(0)).max() < 1e-8 * np.abs(g["f_both"]).max()   # Newton's third law
+    # five steps of velocity Verlet with pair + bond forces, device vs oracle
+    p = O.make_fix(box[:, 0], box[:, 1], temperature=0.0, dt=DT)
+    a = O.OracleAtoms(x, v=g["v"], tag=tag)
+    L = O.lib()
+    L.orc_bond_harmonic.restype = C.c_double
+    bt, t1, t2 = (np.ascontiguousarray(b[:, k], np.int32) for k in range(3))
+    kk = np.ascontiguousarray(g["k"]); rr = np.ascontiguousarray(g["r0"])
+    ip = lambda v: v.ctypes.data_as(C.POINTER(C.c_int))
+    dp = lambda v: v.ctypes.data_as(C.POINTER(C.c_double))
+
+    def oracle_forces(step):
+        L.orc_pair_compute(C.byref(p), C.byref(a.c), 0, step, None, None)
+        L.orc_bond_harmonic(C.byref(p), C.byref(a.c), len(b), ip(bt), ip(t1), ip(t2), dp(kk), dp(rr))
+    oracle_forces(0)
+    for step in range(1, 6):
+        sim.nve_initial(); sim.build_cells(); sim.pbc(); sim.pair_compute(step); sim.bond_compute(0); sim.nve_final()
+        L.orc_nve_initial(C.byref(p), C.byref(a.c)); L.orc_pbc(C.byref(p), C.byref(a.c))
+        oracle_forces(step)
+        L.orc_nve_final(C.byref(p), C.byref(a.c))
+    o = sim.download(("x", "v", "f", "tag"))
+    assert np.array_equal(o["tag"], a.view("tag"))
+    assert np.abs(o["x"] - a.view("x")).max() < 1e-11
+    assert cc.mixed_rel_err(o["f"], a.view("f")) < FTOL
+    sim.close()

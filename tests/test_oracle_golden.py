@@ -306,3 +306,31 @@ def test_b8_ballistic_two_masses_bit_exact(shipped):
     assert np.array_equal(a.view("x"), g["x20"])
     assert np.array_equal(a.view("v"), g["v20"])
     assert np.array_equal(a.view("f"), g["f20"])
+
+
+def test_m0_bond_harmonic_vs_reference(shipped):
+    """Bonded path (BASELINE config 4, the bonded forces only): orc_bond_harmonic against a run of the
+    reference binary in atom_style bond with 6803 harmonic bonds of two types, some across the periodic
+    faces (tests/golden/make_golden.py m0): bond-only forces and energy, then bonds + T = 0 DPD forces."""
+    tag, x, box = shipped
+    g = load("m0_bond_harmonic.npz")
+    b = np.ascontiguousarray(g["bonds"], np.int32)
+    bt, t1, t2 = (np.ascontiguousarray(b[:, k]) for k in range(3))
+    k = np.ascontiguousarray(g["k"]); r0 = np.ascontiguousarray(g["r0"])
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    L = O.lib()
+    L.orc_bond_harmonic.restype = C.c_double
+    p = O.make_fix(box[:, 0], box[:, 1], temperature=0.0)
+    a = O.OracleAtoms(x, v=g["v"], tag=tag)
+    e = L.orc_bond_harmonic(C.byref(p), C.byref(a.c), len(b), ip(bt), ip(t1), ip(t2), dp(k), dp(r0))
+    f = a.view("f")
+    assert np.abs(g["f_bond"]).max() > 10.0
+    assert np.abs(f - g["f_bond"]).max() <= 1e-9 * np.abs(g["f_bond"]).max()
+    assert abs(e - float(g["ebond"])) <= 1e-10 * abs(float(g["ebond"]))
+    # bonds + pair forces (special_bonds lj 1 1 1: no exclusions)
+    a2 = O.OracleAtoms(x, v=g["v"], tag=tag)
+    L.orc_pair_compute(C.byref(p), C.byref(a2.c), 0, 0, None, None)
+    L.orc_bond_harmonic(C.byref(p), C.byref(a2.c), len(b), ip(bt), ip(t1), ip(t2), dp(k), dp(r0))
+    scale = np.abs(g["f_both"]).max()
+    assert np.abs(a2.view("f") - g["f_both"]).max() <= 1e-9 * scale
