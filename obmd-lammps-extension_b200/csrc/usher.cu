@@ -104,6 +104,14 @@ struct SpecSm {
   int n_sm, n_all;
 };
 
+// Pull a line into L1 with a real load whose result is never used (no scoreboard wait): unlike
+// prefetch.global.L1 it cannot be dropped.
+__device__ __forceinline__ void touch_l1(const void *p)
+{
+  unsigned d;
+  asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(d) : "l"(p) : "memory");
+}
+
 __device__ __forceinline__ int ranpark_pow(long long n)
 {
   unsigned long long m = 2147483647ULL, a = 16807ULL, r = 1ULL;
@@ -394,12 +402,12 @@ __device__ __forceinline__ int usher_gather(const UsherArgs &A, UGroupT<FAT> &S,
     const char *pz = reinterpret_cast<const char *>(A.p.z), *pk = reinterpret_cast<const char *>(A.keys);
     const size_t d0 = ((size_t) pf_a * 8) & ~(size_t) 127, d1 = (size_t) pf_b * 8;
     for (size_t o = d0; o < d1; o += 128) {
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(px + o));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(py + o));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(pz + o));
+      touch_l1(px + o);
+      touch_l1(py + o);
+      touch_l1(pz + o);
     }
     for (size_t o = ((size_t) pf_a * 4) & ~(size_t) 127; o < (size_t) pf_b * 4; o += 128)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(pk + o));
+      touch_l1(pk + o);
   }
   if (sp && sp->n_all > sp->n_sm) {
     // accepted atoms beyond the shared-memory cache (thousands of insertions in one call): the entries
@@ -1268,14 +1276,14 @@ __global__ void k_usher_commit(Planes p, Extras ex, int tag0, FixDev fd, obmd_tr
 // ---- host side ---------------------------------------------------------------------------------
 
 // Device buffers of the USHER trials.  Regrowing them costs a dozen cudaFree/cudaMalloc pairs (each
-// an implicit device synchronisation) in the middle of a step, so they start at 16 Ki trials and
-// double; the pinned host copy of the trial records is only made when a caller asks for them.
+// an implicit device synchronisation, ~150 ms in all) in the middle of a step, so they start at 64 Ki
+// trials (80 MB; the 4 M-atom workload hovers around 16 k trials per step) and double; the pinned host copy of the trial records is only made when a caller asks for them.
 static int ensure_trials(obmd_ctx *c, int ntr, int natt)
 {
   if (ntr <= c->tr_cap && natt <= c->tr_natt) return OBMD_OK;
   int cap = c->tr_cap;
   if (ntr > cap) {
-    cap = cap < 16384 ? 16384 : cap;
+    cap = cap < 65536 ? 65536 : cap;
     while (cap < ntr) cap *= 2;
   }
   int na = natt > c->tr_natt ? natt : c->tr_natt;
