@@ -210,9 +210,10 @@ int obmd_bond_style_harmonic(obmd_ctx *ctx, int nbondtypes, const double *k, con
  * obmd_bond_compute reports an error when a bonded atom has been deleted. */
 int obmd_upload_bonds(obmd_ctx *ctx, int nbonds, const int *type, const int *tag1, const int *tag2);
 /* BondHarmonic::compute (MOLECULE/bond_harmonic.cpp:48-103): adds the bond forces to the device forces
- * (call after obmd_pair_compute, which overwrites them).  eflag != 0 also reduces the bond energy. */
+ * (call after obmd_pair_compute, which overwrites them).  eflag != 0 also reduces the bond energy and
+ * the six virial components (Bond::ev_tally, bond.cpp:174-240; order xx yy zz xy xz yz). */
 int obmd_bond_compute(obmd_ctx *ctx, int eflag);
-int obmd_bond_energy(obmd_ctx *ctx, double *ebond);
+int obmd_bond_tallies(obmd_ctx *ctx, double *ebond, double virial[6] /* may be NULL */);
 
 /* ---- timing / introspection ----------------------------------------------------- */
 /* Accumulated CUDA-event milliseconds and launch counts per kernel family since the last

@@ -103,7 +103,7 @@ SIGNATURES = {
     "obmd_bond_style_harmonic": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
     "obmd_upload_bonds": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip, _ip]),
     "obmd_bond_compute": (C.c_int, [C.c_void_p, C.c_int]),
-    "obmd_bond_energy": (C.c_int, [C.c_void_p, _dp]),
+    "obmd_bond_tallies": (C.c_int, [C.c_void_p, _dp, _dp]),
     "obmd_pair_gaussian_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, _dp]),
     "obmd_comm_unique_id": (C.c_int, [C.c_char_p]),
     "obmd_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
@@ -404,10 +404,15 @@ class ObmdB200:
     def bond_compute(self, eflag=0):
         self._ck(self.L.obmd_bond_compute(self.h, eflag))
 
-    def bond_energy(self):
+    def bond_tallies(self):
+        """(bond energy, virial[6]) of the latest bond_compute(eflag = 1)."""
         e = C.c_double(0.0)
-        self._ck(self.L.obmd_bond_energy(self.h, C.byref(e)))
-        return e.value
+        v = (C.c_double * 6)()
+        self._ck(self.L.obmd_bond_tallies(self.h, C.byref(e), v))
+        return e.value, np.array(list(v))
+
+    def bond_energy(self):
+        return self.bond_tallies()[0]
 
     def zero_forces(self): self._ck(self.L.obmd_zero_forces(self.h))
     def nve_initial(self): self._ck(self.L.obmd_nve_initial(self.h))

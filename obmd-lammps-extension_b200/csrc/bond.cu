@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256)
 {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   int i = q < nsorted ? q : extras_slot(ex, 1, q - nsorted);  // owned atoms: sorted + arrivals + insertions
-  double e = 0.0;
+  double e = 0.0, v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0, v4 = 0.0, v5 = 0.0;
   if (i >= 0) {
     const int t = p.tag[i];
     if (t >= 0 && t <= maxtag) {
@@ -74,6 +74,15 @@ __global__ void __launch_bounds__(256)
           ay += dely * fbond;
           az += delz * fbond;
           e += 0.5 * (rk * dr);  // each bond is seen from both of its atoms
+          if (partials) {        // Bond::ev_tally (bond.cpp:174-240), half per atom
+            const double h = 0.5 * fbond;
+            v0 += h * delx * delx;
+            v1 += h * dely * dely;
+            v2 += h * delz * delz;
+            v3 += h * delx * dely;
+            v4 += h * delx * delz;
+            v5 += h * dely * delz;
+          }
         }
         fx[i] += ax;
         fy[i] += ay;
@@ -81,31 +90,40 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
-  if (partials) {  // deterministic block reduction of the energy
-    __shared__ double sh[8];
-    for (int d = 16; d > 0; d >>= 1) e += __shfl_down_sync(0xffffffffu, e, d);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = e;
+  if (partials) {  // deterministic block reduction of the energy and the virial
+    __shared__ double sh[7][8];
+    double v[7] = {e, v0, v1, v2, v3, v4, v5};
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+      double s = v[k];
+      for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+      if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = s;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      double v = 0.0;
-      for (int w = 0; w < 8; w++) v += sh[w];
-      partials[blockIdx.x] = v;
+    if (threadIdx.x < 7) {
+      double s = 0.0;
+      for (int w = 0; w < 8; w++) s += sh[threadIdx.x][w];
+      partials[blockIdx.x * 7 + threadIdx.x] = s;
     }
   }
 }
 
+// fixed-order final sums: out[0] = energy, out[1..6] = virial
 __global__ void k_bond_energy_final(const double *__restrict__ partials, int nb, double *__restrict__ out)
 {
   __shared__ double sh[256];
-  double s = 0.0;
-  for (int b = threadIdx.x; b < nb; b += blockDim.x) s += partials[b];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int d = blockDim.x / 2; d > 0; d >>= 1) {
-    if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+  for (int k = 0; k < 7; k++) {
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) s += partials[b * 7 + k];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = blockDim.x / 2; d > 0; d >>= 1) {
+      if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[k] = sh[0];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *out = sh[0];
 }
 
 void bond_free(obmd_ctx *c)
@@ -166,11 +184,11 @@ extern "C" int obmd_upload_bonds(obmd_ctx *c, int nbonds, const int *type, const
   CK(cudaMalloc(&c->bond_partner, sizeof(int) * partner.size()));
   CK(cudaMalloc(&c->bond_ptype, sizeof(int) * ptype.size()));
   CK(cudaMalloc(&c->tag_map, sizeof(int) * (size_t) (maxtag + 1)));
-  CK(cudaMalloc(&c->bond_e, sizeof(double)));
+  CK(cudaMalloc(&c->bond_e, 7 * sizeof(double)));
   CK(cudaMemcpyAsync(c->bond_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->bond_partner, partner.data(), sizeof(int) * partner.size(), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->bond_ptype, ptype.data(), sizeof(int) * ptype.size(), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemsetAsync(c->bond_e, 0, sizeof(double), c->stream));
+  CK(cudaMemsetAsync(c->bond_e, 0, 7 * sizeof(double), c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->nbonds = nbonds;
   c->bond_maxtag = maxtag;
@@ -195,9 +213,9 @@ extern "C" int obmd_bond_compute(obmd_ctx *c, int eflag)
     bt.r0[k] = k <= c->nbondtypes ? c->bond_r0[k] : 0.0;
   }
   const int nb = cdiv(nown, 256);
-  if (eflag && nb > c->partial_cap) {
+  if (eflag && nb * 7 > c->partial_cap) {
     if (c->partials) cudaFree(c->partials);
-    c->partial_cap = nb + 1024;
+    c->partial_cap = nb * 7 + 1024;
     CK(cudaMalloc(&c->partials, sizeof(double) * c->partial_cap));
   }
   CK(cudaMemsetAsync(&c->sc_d->usher_error, 0, sizeof(int), c->stream));
@@ -215,12 +233,16 @@ extern "C" int obmd_bond_compute(obmd_ctx *c, int eflag)
   return OBMD_OK;
 }
 
-extern "C" int obmd_bond_energy(obmd_ctx *c, double *ebond)
+extern "C" int obmd_bond_tallies(obmd_ctx *c, double *ebond, double virial[6])
 {
-  NEED(c && ebond, OBMD_ERR_ARG, "obmd_bond_energy: NULL argument");
-  *ebond = 0.0;
-  if (c->nbonds == 0) return OBMD_OK;
-  CK(cudaMemcpyAsync(ebond, c->bond_e, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  NEED(c && ebond, OBMD_ERR_ARG, "obmd_bond_tallies: NULL argument");
+  double h[7] = {0, 0, 0, 0, 0, 0, 0};
+  if (c->nbonds > 0) {
+    CK(cudaMemcpyAsync(h, c->bond_e, 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  *ebond = h[0];
+  if (virial)
+    for (int k = 0; k < 6; k++) virial[k] = h[1 + k];
   return OBMD_OK;
 }

@@ -226,7 +226,7 @@ struct obmd_ctx {
   double bond_k[MAXT + 1], bond_r0[MAXT + 1];
   int nbonds = 0, bond_maxtag = 0;
   int *bond_off = nullptr, *bond_partner = nullptr, *bond_ptype = nullptr, *tag_map = nullptr;
-  double *bond_e = nullptr;         // [1] bond energy of the latest obmd_bond_compute(eflag = 1)
+  double *bond_e = nullptr;         // [7] bond energy and virial of the latest obmd_bond_compute(eflag = 1)
   // last pre_exchange report
   obmd_pre_exchange_report rep;
 };

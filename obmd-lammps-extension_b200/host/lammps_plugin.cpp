@@ -15,6 +15,7 @@
 // symbols (ENABLE_EXPORTS) and would interpose them (SURVEY 8b "Gotcha").
 #include "atom.h"
 #include "atom_vec.h"
+#include "bond.h"
 #include "comm.h"
 #include "command.h"
 #include "domain.h"
@@ -34,6 +35,7 @@
 #include "update.h"
 #include "version.h"
 
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <string>
@@ -248,6 +250,140 @@ class PairDPDB200 : public Pair {
   double cut_global = 0.0, temperature = 0.0;
   int seed = 0;
   double **cut = nullptr, **a0 = nullptr, **gamma = nullptr;
+  std::vector<double> fbuf;
+};
+
+// ------------------------------------------------------------------------------------------
+// bond_style harmonic ; bond_coeff t K r0                         (MOLECULE/bond_harmonic.cpp)
+// Stage A: the pair style has put this step's atoms on the device; the bond list NTopoBondAll::build
+// (ntopo_bond_all.cpp:36-77) would walk is handed over as tags once (static topology).
+// ------------------------------------------------------------------------------------------
+class BondHarmonicB200 : public Bond {
+ public:
+  BondHarmonicB200(LAMMPS *lmp) : Bond(lmp), sh(acquire(lmp)) {}
+  ~BondHarmonicB200() override
+  {
+    if (allocated && !copymode) {
+      memory->destroy(setflag);
+      memory->destroy(k);
+      memory->destroy(r0);
+    }
+    release(lmp);
+  }
+
+  void compute(int eflag, int vflag) override  // bond_harmonic.cpp:48-103
+  {
+    ev_init(eflag, vflag);
+    Atom *a = atom;
+    if (eflag_atom || vflag_atom) error->all(FLERR, "bond_style harmonic (obmd_b200 plugin): per-atom tallies are not available");
+    if (sh.resident != a->nlocal)
+      error->all(FLERR, "bond_style harmonic (obmd_b200 plugin) needs pair_style dpd from the same plugin (it uploads the atoms)");
+    if (topo_bonds != a->nbonds || topo_step < 0) upload_topology();
+    OBMD_CK(lmp, sh, obmd_zero_forces(sh.ctx));
+    OBMD_CK(lmp, sh, obmd_bond_compute(sh.ctx, (eflag_either || vflag_either) ? 1 : 0));
+    int n = 0;
+    if ((int) fbuf.size() < 3 * a->nmax) fbuf.resize(3 * (size_t) a->nmax);
+    OBMD_CK(lmp, sh, obmd_download(sh.ctx, &n, nullptr, nullptr, fbuf.data(), nullptr, nullptr, nullptr));
+    double **f = a->f;
+    for (int i = 0; i < n; i++) {
+      f[i][0] += fbuf[3 * i];
+      f[i][1] += fbuf[3 * i + 1];
+      f[i][2] += fbuf[3 * i + 2];
+    }
+    if (eflag_either || vflag_either) {
+      double e, v[6];
+      OBMD_CK(lmp, sh, obmd_bond_tallies(sh.ctx, &e, v));
+      if (eflag_global) energy += e;
+      if (vflag_global)
+        for (int q = 0; q < 6; q++) virial[q] += v[q];
+    }
+  }
+
+  void coeff(int narg, char **arg) override  // bond_harmonic.cpp:123-143
+  {
+    if (narg != 3) error->all(FLERR, "Incorrect args for bond coefficients");
+    if (!allocated) allocate();
+    int ilo, ihi;
+    utils::bounds(FLERR, arg[0], 1, atom->nbondtypes, ilo, ihi, error);
+    const double k_one = utils::numeric(FLERR, arg[1], false, lmp);
+    const double r0_one = utils::numeric(FLERR, arg[2], false, lmp);
+    int count = 0;
+    for (int i = ilo; i <= ihi; i++) {
+      k[i] = k_one;
+      r0[i] = r0_one;
+      setflag[i] = 1;
+      count++;
+    }
+    if (count == 0) error->all(FLERR, "Incorrect args for bond coefficients");
+    topo_step = -1;  // coefficients go to the device with the next topology upload
+  }
+
+  double equilibrium_distance(int i) override { return r0[i]; }  // :149-152
+
+  void write_restart(FILE *fp) override  // :158-162
+  {
+    fwrite(&k[1], sizeof(double), atom->nbondtypes, fp);
+    fwrite(&r0[1], sizeof(double), atom->nbondtypes, fp);
+  }
+
+  void read_restart(FILE *fp) override  // :168-180 (one rank)
+  {
+    allocate();
+    utils::sfread(FLERR, &k[1], sizeof(double), atom->nbondtypes, fp, nullptr, error);
+    utils::sfread(FLERR, &r0[1], sizeof(double), atom->nbondtypes, fp, nullptr, error);
+    for (int i = 1; i <= atom->nbondtypes; i++) setflag[i] = 1;
+  }
+
+  void write_data(FILE *fp) override  // :186-189
+  {
+    for (int i = 1; i <= atom->nbondtypes; i++) fprintf(fp, "%d %g %g\n", i, k[i], r0[i]);
+  }
+
+  double single(int type, double rsq, int, int, double &fforce) override  // :193-201
+  {
+    const double r = sqrt(rsq);
+    const double dr = r - r0[type];
+    const double rk = k[type] * dr;
+    fforce = 0;
+    if (r > 0.0) fforce = -2.0 * rk / r;
+    return rk * dr;
+  }
+
+ private:
+  void allocate()
+  {
+    allocated = 1;
+    const int np1 = atom->nbondtypes + 1;
+    memory->create(k, np1, "bond:k");
+    memory->create(r0, np1, "bond:r0");
+    memory->create(setflag, np1, "bond:setflag");
+    for (int i = 1; i < np1; i++) setflag[i] = 0;
+  }
+
+  // Atom::bond_type / bond_atom (newton_bond on: every bond stored once) -> (type, tag, tag)
+  void upload_topology()
+  {
+    Atom *a = atom;
+    if (a->nbondtypes > OBMD_MAXTYPES) error->all(FLERR, "obmd_b200: too many bond types");
+    for (int i = 1; i <= a->nbondtypes; i++)
+      if (!setflag[i]) error->all(FLERR, "All bond coeffs are not set");
+    OBMD_CK(lmp, sh, obmd_bond_style_harmonic(sh.ctx, a->nbondtypes, k, r0));
+    std::vector<int> bt, t1, t2;
+    for (int i = 0; i < a->nlocal; i++)
+      for (int m = 0; m < a->num_bond[i]; m++) {
+        if (a->bond_type[i][m] <= 0) continue;
+        bt.push_back(a->bond_type[i][m]);
+        t1.push_back(a->tag[i]);
+        t2.push_back(a->bond_atom[i][m]);
+      }
+    OBMD_CK(lmp, sh, obmd_upload_bonds(sh.ctx, (int) bt.size(), bt.data(), t1.data(), t2.data()));
+    topo_bonds = a->nbonds;
+    topo_step = update->ntimestep;
+  }
+
+  Shared &sh;
+  double *k = nullptr, *r0 = nullptr;
+  bigint topo_bonds = -1, topo_step = -1;
   std::vector<double> fbuf;
 };
 
@@ -637,6 +773,7 @@ double FixObmdB200::input_variable_equal(int iv)
 }
 
 static Pair *pair_creator(LAMMPS *lmp) { return new PairDPDB200(lmp); }
+static Bond *bond_creator(LAMMPS *lmp) { return new BondHarmonicB200(lmp); }
 static Command *run_creator(LAMMPS *lmp) { return new RunObmd(lmp); }
 static Fix *fix_creator(LAMMPS *lmp, int argc, char **argv) { return new FixObmdB200(lmp, argc, argv); }
 
@@ -652,6 +789,12 @@ extern "C" void lammpsplugin_init(void *lmp, void *handle, void *regfunc)
   plugin.name = "dpd";  // same name as the built-in: overrides it (PLUGIN/plugin.cpp:169-174)
   plugin.info = "pair_style dpd on B200 (libobmd_b200)";
   plugin.creator.v1 = (lammpsplugin_factory1 *) &pair_creator;
+  (*register_plugin)(&plugin, lmp);
+
+  plugin.style = "bond";
+  plugin.name = "harmonic";  // overrides MOLECULE's bond_style harmonic (PLUGIN/plugin.cpp:176-183)
+  plugin.info = "bond_style harmonic on B200 (libobmd_b200)";
+  plugin.creator.v1 = (lammpsplugin_factory1 *) &bond_creator;
   (*register_plugin)(&plugin, lmp);
 
   plugin.style = "fix";

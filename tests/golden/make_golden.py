@@ -300,7 +300,9 @@ def make_m0(wd):
                 "special_bonds lj 1.0 1.0 1.0\nneighbor 0.4 bin\nneigh_modify delay 0 every 1\ntimestep 0.001464\n"
                 "velocity all create 1.0 4928459 loop geom\n"
                 "dump d all custom 1 dump.m0 id vx vy vz fx fy fz\ndump_modify d format float %%.17g\n"
-                "thermo_style custom step pe ebond\nthermo_modify format float %%.15g norm no\nrun 0\n" % (data, pair))
+                "compute pb all pressure NULL bond\n"
+                "thermo_style custom step pe ebond c_pb[1] c_pb[2] c_pb[3] c_pb[4] c_pb[5] c_pb[6] vol\n"
+                "thermo_modify format float %%.15g norm no\nrun 0\n" % (data, pair))
         lines = run_deck("m0" + name, deck, wd)
         (_, r), = read_dump(os.path.join(wd, "dump.m0"))
         th = None
@@ -312,6 +314,8 @@ def make_m0(wd):
     np.savez_compressed(os.path.join(HERE, "m0_bond_harmonic.npz"), bonds=bonds, v=out["both"][0][:, 1:4].copy(),
                         f_bond=out["bond"][0][:, 4:7].copy(), f_both=out["both"][0][:, 4:7].copy(),
                         ebond=out["bond"][1][2], thermo_both=out["both"][1], k=np.array([0.0, 100.0, 50.0]),
+                        # virial of the bond forces: c_pb = W_ab / V (compute pressure NULL bond; xx yy zz xy xz yz)
+                        virial_bond=out["bond"][1][3:9] * out["bond"][1][9],
                         r0=np.array([0.0, 0.5, 0.8]))
     print("m0: bonds", len(bonds), "type-2", int((bonds[:, 0] == 2).sum()), "ebond", out["bond"][1][2],
           "|f_bond|max", np.abs(out["bond"][0][:, 4:7]).max())

@@ -938,7 +938,10 @@ def test_bond_harmonic_vs_reference_and_oracle(shipped):
     sim.zero_forces(); sim.bond_compute(1)                       # storage order is now the cell order
     f1 = sim.download(("f",))["f"]
     assert np.abs(f1 - g["f_bond"]).max() <= 1e-9 * scale
-    assert abs(sim.bond_energy() - float(g["ebond"])) <= 1e-10 * abs(float(g["ebond"]))
+    e1, w1 = sim.bond_tallies()
+    assert abs(e1 - float(g["ebond"])) <= 1e-10 * abs(float(g["ebond"]))
+    # virial of the bond forces vs `compute pressure NULL bond` of the reference (Bond::ev_tally, bond.cpp:174-240)
+    assert np.abs(w1 - g["virial_bond"]).max() <= 1e-9 * np.abs(g["virial_bond"]).max()
     sim.pair_compute(0); sim.bond_compute(0)                     # pair forces overwrite, bonds add
     f2 = sim.download(("f",))["f"]
     assert np.abs(f2 - g["f_both"]).max() <= 1e-9 * np.abs(g["f_both"]).max()

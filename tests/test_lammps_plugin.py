@@ -255,3 +255,53 @@ def test_plugin_argument_errors(tmp_path):
     no_sort = HEAD.replace("atom_modify     sort 0 0\n", "")
     out, _ = run_expecting_error(tmp_path, "fix 1 all nve\n" + good + "run 0\n", head=no_sort)
     assert "requires 'atom_modify sort 0 0'" in out
+
+
+def test_plugin_bond_harmonic(tmp_path):
+    """`bond_style harmonic` overridden by the plugin (BondHarmonicB200 -> obmd_bond_compute) next to its
+    `pair_style dpd`, in atom_style bond inside the reference binary: forces, bond energy and bond virial
+    of the fixture deck (tests/golden/make_golden.py m0: 6803 bonds of two types) against what the
+    built-in styles produced."""
+    need()
+    tag, x, box = cc.shipped()
+    g = cc.load("m0_bond_harmonic.npz")
+    b = g["bonds"]
+    data = str(tmp_path / "m0.data")
+    with open(data, "w") as fh:
+        fh.write("bonded DPD beads\n\n%d atoms\n1 atom types\n%d bonds\n2 bond types\n\n" % (len(x), len(b)))
+        for d, n in enumerate("xyz"):
+            fh.write("%.17g %.17g %slo %shi\n" % (box[d, 0], box[d, 1], n, n))
+        fh.write("\nMasses\n\n1 1\n\nAtoms # bond\n\n")
+        for t, r in zip(tag, x):
+            fh.write("%d 0 1 %.17g %.17g %.17g\n" % (t, r[0], r[1], r[2]))
+        fh.write("\nBonds\n\n")
+        for k, (bt, a1, a2) in enumerate(b):
+            fh.write("%d %d %d %d\n" % (k + 1, bt, a1, a2))
+    deck = ("plugin load %s\nunits lj\nboundary f p p\natom_style bond\natom_modify sort 0 0\ncomm_modify vel yes\n"
+            "newton on\nread_data %s\npair_style dpd 0.0 1.0 2616\npair_coeff * * 209.6 4.5 1.0\n"
+            "bond_style harmonic\nbond_coeff 1 100.0 0.5\nbond_coeff 2 50.0 0.8\nspecial_bonds lj 1.0 1.0 1.0\n"
+            "neighbor 0.4 bin\nneigh_modify delay 0 every 1\ntimestep 0.001464\n"
+            "velocity all create 1.0 4928459 loop geom\n"
+            "dump d all custom 1 dump.m0 id vx vy vz fx fy fz\ndump_modify d format float %%.17g\n"
+            "compute pb all pressure NULL bond\n"
+            "thermo_style custom step pe ebond c_pb[1] c_pb[2] c_pb[3] c_pb[4] c_pb[5] c_pb[6] vol\n"
+            "thermo_modify format float %%.15g norm no\nrun 0\n" % (PLUGIN, data))
+    inp = str(tmp_path / "in.m0")
+    open(inp, "w").write(deck)
+    r = subprocess.run([LMP, "-in", inp, "-log", "none"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    out = r.stdout + r.stderr
+    assert "Overriding built-in bond style harmonic from plugin" in out
+    (_, rows), = read_dump(str(tmp_path / "dump.m0"))
+    assert np.array_equal(rows[:, 1:4], g["v"])
+    assert np.abs(rows[:, 4:7] - g["f_both"]).max() <= 1e-9 * np.abs(g["f_both"]).max()
+    th = None
+    lines = r.stdout.split("\n")
+    for k, ln in enumerate(lines):
+        if ln.split()[:2] == ["Step", "PotEng"]:
+            th = np.array(lines[k + 1].split(), dtype=np.float64)
+    assert th is not None
+    assert abs(th[2] - float(g["ebond"])) <= 1e-10 * abs(float(g["ebond"]))
+    w = th[3:9] * th[9]
+    assert np.abs(w - g["virial_bond"]).max() <= 1e-9 * np.abs(g["virial_bond"]).max()
+    assert abs(th[1] - g["thermo_both"][1]) <= 1e-9 * abs(g["thermo_both"][1])      # pe = evdwl + ebond
