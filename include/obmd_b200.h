@@ -185,6 +185,10 @@ int obmd_pair_gaussian_sample(obmd_ctx *ctx, int n, int tag0, long long ntimeste
 int obmd_comm_unique_id(char *out128);
 int obmd_comm_init(obmd_ctx *ctx, int rank, int nranks, const char *id128);
 int obmd_comm_finalize(obmd_ctx *ctx);
+/* The slab partition itself (pure host arithmetic; no device or context needed): owned cell columns
+ * [c0, c1) of `rank`.  edge_cols = columns an edge rank must hold (its insertion region + one cutoff), 0
+ * for an even split.  Replaces the processor grid of comm_brick.cpp / procmap.cpp for one decomposed axis. */
+int obmd_slab_partition(int ncols, int nranks, int rank, int edge_cols, int *c0, int *c1);
 /* x-range [lo, hi) of the columns this rank owns (what the host uses to split the atoms). */
 int obmd_comm_slab(const obmd_ctx *ctx, double *lo, double *hi);
 /* Comm::exchange + Comm::borders (comm_brick.cpp:652-978) for callers that drive the per-step hooks

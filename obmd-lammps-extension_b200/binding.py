@@ -100,6 +100,7 @@ SIGNATURES = {
     "obmd_exchange": (C.c_int, [C.c_void_p]),
     "obmd_set_usher_order": (C.c_int, [C.c_void_p, C.c_int]),
     "obmd_profile_x2": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]),
+    "obmd_slab_partition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip]),
     "obmd_bond_style_harmonic": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
     "obmd_upload_bonds": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip, _ip]),
     "obmd_bond_compute": (C.c_int, [C.c_void_p, C.c_int]),
@@ -151,11 +152,14 @@ def default_regions(boxlo, boxhi, B, shear_size=0.0):
     return [leftB, rightB, lsh, rsh, leftB, rightB]
 
 
-def slab_columns(ncols, nranks, rank):
-    """Owned cell columns [c0, c1) of `rank`: the split setup_grid() (csrc/api.cu) uses."""
-    per, rem = divmod(ncols, nranks)
-    c0 = rank * per + min(rank, rem)
-    return c0, c0 + per + (1 if rank < rem else 0)
+def slab_columns(ncols, nranks, rank, edge_cols=0):
+    """Owned cell columns [c0, c1) of `rank`: obmd_slab_partition, the function setup_grid() (csrc/api.cu)
+    itself calls (host arithmetic inside the shipped library: loads and runs without a GPU)."""
+    c0, c1 = C.c_int(0), C.c_int(0)
+    rc = lib().obmd_slab_partition(ncols, nranks, rank, edge_cols, C.byref(c0), C.byref(c1))
+    if rc != 0:
+        raise ObmdError(rc, "obmd_slab_partition(%d, %d, %d, %d)" % (ncols, nranks, rank, edge_cols))
+    return c0.value, c1.value
 
 
 def slab_bounds(boxlo_x, boxhi_x, cutmax, nranks, rank):

@@ -245,6 +245,33 @@ extern "C" int obmd_pair_init(obmd_ctx *c, double boltz)
   return setup_grid(c);
 }
 
+// Owned cell columns [c0, c1) of `rank` in an x-slab decomposition of `ncols` columns over `nranks` ranks.
+// Even split; when `edge_cols` (the columns an edge rank needs to hold its insertion region plus one
+// cutoff) exceeds an even share and there are interior ranks, the two edge slabs get `edge_cols` columns
+// and the interior ranks share the rest evenly -- BASELINE config 5: 16 M atoms on 8 GPUs, buffer
+// 0.15 Lx > Lx / 8 (SURVEY 8(e) "non-uniform slabs").  Pure host arithmetic: no device, no context.
+extern "C" int obmd_slab_partition(int ncols, int nranks, int rank, int edge_cols, int *c0, int *c1)
+{
+  if (!c0 || !c1 || nranks < 1 || rank < 0 || rank >= nranks || ncols < 2 * nranks) return OBMD_ERR_ARG;
+  const int P = nranks, r = rank;
+  const int per = ncols / P, rem = ncols % P;
+  *c0 = r * per + (r < rem ? r : rem);
+  *c1 = *c0 + per + (r < rem ? 1 : 0);
+  if (P > 2 && edge_cols > per) {
+    const int inner = ncols - 2 * edge_cols;
+    if (inner < 2 * (P - 2)) return OBMD_ERR_ARG;
+    const int iper = inner / (P - 2), irem = inner % (P - 2);
+    if (r == 0) { *c0 = 0; *c1 = edge_cols; }
+    else if (r == P - 1) { *c0 = ncols - edge_cols; *c1 = ncols; }
+    else {
+      const int k = r - 1;
+      *c0 = edge_cols + k * iper + (k < irem ? k : irem);
+      *c1 = *c0 + iper + (k < irem ? 1 : 0);
+    }
+  }
+  return OBMD_OK;
+}
+
 // Cell grid (cell size >= cutmax) and this rank's window of it: owned columns [gx0, gx1) plus one
 // ghost column towards each x-neighbour.
 int setup_grid(obmd_ctx *c)
@@ -267,33 +294,18 @@ int setup_grid(obmd_ctx *c)
   NEED(nn[0] >= 2 * c->nranks, OBMD_ERR_ARG, "slab run: fewer than 2 cell columns per rank (%d columns, %d ranks)",
        nn[0], c->nranks);
   const int P = c->nranks, r = c->myrank;
-  const int per = nn[0] / P, rem = nn[0] % P;
-  c->gx0 = r * per + (r < rem ? r : rem);
-  c->gx1 = c->gx0 + per + (r < rem ? 1 : 0);
   // The edge ranks run the USHER trials of their side, so the insertion regions (region5 / region6)
-  // plus one cutoff must fit inside the first / last slab.  When an even split is too narrow for that
-  // (BASELINE config 5: 16 M atoms on 8 GPUs, buffer 0.15 Lx > Lx / 8) the two edge slabs are widened
-  // to hold them and the interior ranks share the rest evenly -- SURVEY 8(e) "non-uniform slabs".
+  // plus one cutoff must fit inside the first / last slab (obmd_slab_partition widens them if needed).
+  int edge = 0;
   if (P > 2 && c->have_fix) {
     const double w = (c->boxhi[0] - c->boxlo[0]) / nn[0];
     const int needL = (int) ceil((c->fd.region[4].hi[0] + pt.cutmax - c->boxlo[0]) / w) + 1;
     const int needR = (int) ceil((c->boxhi[0] - c->fd.region[5].lo[0] + pt.cutmax) / w) + 1;
-    const int edge = needL > needR ? needL : needR;
-    if (edge > per) {
-      const int inner = nn[0] - 2 * edge;
-      NEED(inner >= 2 * (P - 2), OBMD_ERR_ARG,
-           "slab run: the insertion regions leave fewer than 2 cell columns per interior rank (%d columns, %d ranks)",
-           nn[0], P);
-      const int iper = inner / (P - 2), irem = inner % (P - 2);
-      if (r == 0) { c->gx0 = 0; c->gx1 = edge; }
-      else if (r == P - 1) { c->gx0 = nn[0] - edge; c->gx1 = nn[0]; }
-      else {
-        const int k = r - 1;
-        c->gx0 = edge + k * iper + (k < irem ? k : irem);
-        c->gx1 = c->gx0 + iper + (k < irem ? 1 : 0);
-      }
-    }
+    edge = needL > needR ? needL : needR;
   }
+  NEED(obmd_slab_partition(nn[0], P, r, edge, &c->gx0, &c->gx1) == OBMD_OK, OBMD_ERR_ARG,
+       "slab run: the insertion regions leave fewer than 2 cell columns per interior rank (%d columns, %d ranks)",
+       nn[0], P);
   g.gnx = nn[0];
   g.cxoff = c->gx0 > 0 ? c->gx0 - 1 : 0;
   const int hi = c->gx1 < nn[0] ? c->gx1 + 1 : nn[0];

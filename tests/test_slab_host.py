@@ -22,6 +22,20 @@ def test_slab_partition_is_complete_and_disjoint():
                 assert c1 - c0 >= ncols // P
                 cover += list(range(c0, c1))
             assert cover == list(range(ncols))
+    # non-uniform slabs (BASELINE config 5: 16 M atoms, 672 columns, buffer 0.15 Lx = 101 columns + margin > 672 / 8)
+    for ncols, P, edge in ((672, 8, 103), (672, 4, 103), (167, 4, 60), (40, 8, 9)):
+        cover, widths = [], []
+        for r in range(P):
+            c0, c1 = ob.slab_columns(ncols, P, r, edge)
+            cover += list(range(c0, c1)); widths.append(c1 - c0)
+        assert cover == list(range(ncols))
+        if edge > ncols // P:
+            assert widths[0] == widths[-1] == edge
+            assert max(widths[1:-1]) - min(widths[1:-1]) <= 1
+    with pytest.raises(ob.ObmdError):
+        ob.slab_columns(40, 8, 3, 15)       # the edge slabs would leave fewer than 2 columns per interior rank
+    with pytest.raises(ob.ObmdError):
+        ob.slab_columns(7, 4, 0)            # fewer than 2 columns per rank
     rng = np.random.default_rng(1)
     L = 134.37849944008956
     x = rng.uniform(0, L, 20000); x[:3] = (0.0, L, L - 1e-12)
