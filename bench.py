@@ -459,8 +459,8 @@ def ours(args):
                                             "instead of 2000: the USHER trial count is still climbing, ~4.5 k per step "
                                             "instead of ~13 k), kept so that round-over-round numbers are comparable")
             extra["strong_16m"] = secondary(TILINGS["16m"], local, "R1", rank, world, sec_steps, args.warmup,
-                                            min(args.equil, 300), "strong")
-            extra["strong_16m"]["note"] = ("BASELINE config 5 on ONE GPU: the N = 1 point of the strong-scaling series "
+                                            args.equil, "strong")
+            extra["strong_16m"]["note"] = ("BASELINE config 5 on ONE GPU, same equilibration as the N > 1 runs: the N = 1 point of the strong-scaling series "
                                            "`bench.py --gpus N` reports as its primary value for N > 1")
             extra["shear_4m"] = secondary(TILINGS["4m"], local, "R1", rank, world, sec_steps, args.warmup,
                                           min(args.equil, 300), "strong", shear=True)
