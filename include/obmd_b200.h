@@ -207,6 +207,10 @@ int obmd_set_usher_order(obmd_ctx *ctx, int by_tag);
 /* bond_style harmonic + bond_coeff t K r0 (MOLECULE/bond_harmonic.cpp:126-149): k and r0 are 1-based,
  * nbondtypes + 1 entries each (entry 0 unused), nbondtypes <= OBMD_MAXTYPES. */
 int obmd_bond_style_harmonic(obmd_ctx *ctx, int nbondtypes, const double *k, const double *r0);
+/* bond_style fene + bond_coeff t K R0 epsilon sigma (MOLECULE/bond_fene.cpp:53-135, :150-175); a bond
+ * longer than 2 R0 makes obmd_bond_compute fail with "Bad FENE bond" (:94). */
+int obmd_bond_style_fene(obmd_ctx *ctx, int nbondtypes, const double *k, const double *r0,
+                         const double *epsilon, const double *sigma);
 /* The bond topology by atom tags, one entry per bond (Atom::bond_type / bond_atom as read_data leaves
  * them with newton_bond on; NTopoBondAll::build, ntopo_bond_all.cpp:36-77, turns them into the bond list
  * every step through Atom::map and Domain::closest_image).  The topology is static: molecule-aware

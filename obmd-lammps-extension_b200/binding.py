@@ -102,6 +102,7 @@ SIGNATURES = {
     "obmd_profile_x2": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]),
     "obmd_slab_partition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip]),
     "obmd_bond_style_harmonic": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
+    "obmd_bond_style_fene": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]),
     "obmd_upload_bonds": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip, _ip]),
     "obmd_bond_compute": (C.c_int, [C.c_void_p, C.c_int]),
     "obmd_bond_tallies": (C.c_int, [C.c_void_p, _dp, _dp]),
@@ -399,6 +400,11 @@ class ObmdB200:
         kk = np.ascontiguousarray([0.0] + list(k), np.float64)
         rr = np.ascontiguousarray([0.0] + list(r0), np.float64)
         self._ck(self.L.obmd_bond_style_harmonic(self.h, len(kk) - 1, _dptr(kk), _dptr(rr)))
+
+    def bond_style_fene(self, k, r0, epsilon, sigma):
+        """per bond type, lists WITHOUT the unused entry 0 (bond_coeff t K R0 epsilon sigma)."""
+        arr = [np.ascontiguousarray([0.0] + list(v), np.float64) for v in (k, r0, epsilon, sigma)]
+        self._ck(self.L.obmd_bond_style_fene(self.h, len(arr[0]) - 1, *[_dptr(a) for a in arr]))
 
     def upload_bonds(self, btype, tag1, tag2):
         t = np.ascontiguousarray(btype, np.int32); a = np.ascontiguousarray(tag1, np.int32)

@@ -1,4 +1,5 @@
-// Bonded forces: BondHarmonic::compute (MOLECULE/bond_harmonic.cpp:48-103) over the bond list
+// Bonded forces: BondHarmonic::compute (MOLECULE/bond_harmonic.cpp:48-103) and BondFENE::compute
+// (MOLECULE/bond_fene.cpp:53-135) over the bond list
 // NTopoBondAll::build (ntopo_bond_all.cpp:36-77) would make -- the bonded path of BASELINE config 4
 // (SURVEY 8f N3).  Molecule-aware insertion / deletion is NOT here: the topology is static.
 //
@@ -14,8 +15,8 @@
 #include "ctx.h"
 
 struct BondTab {
-  int ntypes;
-  double k[MAXT + 1], r0[MAXT + 1];
+  int ntypes, style;  // style 0: harmonic (k, r0); 1: fene (k, r0, eps, sig)
+  double k[MAXT + 1], r0[MAXT + 1], eps[MAXT + 1], sig[MAXT + 1];
 };
 
 __global__ void k_tag_map_clear(int *__restrict__ map, int n)
@@ -65,15 +66,36 @@ __global__ void __launch_bounds__(256)
           if (delz > g.half[2]) delz -= g.prd[2];
           else if (delz < -g.half[2]) delz += g.prd[2];
           const double rsq = delx * delx + dely * dely + delz * delz;
-          const double r = sqrt(rsq);
           const int ty = ptype[b];
-          const double dr = r - bt.r0[ty];
-          const double rk = bt.k[ty] * dr;
-          const double fbond = (r > 0.0) ? -2.0 * rk / r : 0.0;  // bond_harmonic.cpp:80-83
+          double fbond, ebond;
+          if (bt.style == 0) {  // bond_harmonic.cpp:73-85
+            const double r = sqrt(rsq);
+            const double dr = r - bt.r0[ty];
+            const double rk = bt.k[ty] * dr;
+            fbond = (r > 0.0) ? -2.0 * rk / r : 0.0;
+            ebond = rk * dr;
+          } else {  // bond_fene.cpp:81-117
+            const double r0sq = bt.r0[ty] * bt.r0[ty];
+            double rlogarg = 1.0 - rsq / r0sq;
+            if (rlogarg < 0.1) {  // "FENE bond too long": the reference warns and clamps, aborts beyond 2 r0
+              if (rlogarg <= -3.0) sc->usher_error = OBMD_ERR_NONFINITE;
+              rlogarg = 0.1;
+            }
+            fbond = -bt.k[ty] / rlogarg;
+            double sr6 = 0.0;
+            const bool lj = rsq < 1.25992104989487316476 * bt.sig[ty] * bt.sig[ty];  // MY_CUBEROOT2
+            if (lj) {
+              const double sr2 = bt.sig[ty] * bt.sig[ty] / rsq;
+              sr6 = sr2 * sr2 * sr2;
+              fbond += 48.0 * bt.eps[ty] * sr6 * (sr6 - 0.5) / rsq;
+            }
+            ebond = -0.5 * bt.k[ty] * r0sq * log(rlogarg);
+            if (lj) ebond += 4.0 * bt.eps[ty] * sr6 * (sr6 - 1.0) + bt.eps[ty];
+          }
           ax += delx * fbond;
           ay += dely * fbond;
           az += delz * fbond;
-          e += 0.5 * (rk * dr);  // each bond is seen from both of its atoms
+          e += 0.5 * ebond;  // each bond is seen from both of its atoms
           if (partials) {        // Bond::ev_tally (bond.cpp:174-240), half per atom
             const double h = 0.5 * fbond;
             v0 += h * delx * delx;
@@ -140,9 +162,26 @@ extern "C" int obmd_bond_style_harmonic(obmd_ctx *c, int nbondtypes, const doubl
   NEED(c && k && r0, OBMD_ERR_ARG, "obmd_bond_style_harmonic: NULL argument");
   NEED(nbondtypes >= 1 && nbondtypes <= MAXT, OBMD_ERR_ARG, "obmd_bond_style_harmonic: 1 <= nbondtypes <= %d", MAXT);
   c->nbondtypes = nbondtypes;
+  c->bond_style = 0;
   for (int t = 1; t <= nbondtypes; t++) {
     c->bond_k[t] = k[t];
     c->bond_r0[t] = r0[t];
+  }
+  return OBMD_OK;
+}
+
+extern "C" int obmd_bond_style_fene(obmd_ctx *c, int nbondtypes, const double *k, const double *r0,
+                                    const double *epsilon, const double *sigma)
+{
+  NEED(c && k && r0 && epsilon && sigma, OBMD_ERR_ARG, "obmd_bond_style_fene: NULL argument");
+  NEED(nbondtypes >= 1 && nbondtypes <= MAXT, OBMD_ERR_ARG, "obmd_bond_style_fene: 1 <= nbondtypes <= %d", MAXT);
+  c->nbondtypes = nbondtypes;
+  c->bond_style = 1;
+  for (int t = 1; t <= nbondtypes; t++) {
+    c->bond_k[t] = k[t];
+    c->bond_r0[t] = r0[t];
+    c->bond_eps[t] = epsilon[t];
+    c->bond_sig[t] = sigma[t];
   }
   return OBMD_OK;
 }
@@ -208,9 +247,13 @@ extern "C" int obmd_bond_compute(obmd_ctx *c, int eflag)
   const int nall = nsorted + ex.narr + ex.nghost + ex.nins, nown = nsorted + ex.narr + ex.nins;
   BondTab bt;
   bt.ntypes = c->nbondtypes;
+  bt.style = c->bond_style;
   for (int k = 0; k <= MAXT; k++) {
-    bt.k[k] = k <= c->nbondtypes ? c->bond_k[k] : 0.0;
-    bt.r0[k] = k <= c->nbondtypes ? c->bond_r0[k] : 0.0;
+    const bool on = k >= 1 && k <= c->nbondtypes;
+    bt.k[k] = on ? c->bond_k[k] : 0.0;
+    bt.r0[k] = on ? c->bond_r0[k] : 0.0;
+    bt.eps[k] = (on && c->bond_style == 1) ? c->bond_eps[k] : 0.0;
+    bt.sig[k] = (on && c->bond_style == 1) ? c->bond_sig[k] : 0.0;
   }
   const int nb = cdiv(nown, 256);
   if (eflag && nb * 7 > c->partial_cap) {
@@ -228,6 +271,7 @@ extern "C" int obmd_bond_compute(obmd_ctx *c, int eflag)
   int err = 0;
   CK(cudaMemcpyAsync(&err, &c->sc_d->usher_error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  NEED(err != OBMD_ERR_NONFINITE, OBMD_ERR_NONFINITE, "Bad FENE bond");  // bond_fene.cpp:94
   NEED(err == 0, OBMD_ERR_STATE,
        "Bond atoms missing: a bonded atom was deleted (molecule-aware deletion, fix_obmd_merged.cpp:709-821, is not implemented)");
   return OBMD_OK;

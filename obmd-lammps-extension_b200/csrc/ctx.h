@@ -222,8 +222,8 @@ struct obmd_ctx {
   bool vatom_valid = false;
   int partial_cap = 0;
   // bonded path (bond.cu): harmonic coefficients, topology in CSR form indexed by atom tag, tag -> slot map
-  int nbondtypes = 0;
-  double bond_k[MAXT + 1], bond_r0[MAXT + 1];
+  int nbondtypes = 0, bond_style = 0;  // 0 harmonic, 1 fene
+  double bond_k[MAXT + 1], bond_r0[MAXT + 1], bond_eps[MAXT + 1], bond_sig[MAXT + 1];
   int nbonds = 0, bond_maxtag = 0;
   int *bond_off = nullptr, *bond_partner = nullptr, *bond_ptype = nullptr, *tag_map = nullptr;
   double *bond_e = nullptr;         // [7] bond energy and virial of the latest obmd_bond_compute(eflag = 1)

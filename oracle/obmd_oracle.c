@@ -851,3 +851,53 @@ double orc_bond_harmonic(const orc_fix *p, orc_atoms *a, int nbonds, const int *
   free(map);
   return etot;
 }
+
+/* MOLECULE/bond_fene.cpp:53-135 */
+double orc_bond_fene(const orc_fix *p, orc_atoms *a, int nbonds, const int *btype, const int *tag1,
+                     const int *tag2, const double *k, const double *r0, const double *epsilon,
+                     const double *sigma)
+{
+  const double CUBEROOT2 = 1.25992104989487316476; /* math_const.h MY_CUBEROOT2 */
+  int maxtag = 0;
+  for (int i = 0; i < a->nlocal; i++)
+    if (a->tag[i] > maxtag) maxtag = a->tag[i];
+  int *map = (int *) malloc(sizeof(int) * (size_t) (maxtag + 1));
+  for (int t = 0; t <= maxtag; t++) map[t] = -1;
+  for (int i = 0; i < a->nlocal; i++) map[a->tag[i]] = i;
+  const double prd[3] = {0.0, p->boxhi[1] - p->boxlo[1], p->boxhi[2] - p->boxlo[2]};
+  double etot = 0.0;
+  for (int n = 0; n < nbonds; n++) {
+    if (tag1[n] > maxtag || tag2[n] > maxtag) continue;
+    const int i1 = map[tag1[n]], i2 = map[tag2[n]], ty = btype[n];
+    if (i1 < 0 || i2 < 0) continue;
+    double del[3];
+    for (int d = 0; d < 3; d++) del[d] = a->x[3 * i1 + d] - a->x[3 * i2 + d];
+    for (int d = 1; d < 3; d++) {
+      if (del[d] > 0.5 * prd[d]) del[d] -= prd[d];
+      else if (del[d] < -0.5 * prd[d]) del[d] += prd[d];
+    }
+    const double rsq = del[0] * del[0] + del[1] * del[1] + del[2] * del[2];
+    const double r0sq = r0[ty] * r0[ty];
+    double rlogarg = 1.0 - rsq / r0sq;
+    if (rlogarg < 0.1) { /* :91-96 */
+      if (rlogarg <= -3.0) { free(map); return -1.0e300; }
+      rlogarg = 0.1;
+    }
+    double fbond = -k[ty] / rlogarg, sr6 = 0.0;
+    const int lj = rsq < CUBEROOT2 * sigma[ty] * sigma[ty];
+    if (lj) {
+      const double sr2 = sigma[ty] * sigma[ty] / rsq;
+      sr6 = sr2 * sr2 * sr2;
+      fbond += 48.0 * epsilon[ty] * sr6 * (sr6 - 0.5) / rsq;
+    }
+    double ebond = -0.5 * k[ty] * r0sq * log(rlogarg);
+    if (lj) ebond += 4.0 * epsilon[ty] * sr6 * (sr6 - 1.0) + epsilon[ty];
+    etot += ebond;
+    for (int d = 0; d < 3; d++) {
+      a->f[3 * i1 + d] += del[d] * fbond;
+      a->f[3 * i2 + d] -= del[d] * fbond;
+    }
+  }
+  free(map);
+  return etot;
+}

@@ -126,6 +126,12 @@ double orc_energy(const orc_fix *p, const orc_atoms *a, int itype, const double 
 double orc_bond_harmonic(const orc_fix *p, orc_atoms *a, int nbonds, const int *btype, const int *tag1,
                          const int *tag2, const double *k, const double *r0);
 
+/* BondFENE::compute (MOLECULE/bond_fene.cpp:53-135), same bond list; k, r0, epsilon, sigma 1-based.
+   Returns the bond energy; -1e300 if a bond is longer than 2 r0 ("Bad FENE bond"). */
+double orc_bond_fene(const orc_fix *p, orc_atoms *a, int nbonds, const int *btype, const int *tag1,
+                     const int *tag2, const double *k, const double *r0, const double *epsilon,
+                     const double *sigma);
+
 /* ---- integrator / geometry ---- */
 void orc_nve_initial(const orc_fix *p, orc_atoms *a);  /* fix_nve.cpp:80-145 */
 void orc_nve_final(const orc_fix *p, orc_atoms *a);    /* fix_nve.cpp:185-244 */

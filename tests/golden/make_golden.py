@@ -292,33 +292,39 @@ def make_m0(wd):
         fh.write("\nBonds\n\n")
         for k, (bt, a, b) in enumerate(bonds):
             fh.write("%d %d %d %d\n" % (k + 1, bt, a, b))
-    out = {}
-    for name, pair in (("bond", "pair_style zero 1.0\npair_coeff * *\n"),
-                       ("both", "pair_style dpd 0.0 1.0 2616\npair_coeff * * 209.6 4.5 1.0\n")):
-        deck = ("units lj\nboundary f p p\natom_style bond\natom_modify sort 0 0\ncomm_modify vel yes\n"
-                "newton on\nread_data %s\n%sbond_style harmonic\nbond_coeff 1 100.0 0.5\nbond_coeff 2 50.0 0.8\n"
-                "special_bonds lj 1.0 1.0 1.0\nneighbor 0.4 bin\nneigh_modify delay 0 every 1\ntimestep 0.001464\n"
-                "velocity all create 1.0 4928459 loop geom\n"
-                "dump d all custom 1 dump.m0 id vx vy vz fx fy fz\ndump_modify d format float %%.17g\n"
-                "compute pb all pressure NULL bond\n"
-                "thermo_style custom step pe ebond c_pb[1] c_pb[2] c_pb[3] c_pb[4] c_pb[5] c_pb[6] vol\n"
-                "thermo_modify format float %%.15g norm no\nrun 0\n" % (data, pair))
-        lines = run_deck("m0" + name, deck, wd)
-        (_, r), = read_dump(os.path.join(wd, "dump.m0"))
-        th = None
-        for k, ln in enumerate(lines):
-            if ln.split()[:2] == ["Step", "PotEng"]:
-                th = np.array(lines[k + 1].split(), dtype=np.float64)
-        assert np.array_equal(r[:, 0].astype(np.int64), tag)
-        out[name] = (r, th)
-    np.savez_compressed(os.path.join(HERE, "m0_bond_harmonic.npz"), bonds=bonds, v=out["both"][0][:, 1:4].copy(),
-                        f_bond=out["bond"][0][:, 4:7].copy(), f_both=out["both"][0][:, 4:7].copy(),
-                        ebond=out["bond"][1][2], thermo_both=out["both"][1], k=np.array([0.0, 100.0, 50.0]),
-                        # virial of the bond forces: c_pb = W_ab / V (compute pressure NULL bond; xx yy zz xy xz yz)
-                        virial_bond=out["bond"][1][3:9] * out["bond"][1][9],
-                        r0=np.array([0.0, 0.5, 0.8]))
-    print("m0: bonds", len(bonds), "type-2", int((bonds[:, 0] == 2).sum()), "ebond", out["bond"][1][2],
-          "|f_bond|max", np.abs(out["bond"][0][:, 4:7]).max())
+    styles = {"m0": ("bond_style harmonic\nbond_coeff 1 100.0 0.5\nbond_coeff 2 50.0 0.8\n", "m0_bond_harmonic.npz",
+                     dict(k=np.array([0.0, 100.0, 50.0]), r0=np.array([0.0, 0.5, 0.8]))),
+              # bond_style fene (MOLECULE/bond_fene.cpp:53-135): K R0 epsilon sigma; the WCA part acts below 2^(1/6) sigma
+              "m1": ("bond_style fene\nbond_coeff 1 30.0 1.5 1.0 0.6\nbond_coeff 2 20.0 1.8 0.5 0.7\n", "m1_bond_fene.npz",
+                     dict(k=np.array([0.0, 30.0, 20.0]), r0=np.array([0.0, 1.5, 1.8]), epsilon=np.array([0.0, 1.0, 0.5]),
+                          sigma=np.array([0.0, 0.6, 0.7])))}
+    for key, (bond_cmds, fname, coeffs) in styles.items():
+        out = {}
+        for name, pair in (("bond", "pair_style zero 1.0\npair_coeff * *\n"),
+                           ("both", "pair_style dpd 0.0 1.0 2616\npair_coeff * * 209.6 4.5 1.0\n")):
+            deck = ("units lj\nboundary f p p\natom_style bond\natom_modify sort 0 0\ncomm_modify vel yes\n"
+                    "newton on\nread_data %s\n%s%s"
+                    "special_bonds lj 1.0 1.0 1.0\nneighbor 0.4 bin\nneigh_modify delay 0 every 1\ntimestep 0.001464\n"
+                    "velocity all create 1.0 4928459 loop geom\n"
+                    "dump d all custom 1 dump.m0 id vx vy vz fx fy fz\ndump_modify d format float %%.17g\n"
+                    "compute pb all pressure NULL bond\n"
+                    "thermo_style custom step pe ebond c_pb[1] c_pb[2] c_pb[3] c_pb[4] c_pb[5] c_pb[6] vol\n"
+                    "thermo_modify format float %%.15g norm no\nrun 0\n" % (data, pair, bond_cmds))
+            lines = run_deck(key + name, deck, wd)
+            (_, r), = read_dump(os.path.join(wd, "dump.m0"))
+            th = None
+            for k, ln in enumerate(lines):
+                if ln.split()[:2] == ["Step", "PotEng"]:
+                    th = np.array(lines[k + 1].split(), dtype=np.float64)
+            assert np.array_equal(r[:, 0].astype(np.int64), tag)
+            out[name] = (r, th)
+        np.savez_compressed(os.path.join(HERE, fname), bonds=bonds, v=out["both"][0][:, 1:4].copy(),
+                            f_bond=out["bond"][0][:, 4:7].copy(), f_both=out["both"][0][:, 4:7].copy(),
+                            ebond=out["bond"][1][2], thermo_both=out["both"][1],
+                            # virial of the bond forces: c_pb = W_ab / V (compute pressure NULL bond; xx yy zz xy xz yz)
+                            virial_bond=out["bond"][1][3:9] * out["bond"][1][9], **coeffs)
+        print(key, ": bonds", len(bonds), "type-2", int((bonds[:, 0] == 2).sum()), "ebond", out["bond"][1][2],
+              "|f_bond|max", np.abs(out["bond"][0][:, 4:7]).max())
 
 
 def read_chunk_file(path, ncol):

@@ -970,3 +970,34 @@ def test_bond_harmonic_vs_reference_and_oracle(shipped):
     assert np.abs(o["x"] - a.view("x")).max() < 1e-11
     assert cc.mixed_rel_err(o["f"], a.view("f")) < FTOL
     sim.close()
+
+
+def test_bond_fene_vs_reference(shipped):
+    """bond_style fene on the device (csrc/bond.cu) against the reference binary's BondFENE
+    (MOLECULE/bond_fene.cpp:53-135): forces, energy, virial; and the reference's abort for a bond longer
+    than 2 R0 ("Bad FENE bond")."""
+    import obmd_b200 as ob
+    tag, x, box = shipped
+    g = cc.load("m1_bond_fene.npz")
+    b = g["bonds"]
+    sim = cc.device_sim(box, temperature=0.0, fix=False)
+    sim.bond_style_fene(g["k"][1:], g["r0"][1:], g["epsilon"][1:], g["sigma"][1:])
+    sim.upload(x, g["v"], np.ones(len(x), np.int32), tag)
+    sim.upload_bonds(b[:, 0], b[:, 1], b[:, 2])
+    sim.build_cells(); sim.pbc()
+    sim.zero_forces(); sim.bond_compute(1)
+    f = sim.download(("f",))["f"]
+    scale = np.abs(g["f_bond"]).max()
+    assert np.abs(f - g["f_bond"]).max() <= 1e-9 * scale
+    e, w = sim.bond_tallies()
+    assert abs(e - float(g["ebond"])) <= 1e-10 * abs(float(g["ebond"]))
+    assert np.abs(w - g["virial_bond"]).max() <= 1e-9 * np.abs(g["virial_bond"]).max()
+    sim.pair_compute(0); sim.bond_compute(0)
+    f2 = sim.download(("f",))["f"]
+    assert np.abs(f2 - g["f_both"]).max() <= 1e-9 * np.abs(g["f_both"]).max()
+    # a bond between two far-apart atoms: longer than 2 R0
+    far = int(np.argmax(x[:, 0])), int(np.argmin(x[:, 0]))
+    sim.upload_bonds([1], [tag[far[0]]], [tag[far[1]]])
+    with pytest.raises(ob.ObmdError, match="Bad FENE bond"):
+        sim.bond_compute(0)
+    sim.close()

@@ -334,3 +334,24 @@ def test_m0_bond_harmonic_vs_reference(shipped):
     L.orc_bond_harmonic(C.byref(p), C.byref(a2.c), len(b), ip(bt), ip(t1), ip(t2), dp(k), dp(r0))
     scale = np.abs(g["f_both"]).max()
     assert np.abs(a2.view("f") - g["f_both"]).max() <= 1e-9 * scale
+
+
+def test_m1_bond_fene_vs_reference(shipped):
+    """orc_bond_fene (MOLECULE/bond_fene.cpp:53-135) against the reference binary on the same 6803 bonds:
+    log term and WCA part (bonds shorter than 2^(1/6) sigma exist: |f| up to 2.7e4)."""
+    tag, x, box = shipped
+    g = load("m1_bond_fene.npz")
+    b = np.ascontiguousarray(g["bonds"], np.int32)
+    bt, t1, t2 = (np.ascontiguousarray(b[:, k]) for k in range(3))
+    co = [np.ascontiguousarray(g[n]) for n in ("k", "r0", "epsilon", "sigma")]
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    L = O.lib()
+    L.orc_bond_fene.restype = C.c_double
+    p = O.make_fix(box[:, 0], box[:, 1], temperature=0.0)
+    a = O.OracleAtoms(x, v=g["v"], tag=tag)
+    e = L.orc_bond_fene(C.byref(p), C.byref(a.c), len(b), ip(bt), ip(t1), ip(t2), *[dp(c) for c in co])
+    scale = np.abs(g["f_bond"]).max()
+    assert scale > 1e3
+    assert np.abs(a.view("f") - g["f_bond"]).max() <= 1e-9 * scale
+    assert abs(e - float(g["ebond"])) <= 1e-10 * abs(float(g["ebond"]))
